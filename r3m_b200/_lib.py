@@ -1,0 +1,63 @@
+"""ctypes binding of libr3m_b200.so (the C ABI declared in include/r3m_b200.h).
+
+The library is the product: there is no Python/CPU fallback.  Importing this module on a machine where the shared
+library has not been built raises ImportError; calling a compute entry point without an sm_100 GPU raises
+RuntimeError with the library's own message.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libr3m_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C r3m_b200/csrc` (nvcc, sm_100a). r3m_b200 has no fallback path."
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_int = ctypes.c_int
+c_void_p = ctypes.c_void_p
+c_float = ctypes.c_float
+c_size_t = ctypes.c_size_t
+
+lib.r3m_b200_last_error.restype = ctypes.c_char_p
+lib.r3m_b200_last_error.argtypes = []
+
+
+class R3MB200Error(RuntimeError):
+    pass
+
+
+def check(code):
+    if code != 0:
+        msg = lib.r3m_b200_last_error().decode("utf-8", "replace")
+        raise R3MB200Error(f"r3m_b200 error {code}: {msg}")
+
+
+def _sig(name, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = c_int
+    fn.argtypes = argtypes
+    return fn
+
+
+_sig("r3m_b200_abi_version", [])
+_sig("r3m_b200_check_device_flag", [])
+_sig("r3m_b200_conv_fwd", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p, c_void_p])
+_sig("r3m_b200_pack_dgrad_filter", [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p])
+_sig("r3m_b200_conv_dgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p])
+_sig("r3m_b200_conv_wgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p])
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, or None."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,348 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16 in / bf16 out, fp32 accumulate.
+//
+//   Y[m, k] = sum_{tap, c} X[pixel(m) + tap, c] * Wp[k, tap, c]          m = flattened (n, p, q)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0    TMA producer : A tile = 128 output pixels x 64 channels of ONE filter tap, fetched by a single
+//                            im2col-mode TMA (the hardware walks W->H->N inside the padded bounding box and
+//                            zero-fills the halo); B tile = BN x 64 slice of the packed filter, tiled TMA.
+//                            Both land in 128B-swizzled K-major shared memory.
+//   warp 1    MMA issuer   : one thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage; accumulators
+//                            live in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
+//                            the main loop of tile i+1.
+//   warp 2    TMEM allocator.
+//   warps 4-7 epilogue     : tcgen05.ld -> bf16 -> swizzled smem staging -> (a) per-channel sum / sum-of-squares
+//                            for train-mode BatchNorm, accumulated per CTA in smem and flushed once with
+//                            atomics, (b) fully coalesced 128-byte row stores (dense or strided scatter).
+//
+// The same kernel serves: every forward conv of ResNet-18/34/50 (ref: torchvision resnet.py conv1/conv2/conv3/
+// downsample and the 7x7 stem re-expressed as a 4x1-tap conv over a space-to-depth view), and every dgrad
+// (stride-1: rotated/transposed filter; stride-2: one launch per output-parity class with scatter stores).
+#include "conv_igemm.cuh"
+
+#include "ptx.cuh"
+
+namespace r3m {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kStagingBytes = 4 * 32 * 128;  // 4 epilogue warps x 32 rows x 64 bf16
+constexpr int kMaxStatC = 2048;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStagingBytes + 2 * kMaxStatC * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKernelParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  float* s_sum = reinterpret_cast<float*>(staging + kStagingBytes);
+  float* s_sq = s_sum + kMaxStatC;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + kMaxStatC);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool do_stats = (p.stat_sum != nullptr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (do_stats) {
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      s_sum[i] = 0.f;
+      s_sq[i] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = p.num_taps * p.cblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int n_img = m0 / p.PQ;
+        const int rem = m0 - n_img * p.PQ;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        const int cw = p.base_w + qq * p.stride;
+        const int ch = p.base_h + pp * p.stride;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) {
+            atomicExch(p.error_flag, 1);
+            ok = false;
+            break;
+          }
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
+          tma_load_2d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_tile * BN);
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+          }
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) {
+          atomicExch(p.error_flag, 2);
+          break;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!mbar_wait(&full_bar[stage], phase)) {
+            atomicExch(p.error_flag, 3);
+            ok = false;
+            break;
+          }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is >>4)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (!ok) break;
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
+    uint8_t* stg = staging + ew * (32 * 128);
+    const uint32_t stg_u32 = smem_u32(stg);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool ok = true;
+    __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m0 = m_tile * kBlockM + ew * 32;
+      const int n0 = n_tile * BN;
+      // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
+      long long row_off[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + 4 * i + (lane >> 3);
+        if (m >= p.M_total) {
+          row_off[i] = -1;
+        } else if (p.out_mode == 0) {
+          row_off[i] = static_cast<long long>(m) * p.ldo;
+        } else {
+          const int n_img = m / p.PQ;
+          const int rem = m - n_img * p.PQ;
+          const int pp = rem / p.Q;
+          const int qq = rem - pp * p.Q;
+          row_off[i] = ((static_cast<long long>(n_img) * p.oH + (pp * p.o_stride + p.o_h0)) * p.oW +
+                        (qq * p.o_stride + p.o_w0)) * p.ldo;
+        }
+      }
+      if (!mbar_wait(&tfull_bar[acc], acc_phase)) {
+        if (lane == 0) atomicExch(p.error_flag, 4);
+        ok = false;
+        break;
+      }
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_row + chunk * 64, v0);
+        tmem_ld_32x32(t_row + chunk * 64 + 32, v1);
+        tc_wait_ld();
+        // thread = row `lane`; write 8 x 16B chunks, XOR-swizzled by row so that both the row-wise writes
+        // here and the transposed reads below are bank-conflict free
+        const uint32_t rbase = stg_u32 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a0 = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+          const uint32_t a1 = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+          const uint32_t a2 = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+          const uint32_t a3 = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
+          const uint32_t addr = rbase + (((j) ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+                       : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a0 = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+          const uint32_t a1 = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+          const uint32_t a2 = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+          const uint32_t a3 = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
+          const uint32_t addr = rbase + (((j + 4) ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+                       : "memory");
+        }
+        __syncwarp();
+        if (do_stats) {
+          // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk; rows beyond M_total are exact zeros
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            uint32_t w;
+            const uint32_t addr = stg_u32 + r * 128 + ((((lane >> 2)) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+            const float a = bf16lo(w), b = bf16hi(w);
+            s0 += a;
+            s1 += b;
+            q0 = fmaf(a, a, q0);
+            q1 = fmaf(b, b, q1);
+          }
+          const int col = n0 + chunk * 64 + 2 * lane;
+          atomicAdd(&s_sum[col], s0);
+          atomicAdd(&s_sum[col + 1], s1);
+          atomicAdd(&s_sq[col], q0);
+          atomicAdd(&s_sq[col + 1], q1);
+        }
+        // coalesced stores: 8 lanes x 16 B = one 128-byte output row segment, 4 rows per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          const int c = lane & 7;
+          uint32_t x0, x1, x2, x3;
+          const uint32_t addr = stg_u32 + r * 128 + ((c ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+          if (row_off[i] >= 0) {
+            uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + chunk * 64 + c * 8);
+            if (p.accumulate) {
+              const uint4 o = *dst;
+              x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
+              x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
+              x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
+              x3 = pack_bf16x2(bf16lo(x3) + bf16lo(o.w), bf16hi(x3) + bf16hi(o.w));
+            }
+            *dst = make_uint4(x0, x1, x2, x3);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (do_stats) {
+      // all four epilogue warps are done with every tile of this CTA -> flush the CTA partials
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < p.Cout; i += 128) {
+        const float s = s_sum[i], q = s_sq[i];
+        if (s != 0.f || q != 0.f) {
+          atomicAdd(&p.stat_sum[i], s);
+          atomicAdd(&p.stat_sq[i], q);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int grid,
+                      cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  conv_igemm_kernel<BN><<<grid, 256, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
+                              int grid, cudaStream_t stream) {
+  switch (bn) {
+    case 64:
+      return launch_bn<64>(tmA, tmB, p, grid, stream);
+    case 128:
+      return launch_bn<128>(tmA, tmB, p, grid, stream);
+    case 256:
+      return launch_bn<256>(tmA, tmB, p, grid, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace r3m

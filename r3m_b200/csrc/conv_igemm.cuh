@@ -1,0 +1,64 @@
+// Internal launch interface of the tcgen05 implicit-GEMM kernels (conv_igemm.cu, wgrad.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace r3m {
+
+constexpr int kMaxTaps = 16;
+
+struct ConvKernelParams {
+  // GEMM rows: flattened (n, p, q) base positions of the im2col traversal
+  int M_total;
+  int PQ, Q;
+  int stride;          // traversal stride of the base pixel (conv stride)
+  int base_w, base_h;  // lower corner of the bounding box (= -pad for a forward conv)
+  // GEMM K: taps x 64-channel blocks
+  int num_taps;
+  int cblocks;
+  uint16_t tap_w[kMaxTaps];
+  uint16_t tap_h[kMaxTaps];
+  // GEMM N
+  int Cout;
+  int num_m_tiles, num_n_tiles;
+  // output
+  void* out;     // bf16
+  int out_mode;  // 0: row m at m*ldo;  1: row m=(n,p,q) scattered to ((n*oH + p*o_stride+o_h0)*oW + q*o_stride+o_w0)*ldo
+  int ldo;
+  int oH, oW, o_stride, o_h0, o_w0;
+  int accumulate;  // out += result (bf16 read-modify-write)
+  // optional per-channel statistics of the (bf16-rounded) output
+  float* stat_sum;
+  float* stat_sq;
+  int* error_flag;
+};
+
+cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
+                              int grid, cudaStream_t stream);
+
+struct WgradKernelParams {
+  int M_total;
+  int PQ, Q;
+  int stride;
+  int base_w, base_h;
+  int cblocks;      // 64-channel blocks of the activation per tap
+  int num_items;    // taps * cblocks   (one item = one 64-wide slice of the filter's K axis)
+  int group;        // items per CTA (<= 8)
+  uint16_t tap_w[kMaxTaps];
+  uint16_t tap_h[kMaxTaps];
+  int Cout;         // rows of dW
+  int ldw;          // elements per dW row (= taps * Cin)
+  int Cin;
+  int mblocks_total;      // ceil(M_total / 64)
+  int mblocks_per_split;
+  int num_stages;
+  float* dW;        // fp32, accumulated with red.add
+  int* error_flag;
+};
+
+cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const WgradKernelParams& p, int splits,
+                         int groups, int ktiles, cudaStream_t stream);
+int wgrad_smem_bytes(int group, int num_stages);
+
+}  // namespace r3m

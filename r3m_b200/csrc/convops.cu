@@ -1,0 +1,216 @@
+#include "convops.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "tmap.h"
+
+namespace r3m {
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int* device_error_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+static int pick_bn(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  return 64;
+}
+
+std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
+  if (g.C % 64 != 0) return "gather conv: source channels must be a multiple of 64";
+  if (g.Cout % 64 != 0) return "gather conv: output channels must be a multiple of 64";
+  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return "gather conv: tap count out of range";
+  if (g.stride < 1 || g.stride > 8) return "gather conv: stride out of range";
+  if (g.ldo % 8 != 0) return "gather conv: output row pitch must be a multiple of 8 elements";
+  *plan = {};
+  const int upper_w = (g.Q - 1) * g.stride + 1 + g.base_w - g.W;
+  const int upper_h = (g.P - 1) * g.stride + 1 + g.base_h - g.H;
+  std::string err = encode_im2col_map(&plan->tmA, g.src, g.C, g.W, g.H, g.N, g.base_w, g.base_h, upper_w, upper_h, 64,
+                                      128, g.stride);
+  if (!err.empty()) return err;
+  const int bn = pick_bn(g.Cout);
+  const uint64_t kdim = (uint64_t)g.ntaps * g.C;
+  err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * 2, 64, bn);
+  if (!err.empty()) return err;
+  ConvKernelParams& p = plan->p;
+  p.M_total = g.N * g.P * g.Q;
+  p.PQ = g.P * g.Q;
+  p.Q = g.Q;
+  p.stride = g.stride;
+  p.base_w = g.base_w;
+  p.base_h = g.base_h;
+  p.num_taps = g.ntaps;
+  p.cblocks = g.C / 64;
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.tap_w[t] < 0 || g.tap_h[t] < 0) return "gather conv: tap offsets must be non-negative";
+    p.tap_w[t] = (uint16_t)g.tap_w[t];
+    p.tap_h[t] = (uint16_t)g.tap_h[t];
+  }
+  p.Cout = g.Cout;
+  p.num_m_tiles = (p.M_total + 127) / 128;
+  p.num_n_tiles = g.Cout / bn;
+  p.out = g.out;
+  p.out_mode = g.out_mode;
+  p.ldo = g.ldo;
+  p.oH = g.oH;
+  p.oW = g.oW;
+  p.o_stride = g.o_stride;
+  p.o_h0 = g.o_h0;
+  p.o_w0 = g.o_w0;
+  p.accumulate = g.accumulate;
+  p.stat_sum = g.stat_sum;
+  p.stat_sq = g.stat_sq;
+  p.error_flag = device_error_flag();
+  if (!p.error_flag) return "could not allocate the device error flag";
+  plan->bn = bn;
+  plan->grid = std::min(p.num_m_tiles * p.num_n_tiles, device_sm_count());
+  return std::string();
+}
+
+cudaError_t run_conv(const ConvPlan& plan, cudaStream_t stream) {
+  return conv_igemm_launch(plan.bn, plan.tmA, plan.tmB, plan.p, plan.grid, stream);
+}
+
+std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
+  if (d.C % 64 != 0 || d.Cout % 64 != 0) return "wgrad: channel counts must be multiples of 64";
+  if (d.ntaps < 1 || d.ntaps > kMaxTaps) return "wgrad: tap count out of range";
+  *plan = {};
+  const int M = d.N * d.P * d.Q;
+  std::string err = encode_tiled_2d_map(&plan->tmDy, d.dy, (uint64_t)d.Cout, (uint64_t)M, (uint64_t)d.Cout * 2, 64, 64);
+  if (!err.empty()) return err;
+  const int upper_w = (d.Q - 1) * d.stride + 1 + d.base_w - d.W;
+  const int upper_h = (d.P - 1) * d.stride + 1 + d.base_h - d.H;
+  err = encode_im2col_map(&plan->tmX, d.x, d.C, d.W, d.H, d.N, d.base_w, d.base_h, upper_w, upper_h, 64, 64, d.stride);
+  if (!err.empty()) return err;
+  WgradKernelParams& p = plan->p;
+  p.M_total = M;
+  p.PQ = d.P * d.Q;
+  p.Q = d.Q;
+  p.stride = d.stride;
+  p.base_w = d.base_w;
+  p.base_h = d.base_h;
+  p.cblocks = d.C / 64;
+  p.num_items = d.ntaps * p.cblocks;
+  p.group = std::min(4, p.num_items);
+  for (int t = 0; t < d.ntaps; ++t) {
+    p.tap_w[t] = (uint16_t)d.tap_w[t];
+    p.tap_h[t] = (uint16_t)d.tap_h[t];
+  }
+  p.Cout = d.Cout;
+  p.Cin = d.C;
+  p.ldw = d.ntaps * d.C;
+  p.mblocks_total = (M + 63) / 64;
+  p.num_stages = std::min(6, (227 * 1024 - 2048) / ((2 + p.group) * 8192));
+  p.dW = d.dw;
+  p.error_flag = device_error_flag();
+  if (!p.error_flag) return "could not allocate the device error flag";
+  plan->groups = (p.num_items + p.group - 1) / p.group;
+  plan->ktiles = (d.Cout + 127) / 128;
+  const int slabs = plan->groups * plan->ktiles;
+  int splits = (2 * device_sm_count() + slabs - 1) / slabs;
+  splits = std::max(1, std::min(splits, p.mblocks_total));
+  p.mblocks_per_split = (p.mblocks_total + splits - 1) / splits;
+  plan->splits = (p.mblocks_total + p.mblocks_per_split - 1) / p.mblocks_per_split;
+  return std::string();
+}
+
+cudaError_t run_wgrad(const WgradPlan& plan, cudaStream_t stream) {
+  return wgrad_launch(plan.tmDy, plan.tmX, plan.p, plan.splits, plan.groups, plan.ktiles, stream);
+}
+
+void fill_fwd_geometry(GatherConv* g, int R, int S, int stride, int pad) {
+  g->P = (g->H + 2 * pad - R) / stride + 1;
+  g->Q = (g->W + 2 * pad - S) / stride + 1;
+  g->stride = stride;
+  g->base_h = -pad;
+  g->base_w = -pad;
+  g->ntaps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      g->tap_h[r * S + s] = r;
+      g->tap_w[r * S + s] = s;
+    }
+}
+
+void fill_fwd_geometry(WgradDesc* d, int R, int S, int stride, int pad) {
+  d->P = (d->H + 2 * pad - R) / stride + 1;
+  d->Q = (d->W + 2 * pad - S) / stride + 1;
+  d->stride = stride;
+  d->base_h = -pad;
+  d->base_w = -pad;
+  d->ntaps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      d->tap_h[r * S + s] = r;
+      d->tap_w[r * S + s] = s;
+    }
+}
+
+namespace {
+struct AxisTap {
+  int src;  // forward filter index
+  int d;    // dY offset relative to the class index i
+};
+// taps along one axis for output parity `par`: forward index r contributes iff (par + pad - r) is a multiple of stride
+std::vector<AxisTap> axis_taps(int par, int R, int stride, int pad) {
+  std::vector<AxisTap> v;
+  for (int r = 0; r < R; ++r) {
+    const int num = par + pad - r;
+    int q = num / stride;
+    if (q * stride != num) continue;
+    v.push_back({r, q});
+  }
+  return v;
+}
+}  // namespace
+
+std::vector<DgradClass> dgrad_classes(int H, int W, int R, int S, int stride, int pad) {
+  std::vector<DgradClass> out;
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      DgradClass c;
+      c.ph = ph;
+      c.pw = pw;
+      c.Pc = (H - ph + stride - 1) / stride;
+      c.Qc = (W - pw + stride - 1) / stride;
+      const std::vector<AxisTap> th = axis_taps(ph, R, stride, pad);
+      const std::vector<AxisTap> tw = axis_taps(pw, S, stride, pad);
+      c.ntaps = 0;
+      if (!th.empty() && !tw.empty()) {
+        int bh = th[0].d, bw = tw[0].d;
+        for (const AxisTap& a : th) bh = std::min(bh, a.d);
+        for (const AxisTap& a : tw) bw = std::min(bw, a.d);
+        c.base_h = bh;
+        c.base_w = bw;
+        for (const AxisTap& a : th)
+          for (const AxisTap& b : tw) {
+            c.tap_h[c.ntaps] = a.d - bh;
+            c.tap_w[c.ntaps] = b.d - bw;
+            c.src_r[c.ntaps] = a.src;
+            c.src_s[c.ntaps] = b.src;
+            ++c.ntaps;
+          }
+      }
+      out.push_back(c);
+    }
+  return out;
+}
+
+}  // namespace r3m

@@ -1,0 +1,89 @@
+// Launch interface of the HBM-bound kernels around the convolutions (NHWC bf16 activations, fp32 statistics).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace r3m {
+
+constexpr float kBnEps = 1e-5f;       // torch.nn.BatchNorm2d default (tv resnet.py: norm_layer = nn.BatchNorm2d)
+constexpr float kBnMomentum = 0.1f;
+
+// obs fp32 NCHW [N,3,224,224] in [0,255]  ->  stem operand bf16 [N,112,112,64]:
+//   channel j = kw*16 + (dy*2+dx)*4 + c  holds  normalise(obs[n, c, 2*i+dy, 2*(q-2+kw)+dx])   (0 outside / c == 3)
+// ref: r3m/models/models_r3m.py:97-98 (x/255, Normalize(mean,std)) fused with the space-to-depth re-layout.
+cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream_t s);
+
+struct BnApplyArgs {
+  const void* y = nullptr;      // bf16 [M][C] raw conv output
+  void* a = nullptr;            // bf16 [M][C] activated output
+  const void* residual = nullptr;  // bf16 [M][C] or null
+  int M = 0, C = 0;
+  int relu = 1;
+  int train = 1;                // 1: batch statistics from (sum, sq);  0: running statistics
+  const float* sum = nullptr;   // [C]
+  const float* sq = nullptr;    // [C]
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float* running_mean = nullptr;
+  float* running_var = nullptr;
+  float* save_mean = nullptr;   // [C] written in train mode (for backward)
+  float* save_rstd = nullptr;
+  int update_running = 1;
+};
+cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s);
+
+// stem: y [N,112,112,64] -> BN -> ReLU -> maxpool 3x3 s2 p1 -> a [N,56,56,64], argmax code (0..8) per element
+struct StemPoolArgs {
+  const void* y = nullptr;
+  void* a = nullptr;
+  uint8_t* argmax = nullptr;  // may be null (eval)
+  int N = 0, H = 112, W = 112, C = 64;
+  int train = 1;
+  const float* sum = nullptr;
+  const float* sq = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float* running_mean = nullptr;
+  float* running_var = nullptr;
+  float* save_mean = nullptr;
+  float* save_rstd = nullptr;
+  int update_running = 1;
+};
+cudaError_t launch_stem_bn_relu_maxpool(const StemPoolArgs& a, cudaStream_t s);
+// dz[n,h,w,c] = sum over pooling windows whose argmax is (h,w) of dA[window] * (a[window] > 0)
+cudaError_t launch_maxpool_bwd(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W,
+                               int C, cudaStream_t s);
+
+cudaError_t launch_avgpool_fwd(const void* a, float* out, int N, int HW, int C, cudaStream_t s);
+cudaError_t launch_avgpool_bwd(const float* dE, void* dA, int N, int HW, int C, cudaStream_t s);
+
+struct BnBwdArgs {
+  const void* dA = nullptr;   // bf16 [M][C] gradient w.r.t. the layer's (activated) output
+  const void* a = nullptr;    // bf16 [M][C] activated output (ReLU mask) or null when no ReLU follows / already masked
+  const void* y = nullptr;    // bf16 [M][C] raw conv output
+  int M = 0, C = 0;
+  const float* mean = nullptr;
+  const float* rstd = nullptr;
+  const float* gamma = nullptr;
+  float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); zeroed by the caller
+  void* dy = nullptr;         // bf16 [M][C] gradient w.r.t. the raw conv output
+  void* dz_out = nullptr;     // optional bf16 [M][C]: masked gradient (feeds the residual branch)
+  float* dgamma = nullptr;    // [C]
+  float* dbeta = nullptr;
+};
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
+cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
+
+// Adam (torch.optim.Adam defaults, ref r3m/models/models_r3m.py:76): flat fp32 p/g/m/v, also emits the bf16 copy.
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, float beta1,
+                        float beta2, float eps, int step, float grad_scale, cudaStream_t s);
+cudaError_t launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+
+// dgrad filter: out[c][t][k] = w[k][src_tap[t]][c]   (w fp32 [Cout][T][Cin] -> bf16 [Cin][nt][Cout])
+cudaError_t launch_pack_dgrad(const float* w, void* out, int Cout, int T, int Cin, int nt, const int* src_tap,
+                              cudaStream_t s);
+// stem filter OIHW fp32 [64,3,7,7] <-> packed [64][4][64] (bf16 forward operand / fp32 gradient)
+cudaError_t launch_stem_pack(const float* w_oihw, void* wp_bf16, cudaStream_t s);
+cudaError_t launch_stem_unpack_grad(const float* dwp, float* dw_oihw, cudaStream_t s);
+
+}  // namespace r3m

@@ -1,0 +1,202 @@
+// Filter-gradient (wgrad) implicit GEMM on tcgen05 (sm_100a).
+//
+//   dW[k, tap, c] = sum_m dY[m, k] * X[pixel(m) + tap, c]            m = flattened (n, p, q)
+//
+// The reduction runs over pixels, which is the OUTER dimension of both NHWC operands, so both are fed to the
+// tensor core as MN-major tiles (channels contiguous, 128B-swizzled rows of 64 channels):
+//   A' = dY tile   [64 pixels][128 out-channels]  -> two tiled-TMA boxes of 64 channels
+//   B' = X  tiles  [64 pixels][64 in-channels] for up to 8 (tap, channel-block) items -> im2col TMA each
+// One CTA owns a 128 x (64*group) slab of dW for a contiguous range of pixel blocks (split-K); the fp32 partial
+// sits in TMEM for the whole CTA lifetime (up to all 512 columns) and is added to global memory once, with
+// vectorised red.global.add.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue.
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+namespace r3m {
+
+namespace {
+
+constexpr int kPixBlock = 64;          // reduction rows per stage
+constexpr int kAtomBytes = 64 * 128;   // one [64 pixels][64 channels] bf16 tile
+constexpr int kTmemCols = 512;
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+             const WgradKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = (2 + p.group) * kAtomBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int item0 = blockIdx.y * p.group;
+  const int g_count = min(p.group, p.num_items - item0);
+  const int k0 = blockIdx.z * 128;
+  const int a_atoms = (p.Cout - k0 >= 128) ? 2 : 1;
+  const int blk_begin = blockIdx.x * p.mblocks_per_split;
+  const int blk_end = min(p.mblocks_total, blk_begin + p.mblocks_per_split);
+  const int nblk = blk_end - blk_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nblk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = static_cast<uint32_t>((a_atoms + g_count) * kAtomBytes);
+        for (int blk = blk_begin; blk < blk_end; ++blk) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) {
+            atomicExch(p.error_flag, 11);
+            break;
+          }
+          const int m0 = blk * kPixBlock;
+          const int n_img = m0 / p.PQ;
+          const int rem = m0 - n_img * p.PQ;
+          const int pp = rem / p.Q;
+          const int qq = rem - pp * p.Q;
+          const int cw = p.base_w + qq * p.stride;
+          const int ch = p.base_h + pp * p.stride;
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + 2 * kAtomBytes;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          for (int a = 0; a < a_atoms; ++a) tma_load_2d(&tmDy, &full_bar[stage], sa + a * kAtomBytes, k0 + a * 64, m0);
+          int tap = item0 / p.cblocks;
+          int cb = item0 - tap * p.cblocks;
+          for (int g = 0; g < g_count; ++g) {
+            tma_load_im2col_4d(&tmX, &full_bar[stage], sb + g * kAtomBytes, cb * 64, cw, ch, n_img, p.tap_w[tap],
+                               p.tap_h[tap]);
+            if (++cb == p.cblocks) {
+              cb = 0;
+              ++tap;
+            }
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // MN-major SW128 canonical layout: 64-channel atoms LBO apart along M/N, 8-pixel groups SBO apart along K.
+        // With a single 64-channel atom of dY (Cout == 64) the second M atom aliases the first (LBO = 0); its
+        // 64 duplicate accumulator rows are never read back.
+        const uint32_t lbo_a = (a_atoms == 2) ? kAtomBytes : 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int blk = 0; blk < nblk; ++blk) {
+          if (!mbar_wait(&full_bar[stage], phase)) {
+            atomicExch(p.error_flag, 12);
+            ok = false;
+            break;
+          }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 2 * kAtomBytes;
+#pragma unroll
+          for (int ks = 0; ks < kPixBlock / 16; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + ks * 2048, lbo_a, 1024);
+            // the items of a group are consecutive 64-wide N atoms (LBO apart), so up to four of them go into one
+            // N = 256 instruction: A is then read from shared memory once per four items
+            for (int g = 0; g < g_count; g += 4) {
+              const int n = min(4, g_count - g) * 64;
+              const uint32_t idesc = make_idesc(/*bf16*/ 1, 128, n, /*a MN-major*/ 1, /*b MN-major*/ 1);
+              const uint64_t db = make_smem_desc_sw128(b_addr + g * kAtomBytes + ks * 2048, kAtomBytes, 1024);
+              umma_bf16(tmem_base + g * 64, da, db, idesc, (blk | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (ok) umma_commit(done_bar);
+      }
+    } else if (warp >= 4) {
+      const int ew = warp - 4;
+      const int row = ew * 32 + lane;  // dW row inside the 128-row slab
+      const bool row_ok = (k0 + row < p.Cout) && (a_atoms == 2 || row < 64);
+      if (!mbar_wait(done_bar, 0)) {
+        if (lane == 0) atomicExch(p.error_flag, 13);
+      } else {
+        tc_fence_after();
+        int tap = item0 / p.cblocks;
+        int cb = item0 - tap * p.cblocks;
+        for (int g = 0; g < g_count; ++g) {
+          float* dst_row = p.dW + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + g * 64 + half * 32, v);
+            tc_wait_ld();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float* d = dst_row + half * 32 + j * 4;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(v[4 * j])),
+                             "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                             "f"(__uint_as_float(v[4 * j + 3]))
+                             : "memory");
+              }
+            }
+          }
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int wgrad_smem_bytes(int group, int num_stages) { return num_stages * (2 + group) * kAtomBytes + 256 + 1024; }
+
+cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const WgradKernelParams& p, int splits,
+                         int groups, int ktiles, cudaStream_t stream) {
+  static int configured_bytes = 0;
+  const int bytes = wgrad_smem_bytes(p.group, p.num_stages);
+  if (bytes > configured_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    configured_bytes = bytes;
+  }
+  wgrad_kernel<<<dim3(splits, groups, ktiles), 256, bytes, stream>>>(tmDy, tmX, p);
+  return cudaGetLastError();
+}
+
+}  // namespace r3m
