@@ -54,6 +54,60 @@ int r3m_b200_conv_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, in
 int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                         int stride, int pad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine: the whole hot path behind R3M.forward (r3m/models/models_r3m.py:84-100) and Trainer.update
+ * (r3m/trainer.py:25-162) for one backbone size and one frame count.  The caller owns two device allocations
+ * (1024-byte aligned, e.g. torch uint8 tensors): the PARAMETER BLOCK (r3m_b200_engine_param_block_bytes(): flat
+ * fp32 parameters / gradients / Adam moments, BN running statistics, bf16 operand copies; depends only on the
+ * model, so engines for different frame counts of one model share it; the caller zero-fills it and then loads
+ * weights) and the per-engine WORKSPACE (r3m_b200_engine_workspace_bytes(): activations, saved statistics).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* size: 18 | 34 | 50 (torchvision resnet, models_r3m.py:44-52); frames: images per call (5 * clips for update);
+ * lang_head: build the LanguageReward MLP (models_language.py:37-55) with hidden_dim units. */
+int r3m_b200_engine_create(int size, int frames, int lang_head, int hidden_dim, void** handle);
+int r3m_b200_engine_destroy(void* handle);
+int r3m_b200_engine_workspace_bytes(void* handle, size_t* bytes);
+int r3m_b200_engine_param_block_bytes(void* handle, size_t* bytes);
+/* Attaches both allocations and builds the launch schedule (TMA descriptors are encoded here). */
+int r3m_b200_engine_bind(void* handle, void* param_block, size_t param_bytes, void* workspace, size_t bytes,
+                         void* stream);
+
+/* state_dict bridge: table of named tensors.  kind: 0 conv filter stored [Cout][R][S][Cin] (state_dict OIHW),
+ * 1 stem filter stored OIHW, 2 BN weight/bias, 3 running_mean, 4 running_var, 5 linear weight, 6 linear bias.
+ * offset: element offset in the parameter region (kinds 0,1,2,5,6) or the BN-buffer region (kinds 3,4). */
+int r3m_b200_engine_num_tensors(void* handle, int* count);
+int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_capacity, int* kind, long long* offset,
+                                int* ndim, int* dims4);
+/* which: 0 params, 1 grads, 2 Adam m, 3 Adam v (fp32, same flat layout), 4 BN buffers fp32, 5 embeddings fp32
+ * [frames][D], 6 d(loss)/d(embeddings) fp32, 7 metrics fp32[16]
+ * (l2loss,l1loss,l0loss,rewloss,rewacc1,rewacc2,rewacc3,tcnloss,aligned,full_loss). count = number of elements. */
+int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
+/* what: 0 embedding dim, 1 frames, 2 kernels launched by the last engine call */
+int r3m_b200_engine_get_int(void* handle, int what, int* value);
+/* Byte offsets of {params, grads, Adam m, Adam v, BN buffers} inside the parameter block, and the element counts of
+ * the flat parameter buffer / the BN-buffer region.  Valid before bind (pure layout query; no GPU needed). */
+int r3m_b200_engine_param_block_layout(void* handle, size_t* offsets5, size_t* num_params, size_t* num_buffer_floats);
+
+/* After writing the parameter region: refresh the bf16 operand copies (forward filters, dgrad re-packs, stem). */
+int r3m_b200_engine_sync_weights(void* handle, void* stream);
+
+/* R3M.forward: obs fp32 NCHW [frames,3,224,224] in [0,255] -> out fp32 [frames][D] (out may be NULL: result stays in
+ * region 5).  train != 0 uses batch statistics and updates the running ones (nn.BatchNorm2d semantics). */
+int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* out, void* stream);
+
+/* Trainer.update up to (and excluding) the optimiser step: forward, LP / TCN / language losses, backward.
+ *   perms: int32 [15][clips] permutations in the reference's draw order (9 language, then 6 TCN; trainer.py:86-92,
+ *   135-137); lang_emb fp32 [clips][768] sentence embeddings and lang_mask fp32 [clips] (both may be NULL when
+ *   langweight == 0).  eval != 0: eval-mode BN, no gradients (trainer.py:28-29,155).  Metrics land in region 7. */
+int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
+                                 const float* lang_mask, float l2weight, float l1weight, float langweight,
+                                 float tcnweight, int eval, void* stream);
+/* torch.optim.Adam step (models_r3m.py:76, defaults) on grads * grad_scale, then refresh of the bf16 operands.
+ * step is the 1-based step count (bias correction).  Between update_grads and adam_step the caller may all-reduce
+ * region 1 across ranks (trainer DDP path: ONE NCCL all-reduce per step). */
+int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

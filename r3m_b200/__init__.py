@@ -1,6 +1,88 @@
 """r3m_b200 — B200-native (sm_100a) implementation of the R3M pretraining hot path.
 
-Public surface mirrors the reference package (r3m/__init__.py:5,44): ``R3M``, ``load_r3m``; the update step lives in
-``r3m_b200.trainer.Trainer`` (reference r3m/trainer.py:21).
+Public surface mirrors the reference package (r3m/__init__.py): ``R3M`` (r3m/__init__.py:5), ``load_r3m``
+(:44-75), ``load_r3m_reproduce`` (:77-113); the update step lives in ``r3m_b200.trainer.Trainer``
+(reference r3m/trainer.py:21).  Importing the package requires the built shared library; there is no fallback.
 """
-__all__ = []
+import copy
+import os
+from os.path import expanduser
+
+import torch
+
+from . import _lib  # noqa: F401  (fails loudly when libr3m_b200.so is missing)
+from .model import R3M, set_lang_encoder_factory  # noqa: F401
+from .trainer import Trainer  # noqa: F401
+
+__all__ = ["R3M", "Trainer", "load_r3m", "load_r3m_reproduce", "set_lang_encoder_factory"]
+
+VALID_ARGS = ["_target_", "device", "lr", "hidden_dim", "size", "l2weight", "l1weight", "langweight", "tcnweight",
+              "l2dist", "bs"]  # r3m/__init__.py:15
+
+_MODELS = {  # r3m/__init__.py:46-57: folder under ~/.r3m, Google-Drive ids of model.pt / config.yaml
+    "resnet50": ("r3m_50", "1Xu0ssuG0N1zjZS54wmWzJ7-nb0-7XzbA", "10jY2VxrrhfOdNPmsFdES568hjjIoBJx8"),
+    "resnet34": ("r3m_34", "15bXD3QRhspIRacOKyWPw5y2HpoWUCEnE", "1RY0NS-Tl4G7M1Ik_lOym0b5VIBxX9dqW"),
+    "resnet18": ("r3m_18", "1A1ic-p4KtYlKXdXHcV2QV0cUzI4kn0u-", "1nitbHQ-GRorxc7vMUiEHjHWP5N11Jvc6"),
+}
+_REPRODUCE = {  # r3m/__init__.py:79-94 (the reference's `modelif` typos make two of these unreachable there)
+    "r3m": ("original_r3m", "1jLb1yldIMfAcGVwYojSQmMpmRM7vqjp9", "1cu-Pb33qcfAieRIUptNlG1AQIMZlAI-q"),
+    "r3m_noaug": ("original_r3m_noaug", "1k_ZlVtvlktoYLtBcfD0aVFnrZcyCNS9D", "1hPmJwDiWPkd6GGez6ywSC7UOTIX7NgeS"),
+    "r3m_nol1": ("original_r3m_nol1", "1LpW3aBMdjoXsjYlkaDnvwx7q22myM_nB", "1rZUBrYJZvlF1ReFwRidZsH7-xe7csvab"),
+    "r3m_nolang": ("original_r3m_nolang", "1FXcniRei2JDaGMJJ_KlVxHaLy0Fs_caV", "192G4UkcNJO4EKN46ECujMcH0AQVhnyQe"),
+}
+
+
+def cleanup_config(agent_cfg):
+    """r3m/__init__.py:21-33: keep the constructor arguments, drop the language head."""
+    cfg = {k: v for k, v in copy.deepcopy(dict(agent_cfg)).items() if k in VALID_ARGS}
+    cfg.pop("_target_", None)
+    cfg["langweight"] = 0
+    return cfg
+
+
+def remove_language_head(state_dict):
+    """r3m/__init__.py:35-42."""
+    for key in list(state_dict.keys()):
+        if ("lang_enc" in key) or ("lang_rew" in key):
+            del state_dict[key]
+    return state_dict
+
+
+def _load(table, modelid):
+    if modelid not in table:
+        raise NameError("Invalid Model ID")  # r3m/__init__.py:59
+    foldername, model_id, config_id = table[modelid]
+    home = os.path.join(expanduser("~"), ".r3m")
+    os.makedirs(os.path.join(home, foldername), exist_ok=True)
+    modelpath = os.path.join(home, foldername, "model.pt")
+    configpath = os.path.join(home, foldername, "config.yaml")
+    if not os.path.exists(modelpath):  # r3m/__init__.py:65-67
+        try:
+            import gdown
+        except ImportError as e:
+            raise RuntimeError(f"{modelpath} is not cached and gdown is not installed: place model.pt and "
+                               f"config.yaml there, or install gdown") from e
+        gdown.download("https://drive.google.com/uc?id=" + model_id, modelpath, quiet=False)
+        gdown.download("https://drive.google.com/uc?id=" + config_id, configpath, quiet=False)
+    import yaml
+
+    with open(configpath) as f:
+        modelcfg = yaml.safe_load(f)
+    cfg = cleanup_config(modelcfg["agent"])
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    cfg["device"] = device
+    rep = R3M(**cfg)
+    rep = torch.nn.DataParallel(rep)
+    payload = torch.load(modelpath, map_location=torch.device(device), weights_only=False)["r3m"]
+    rep.load_state_dict(remove_language_head(payload))
+    return rep
+
+
+def load_r3m(modelid):
+    """r3m/__init__.py:44-75 -> DataParallel(R3M) with the cached checkpoint loaded."""
+    return _load(_MODELS, modelid)
+
+
+def load_r3m_reproduce(modelid):
+    """r3m/__init__.py:77-113."""
+    return _load(_REPRODUCE, modelid)

@@ -51,6 +51,26 @@ _sig("r3m_b200_pack_dgrad_filter", [c_void_p, c_void_p] + [c_int] * 6 + [c_void_
 _sig("r3m_b200_conv_dgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p])
 _sig("r3m_b200_conv_wgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p])
 
+c_void_pp = ctypes.POINTER(c_void_p)
+c_size_p = ctypes.POINTER(c_size_t)
+c_int_p = ctypes.POINTER(c_int)
+_sig("r3m_b200_engine_create", [c_int, c_int, c_int, c_int, c_void_pp])
+_sig("r3m_b200_engine_destroy", [c_void_p])
+_sig("r3m_b200_engine_workspace_bytes", [c_void_p, c_size_p])
+_sig("r3m_b200_engine_param_block_bytes", [c_void_p, c_size_p])
+_sig("r3m_b200_engine_bind", [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p])
+_sig("r3m_b200_engine_num_tensors", [c_void_p, c_int_p])
+_sig("r3m_b200_engine_tensor_info", [c_void_p, c_int, ctypes.c_char_p, c_int, c_int_p,
+                                     ctypes.POINTER(ctypes.c_longlong), c_int_p, c_int_p])
+_sig("r3m_b200_engine_region", [c_void_p, c_int, c_void_pp, c_size_p])
+_sig("r3m_b200_engine_get_int", [c_void_p, c_int, c_int_p])
+_sig("r3m_b200_engine_param_block_layout", [c_void_p, c_size_p, c_size_p, c_size_p])
+_sig("r3m_b200_engine_sync_weights", [c_void_p, c_void_p])
+_sig("r3m_b200_engine_forward", [c_void_p, c_void_p, c_int, c_void_p, c_void_p])
+_sig("r3m_b200_engine_update_grads", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                      c_float, c_int, c_void_p])
+_sig("r3m_b200_engine_adam_step", [c_void_p, c_float, c_float, c_int, c_void_p])
+
 
 def ptr(t):
     """Device (or host) address of a torch tensor, or None."""

@@ -8,6 +8,7 @@
 #include "api_util.h"
 #include "convops.h"
 #include "elementwise.cuh"
+#include "engine.h"
 
 namespace r3m {
 thread_local std::string g_last_error;
@@ -154,6 +155,119 @@ int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, 
   cudaError_t e = run_wgrad(plan, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(e, "conv_wgrad launch");
   return R3M_B200_OK;
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------
+// engine
+// ----------------------------------------------------------------------------------------------------------------
+#define ENGINE_OR_FAIL(h)                                                        \
+  Engine* eng = reinterpret_cast<Engine*>(h);                                    \
+  if (!eng) return fail(R3M_B200_ERR_INVALID, "null engine handle")
+#define RETURN_STR(expr)                                                         \
+  do {                                                                           \
+    std::string _e = (expr);                                                     \
+    if (!_e.empty()) return fail(R3M_B200_ERR_STATE, _e);                        \
+    return R3M_B200_OK;                                                          \
+  } while (0)
+
+int r3m_b200_engine_create(int size, int frames, int lang_head, int hidden_dim, void** handle) {
+  if (!handle) return fail(R3M_B200_ERR_INVALID, "null handle pointer");
+  Engine* e = nullptr;
+  std::string err = Engine::create(size, frames, lang_head, hidden_dim, &e);
+  if (!err.empty()) return fail(R3M_B200_ERR_INVALID, err);
+  *handle = e;
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_destroy(void* handle) {
+  delete reinterpret_cast<Engine*>(handle);
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_workspace_bytes(void* handle, size_t* bytes) {
+  ENGINE_OR_FAIL(handle);
+  *bytes = eng->workspace_bytes();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_param_block_bytes(void* handle, size_t* bytes) {
+  ENGINE_OR_FAIL(handle);
+  *bytes = eng->param_block_bytes();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_bind(void* handle, void* param_block, size_t param_bytes, void* workspace, size_t bytes,
+                         void* stream) {
+  ENGINE_OR_FAIL(handle);
+  RETURN_STR(eng->bind(param_block, param_bytes, workspace, bytes, (cudaStream_t)stream));
+}
+int r3m_b200_engine_num_tensors(void* handle, int* count) {
+  ENGINE_OR_FAIL(handle);
+  *count = (int)eng->tensors().size();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_capacity, int* kind, long long* offset,
+                                int* ndim, int* dims4) {
+  ENGINE_OR_FAIL(handle);
+  if (index < 0 || index >= (int)eng->tensors().size()) return fail(R3M_B200_ERR_INVALID, "tensor index out of range");
+  const TensorInfo& t = eng->tensors()[index];
+  if ((int)t.name.size() + 1 > name_capacity) return fail(R3M_B200_ERR_INVALID, "name buffer too small");
+  std::snprintf(name, name_capacity, "%s", t.name.c_str());
+  *kind = t.kind;
+  *offset = (long long)t.offset;
+  *ndim = t.ndim;
+  for (int i = 0; i < 4; ++i) dims4[i] = t.dims[i];
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count) {
+  ENGINE_OR_FAIL(handle);
+  void* p = eng->region(which);
+  if (!p) return fail(R3M_B200_ERR_STATE, "unknown region, or no workspace bound");
+  *ptr = p;
+  if (which <= 3) *count = eng->num_params();
+  else if (which == 4) *count = eng->num_buffer_floats();
+  else if (which == 5 || which == 6) *count = (size_t)eng->frames() * eng->embed_dim();
+  else *count = 16;
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_get_int(void* handle, int what, int* value) {
+  ENGINE_OR_FAIL(handle);
+  switch (what) {
+    case 0: *value = eng->embed_dim(); break;
+    case 1: *value = eng->frames(); break;
+    case 2: *value = eng->launches_last_call(); break;
+    default: return fail(R3M_B200_ERR_INVALID, "unknown query");
+  }
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_param_block_layout(void* handle, size_t* offsets5, size_t* num_params, size_t* num_buffer_floats) {
+  ENGINE_OR_FAIL(handle);
+  eng->param_block_layout(offsets5);
+  *num_params = eng->num_params();
+  *num_buffer_floats = eng->num_buffer_floats();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_sync_weights(void* handle, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  RETURN_STR(eng->sync_weights((cudaStream_t)stream));
+}
+int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* out, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  if (!obs) return fail(R3M_B200_ERR_INVALID, "null observation pointer");
+  RETURN_STR(eng->forward(obs, train, out, (cudaStream_t)stream));
+}
+int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
+                                 const float* lang_mask, float l2weight, float l1weight, float langweight,
+                                 float tcnweight, int eval, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  if (!obs || !perms) return fail(R3M_B200_ERR_INVALID, "null observation / permutation pointer");
+  Hyper h;
+  h.l2weight = l2weight;
+  h.l1weight = l1weight;
+  h.langweight = langweight;
+  h.tcnweight = tcnweight;
+  RETURN_STR(eng->update_grads(obs, perms, lang_emb, lang_mask, h, eval, (cudaStream_t)stream));
+}
+int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  RETURN_STR(eng->adam_step(lr, grad_scale, step, (cudaStream_t)stream));
 }
 
 }  // extern "C"

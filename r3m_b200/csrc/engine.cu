@@ -1,0 +1,651 @@
+#include "engine.h"
+
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "elementwise.cuh"
+#include "loss.cuh"
+
+namespace r3m {
+
+typedef __nv_bfloat16 bf16;
+
+struct Engine::Conv {
+  std::string name, bn;
+  int Cin = 0, Cout = 0, R = 1, stride = 1, pad = 0, H = 0, W = 0, P = 0, Q = 0;
+  bool stem = false;
+  size_t w_off = 0, gamma_off = 0, beta_off = 0;  // flat parameter buffer (elements)
+  size_t rm_off = 0, rv_off = 0;                  // BN buffers region (floats)
+  size_t zero_off = 0;                            // per-step zeroed region (floats): sum[C] sq[C] bwd_sums[2C]
+  size_t save_off = 0;                            // saved batch statistics (floats): mean[C] rstd[C]
+  size_t wd_off = 0;                              // dgrad-packed filters (bf16 elements)
+  size_t y_off = 0, a_off = 0;                    // arena byte offsets of the raw / activated outputs
+  const bf16* x = nullptr;                        // input activation
+  bf16* y = nullptr;
+  bf16* a = nullptr;
+  size_t out_elems(int N) const { return (size_t)N * P * Q * Cout; }
+};
+
+struct Engine::Block {
+  std::vector<int> main;  // conv indices of the residual branch, in order
+  int ds = -1;            // downsample conv index or -1
+  const bf16* x_in = nullptr;
+  bf16* a_out = nullptr;
+  int Hin = 0, Win = 0, Cin = 0;
+};
+
+namespace {
+constexpr size_t kAlign = 1024;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kMaxActPerFrame = 112 * 112 * 64;  // largest activation (stem output == layer1 bottleneck output)
+}  // namespace
+
+Engine::~Engine() {
+  for (Conv* c : convs_) delete c;
+  for (Block* b : blocks_) delete b;
+}
+
+void* Engine::region(int which) const {
+  if (!bound_) return nullptr;
+  switch (which) {
+    case 0: return pws_ + off_P_;
+    case 1: return pws_ + off_G_;
+    case 2: return pws_ + off_M_;
+    case 3: return pws_ + off_V_;
+    case 4: return pws_ + off_buf_;
+    case 5: return ws_ + off_E_;
+    case 6: return ws_ + off_dE_;
+    case 7: return ws_ + off_metrics_;
+    default: return nullptr;
+  }
+}
+
+std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, Engine** out) {
+  if (size != 18 && size != 34 && size != 50) return "size must be 18, 34 or 50 (r3m/models/models_r3m.py:44-52)";
+  if (frames < 1) return "frames must be positive";
+  if (lang_head) return "language head is not built into this engine yet";
+  Engine* e = new Engine();
+  e->size_ = size;
+  e->N_ = frames;
+  e->B_ = (frames % 5 == 0) ? frames / 5 : 0;
+  e->lang_ = lang_head;
+  e->hidden_ = hidden_dim;
+  e->bottleneck_ = (size == 50);
+  e->D_ = e->bottleneck_ ? 2048 : 512;
+
+  // ---- architecture (tv resnet.py:166-262; layer counts :705,:731,:763) -------------------------------------
+  const int layers18[4] = {2, 2, 2, 2}, layers34[4] = {3, 4, 6, 3};
+  const int* layers = (size == 18) ? layers18 : layers34;
+  auto add_conv = [&](const std::string& name, const std::string& bn, int cin, int cout, int r, int stride, int pad,
+                      int h, int w) {
+    Conv* c = new Conv();
+    c->name = name;
+    c->bn = bn;
+    c->Cin = cin;
+    c->Cout = cout;
+    c->R = r;
+    c->stride = stride;
+    c->pad = pad;
+    c->H = h;
+    c->W = w;
+    c->P = (h + 2 * pad - r) / stride + 1;
+    c->Q = (w + 2 * pad - r) / stride + 1;
+    e->convs_.push_back(c);
+    return (int)e->convs_.size() - 1;
+  };
+  const int stem = add_conv("conv1", "bn1", 3, 64, 7, 2, 3, 224, 224);
+  e->convs_[stem]->stem = true;
+  int inplanes = 64, hw = 56;
+  const int expansion = e->bottleneck_ ? 4 : 1;
+  const int planes_l[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    const int planes = planes_l[li];
+    for (int b = 0; b < layers[li]; ++b) {
+      const int stride = (li > 0 && b == 0) ? 2 : 1;
+      const std::string pre = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      Block* blk = new Block();
+      blk->Hin = hw;
+      blk->Win = hw;
+      blk->Cin = inplanes;
+      const int hout = hw / stride;
+      if (!e->bottleneck_) {
+        blk->main.push_back(add_conv(pre + ".conv1", pre + ".bn1", inplanes, planes, 3, stride, 1, hw, hw));
+        blk->main.push_back(add_conv(pre + ".conv2", pre + ".bn2", planes, planes, 3, 1, 1, hout, hout));
+      } else {
+        blk->main.push_back(add_conv(pre + ".conv1", pre + ".bn1", inplanes, planes, 1, 1, 0, hw, hw));
+        blk->main.push_back(add_conv(pre + ".conv2", pre + ".bn2", planes, planes, 3, stride, 1, hw, hw));
+        blk->main.push_back(add_conv(pre + ".conv3", pre + ".bn3", planes, planes * 4, 1, 1, 0, hout, hout));
+      }
+      if (b == 0 && (stride != 1 || inplanes != planes * expansion))
+        blk->ds = add_conv(pre + ".downsample.0", pre + ".downsample.1", inplanes, planes * expansion, 1, stride, 0, hw,
+                           hw);
+      inplanes = planes * expansion;
+      hw = hout;
+      e->blocks_.push_back(blk);
+    }
+  }
+
+  // ---- flat parameter / buffer layout -------------------------------------------------------------------------
+  size_t np = 0, nb = 0, nz = 0, ns = 0, nwd = 0;
+  auto take = [](size_t& cursor, size_t n, size_t align) {
+    cursor = align_up(cursor, align);
+    const size_t o = cursor;
+    cursor += n;
+    return o;
+  };
+  for (Conv* c : e->convs_) {
+    const size_t wn = (size_t)c->Cout * c->R * c->R * c->Cin;
+    c->w_off = take(np, wn, 128);
+    c->gamma_off = take(np, c->Cout, 128);
+    c->beta_off = take(np, c->Cout, 128);
+    c->rm_off = take(nb, c->Cout, 32);
+    c->rv_off = take(nb, c->Cout, 32);
+    c->zero_off = take(nz, 4 * (size_t)c->Cout, 32);
+    c->save_off = take(ns, 2 * (size_t)c->Cout, 32);
+    if (!c->stem) c->wd_off = take(nwd, wn, 128);
+    TensorInfo t;
+    t.name = "convnet." + c->name + ".weight";
+    t.kind = c->stem ? kStemOIHW : kConvKRSC;
+    t.offset = c->w_off;
+    t.ndim = 4;
+    t.dims[0] = c->Cout;
+    t.dims[1] = c->Cin;
+    t.dims[2] = c->R;
+    t.dims[3] = c->R;
+    e->tensors_.push_back(t);
+    const char* suffix[4] = {".weight", ".bias", ".running_mean", ".running_var"};
+    const int kinds[4] = {kVector, kVector, kRunMean, kRunVar};
+    const size_t offs[4] = {c->gamma_off, c->beta_off, c->rm_off, c->rv_off};
+    for (int i = 0; i < 4; ++i) {
+      TensorInfo v;
+      v.name = "convnet." + c->bn + suffix[i];
+      v.kind = kinds[i];
+      v.offset = offs[i];
+      v.ndim = 1;
+      v.dims[0] = c->Cout;
+      e->tensors_.push_back(v);
+    }
+  }
+  np = align_up(np, 128);
+  e->nparams_ = np;
+  e->nbuf_ = align_up(nb, 32);
+  e->nsaved_ = align_up(ns, 32);
+  e->nwd_ = align_up(nwd, 128);
+
+  // ---- two arenas: the parameter block (shared by every engine of one model) and the activation block ----------
+  size_t cur = 0;
+  auto arena = [&](size_t bytes) { return take(cur, bytes, kAlign); };
+  const size_t N = (size_t)frames;
+  e->off_P_ = arena(np * 4);
+  e->off_G_ = arena(np * 4);
+  e->off_M_ = arena(np * 4);
+  e->off_V_ = arena(np * 4);
+  e->off_Pb_ = arena(np * 2);
+  e->off_buf_ = arena(e->nbuf_ * 4);
+  e->off_wd_ = arena(e->nwd_ * 2);
+  e->off_stem_wp_ = arena(64 * 4 * 64 * 2);
+  e->pws_bytes_ = align_up(cur, kAlign);
+
+  cur = 0;
+  e->off_saved_ = arena(e->nsaved_ * 4);
+  // region cleared at the start of every step: BN statistics, BN-backward sums, metrics, stem filter gradient
+  const size_t zero_floats = align_up(nz, 32) + kNumMetrics + 64 * 4 * 64;
+  e->off_zero_ = arena(zero_floats * 4);
+  e->zero_bytes_ = zero_floats * 4;
+  e->off_metrics_ = e->off_zero_ + align_up(nz, 32) * 4;
+  e->off_stem_dwp_ = e->off_metrics_ + kNumMetrics * 4;
+  e->off_xs_ = arena(N * 112 * 112 * 64 * 2);
+  e->off_argmax_ = arena(N * 56 * 56 * 64);
+  for (Conv* c : e->convs_) {
+    c->y_off = arena(c->out_elems(frames) * 2);
+    if (c->stem)
+      c->a_off = arena(N * 56 * 56 * 64 * 2);  // pooled
+    else
+      c->a_off = arena(c->out_elems(frames) * 2);
+  }
+  e->off_E_ = arena(N * e->D_ * 4);
+  e->off_dE_ = arena(N * e->D_ * 4);
+  for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
+  e->ws_bytes_ = align_up(cur, kAlign);
+  *out = e;
+  return std::string();
+}
+
+std::string Engine::bind(void* params, size_t param_bytes, void* ws, size_t bytes, cudaStream_t stream) {
+  if (param_bytes < pws_bytes_) return "parameter block too small";
+  if (bytes < ws_bytes_) return "workspace too small";
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0 || (reinterpret_cast<uintptr_t>(params) & 1023) != 0)
+    return "parameter block and workspace must be 1024-byte aligned";
+  pws_ = reinterpret_cast<uint8_t*>(params);
+  ws_ = reinterpret_cast<uint8_t*>(ws);
+  cudaError_t e = cudaMemsetAsync(ws_ + off_saved_, 0, nsaved_ * 4 + 0, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+  if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  for (Conv* c : convs_) {
+    c->y = reinterpret_cast<bf16*>(ws_ + c->y_off);
+    c->a = reinterpret_cast<bf16*>(ws_ + c->a_off);
+  }
+  bound_ = true;
+  return plan_all();
+}
+
+void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train) {
+  float* P = reinterpret_cast<float*>(pws_ + off_P_);
+  float* buf = reinterpret_cast<float*>(pws_ + off_buf_);
+  float* zero = reinterpret_cast<float*>(ws_ + off_zero_);
+  float* saved = reinterpret_cast<float*>(ws_ + off_saved_);
+  BnApplyArgs a;
+  a.y = c.y;
+  a.a = dst;
+  a.residual = residual;
+  a.M = N_ * c.P * c.Q;
+  a.C = c.Cout;
+  a.relu = relu;
+  a.train = train;
+  a.sum = zero + c.zero_off;
+  a.sq = zero + c.zero_off + c.Cout;
+  a.gamma = P + c.gamma_off;
+  a.beta = P + c.beta_off;
+  a.running_mean = buf + c.rm_off;
+  a.running_var = buf + c.rv_off;
+  a.save_mean = saved + c.save_off;
+  a.save_rstd = saved + c.save_off + c.Cout;
+  ops.push_back([a](cudaStream_t s) { return launch_bn_apply(a, s); });
+}
+
+std::string Engine::plan_all() {
+  float* P = reinterpret_cast<float*>(pws_ + off_P_);
+  float* G = reinterpret_cast<float*>(pws_ + off_G_);
+  bf16* Pb = reinterpret_cast<bf16*>(pws_ + off_Pb_);
+  float* buf = reinterpret_cast<float*>(pws_ + off_buf_);
+  float* zero = reinterpret_cast<float*>(ws_ + off_zero_);
+  float* saved = reinterpret_cast<float*>(ws_ + off_saved_);
+  bf16* wd = reinterpret_cast<bf16*>(pws_ + off_wd_);
+  bf16* stem_wp = reinterpret_cast<bf16*>(pws_ + off_stem_wp_);
+  float* stem_dwp = reinterpret_cast<float*>(ws_ + off_stem_dwp_);
+  bf16* xs = reinterpret_cast<bf16*>(ws_ + off_xs_);
+  uint8_t* argmax = ws_ + off_argmax_;
+  float* E = reinterpret_cast<float*>(ws_ + off_E_);
+  bf16* g[5];
+  for (int i = 0; i < 5; ++i) g[i] = reinterpret_cast<bf16*>(ws_ + off_g_[i]);
+  const int N = N_;
+  std::string err;
+
+  auto push_conv = [&](std::vector<Op>& ops, const GatherConv& gc) {
+    ConvPlan plan;
+    std::string e2 = plan_conv(gc, &plan);
+    if (!e2.empty()) {
+      err = e2;
+      return;
+    }
+    ops.push_back([plan](cudaStream_t s) { return run_conv(plan, s); });
+  };
+  auto fwd_geom = [&](const Conv& c, int train) {
+    GatherConv gc;
+    gc.N = N;
+    gc.out = c.y;
+    gc.Cout = c.Cout;
+    gc.ldo = c.Cout;
+    if (c.stem) {
+      // 7x7 s2 p3 over 3 channels == 4 vertical taps over the 64-wide space-to-depth operand (elementwise.cuh)
+      gc.src = xs;
+      gc.H = 112;
+      gc.W = 112;
+      gc.C = 64;
+      gc.P = 112;
+      gc.Q = 112;
+      gc.stride = 1;
+      gc.base_h = -2;
+      gc.base_w = 0;
+      gc.ntaps = 4;
+      for (int t = 0; t < 4; ++t) {
+        gc.tap_h[t] = t;
+        gc.tap_w[t] = 0;
+      }
+      gc.wpk = stem_wp;
+    } else {
+      gc.src = c.x;
+      gc.H = c.H;
+      gc.W = c.W;
+      gc.C = c.Cin;
+      fill_fwd_geometry(&gc, c.R, c.R, c.stride, c.pad);
+      gc.wpk = Pb + c.w_off;
+    }
+    if (train) {
+      gc.stat_sum = zero + c.zero_off;
+      gc.stat_sq = zero + c.zero_off + c.Cout;
+    }
+    return gc;
+  };
+
+  // ------------------------------------------------------------------------------------------------ forward
+  for (int train = 0; train < 2; ++train) {
+    std::vector<Op>& ops = train ? fwd_train_ : fwd_eval_;
+    ops.clear();
+    Conv& st = *convs_[0];
+    push_conv(ops, fwd_geom(st, train));
+    {
+      StemPoolArgs a;
+      a.y = st.y;
+      a.a = st.a;
+      a.argmax = train ? argmax : nullptr;
+      a.N = N;
+      a.train = train;
+      a.sum = zero + st.zero_off;
+      a.sq = zero + st.zero_off + 64;
+      a.gamma = P + st.gamma_off;
+      a.beta = P + st.beta_off;
+      a.running_mean = buf + st.rm_off;
+      a.running_var = buf + st.rv_off;
+      a.save_mean = saved + st.save_off;
+      a.save_rstd = saved + st.save_off + 64;
+      ops.push_back([a](cudaStream_t s) { return launch_stem_bn_relu_maxpool(a, s); });
+    }
+    const bf16* x = st.a;
+    for (Block* blk : blocks_) {
+      blk->x_in = x;
+      const bf16* cur = x;
+      for (size_t i = 0; i < blk->main.size(); ++i) {
+        Conv& c = *convs_[blk->main[i]];
+        c.x = cur;
+        push_conv(ops, fwd_geom(c, train));
+        if (i + 1 < blk->main.size()) {
+          add_bn_apply(ops, c, nullptr, c.a, 1, train);
+          cur = c.a;
+        }
+      }
+      Conv& last = *convs_[blk->main.back()];
+      const void* residual = blk->x_in;
+      if (blk->ds >= 0) {
+        Conv& d = *convs_[blk->ds];
+        d.x = blk->x_in;
+        push_conv(ops, fwd_geom(d, train));
+        add_bn_apply(ops, d, nullptr, d.a, 0, train);
+        residual = d.a;
+      }
+      add_bn_apply(ops, last, residual, last.a, 1, train);
+      blk->a_out = last.a;
+      x = last.a;
+    }
+    {
+      const bf16* a_last = x;
+      const int HW = 49, C = D_;
+      ops.push_back([a_last, E, N, HW, C](cudaStream_t s) { return launch_avgpool_fwd(a_last, E, N, HW, C, s); });
+    }
+    if (!err.empty()) return err;
+  }
+
+  // ------------------------------------------------------------------------------------------------ backward
+  bwd_.clear();
+  auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const bf16* mask, bf16* dy, bf16* dz_out) {
+    BnBwdArgs a;
+    a.dA = dA;
+    a.a = mask;
+    a.y = c.y;
+    a.M = N * c.P * c.Q;
+    a.C = c.Cout;
+    a.mean = saved + c.save_off;
+    a.rstd = saved + c.save_off + c.Cout;
+    a.gamma = P + c.gamma_off;
+    a.sums = zero + c.zero_off + 2 * c.Cout;
+    a.dy = dy;
+    a.dz_out = dz_out;
+    a.dgamma = G + c.gamma_off;
+    a.dbeta = G + c.beta_off;
+    bwd_.push_back([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); });
+    bwd_.push_back([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); });
+  };
+  auto push_wgrad = [&](const Conv& c, const bf16* dy) {
+    WgradDesc d;
+    d.dy = dy;
+    d.x = c.x;
+    d.N = N;
+    d.H = c.H;
+    d.W = c.W;
+    d.C = c.Cin;
+    fill_fwd_geometry(&d, c.R, c.R, c.stride, c.pad);
+    d.Cout = c.Cout;
+    d.dw = G + c.w_off;
+    WgradPlan plan;
+    std::string e2 = plan_wgrad(d, &plan);
+    if (!e2.empty()) {
+      err = e2;
+      return;
+    }
+    bwd_.push_back([plan](cudaStream_t s) { return run_wgrad(plan, s); });
+  };
+  auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
+    std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
+    size_t off = 0;
+    for (const DgradClass& k : cls) {
+      if (k.ntaps == 0) {
+        if (!accumulate) err = "dgrad with an empty parity class needs accumulate mode (" + c.name + ")";
+        continue;
+      }
+      GatherConv gc;
+      gc.src = dy;
+      gc.N = N;
+      gc.H = c.P;
+      gc.W = c.Q;
+      gc.C = c.Cout;
+      gc.P = k.Pc;
+      gc.Q = k.Qc;
+      gc.stride = 1;
+      gc.base_h = k.base_h;
+      gc.base_w = k.base_w;
+      gc.ntaps = k.ntaps;
+      for (int t = 0; t < k.ntaps; ++t) {
+        gc.tap_h[t] = k.tap_h[t];
+        gc.tap_w[t] = k.tap_w[t];
+      }
+      gc.wpk = wd + c.wd_off + off;
+      gc.Cout = c.Cin;
+      gc.out = dx;
+      gc.ldo = c.Cin;
+      if (c.stride > 1) {
+        gc.out_mode = 1;
+        gc.oH = c.H;
+        gc.oW = c.W;
+        gc.o_stride = c.stride;
+        gc.o_h0 = k.ph;
+        gc.o_w0 = k.pw;
+      }
+      gc.accumulate = accumulate;
+      push_conv(bwd_, gc);
+      off += (size_t)c.Cin * k.ntaps * c.Cout;
+    }
+  };
+
+  bf16* d_out = g[0];
+  bf16* d_in = g[1];
+  bf16 *s1 = g[2], *s2 = g[3], *s3 = g[4];
+  {
+    const float* dE = reinterpret_cast<const float*>(ws_ + off_dE_);
+    bf16* dst = d_out;
+    const int C = D_;
+    bwd_.push_back([dE, dst, N, C](cudaStream_t s) { return launch_avgpool_bwd(dE, dst, N, 49, C, s); });
+  }
+  for (int bi = (int)blocks_.size() - 1; bi >= 0; --bi) {
+    Block* blk = blocks_[bi];
+    const int n = (int)blk->main.size();
+    Conv& last = *convs_[blk->main[n - 1]];
+    const bool has_ds = blk->ds >= 0;
+    // last BN of the residual branch: mask with the block output; the masked gradient also feeds the skip path
+    push_bn_bwd(last, d_out, blk->a_out, s1, has_ds ? s3 : d_in);
+    const bf16* dy = s1;
+    for (int i = n - 1; i >= 0; --i) {
+      Conv& c = *convs_[blk->main[i]];
+      push_wgrad(c, dy);
+      if (i > 0) {
+        Conv& prev = *convs_[blk->main[i - 1]];
+        push_dgrad(c, dy, s2, 0);
+        push_bn_bwd(prev, s2, prev.a, s1, nullptr);
+        dy = s1;
+      } else {
+        push_dgrad(c, dy, d_in, has_ds ? 0 : 1);
+      }
+    }
+    if (has_ds) {
+      Conv& d = *convs_[blk->ds];
+      push_bn_bwd(d, s3, nullptr, s1, nullptr);
+      push_wgrad(d, s1);
+      push_dgrad(d, s1, d_in, 1);
+    }
+    std::swap(d_out, d_in);
+    if (!err.empty()) return err;
+  }
+  {
+    // stem: maxpool backward (+ReLU mask) -> BN backward -> filter gradient (no data gradient needed)
+    Conv& st = *convs_[0];
+    const bf16* dpool = d_out;
+    const bf16* apool = st.a;
+    bf16* dz = s1;
+    bwd_.push_back([dpool, apool, argmax, dz, N](cudaStream_t s) {
+      return launch_maxpool_bwd(dpool, apool, argmax, dz, N, 112, 112, 64, s);
+    });
+    push_bn_bwd(st, s1, nullptr, s2, nullptr);
+    WgradDesc d;
+    d.dy = s2;
+    d.x = xs;
+    d.N = N;
+    d.H = 112;
+    d.W = 112;
+    d.C = 64;
+    d.P = 112;
+    d.Q = 112;
+    d.stride = 1;
+    d.base_h = -2;
+    d.base_w = 0;
+    d.ntaps = 4;
+    for (int t = 0; t < 4; ++t) {
+      d.tap_h[t] = t;
+      d.tap_w[t] = 0;
+    }
+    d.Cout = 64;
+    d.dw = stem_dwp;
+    WgradPlan plan;
+    err = plan_wgrad(d, &plan);
+    if (!err.empty()) return err;
+    bwd_.push_back([plan](cudaStream_t s) { return run_wgrad(plan, s); });
+    float* dst = G + st.w_off;
+    bwd_.push_back([stem_dwp, dst](cudaStream_t s) { return launch_stem_unpack_grad(stem_dwp, dst, s); });
+  }
+
+  // ------------------------------------------------------------------------------------------------ re-packs
+  repack_.clear();
+  for (Conv* cp : convs_) {
+    const Conv& c = *cp;
+    if (c.stem) {
+      const float* w = P + c.w_off;
+      repack_.push_back([w, stem_wp](cudaStream_t s) { return launch_stem_pack(w, stem_wp, s); });
+      continue;
+    }
+    std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
+    size_t off = 0;
+    for (const DgradClass& k : cls) {
+      if (k.ntaps == 0) continue;
+      struct Taps {
+        int t[kMaxTaps];
+      } taps;
+      for (int t = 0; t < kMaxTaps; ++t) taps.t[t] = t < k.ntaps ? k.src_r[t] * c.R + k.src_s[t] : 0;
+      const float* w = P + c.w_off;
+      bf16* dst = wd + c.wd_off + off;
+      const int Cout = c.Cout, T = c.R * c.R, Cin = c.Cin, nt = k.ntaps;
+      repack_.push_back(
+          [w, dst, Cout, T, Cin, nt, taps](cudaStream_t s) { return launch_pack_dgrad(w, dst, Cout, T, Cin, nt, taps.t, s); });
+      off += (size_t)Cin * nt * Cout;
+    }
+  }
+  return err;
+}
+
+std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
+  for (const Op& op : ops) {
+    cudaError_t e = op(stream);
+    if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
+    ++launches_;
+  }
+  return std::string();
+}
+
+std::string Engine::sync_weights(cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  launches_ = 0;
+  cudaError_t e = launch_cast_bf16(reinterpret_cast<const float*>(pws_ + off_P_), pws_ + off_Pb_, nparams_, stream);
+  if (e != cudaSuccess) return std::string("cast: ") + cudaGetErrorString(e);
+  ++launches_;
+  return run(repack_, stream);
+}
+
+std::string Engine::forward(const float* obs, int train, float* out, cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  launches_ = 0;
+  cudaError_t e;
+  if (train) {
+    e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  }
+  e = launch_preprocess_stem(obs, ws_ + off_xs_, N_, stream);
+  if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
+  ++launches_;
+  std::string err = run(train ? fwd_train_ : fwd_eval_, stream);
+  if (!err.empty()) return err;
+  if (out) {
+    e = cudaMemcpyAsync(out, ws_ + off_E_, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return std::string("copy out: ") + cudaGetErrorString(e);
+  }
+  return std::string();
+}
+
+std::string Engine::update_grads(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+                                 const Hyper& h, int eval, cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  if (B_ == 0) return "update needs frames == 5 * clips (r3m/trainer.py:39-40)";
+  if (h.langweight > 0.f) return "language head is not built into this engine yet";
+  (void)lang_emb;
+  (void)lang_mask;
+  launches_ = 0;
+  cudaError_t e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+  if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  if (!eval) {
+    e = cudaMemsetAsync(pws_ + off_G_, 0, nparams_ * 4, stream);
+    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  }
+  e = launch_preprocess_stem(obs, ws_ + off_xs_, N_, stream);
+  if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
+  ++launches_;
+  std::string err = run(eval ? fwd_eval_ : fwd_train_, stream);
+  if (!err.empty()) return err;
+  const float* E = reinterpret_cast<const float*>(ws_ + off_E_);
+  float* dE = eval ? nullptr : reinterpret_cast<float*>(ws_ + off_dE_);
+  float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
+  e = launch_loss_lp(E, dE, N_, D_, h.l2weight, h.l1weight, metrics, stream);
+  if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
+  ++launches_;
+  if (h.tcnweight > 0.f) {
+    e = launch_loss_tcn(E, dE, perms, B_, D_, h.tcnweight, metrics, stream);
+    if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
+    ++launches_;
+  }
+  if (!eval) {
+    err = run(bwd_, stream);
+    if (!err.empty()) return err;
+  }
+  return std::string();
+}
+
+std::string Engine::adam_step(float lr, float grad_scale, int step, cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  if (step < 1) return "Adam step count starts at 1";
+  launches_ = 0;
+  cudaError_t e = launch_adam(reinterpret_cast<float*>(pws_ + off_P_), reinterpret_cast<const float*>(pws_ + off_G_),
+                              reinterpret_cast<float*>(pws_ + off_M_), reinterpret_cast<float*>(pws_ + off_V_),
+                              pws_ + off_Pb_, nparams_, lr, 0.9f, 0.999f, 1e-8f, step, grad_scale, stream);
+  if (e != cudaSuccess) return std::string("adam: ") + cudaGetErrorString(e);
+  ++launches_;
+  return run(repack_, stream);
+}
+
+}  // namespace r3m

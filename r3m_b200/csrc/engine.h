@@ -1,0 +1,100 @@
+// The R3M pretraining engine: a static launch schedule (forward, loss heads, backward, Adam) over one arena of
+// device memory, for one backbone size and one frame count.  Mirrors what R3M.forward (r3m/models/models_r3m.py:84)
+// and Trainer.update (r3m/trainer.py:25) make ATen do, re-planned for sm_100a.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "convops.h"
+
+namespace r3m {
+
+enum TensorKind {
+  kConvKRSC = 0,   // conv filter, stored [Cout][R][S][Cin] fp32 (state_dict: OIHW)
+  kStemOIHW = 1,   // the 7x7 stem filter, stored OIHW fp32
+  kVector = 2,     // BN gamma / beta
+  kRunMean = 3,    // BN running_mean  (buffers region)
+  kRunVar = 4,     // BN running_var   (buffers region)
+  kLinearW = 5,    // language head weight [out][in]
+  kLinearB = 6,    // language head bias
+};
+
+struct TensorInfo {
+  std::string name;  // state_dict key without the "module." prefix
+  int kind = 0;
+  size_t offset = 0;  // element offset inside the flat parameter buffer (kinds 0,1,2,5,6) or the buffers region (3,4)
+  int dims[4] = {1, 1, 1, 1};  // logical (state_dict) shape
+  int ndim = 1;
+};
+
+struct Hyper {
+  float l2weight = 1e-5f, l1weight = 1e-5f, langweight = 0.f, tcnweight = 1.f;
+};
+
+class Engine {
+ public:
+  // size in {18, 34, 50}; frames = images per forward (5 * clips for update()).
+  static std::string create(int size, int frames, int lang_head, int hidden_dim, Engine** out);
+  ~Engine();
+
+  size_t workspace_bytes() const { return ws_bytes_; }
+  size_t param_block_bytes() const { return pws_bytes_; }
+  // params: the model's parameter block (shared between engines of different frame counts; caller-initialised);
+  // ws: this engine's activation workspace.
+  std::string bind(void* params, size_t param_bytes, void* ws, size_t bytes, cudaStream_t stream);
+  const std::vector<TensorInfo>& tensors() const { return tensors_; }
+  size_t num_params() const { return nparams_; }
+  size_t num_buffer_floats() const { return nbuf_; }
+  // 0: params fp32, 1: grads fp32, 2: adam m, 3: adam v, 4: BN buffers fp32, 5: embeddings fp32 [frames][D],
+  // 6: d(loss)/d(embeddings) fp32, 7: metrics fp32[16]
+  void* region(int which) const;
+  int embed_dim() const { return D_; }
+  int frames() const { return N_; }
+
+  std::string sync_weights(cudaStream_t stream);  // params fp32 -> bf16 operands (+ dgrad / stem re-packs)
+  std::string forward(const float* obs, int train, float* out, cudaStream_t stream);
+  std::string update_grads(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+                           const Hyper& h, int eval, cudaStream_t stream);
+  // step: 1-based Adam step count (bias correction); the caller owns it because engines share a parameter block
+  std::string adam_step(float lr, float grad_scale, int step, cudaStream_t stream);
+  int launches_last_call() const { return launches_; }
+  void param_block_layout(size_t* offsets5) const {
+    offsets5[0] = off_P_; offsets5[1] = off_G_; offsets5[2] = off_M_; offsets5[3] = off_V_; offsets5[4] = off_buf_;
+  }
+
+ private:
+  Engine() {}
+  struct Conv;
+  struct Block;
+  typedef std::function<cudaError_t(cudaStream_t)> Op;
+
+  std::string plan_all();
+  std::string run(const std::vector<Op>& ops, cudaStream_t stream);
+  void add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train);
+
+  int size_ = 0, N_ = 0, D_ = 0, B_ = 0, lang_ = 0, hidden_ = 0;
+  bool bottleneck_ = false;
+  std::vector<Conv*> convs_;
+  std::vector<Block*> blocks_;
+  std::vector<TensorInfo> tensors_;
+  size_t nparams_ = 0, nbuf_ = 0;
+  size_t ws_bytes_ = 0, pws_bytes_ = 0;
+  uint8_t* ws_ = nullptr;
+  uint8_t* pws_ = nullptr;
+  bool bound_ = false;
+  int launches_ = 0;
+
+  // arena offsets (bytes)
+  size_t off_P_ = 0, off_G_ = 0, off_M_ = 0, off_V_ = 0, off_Pb_ = 0, off_buf_ = 0, off_saved_ = 0, off_zero_ = 0,
+         zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0,
+         off_E_ = 0, off_dE_ = 0, off_g_[5] = {0, 0, 0, 0, 0};
+  size_t nsaved_ = 0, nwd_ = 0;
+
+  std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;
+};
+
+}  // namespace r3m

@@ -1,0 +1,153 @@
+// Fused warp-reduction kernels for the embedding penalties and the time-contrastive InfoNCE head.
+// Semantics follow r3m/trainer.py exactly: raw exp (no max subtraction) with epsilon = 1e-8 in both places of each
+// -log term (:144-145), mean over clips, zero gradient at zero distance (torch.linalg.norm backward) and sign(0) = 0.
+#include "loss.cuh"
+
+#include "ptx.cuh"
+
+namespace r3m {
+
+namespace {
+
+template <int kN>
+__device__ __forceinline__ void block_sum(float (&v)[kN], float* smem /* [kN][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float x = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
+    v[i] = warp_sum(x);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ E, float* __restrict__ dE, int rows,
+                                                      int D, float l2w, float l1w, float* __restrict__ metrics) {
+  __shared__ float red[3 * 32];
+  const int row = blockIdx.x;
+  const float* e = E + (size_t)row * D;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float x = e[d];
+    acc[0] = fmaf(x, x, acc[0]);
+    acc[1] += fabsf(x);
+    acc[2] += (x != 0.f) ? 1.f : 0.f;
+  }
+  block_sum<3>(acc, red);
+  const float norm = sqrtf(acc[0]);
+  const float inv_rows = 1.0f / (float)rows;
+  if (threadIdx.x == 0) {
+    atomicAdd(&metrics[kL2], norm * inv_rows);
+    atomicAdd(&metrics[kL1], acc[1] * inv_rows);
+    atomicAdd(&metrics[kL0], acc[2] * inv_rows);
+    atomicAdd(&metrics[kFullLoss], (l2w * norm + l1w * acc[1]) * inv_rows);
+  }
+  if (dE) {
+    const float c2 = norm > 0.f ? l2w * inv_rows / norm : 0.f;
+    const float c1 = l1w * inv_rows;
+    float* g = dE + (size_t)row * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float x = e[d];
+      const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+      g[d] = c2 * x + c1 * sgn;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__ E, float* __restrict__ dE,
+                                                       const int* __restrict__ perms, int B, int D, float tcnw,
+                                                       float* __restrict__ metrics) {
+  __shared__ float red[9 * 32];
+  __shared__ float coef[9];
+  __shared__ int urow[9], vrow[9];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    urow[0] = 5 * b + 4; vrow[0] = 5 * b + 2;  // sim_0_2 = sim(es2, es0)
+    urow[1] = 5 * b + 4; vrow[1] = 5 * b + 3;  // sim_1_2 = sim(es2, es1)
+    urow[2] = 5 * b + 3; vrow[2] = 5 * b + 2;  // sim_0_1 = sim(es1, es0)
+    for (int j = 0; j < 3; ++j) {
+      urow[3 + j] = 5 * b + 2; vrow[3 + j] = 5 * perms[(9 + 2 * j) * B + b] + 2;   // neg0: sim(es0, es0[perm])
+      urow[6 + j] = 5 * b + 4; vrow[6 + j] = 5 * perms[(10 + 2 * j) * B + b] + 4;  // neg2: sim(es2, es2[perm])
+    }
+  }
+  __syncthreads();
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float diff = E[(size_t)urow[k] * D + d] - E[(size_t)vrow[k] * D + d];
+      acc[k] = fmaf(diff, diff, acc[k]);
+    }
+  }
+  block_sum<9>(acc, red);
+  float dist[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dist[k] = sqrtf(acc[k]);
+  if (threadIdx.x == 0) {
+    const float s02 = -dist[0], s12 = -dist[1], s01 = -dist[2];
+    const float e02 = expf(s02), e12 = expf(s12), e01 = expf(s01);
+    float en0[3], en2[3], sum0 = 0.f, sum2 = 0.f;
+    for (int j = 0; j < 3; ++j) {
+      en0[j] = expf(-dist[3 + j]);
+      en2[j] = expf(-dist[6 + j]);
+      sum0 += en0[j];
+      sum2 += en2[j];
+    }
+    const float D1 = kLossEps + e02 + e12 + sum2;
+    const float D2 = kLossEps + e01 + e02 + sum0;
+    const float r1 = e12 / D1, r2 = e01 / D2;
+    const float L1 = -logf(kLossEps + r1), L2 = -logf(kLossEps + r2);
+    const float invB = 1.0f / (float)B;
+    atomicAdd(&metrics[kTcnLoss], 0.5f * (L1 + L2) * invB);
+    atomicAdd(&metrics[kFullLoss], tcnw * 0.5f * (L1 + L2) * invB);
+    atomicAdd(&metrics[kAligned], ((s02 < s12) && (s01 > s02)) ? invB : 0.f);
+    const float f = tcnw * 0.5f * invB;
+    const float g1 = -f / (kLossEps + r1), g2 = -f / (kLossEps + r2);  // dLoss/dr1, dLoss/dr2
+    coef[1] = g1 * (r1 - r1 * r1);
+    coef[2] = g2 * (r2 - r2 * r2);
+    coef[0] = g1 * (-r1 * e02 / D1) + g2 * (-r2 * e02 / D2);
+    for (int j = 0; j < 3; ++j) {
+      coef[3 + j] = g2 * (-r2 * en0[j] / D2);
+      coef[6 + j] = g1 * (-r1 * en2[j] / D1);
+    }
+  }
+  __syncthreads();
+  if (!dE) return;
+  float scale[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) scale[k] = dist[k] > 0.f ? coef[k] / dist[k] : 0.f;  // ds/du = -(u-v)/dist
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (scale[k] == 0.f) continue;
+      const float diff = E[(size_t)urow[k] * D + d] - E[(size_t)vrow[k] * D + d];
+      const float g = -scale[k] * diff;
+      atomicAdd(&dE[(size_t)urow[k] * D + d], g);
+      atomicAdd(&dE[(size_t)vrow[k] * D + d], -g);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w, float l1w, float* metrics,
+                           cudaStream_t s) {
+  loss_lp_kernel<<<rows, 256, 0, s>>>(E, dE, rows, D, l2w, l1w, metrics);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, float* metrics,
+                            cudaStream_t s) {
+  loss_tcn_kernel<<<B, 256, 0, s>>>(E, dE, perms, B, D, tcnw, metrics);
+  return cudaGetLastError();
+}
+
+}  // namespace r3m

@@ -1,0 +1,25 @@
+// Loss heads of Trainer.update (reference r3m/trainer.py:51-59 LP norms, :63-118 language InfoNCE, :120-150 TCN InfoNCE).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace r3m {
+
+// slots of the device metrics buffer (fp32[16]); same key set as the reference's metrics dict
+enum Metric {
+  kL2 = 0, kL1 = 1, kL0 = 2, kRewLoss = 3, kRewAcc1 = 4, kRewAcc2 = 5, kRewAcc3 = 6, kTcnLoss = 7, kAligned = 8,
+  kFullLoss = 9, kNumMetrics = 16
+};
+constexpr float kLossEps = 1e-8f;  // r3m/trainer.py:18
+
+// One block per embedding row: L2 / L1 / L0 row norms -> metrics (means) and, when dE != null,
+// dE[row] = l2w * e/(|e|_2 * rows) + l1w * sign(e)/rows   (this INITIALISES dE; the other heads accumulate on top).
+cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w, float l1w, float* metrics,
+                           cudaStream_t s);
+
+// One block per clip: 9 negative-L2 "sim" values (3 in-clip, 3+3 against permuted clips), the two InfoNCE terms, the
+// `aligned` metric and, when dE != null, atomic accumulation of d(tcnw * tcnloss)/dE.  perms: int32 [15][B] in the
+// reference's draw order (rows 9..14 are the TCN permutations: es0 then es2 per iteration).
+cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, float* metrics,
+                            cudaStream_t s);
+
+}  // namespace r3m

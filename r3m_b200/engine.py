@@ -1,0 +1,157 @@
+"""Thin Python handle over the C-ABI engine (include/r3m_b200.h "Engine").  torch is used for device memory and
+streams only; every kernel is launched from inside libr3m_b200.so."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+METRIC_KEYS = ("l2loss", "l1loss", "l0loss", "rewloss", "rewacc1", "rewacc2", "rewacc3", "tcnloss", "aligned",
+               "full_loss")  # slot order of region 7; key set of r3m/trainer.py:55-57,114-117,148-149,152
+
+KIND_CONV, KIND_STEM, KIND_VECTOR, KIND_RUN_MEAN, KIND_RUN_VAR, KIND_LINEAR_W, KIND_LINEAR_B = range(7)
+
+
+class TensorInfo:
+    __slots__ = ("name", "kind", "offset", "shape")
+
+    def __init__(self, name, kind, offset, shape):
+        self.name, self.kind, self.offset, self.shape = name, kind, offset, shape
+
+    @property
+    def numel(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+
+class Layout:
+    """Parameter-block layout of one model (size, language head): needs no GPU."""
+
+    def __init__(self, size, lang_head=False, hidden_dim=1024):
+        h = ctypes.c_void_p()
+        L.check(L.lib.r3m_b200_engine_create(size, 5, int(lang_head), hidden_dim, ctypes.byref(h)))
+        try:
+            n = ctypes.c_int()
+            L.check(L.lib.r3m_b200_engine_num_tensors(h, ctypes.byref(n)))
+            self.tensors = []
+            buf = ctypes.create_string_buffer(256)
+            for i in range(n.value):
+                kind, ndim = ctypes.c_int(), ctypes.c_int()
+                off = ctypes.c_longlong()
+                dims = (ctypes.c_int * 4)()
+                L.check(L.lib.r3m_b200_engine_tensor_info(h, i, buf, 256, ctypes.byref(kind), ctypes.byref(off),
+                                                          ctypes.byref(ndim), dims))
+                self.tensors.append(TensorInfo(buf.value.decode(), kind.value, off.value,
+                                               tuple(dims[j] for j in range(ndim.value))))
+            offs = (ctypes.c_size_t * 5)()
+            npar, nbuf, nbytes = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            L.check(L.lib.r3m_b200_engine_param_block_layout(h, offs, ctypes.byref(npar), ctypes.byref(nbuf)))
+            L.check(L.lib.r3m_b200_engine_param_block_bytes(h, ctypes.byref(nbytes)))
+            self.region_offsets = tuple(int(o) for o in offs)  # bytes: params, grads, m, v, buffers
+            self.num_params = int(npar.value)
+            self.num_buffer_floats = int(nbuf.value)
+            self.param_block_bytes = int(nbytes.value)
+        finally:
+            L.lib.r3m_b200_engine_destroy(h)
+
+
+def _aligned_empty(nbytes, device, zero):
+    """uint8 tensor whose data pointer is 1024-byte aligned."""
+    raw = (torch.zeros if zero else torch.empty)(nbytes + 1024, dtype=torch.uint8, device=device)
+    shift = (-raw.data_ptr()) % 1024
+    return raw[shift:shift + nbytes]
+
+
+class Engine:
+    """One launch schedule: (model parameter block, frame count)."""
+
+    def __init__(self, size, frames, param_block, lang_head=False, hidden_dim=1024):
+        if not param_block.is_cuda:
+            raise L.R3MB200Error("r3m_b200 computes on an sm_100 GPU only; the parameter block is on "
+                                 f"{param_block.device} (there is no CPU path)")
+        self.frames = frames
+        self.device = param_block.device
+        self._h = ctypes.c_void_p()
+        L.check(L.lib.r3m_b200_engine_create(size, frames, int(lang_head), hidden_dim, ctypes.byref(self._h)))
+        nbytes = ctypes.c_size_t()
+        L.check(L.lib.r3m_b200_engine_workspace_bytes(self._h, ctypes.byref(nbytes)))
+        self.workspace_bytes = int(nbytes.value)
+        with torch.cuda.device(self.device):
+            self._ws = _aligned_empty(self.workspace_bytes, self.device, zero=False)
+            self._params = param_block
+            L.check(L.lib.r3m_b200_engine_bind(self._h, L.ptr(param_block), param_block.numel(), L.ptr(self._ws),
+                                               self._ws.numel(), L.current_stream()))
+        d = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_get_int(self._h, 0, ctypes.byref(d)))
+        self.embed_dim = d.value
+        self._metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib.r3m_b200_engine_destroy(h)
+
+    def _region(self, which, dtype=torch.float32):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        L.check(L.lib.r3m_b200_engine_region(self._h, which, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, int(n.value)
+
+    def launches(self):
+        v = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_get_int(self._h, 2, ctypes.byref(v)))
+        return v.value
+
+    def sync_weights(self):
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_sync_weights(self._h, L.current_stream()))
+
+    def forward(self, obs, train):
+        """obs: float32 contiguous CUDA [frames,3,224,224] in [0,255] -> new float32 [frames, D]."""
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (self.frames, 3, 224, 224)
+        out = torch.empty(self.frames, self.embed_dim, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_forward(self._h, L.ptr(obs), int(train), L.ptr(out), L.current_stream()))
+        return out
+
+    def update_grads(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, eval_mode):
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.frames * 3 * 224 * 224
+        assert perms.dtype == torch.int32 and perms.is_cuda and perms.is_contiguous()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_update_grads(self._h, L.ptr(obs), L.ptr(perms), L.ptr(lang_emb),
+                                                       L.ptr(lang_mask), l2w, l1w, langw, tcnw, int(eval_mode),
+                                                       L.current_stream()))
+
+    def adam_step(self, lr, grad_scale, step):
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_adam_step(self._h, lr, grad_scale, step, L.current_stream()))
+
+    def read_metrics(self):
+        """ONE device->host copy of the 16-float metrics buffer (the reference does ~10 .item() syncs)."""
+        p, n = self._region(7)
+        dev = _as_tensor(p, n, torch.float32, self.device)
+        self._metrics_host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._metrics_host.tolist()
+
+    def embeddings(self):
+        p, n = self._region(5)
+        return _as_tensor(p, n, torch.float32, self.device).view(self.frames, self.embed_dim)
+
+    def embedding_grads(self):
+        p, n = self._region(6)
+        return _as_tensor(p, n, torch.float32, self.device).view(self.frames, self.embed_dim)
+
+
+class _CudaArrayView:
+    """__cuda_array_interface__ carrier so torch can alias raw device memory owned by the engine's allocations."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr, n, dtype, device):
+    assert dtype == torch.float32
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArrayView(ptr, n, "<f4"), device=device)

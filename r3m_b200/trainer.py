@@ -1,0 +1,100 @@
+"""``Trainer`` — drop-in for r3m/trainer.py:21-162 on top of the sm_100a engine.
+
+``update(model, batch, step, eval=False) -> (metrics, st)`` keeps the reference's contract: same ``metrics`` key set
+(python floats), same ``st`` timing-string format, ``model`` is the ``nn.DataParallel``-wrapped ``R3M`` that
+``train_representation.py:27-31`` builds.  Inside, one engine call runs forward + loss heads + backward, the 15
+permutations are drawn from torch's global CPU generator in the reference's order (trainer.py:86-92,135-137) and
+shipped to the device in one copy, and the metrics come back in one 64-byte read instead of ~10 ``.item()`` syncs.
+
+Multi-GPU: one process per GPU (``torch.distributed`` initialised, backend nccl).  The step then contains exactly
+one collective — an all-reduce (sum) of the flat fp32 gradient buffer over NVLink — and Adam applies 1/world.
+"""
+import time
+
+import torch
+
+from .engine import METRIC_KEYS
+
+
+def _world():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def draw_permutations(batch_size, langweight, tcnweight, num_negatives=3):
+    """[15, B] int32 permutations drawn exactly as the reference draws them (same count, same order, global CPU
+    generator): 3*num_neg for the language branch if it is on, then 2*num_neg for TCN if it is on."""
+    perms = torch.zeros(15, batch_size, dtype=torch.int64)
+    if langweight > 0:
+        for i in range(num_negatives * 3):
+            perms[i] = torch.randperm(batch_size)
+    if tcnweight > 0:
+        for i in range(num_negatives * 2):
+            perms[9 + i] = torch.randperm(batch_size)
+    return perms.to(torch.int32)
+
+
+class Trainer:
+    def __init__(self, eval_freq):
+        self.eval_freq = eval_freq
+
+    def update(self, model, batch, step, eval=False, perms=None, lang_emb=None):
+        """``perms`` / ``lang_emb`` are optional injection points for parity tests; by default they are produced the
+        way the reference produces them."""
+        t0 = time.time()
+        metrics = dict()
+        if eval:
+            model.eval()
+        else:
+            model.train()
+        m = model.module
+        t1 = time.time()
+        b_im, b_lang = batch
+        t2 = time.time()
+
+        bs = b_im.shape[0]
+        frames = b_im.reshape(bs * 5, 3, 224, 224)  # trainer.py:39-40
+        if frames.dtype != torch.float32:
+            frames = frames.float()
+        if not frames.is_cuda:
+            frames = frames.to(m._block.device, non_blocking=True)
+        frames = frames.contiguous()
+        eng = m._engine(bs * 5)
+        dev = frames.device
+
+        if perms is None:
+            perms = draw_permutations(bs, m.langweight, m.tcnweight, m.num_negatives)
+        perms_dev = perms.to(torch.int32).contiguous().to(dev, non_blocking=True)
+        t3 = time.time()
+        emb_dev = mask_dev = None
+        if m.langweight > 0:
+            if lang_emb is None:
+                lang_emb = m.lang_enc(b_lang)  # identical for all 15 get_reward calls of the reference: run it once
+            emb_dev = lang_emb.to(device=dev, dtype=torch.float32).contiguous()
+            mask_dev = torch.tensor([1.0 * (b != "") for b in b_lang], dtype=torch.float32).to(dev)  # trainer.py:108
+        eng.update_grads(frames, perms_dev, emb_dev, mask_dev, float(m.l2weight), float(m.l1weight),
+                         float(m.langweight), float(m.tcnweight), bool(eval))
+        t5 = time.time()
+        t6 = time.time()
+        if not eval:
+            m._nbt += 1
+            world = _world()
+            if world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(m._flat(1), op=dist.ReduceOp.SUM)  # the step's only collective
+            m.encoder_opt.step(grad_scale=1.0 / world)
+        vals = eng.read_metrics()
+        for i, k in enumerate(METRIC_KEYS):
+            if k.startswith("rew") and not m.langweight > 0:
+                continue
+            if k in ("tcnloss", "aligned") and not m.tcnweight > 0:
+                continue
+            metrics[k] = vals[i]
+        t7 = time.time()
+        st = (f"Load time {t1-t0}, Batch time {t2-t1}, Encode and LP tine {t3-t2}, Lang time {t5-t3}, "
+              f"TCN time {t6-t5}, Backprop time {t7-t6}")
+        return metrics, st
