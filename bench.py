@@ -1,0 +1,322 @@
+"""Headline benchmark: R3M pretrain-step frames/s (224x224, ResNet-50), BASELINE.json config c3 per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # our arm (sm_100a engine)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # CPU arm: the reference algorithm on host cores
+
+One JSON line on stdout (rank 0).  A "step" is one ``Trainer.update``: forward over 64 clips x 5 frames, L1/L2 + TCN
+(+ language) losses, backward, Adam.  ``value`` is device-timed with the frames resident in HBM; ``e2e`` is the same
+step through the public API starting from pinned HOST frames (H2D inside the timed region, metrics read back).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pretrain-step frames/s (224x224, ResNet-50)"
+HYPER = dict(l2weight=1e-5, l1weight=1e-5, tcnweight=1.0, lr=1e-4, hidden_dim=1024)  # README.md:32 + config_rep.yaml
+CLIPS_PER_GPU = 64          # BASELINE.json configs[2] (c3) / configs[4] (c5: 512 global over 8 GPUs)
+TRAIN_GFLOP_PER_FRAME = 24.287  # fwd + dgrad + wgrad conv FLOPs, ResNet-50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=50)
+    ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU)
+    ap.add_argument("--lang", type=int, default=1, help="language head on (c3) / off")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) == 7:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001 - sampling is best effort
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max((float(r[2]) for r in self.rows), default=None),
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+class StubLangEncoder:
+    """Frozen-sentence-encoder stand-in (DistilBERT weights are unreachable offline): a seeded
+    [B,768] embedding, identical on both arms, produced once per step like the real encoder would be."""
+    lang_size = 768
+
+    def __init__(self, device):
+        self.device = device
+        self._cache = {}
+
+    def __call__(self, sentences):
+        import torch
+
+        n = len(sentences)
+        if n not in self._cache:
+            g = torch.Generator().manual_seed(1234)
+            self._cache[n] = torch.randn(n, 768, generator=g)
+        return self._cache[n]
+
+
+def sentences_for(n):
+    return ["" if i % 10 == 9 else "C does something %d" % i for i in range(n)]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "hbm_gbs": p.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step_runner(size, clips, lang):
+    """The reference algorithm (oracle port of R3M.forward + Trainer.update) on host cores, all threads."""
+    import torch
+    from oracle import r3m_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    params, buffers = O.init_state(size, 0, lang=lang)
+    frames = O.synthetic_frames(clips, 1)
+    perms = O.draw_permutations(clips, 2)
+    hyper = dict(l2weight=HYPER["l2weight"], l1weight=HYPER["l1weight"], tcnweight=HYPER["tcnweight"],
+                 langweight=1.0 if lang else 0.0, lr=HYPER["lr"])
+    lang_emb = O.stub_lang_embedding(clips, 3) if lang else None
+    mask = torch.tensor([1.0 * (s != "") for s in sentences_for(clips)]) if lang else None
+    opt = O.new_opt_state()
+
+    def step():
+        O.update(params, buffers, opt, frames, perms, hyper, size, lang_emb, mask)
+
+    return step
+
+
+def cpu_baseline(size, lang, clips=2, steps=3):
+    step = cpu_step_runner(size, clips, lang)
+    step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / steps
+    import torch
+
+    return {"value": clips * 5 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} timed Trainer.update steps of {clips} clips ({clips * 5} frames) after 1 warm-up, "
+                      f"oracle port (fp32, torch CPU ops), {os.cpu_count()} host CPUs visible"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lang = bool(args.lang)
+    clips = 2
+    step = cpu_step_runner(args.size, clips, lang)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = (time.time() - t0) / max(args.steps, 1)
+    import torch
+
+    v = clips * 5 / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, clips_override=clips),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"each step = one Trainer.update of {clips} clips ({clips * 5} frames): the "
+                                       "reference algorithm (oracle port; /root/reference is pure Python whose "
+                                       "arithmetic is torch CPU ops) on all host threads"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, clips_override=None):
+    clips = clips_override or args.clips
+    return {"workload": f"c3/c5: full Trainer.update(): ResNet-{args.size}, 5 frames/clip, {clips} clips per GPU, "
+                        f"TCN + {'language + ' if args.lang else ''}L1/L2 losses, backward, Adam",
+            "clips_per_gpu": clips, "frames_per_step_per_gpu": clips * 5, "language_head": bool(args.lang),
+            "language_encoder": "stub embedding (DistilBERT weights unreachable offline; excluded on both arms)",
+            "l2_policy": "per-step inputs + saved activations (>10 GB) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"dp{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import r3m_b200
+    from r3m_b200 import R3M, Trainer
+
+    lang = bool(args.lang)
+    r3m_b200.set_lang_encoder_factory(StubLangEncoder)
+    torch.manual_seed(0)  # identical initial weights on every rank
+    model = R3M("cuda", HYPER["lr"], HYPER["hidden_dim"], size=args.size, l2weight=HYPER["l2weight"],
+                l1weight=HYPER["l1weight"], langweight=1.0 if lang else 0.0, tcnweight=HYPER["tcnweight"])
+    model = torch.nn.DataParallel(model.to(dev), device_ids=[local])
+    trainer = Trainer(eval_freq=10 ** 9)
+    B = args.clips
+    g = torch.Generator(device=dev).manual_seed(1 + rank)  # config_rep.yaml:16 seed 1 (+ rank)
+    frames = torch.randint(0, 255, (B, 5, 3, 224, 224), generator=g, device=dev).float()
+    b_lang = sentences_for(B)
+    torch.manual_seed(100 + rank)  # permutation stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    metrics_box = {}
+
+    def step_resident():
+        metrics_box["m"], _ = trainer.update(model, (frames, b_lang), 0)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    launches = trainer.last_launches
+    frames_per_step = B * 5 * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host frames -> H2D -> update -> metrics D2H, every step
+    host = torch.empty(frames.shape, dtype=torch.float32).pin_memory()
+    host.copy_(frames)
+    staging = torch.empty_like(frames)
+
+    def step_e2e():
+        staging.copy_(host, non_blocking=True)
+        metrics_box["m"], _ = trainer.update(model, (staging, b_lang), 0)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = {"value": frames_per_step * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+           "h2d_bytes_per_step": int(host.numel() * 4 + 15 * B * 4 + (B * 769 * 4 if lang else 0)),
+           "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e / args.steps,
+           "api": "r3m_b200.Trainer.update(DataParallel(R3M), (frames, sentences), step)"}
+
+    # ---- roofline of the dominant kernel family, measured live with in-stream CUDA events
+    m = model.module
+    eng = m._engine(B * 5)
+    from r3m_b200.trainer import draw_permutations
+
+    perms = draw_permutations(B, m.langweight, m.tcnweight).to(dev)
+    emb = mask = None
+    if lang:
+        emb = m.lang_enc(b_lang).to(dev).float().contiguous()
+        mask = torch.tensor([1.0 * (s != "") for s in b_lang], device=dev)
+    fam = None
+    for _ in range(3):
+        m.encoder_opt.steps += 1
+        fam = eng.profile_update(frames.reshape(-1, 3, 224, 224), perms, emb, mask, HYPER["l2weight"],
+                                 HYPER["l1weight"], float(m.langweight), HYPER["tcnweight"], HYPER["lr"],
+                                 m.encoder_opt.steps)
+    pk = peaks()
+    total_ms = sum(f["ms"] for f in fam.values())
+    dom = max(fam, key=lambda k: fam[k]["ms"])
+    conv = fam["conv_igemm"]
+    roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: forward convs + dgrad)", "bound": "tensor",
+                "achieved": conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "peak_source": pk["source"] + ", of measured",
+                "launches_per_step": conv["launches"], "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
+                "share_of_step": conv["ms"] / total_ms if total_ms else None, "traffic": None,
+                "dominant_family": dom,
+                "families": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None,
+                                 "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                             for k, v in fam.items() if v["launches"]},
+                "whole_step_fraction_of_tensor_peak": value / world * TRAIN_GFLOP_PER_FRAME / 1e3 / pk["tflops"]
+                if args.size == 50 else None}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["achieved"] else None
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "launches_per_step": launches,
+            "roofline": roofline, "last_metrics": metrics_box.get("m")}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.size, lang)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,14 @@ int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perm
  * region 1 across ranks (trainer DDP path: ONE NCCL all-reduce per step). */
 int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream);
 
+/* Measurement aid for bench.py: runs ONE full step (update_grads + adam_step) with a CUDA-event pair recorded
+ * in-stream around every kernel launch and returns, per kernel family f (0 conv_igemm [forward + dgrad], 1 wgrad,
+ * 2 BatchNorm/normalise, 3 pooling, 4 loss heads, 5 optimiser + filter re-packs, 6 language head, 7 unused):
+ * out32[4*f + {0,1,2,3}] = {device ms, algorithmic FLOPs, algorithmic HBM bytes, launches}.  out32 is HOST memory. */
+int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* perms, const float* lang_emb,
+                                   const float* lang_mask, float l2weight, float l1weight, float langweight,
+                                   float tcnweight, float lr, int step, double* out32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,28 @@ def stub_lang_embedding(batch, seed, dim=768):
 # ---------------------------------------------------------------------------------------------------------------
 # forward
 # ---------------------------------------------------------------------------------------------------------------
+class _RoundBf16(torch.autograd.Function):
+    """Storage-precision model of the sm_100a path: a tensor that the CUDA path keeps in HBM as bf16 is rounded to
+    bf16 here (value AND incoming gradient), all arithmetic stays fp32 — "the reference under the same dtype policy"
+    (SURVEY.md §7 hard part 1(c))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _policy_round(policy):
+    if policy == "fp32":
+        return lambda t: t
+    if policy == "bf16":
+        return _RoundBf16.apply
+    raise ValueError(policy)
+
+
 def _bn(x, params, buffers, name, train):
     """nn.BatchNorm2d forward; in train mode also the running-stat update (momentum 0.1, unbiased variance)."""
     w, b = params[f"{name}.weight"], params[f"{name}.bias"]
@@ -141,14 +163,17 @@ def _bn(x, params, buffers, name, train):
     return xhat * w[None, :, None, None] + b[None, :, None, None]
 
 
-def resnet_forward(params, buffers, x, size, train, taps=None):
+def resnet_forward(params, buffers, x, size, train, taps=None, policy="fp32"):
     """tv resnet.py:266-282 with fc = Identity (models_r3m.py:62).  ``taps`` (optional dict) collects intermediate
-    activations keyed by layer name for per-layer parity."""
+    activations keyed by layer name for per-layer parity.  ``policy="bf16"`` rounds exactly the tensors the CUDA path
+    stores as bf16 (network input, filters, raw conv outputs, post-ReLU activations, the downsample BN output)."""
     kind, layers = _CFG[size]
     P = lambda k: params["convnet." + k]  # noqa: E731
+    q = _policy_round(policy)
+    x = q(x)
 
     def conv(t, name, stride, pad):
-        return F.conv2d(t, P(name + ".weight"), None, stride, pad)
+        return q(F.conv2d(t, q(P(name + ".weight")), None, stride, pad))
 
     def bn(t, name):
         return _bn(t, params, buffers, "convnet." + name, train)
@@ -156,7 +181,7 @@ def resnet_forward(params, buffers, x, size, train, taps=None):
     x = conv(x, "conv1", 2, 3)
     if taps is not None:
         taps["conv1.raw"] = x
-    x = F.relu(bn(x, "bn1"))
+    x = q(F.relu(bn(x, "bn1")))
     x = F.max_pool2d(x, 3, 2, 1)
     if taps is not None:
         taps["maxpool"] = x
@@ -168,28 +193,28 @@ def resnet_forward(params, buffers, x, size, train, taps=None):
             pre = f"layer{li + 1}.{b}"
             identity = x
             if kind == "basic":
-                out = F.relu(bn(conv(x, f"{pre}.conv1", stride, 1), f"{pre}.bn1"))
+                out = q(F.relu(bn(conv(x, f"{pre}.conv1", stride, 1), f"{pre}.bn1")))
                 out = bn(conv(out, f"{pre}.conv2", 1, 1), f"{pre}.bn2")
             else:
-                out = F.relu(bn(conv(x, f"{pre}.conv1", 1, 0), f"{pre}.bn1"))
-                out = F.relu(bn(conv(out, f"{pre}.conv2", stride, 1), f"{pre}.bn2"))
+                out = q(F.relu(bn(conv(x, f"{pre}.conv1", 1, 0), f"{pre}.bn1")))
+                out = q(F.relu(bn(conv(out, f"{pre}.conv2", stride, 1), f"{pre}.bn2")))
                 out = bn(conv(out, f"{pre}.conv3", 1, 0), f"{pre}.bn3")
             if b == 0 and (stride != 1 or inplanes != planes * expansion):
-                identity = bn(conv(x, f"{pre}.downsample.0", stride, 0), f"{pre}.downsample.1")
-            x = F.relu(out + identity)
+                identity = q(bn(conv(x, f"{pre}.downsample.0", stride, 0), f"{pre}.downsample.1"))
+            x = q(F.relu(out + identity))
             if taps is not None:
                 taps[pre] = x
             inplanes = planes * expansion
     return x.mean((2, 3))  # AdaptiveAvgPool2d((1,1)) + flatten
 
 
-def r3m_forward(params, buffers, obs, size, train, taps=None):
+def r3m_forward(params, buffers, obs, size, train, taps=None, policy="fp32"):
     """models_r3m.py:84-100 for obs_shape == [3,224,224]: obs.float()/255 -> Normalize -> convnet."""
     x = obs.float() / 255.0
     mean = torch.tensor(MEAN, dtype=x.dtype)[None, :, None, None]
     std = torch.tensor(STD, dtype=x.dtype)[None, :, None, None]
     x = (x - mean) / std
-    return resnet_forward(params, buffers, x, size, train, taps)
+    return resnet_forward(params, buffers, x, size, train, taps, policy)
 
 
 def sim(a, b):
@@ -275,13 +300,15 @@ def adam_step(params, grads, opt_state, lr, beta1=0.9, beta2=0.999, eps=1e-8):
         p.addcdiv_(m, denom, value=-lr / bc1)
 
 
-def update(params, buffers, opt_state, frames, perms, hyper, size, lang_emb=None, lang_mask=None, eval_mode=False):
+def update(params, buffers, opt_state, frames, perms, hyper, size, lang_emb=None, lang_mask=None, eval_mode=False,
+           policy="fp32"):
     """One ``Trainer.update`` (trainer.py:25-162).  Mutates params / buffers / opt_state in place; returns
     (metrics, grads, embeddings)."""
     bs = frames.shape[0]
     leaf = OrderedDict((k, v.detach().clone().requires_grad_(not eval_mode)) for k, v in params.items())
     with torch.set_grad_enabled(not eval_mode):
-        alles = r3m_forward(leaf, buffers, frames.reshape(bs * 5, 3, 224, 224), size, train=not eval_mode)
+        alles = r3m_forward(leaf, buffers, frames.reshape(bs * 5, 3, 224, 224), size, train=not eval_mode,
+                            policy=policy)
         full, metrics = losses(leaf, alles, perms, hyper, lang_emb, lang_mask)
     grads = None
     if not eval_mode:

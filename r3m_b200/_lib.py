@@ -70,6 +70,8 @@ _sig("r3m_b200_engine_forward", [c_void_p, c_void_p, c_int, c_void_p, c_void_p])
 _sig("r3m_b200_engine_update_grads", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                       c_float, c_int, c_void_p])
 _sig("r3m_b200_engine_adam_step", [c_void_p, c_float, c_float, c_int, c_void_p])
+_sig("r3m_b200_engine_profile_update", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                        c_float, c_float, c_int, ctypes.POINTER(ctypes.c_double), c_void_p])
 
 
 def ptr(t):

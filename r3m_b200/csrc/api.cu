@@ -265,6 +265,18 @@ int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perm
   h.tcnweight = tcnweight;
   RETURN_STR(eng->update_grads(obs, perms, lang_emb, lang_mask, h, eval, (cudaStream_t)stream));
 }
+int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* perms, const float* lang_emb,
+                                   const float* lang_mask, float l2weight, float l1weight, float langweight,
+                                   float tcnweight, float lr, int step, double* out32, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  if (!obs || !perms || !out32) return fail(R3M_B200_ERR_INVALID, "null pointer");
+  Hyper h;
+  h.l2weight = l2weight;
+  h.l1weight = l1weight;
+  h.langweight = langweight;
+  h.tcnweight = tcnweight;
+  RETURN_STR(eng->profile_update(obs, perms, lang_emb, lang_mask, h, lr, step, out32, (cudaStream_t)stream));
+}
 int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream) {
   ENGINE_OR_FAIL(handle);
   RETURN_STR(eng->adam_step(lr, grad_scale, step, (cudaStream_t)stream));

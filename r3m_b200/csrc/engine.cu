@@ -65,7 +65,8 @@ void* Engine::region(int which) const {
 std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, Engine** out) {
   if (size != 18 && size != 34 && size != 50) return "size must be 18, 34 or 50 (r3m/models/models_r3m.py:44-52)";
   if (frames < 1) return "frames must be positive";
-  if (lang_head) return "language head is not built into this engine yet";
+  if (lang_head && (hidden_dim < 64 || hidden_dim % 64 != 0)) return "hidden_dim must be a positive multiple of 64";
+  if (lang_head && frames % 5 != 0) return "the language head needs frames == 5 * clips";
   Engine* e = new Engine();
   e->size_ = size;
   e->N_ = frames;
@@ -168,6 +169,33 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
       e->tensors_.push_back(v);
     }
   }
+  if (lang_head) {
+    // LanguageReward.pred (models_language.py:43-51): Linear(2D+768,H) ReLU (Linear(H,H) ReLU)x3 Linear(H,1)
+    const int dims[6] = {2 * e->D_ + 768, hidden_dim, hidden_dim, hidden_dim, hidden_dim, 1};
+    for (int l = 0; l < 5; ++l) {
+      e->lang_w_off_[l] = take(np, (size_t)dims[l + 1] * dims[l], 128);
+      e->lang_b_off_[l] = take(np, (size_t)dims[l + 1], 128);
+      TensorInfo w;
+      w.name = "lang_rew.pred." + std::to_string(2 * l) + ".weight";
+      w.kind = kLinearW;
+      w.offset = e->lang_w_off_[l];
+      w.ndim = 2;
+      w.dims[0] = dims[l + 1];
+      w.dims[1] = dims[l];
+      e->tensors_.push_back(w);
+      TensorInfo b;
+      b.name = "lang_rew.pred." + std::to_string(2 * l) + ".bias";
+      b.kind = kLinearB;
+      b.offset = e->lang_b_off_[l];
+      b.ndim = 1;
+      b.dims[0] = dims[l + 1];
+      e->tensors_.push_back(b);
+    }
+    e->lang_dims_.B = e->B_;
+    e->lang_dims_.D = e->D_;
+    e->lang_dims_.L = 768;
+    e->lang_dims_.H = hidden_dim;
+  }
   np = align_up(np, 128);
   e->nparams_ = np;
   e->nbuf_ = align_up(nb, 32);
@@ -208,6 +236,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   e->off_E_ = arena(N * e->D_ * 4);
   e->off_dE_ = arena(N * e->D_ * 4);
   for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
+  if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
   e->ws_bytes_ = align_up(cur, kAlign);
   *out = e;
   return std::string();
@@ -252,7 +281,8 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.running_var = buf + c.rv_off;
   a.save_mean = saved + c.save_off;
   a.save_rstd = saved + c.save_off + c.Cout;
-  ops.push_back([a](cudaStream_t s) { return launch_bn_apply(a, s); });
+  const double mc = (double)a.M * a.C * 2;
+  ops.push_back(Op([a](cudaStream_t s) { return launch_bn_apply(a, s); }, kFamNorm, 0.0, mc * (residual ? 3 : 2)));
 }
 
 std::string Engine::plan_all() {
@@ -280,7 +310,11 @@ std::string Engine::plan_all() {
       err = e2;
       return;
     }
-    ops.push_back([plan](cudaStream_t s) { return run_conv(plan, s); });
+    // algorithmic cost: the stem is charged for its real 7x7x3 taps, not the zero-padded 4x64 operand
+    const double kdim = (gc.src == xs) ? 147.0 : (double)gc.ntaps * gc.C;
+    const double m = (double)gc.N * gc.P * gc.Q;
+    ops.push_back(Op([plan](cudaStream_t s) { return run_conv(plan, s); }, kFamConv, 2.0 * m * gc.Cout * kdim,
+                     2.0 * ((double)gc.N * gc.H * gc.W * gc.C + m * gc.Cout * (gc.accumulate ? 2 : 1) + gc.Cout * kdim)));
   };
   auto fwd_geom = [&](const Conv& c, int train) {
     GatherConv gc;
@@ -341,7 +375,8 @@ std::string Engine::plan_all() {
       a.running_var = buf + st.rv_off;
       a.save_mean = saved + st.save_off;
       a.save_rstd = saved + st.save_off + 64;
-      ops.push_back([a](cudaStream_t s) { return launch_stem_bn_relu_maxpool(a, s); });
+      ops.push_back(Op([a](cudaStream_t s) { return launch_stem_bn_relu_maxpool(a, s); }, kFamPool, 0.0,
+                       (double)N * 64 * (112.0 * 112 * 2 + 56.0 * 56 * 3)));
     }
     const bf16* x = st.a;
     for (Block* blk : blocks_) {
@@ -372,7 +407,8 @@ std::string Engine::plan_all() {
     {
       const bf16* a_last = x;
       const int HW = 49, C = D_;
-      ops.push_back([a_last, E, N, HW, C](cudaStream_t s) { return launch_avgpool_fwd(a_last, E, N, HW, C, s); });
+      ops.push_back(Op([a_last, E, N, HW, C](cudaStream_t s) { return launch_avgpool_fwd(a_last, E, N, HW, C, s); },
+                       kFamPool, 0.0, (double)N * C * (HW * 2 + 4)));
     }
     if (!err.empty()) return err;
   }
@@ -394,8 +430,10 @@ std::string Engine::plan_all() {
     a.dz_out = dz_out;
     a.dgamma = G + c.gamma_off;
     a.dbeta = G + c.beta_off;
-    bwd_.push_back([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); });
-    bwd_.push_back([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); });
+    const double mc = (double)a.M * a.C * 2;
+    bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * (mask ? 3 : 2)));
+    bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); }, kFamNorm, 0.0,
+                      mc * ((mask ? 3 : 2) + 1 + (dz_out ? 1 : 0))));
   };
   auto push_wgrad = [&](const Conv& c, const bf16* dy) {
     WgradDesc d;
@@ -414,7 +452,10 @@ std::string Engine::plan_all() {
       err = e2;
       return;
     }
-    bwd_.push_back([plan](cudaStream_t s) { return run_wgrad(plan, s); });
+    const double m = (double)N * c.P * c.Q;
+    const double kdim = (double)c.R * c.R * c.Cin;
+    bwd_.push_back(Op([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad, 2.0 * m * c.Cout * kdim,
+                      2.0 * (m * c.Cout + (double)N * c.H * c.W * c.Cin) + 4.0 * c.Cout * kdim));
   };
   auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
@@ -465,7 +506,8 @@ std::string Engine::plan_all() {
     const float* dE = reinterpret_cast<const float*>(ws_ + off_dE_);
     bf16* dst = d_out;
     const int C = D_;
-    bwd_.push_back([dE, dst, N, C](cudaStream_t s) { return launch_avgpool_bwd(dE, dst, N, 49, C, s); });
+    bwd_.push_back(Op([dE, dst, N, C](cudaStream_t s) { return launch_avgpool_bwd(dE, dst, N, 49, C, s); }, kFamPool, 0.0,
+                      (double)N * C * (4 + 49 * 2)));
   }
   for (int bi = (int)blocks_.size() - 1; bi >= 0; --bi) {
     Block* blk = blocks_[bi];
@@ -502,9 +544,9 @@ std::string Engine::plan_all() {
     const bf16* dpool = d_out;
     const bf16* apool = st.a;
     bf16* dz = s1;
-    bwd_.push_back([dpool, apool, argmax, dz, N](cudaStream_t s) {
+    bwd_.push_back(Op([dpool, apool, argmax, dz, N](cudaStream_t s) {
       return launch_maxpool_bwd(dpool, apool, argmax, dz, N, 112, 112, 64, s);
-    });
+    }, kFamPool, 0.0, (double)N * 64 * (56.0 * 56 * 5 + 112.0 * 112 * 2)));
     push_bn_bwd(st, s1, nullptr, s2, nullptr);
     WgradDesc d;
     d.dy = s2;
@@ -528,9 +570,10 @@ std::string Engine::plan_all() {
     WgradPlan plan;
     err = plan_wgrad(d, &plan);
     if (!err.empty()) return err;
-    bwd_.push_back([plan](cudaStream_t s) { return run_wgrad(plan, s); });
+    bwd_.push_back(Op([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad,
+                      2.0 * N * 112.0 * 112 * 64 * 147, 2.0 * N * 112.0 * 112 * 128));
     float* dst = G + st.w_off;
-    bwd_.push_back([stem_dwp, dst](cudaStream_t s) { return launch_stem_unpack_grad(stem_dwp, dst, s); });
+    bwd_.push_back(Op([stem_dwp, dst](cudaStream_t s) { return launch_stem_unpack_grad(stem_dwp, dst, s); }, kFamOptim));
   }
 
   // ------------------------------------------------------------------------------------------------ re-packs
@@ -539,7 +582,7 @@ std::string Engine::plan_all() {
     const Conv& c = *cp;
     if (c.stem) {
       const float* w = P + c.w_off;
-      repack_.push_back([w, stem_wp](cudaStream_t s) { return launch_stem_pack(w, stem_wp, s); });
+      repack_.push_back(Op([w, stem_wp](cudaStream_t s) { return launch_stem_pack(w, stem_wp, s); }, kFamOptim));
       continue;
     }
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
@@ -553,8 +596,9 @@ std::string Engine::plan_all() {
       const float* w = P + c.w_off;
       bf16* dst = wd + c.wd_off + off;
       const int Cout = c.Cout, T = c.R * c.R, Cin = c.Cin, nt = k.ntaps;
-      repack_.push_back(
-          [w, dst, Cout, T, Cin, nt, taps](cudaStream_t s) { return launch_pack_dgrad(w, dst, Cout, T, Cin, nt, taps.t, s); });
+      repack_.push_back(Op(
+          [w, dst, Cout, T, Cin, nt, taps](cudaStream_t s) { return launch_pack_dgrad(w, dst, Cout, T, Cin, nt, taps.t, s); },
+          kFamOptim, 0.0, 6.0 * Cin * nt * Cout));
       off += (size_t)Cin * nt * Cout;
     }
   }
@@ -563,19 +607,65 @@ std::string Engine::plan_all() {
 
 std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
   for (const Op& op : ops) {
-    cudaError_t e = op(stream);
+    cudaError_t e = launch(op, stream);
     if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
-    ++launches_;
   }
   return std::string();
+}
+
+cudaError_t Engine::launch(const Op& op, cudaStream_t stream) {
+  ++launches_;
+  if (!profiling_) return op.fn(stream);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, stream);
+  cudaError_t e = op.fn(stream);
+  cudaEventRecord(b, stream);
+  prof_events_.push_back(a);
+  prof_events_.push_back(b);
+  prof_ops_family_.push_back(op.family);
+  prof_flops_.push_back(op.flops);
+  prof_bytes_.push_back(op.bytes);
+  return e;
+}
+
+std::string Engine::profile_update(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+                                   const Hyper& h, float lr, int step, double* out, cudaStream_t stream) {
+  profiling_ = true;
+  prof_events_.clear();
+  prof_ops_family_.clear();
+  prof_flops_.clear();
+  prof_bytes_.clear();
+  std::string err = update_grads(obs, perms, lang_emb, lang_mask, h, 0, stream);
+  if (err.empty()) err = adam_step(lr, 1.0f, step, stream);
+  profiling_ = false;
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (err.empty() && e != cudaSuccess) err = std::string("profile sync: ") + cudaGetErrorString(e);
+  for (int i = 0; i < kNumFamilies * 4; ++i) out[i] = 0.0;
+  for (size_t i = 0; i < prof_ops_family_.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prof_events_[2 * i], prof_events_[2 * i + 1]);
+    const int f = prof_ops_family_[i];
+    out[f * 4 + 0] += ms;
+    out[f * 4 + 1] += prof_flops_[i];
+    out[f * 4 + 2] += prof_bytes_[i];
+    out[f * 4 + 3] += 1.0;
+  }
+  for (cudaEvent_t ev : prof_events_) cudaEventDestroy(ev);
+  prof_events_.clear();
+  return err;
 }
 
 std::string Engine::sync_weights(cudaStream_t stream) {
   if (!bound_) return "engine has no workspace bound";
   launches_ = 0;
-  cudaError_t e = launch_cast_bf16(reinterpret_cast<const float*>(pws_ + off_P_), pws_ + off_Pb_, nparams_, stream);
+  const float* P = reinterpret_cast<const float*>(pws_ + off_P_);
+  void* Pb = pws_ + off_Pb_;
+  const size_t n = nparams_;
+  cudaError_t e = launch(Op([=](cudaStream_t s) { return launch_cast_bf16(P, Pb, n, s); }, kFamOptim, 0.0, (double)n * 6),
+                         stream);
   if (e != cudaSuccess) return std::string("cast: ") + cudaGetErrorString(e);
-  ++launches_;
   return run(repack_, stream);
 }
 
@@ -587,9 +677,14 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
     e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   }
-  e = launch_preprocess_stem(obs, ws_ + off_xs_, N_, stream);
+  {
+    void* xs = ws_ + off_xs_;
+    const int N = N_;
+    e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
+                  (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+               stream);
+  }
   if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
-  ++launches_;
   std::string err = run(train ? fwd_train_ : fwd_eval_, stream);
   if (!err.empty()) return err;
   if (out) {
@@ -603,9 +698,8 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
                                  const Hyper& h, int eval, cudaStream_t stream) {
   if (!bound_) return "engine has no workspace bound";
   if (B_ == 0) return "update needs frames == 5 * clips (r3m/trainer.py:39-40)";
-  if (h.langweight > 0.f) return "language head is not built into this engine yet";
-  (void)lang_emb;
-  (void)lang_mask;
+  if (h.langweight > 0.f && !lang_) return "engine was created without the language head";
+  if (h.langweight > 0.f && (!lang_emb || !lang_mask)) return "language head needs lang_emb and lang_mask";
   launches_ = 0;
   cudaError_t e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
   if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
@@ -613,21 +707,60 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
     e = cudaMemsetAsync(pws_ + off_G_, 0, nparams_ * 4, stream);
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   }
-  e = launch_preprocess_stem(obs, ws_ + off_xs_, N_, stream);
+  {
+    void* xs = ws_ + off_xs_;
+    const int N = N_;
+    e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
+                  (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+               stream);
+  }
   if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
-  ++launches_;
   std::string err = run(eval ? fwd_eval_ : fwd_train_, stream);
   if (!err.empty()) return err;
   const float* E = reinterpret_cast<const float*>(ws_ + off_E_);
   float* dE = eval ? nullptr : reinterpret_cast<float*>(ws_ + off_dE_);
   float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
-  e = launch_loss_lp(E, dE, N_, D_, h.l2weight, h.l1weight, metrics, stream);
-  if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
-  ++launches_;
-  if (h.tcnweight > 0.f) {
-    e = launch_loss_tcn(E, dE, perms, B_, D_, h.tcnweight, metrics, stream);
-    if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
-    ++launches_;
+  {
+    const int N = N_, D = D_, B = B_;
+    const float l2w = h.l2weight, l1w = h.l1weight, tcnw = h.tcnweight;
+    e = launch(Op([=](cudaStream_t s) { return launch_loss_lp(E, dE, N, D, l2w, l1w, metrics, s); }, kFamLoss, 0.0,
+                  (double)N * D * 8),
+               stream);
+    if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
+    if (tcnw > 0.f) {
+      e = launch(Op([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, metrics, s); }, kFamLoss, 0.0,
+                    (double)B * 18 * D * 4 * 2),
+                 stream);
+      if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
+    }
+  }
+  if (h.langweight > 0.f) {
+    float* P = reinterpret_cast<float*>(pws_ + off_P_);
+    float* G = reinterpret_cast<float*>(pws_ + off_G_);
+    LangParams lp;
+    for (int l = 0; l < 5; ++l) {
+      lp.w[l] = P + lang_w_off_[l];
+      lp.b[l] = P + lang_b_off_[l];
+      lp.dw[l] = G + lang_w_off_[l];
+      lp.db[l] = G + lang_b_off_[l];
+    }
+    LangWorkspace lw;
+    lang_carve_workspace(reinterpret_cast<float*>(ws_ + off_lang_ws_), lang_dims_, &lw);
+    const LangDims ld = lang_dims_;
+    const float langw = h.langweight;
+    int n_lang = 0;
+    int* n_ptr = &n_lang;
+    // the head is ~25 launches; it is charged to the "lang" family as one profiled unit
+    const double rows = ld.rows(), H = ld.H, K1 = ld.k1();
+    const double fwd_mac = rows * (K1 * H + 3 * H * H + H);
+    const double bwd_mac = rows * (K1 * H + 3 * H * H) + rows * (2.0 * ld.D * H + 3 * H * H);
+    e = launch(Op([=](cudaStream_t s) {
+                 return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s);
+               },
+               kFamLang, 2.0 * (fwd_mac + (eval ? 0.0 : bwd_mac)), 0.0),
+               stream);
+    if (e != cudaSuccess) return std::string("lang head: ") + cudaGetErrorString(e);
+    launches_ += n_lang - 1;
   }
   if (!eval) {
     err = run(bwd_, stream);
@@ -640,11 +773,18 @@ std::string Engine::adam_step(float lr, float grad_scale, int step, cudaStream_t
   if (!bound_) return "engine has no workspace bound";
   if (step < 1) return "Adam step count starts at 1";
   launches_ = 0;
-  cudaError_t e = launch_adam(reinterpret_cast<float*>(pws_ + off_P_), reinterpret_cast<const float*>(pws_ + off_G_),
-                              reinterpret_cast<float*>(pws_ + off_M_), reinterpret_cast<float*>(pws_ + off_V_),
-                              pws_ + off_Pb_, nparams_, lr, 0.9f, 0.999f, 1e-8f, step, grad_scale, stream);
+  float* P = reinterpret_cast<float*>(pws_ + off_P_);
+  const float* G = reinterpret_cast<const float*>(pws_ + off_G_);
+  float* M = reinterpret_cast<float*>(pws_ + off_M_);
+  float* V = reinterpret_cast<float*>(pws_ + off_V_);
+  void* Pb = pws_ + off_Pb_;
+  const size_t n = nparams_;
+  cudaError_t e = launch(Op([=](cudaStream_t s) {
+                              return launch_adam(P, G, M, V, Pb, n, lr, 0.9f, 0.999f, 1e-8f, step, grad_scale, s);
+                            },
+                            kFamOptim, 0.0, (double)n * (16 + 14)),
+                         stream);
   if (e != cudaSuccess) return std::string("adam: ") + cudaGetErrorString(e);
-  ++launches_;
   return run(repack_, stream);
 }
 

@@ -10,8 +10,12 @@
 #include <vector>
 
 #include "convops.h"
+#include "lang.cuh"
 
 namespace r3m {
+
+enum OpFamily { kFamConv = 0, kFamWgrad = 1, kFamNorm = 2, kFamPool = 3, kFamLoss = 4, kFamOptim = 5, kFamLang = 6,
+                kNumFamilies = 8 };
 
 enum TensorKind {
   kConvKRSC = 0,   // conv filter, stored [Cout][R][S][Cin] fp32 (state_dict: OIHW)
@@ -62,6 +66,10 @@ class Engine {
   // step: 1-based Adam step count (bias correction); the caller owns it because engines share a parameter block
   std::string adam_step(float lr, float grad_scale, int step, cudaStream_t stream);
   int launches_last_call() const { return launches_; }
+  // Runs ONE update_grads + adam_step with a CUDA-event pair around every launch (serialises nothing: events are
+  // recorded in-stream) and accumulates per-family device time.  out: [kNumFamilies][4] = {ms, flops, bytes, launches}.
+  std::string profile_update(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+                             const Hyper& h, float lr, int step, double* out, cudaStream_t stream);
   void param_block_layout(size_t* offsets5) const {
     offsets5[0] = off_P_; offsets5[1] = off_G_; offsets5[2] = off_M_; offsets5[3] = off_V_; offsets5[4] = off_buf_;
   }
@@ -70,7 +78,15 @@ class Engine {
   Engine() {}
   struct Conv;
   struct Block;
-  typedef std::function<cudaError_t(cudaStream_t)> Op;
+  struct Op {  // one kernel launch of the static schedule + what it costs algorithmically
+    std::function<cudaError_t(cudaStream_t)> fn;
+    int family = 0;      // OpFamily
+    double flops = 0.0;  // algorithmic FLOPs (2*MAC) of the launch
+    double bytes = 0.0;  // algorithmic HBM bytes (operands read once + results written once)
+    Op() {}
+    template <class F>
+    Op(F f, int fam = 0, double fl = 0.0, double by = 0.0) : fn(f), family(fam), flops(fl), bytes(by) {}
+  };
 
   std::string plan_all();
   std::string run(const std::vector<Op>& ops, cudaStream_t stream);
@@ -87,12 +103,21 @@ class Engine {
   uint8_t* pws_ = nullptr;
   bool bound_ = false;
   int launches_ = 0;
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> prof_events_;
+  std::vector<int> prof_ops_family_;
+  std::vector<double> prof_flops_, prof_bytes_;
+  cudaError_t launch(const Op& op, cudaStream_t stream);
 
   // arena offsets (bytes)
   size_t off_P_ = 0, off_G_ = 0, off_M_ = 0, off_V_ = 0, off_Pb_ = 0, off_buf_ = 0, off_saved_ = 0, off_zero_ = 0,
          zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0,
          off_E_ = 0, off_dE_ = 0, off_g_[5] = {0, 0, 0, 0, 0};
   size_t nsaved_ = 0, nwd_ = 0;
+  // language head (optional)
+  size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
+  size_t off_lang_ws_ = 0;
+  LangDims lang_dims_;
 
   std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;
 };

@@ -1,0 +1,384 @@
+#include "lang.cuh"
+
+#include "loss.cuh"
+#include "ptx.cuh"
+
+namespace r3m {
+
+namespace {
+
+// (e0, e_t) row pair of evaluation j for clip b — r3m/trainer.py:72-92:
+//   j = 0..2  positives        G(e0, {eg, es1, es2})
+//   j = 3..5  in-clip negatives G(e0, {e0, es0, es1})
+//   j = 6..14 shuffled negatives, iteration i = (j-6)/3, target t = (j-6)%3, permutation perms[3i+t]:
+//             G(e0[perm], {eg, es1, es2}[perm]) — the sentence embedding is NOT permuted.
+__device__ __forceinline__ void eval_rows(int j, int b, const int* __restrict__ perms, int B, int& r0, int& r1) {
+  if (j < 3) {
+    r0 = 5 * b;
+    r1 = 5 * b + (j == 0 ? 1 : (j == 1 ? 3 : 4));
+  } else if (j < 6) {
+    r0 = 5 * b;
+    r1 = 5 * b + (j == 3 ? 0 : (j == 4 ? 2 : 3));
+  } else {
+    const int q = j - 6, t = q % 3;
+    const int pb = perms[q * B + b];
+    r0 = 5 * pb;
+    r1 = 5 * pb + (t == 0 ? 1 : (t == 1 ? 3 : 4));
+  }
+}
+
+__global__ void __launch_bounds__(256) lang_gather_kernel(const float* __restrict__ E, const float* __restrict__ Lemb,
+                                                          const int* __restrict__ perms, float* __restrict__ X,
+                                                          LangDims d) {
+  const int row = blockIdx.x;
+  const int j = row / d.B, b = row - j * d.B;
+  int r0, r1;
+  eval_rows(j, b, perms, d.B, r0, r1);
+  float* x = X + (size_t)row * d.k1();
+  const float4* a = reinterpret_cast<const float4*>(E + (size_t)r0 * d.D);
+  const float4* c = reinterpret_cast<const float4*>(E + (size_t)r1 * d.D);
+  const float4* l = reinterpret_cast<const float4*>(Lemb + (size_t)b * d.L);
+  float4* x4 = reinterpret_cast<float4*>(x);
+  const int d4 = d.D / 4, l4 = d.L / 4;
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) {
+    x4[i] = a[i];
+    x4[d4 + i] = c[i];
+  }
+  for (int i = threadIdx.x; i < l4; i += blockDim.x) x4[2 * d4 + i] = l[i];
+}
+
+__global__ void __launch_bounds__(256) lang_scatter_kernel(const float* __restrict__ dX, const int* __restrict__ perms,
+                                                           float* __restrict__ dE, LangDims d) {
+  const int row = blockIdx.x;
+  const int j = row / d.B, b = row - j * d.B;
+  int r0, r1;
+  eval_rows(j, b, perms, d.B, r0, r1);
+  const float* x = dX + (size_t)row * d.k1();
+  for (int i = threadIdx.x; i < d.D; i += blockDim.x) {
+    atomicAdd(&dE[(size_t)r0 * d.D + i], x[i]);
+    atomicAdd(&dE[(size_t)r1 * d.D + i], x[d.D + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM, 64x64x16 tiles, 4x4 per thread.  C[M,N] = A . B with selectable operand storage:
+//   kAK: A stored [M][K] (K contiguous) else [K][M];   kBK: B stored [N][K] (K contiguous) else [K][N].
+// Epilogue: + bias[col], ReLU, or gating by mask[row][col] > 0 (ReLU backward).
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K;
+  int lda, ldb, ldc;
+  const float* bias;
+  int relu;
+  const float* mask;
+  int ldm;
+};
+
+template <bool kAK, bool kBK>
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+    // ---- A tile -> As[k][m]
+    if (kAK) {
+      const int row = t >> 2, kq = (t & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + row < g.M) {
+        const float* src = g.A + (size_t)(m0 + row) * g.lda + k0 + kq;
+        if (k0 + kq + 3 < g.K) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (k0 + kq + 0 < g.K) v.x = src[0];
+          if (k0 + kq + 1 < g.K) v.y = src[1];
+          if (k0 + kq + 2 < g.K) v.z = src[2];
+        }
+      }
+      As[kq + 0][row] = v.x;
+      As[kq + 1][row] = v.y;
+      As[kq + 2][row] = v.z;
+      As[kq + 3][row] = v.w;
+    } else {
+      const int k = t >> 4, mq = (t & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < g.K) {
+        const float* src = g.A + (size_t)(k0 + k) * g.lda + m0 + mq;
+        if (m0 + mq + 3 < g.M) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (m0 + mq + 0 < g.M) v.x = src[0];
+          if (m0 + mq + 1 < g.M) v.y = src[1];
+          if (m0 + mq + 2 < g.M) v.z = src[2];
+        }
+      }
+      *reinterpret_cast<float4*>(&As[k][mq]) = v;
+    }
+    // ---- B tile -> Bs[k][n]
+    if (kBK) {
+      const int col = t >> 2, kq = (t & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + col < g.N) {
+        const float* src = g.B + (size_t)(n0 + col) * g.ldb + k0 + kq;
+        if (k0 + kq + 3 < g.K) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (k0 + kq + 0 < g.K) v.x = src[0];
+          if (k0 + kq + 1 < g.K) v.y = src[1];
+          if (k0 + kq + 2 < g.K) v.z = src[2];
+        }
+      }
+      Bs[kq + 0][col] = v.x;
+      Bs[kq + 1][col] = v.y;
+      Bs[kq + 2][col] = v.z;
+      Bs[kq + 3][col] = v.w;
+    } else {
+      const int k = t >> 4, nq = (t & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < g.K) {
+        const float* src = g.B + (size_t)(k0 + k) * g.ldb + n0 + nq;
+        if (n0 + nq + 3 < g.N) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (n0 + nq + 0 < g.N) v.x = src[0];
+          if (n0 + nq + 1 < g.N) v.y = src[1];
+          if (n0 + nq + 2 < g.N) v.z = src[2];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[k][nq]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[col];
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.mask) v = g.mask[(size_t)row * g.ldm + col] > 0.f ? v : 0.f;
+      g.C[(size_t)row * g.ldc + col] = v;
+    }
+  }
+}
+
+template <bool kAK, bool kBK>
+cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  sgemm_kernel<kAK, kBK><<<grid, 256, 0, s>>>(g);
+  return cudaGetLastError();
+}
+
+// S[row] = H4[row,:] . w5 + b5
+__global__ void __launch_bounds__(256) lang_score_kernel(const float* __restrict__ H4, const float* __restrict__ w5,
+                                                         const float* __restrict__ b5, float* __restrict__ S, int H) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) acc = fmaf(H4[(size_t)row * H + i], w5[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) S[row] = v + b5[0];
+  }
+}
+
+// InfoNCE over 1 positive + 4 negatives, 3 targets per clip (trainer.py:93-117); one thread per clip.
+__global__ void lang_loss_kernel(const float* __restrict__ S, const float* __restrict__ mask, float* __restrict__ dS,
+                                 int B, float langw, float* __restrict__ metrics) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float invB = 1.0f / (float)B;
+  const float mk = mask[b];
+  float loss = 0.f;
+  for (int t = 0; t < 3; ++t) {
+    const float pos = S[t * B + b];
+    float neg[4];
+    neg[0] = S[(3 + t) * B + b];
+    for (int i = 0; i < 3; ++i) neg[1 + i] = S[(6 + 3 * i + t) * B + b];
+    const float ep = expf(pos);
+    float en[4], sum = 0.f, mx = neg[0];
+    for (int k = 0; k < 4; ++k) {
+      en[k] = expf(neg[k]);
+      sum += en[k];
+      mx = fmaxf(mx, neg[k]);
+    }
+    const float Dn = kLossEps + ep + sum;
+    const float r = ep / Dn;
+    loss += -logf(kLossEps + r);
+    atomicAdd(&metrics[kRewAcc1 + t], (mx < pos) ? invB : 0.f);
+    if (dS) {
+      const float f = langw * mk * invB * (1.0f / 3.0f);
+      const float gr = -f / (kLossEps + r);
+      dS[t * B + b] = gr * (r - r * r);
+      dS[(3 + t) * B + b] = gr * (-r * en[0] / Dn);
+      for (int i = 0; i < 3; ++i) dS[(6 + 3 * i + t) * B + b] = gr * (-r * en[1 + i] / Dn);
+    }
+  }
+  const float lb = mk * loss * (1.0f / 3.0f) * invB;
+  atomicAdd(&metrics[kRewLoss], lb);
+  atomicAdd(&metrics[kFullLoss], langw * lb);
+}
+
+// dH4[row, j] = dS[row] * w5[j] * (H4[row, j] > 0)
+__global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restrict__ dS, const float* __restrict__ w5,
+                                                          const float* __restrict__ H4, float* __restrict__ dH4,
+                                                          int rows, int H) {
+  const size_t total = (size_t)rows * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / H), j = (int)(i - (size_t)row * H);
+    dH4[i] = H4[i] > 0.f ? dS[row] * w5[j] : 0.f;
+  }
+}
+
+// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  One thread per column; rows are coalesced.
+__global__ void __launch_bounds__(128) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
+                                                      float* __restrict__ out, int rows, int cols) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
+  out[j] = acc;
+}
+
+__global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    x = warp_sum(x);
+    if (threadIdx.x == 0) out[0] = x;
+  }
+}
+
+}  // namespace
+
+size_t lang_workspace_floats(const LangDims& d) {
+  const size_t r = (size_t)d.rows();
+  auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+  return 2 * up(r * d.k1()) + 6 * up(r * d.H) + 2 * up(r);
+}
+
+void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws) {
+  const size_t r = (size_t)d.rows();
+  auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+  float* p = base;
+  ws->X = p;
+  p += up(r * d.k1());
+  ws->dX = p;
+  p += up(r * d.k1());
+  for (int i = 0; i < 4; ++i) {
+    ws->Hact[i] = p;
+    p += up(r * d.H);
+  }
+  for (int i = 0; i < 2; ++i) {
+    ws->dH[i] = p;
+    p += up(r * d.H);
+  }
+  ws->S = p;
+  p += up(r);
+  ws->dS = p;
+}
+
+cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWorkspace& ws, const float* E, float* dE,
+                          const int* perms, const float* lang_emb, const float* lang_mask, float langw,
+                          float* metrics, int* launches, cudaStream_t s) {
+  const int rows = d.rows(), H = d.H, K1 = d.k1();
+  int n = 0;
+  cudaError_t e;
+#define R3M_TRY(expr)            \
+  do {                           \
+    e = (expr);                  \
+    ++n;                         \
+    if (e != cudaSuccess) {      \
+      if (launches) *launches = n; \
+      return e;                  \
+    }                            \
+  } while (0)
+
+  lang_gather_kernel<<<rows, 256, 0, s>>>(E, lang_emb, perms, ws.X, d);
+  R3M_TRY(cudaGetLastError());
+  // ---- forward: 4 x (Linear + ReLU), then Linear(H -> 1)
+  const float* in = ws.X;
+  int kin = K1;
+  for (int l = 0; l < 4; ++l) {
+    GemmArgs g{in, p.w[l], ws.Hact[l], rows, H, kin, kin, kin, H, p.b[l], 1, nullptr, 0};
+    R3M_TRY((run_gemm<true, true>(g, s)));
+    in = ws.Hact[l];
+    kin = H;
+  }
+  lang_score_kernel<<<rows, 256, 0, s>>>(ws.Hact[3], p.w[4], p.b[4], ws.S, H);
+  R3M_TRY(cudaGetLastError());
+  lang_loss_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.S, lang_mask, dE ? ws.dS : nullptr, d.B, langw, metrics);
+  R3M_TRY(cudaGetLastError());
+  if (dE) {
+    // ---- backward
+    col_sum_kernel<<<(H + 127) / 128, 128, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    R3M_TRY(cudaGetLastError());
+    vec_sum_kernel<<<1, 256, 0, s>>>(ws.dS, p.db[4], rows);
+    R3M_TRY(cudaGetLastError());
+    lang_dscore_kernel<<<148 * 4, 256, 0, s>>>(ws.dS, p.w[4], ws.Hact[3], ws.dH[0], rows, H);
+    R3M_TRY(cudaGetLastError());
+    int cur = 0;
+    for (int l = 3; l >= 0; --l) {
+      const float* dHl = ws.dH[cur];
+      const float* inl = (l == 0) ? ws.X : ws.Hact[l - 1];
+      const int kl = (l == 0) ? K1 : H;
+      // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * in[m][k]
+      col_sum_kernel<<<(H + 127) / 128, 128, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
+      R3M_TRY(cudaGetLastError());
+      GemmArgs gw{dHl, inl, p.dw[l], H, kl, rows, H, kl, kl, nullptr, 0, nullptr, 0};
+      R3M_TRY((run_gemm<false, false>(gw, s)));
+      // d(in)[m][k] = sum_n dH_l[m][n] * W_l[n][k], gated by ReLU of the layer below
+      if (l > 0) {
+        GemmArgs gx{dHl, p.w[l], ws.dH[cur ^ 1], rows, H, H, H, H, H, nullptr, 0, ws.Hact[l - 1], H};
+        R3M_TRY((run_gemm<true, false>(gx, s)));
+        cur ^= 1;
+      } else {
+        // only the two embedding slices of dX feed back into the network (the sentence embedding is frozen)
+        GemmArgs gx{dHl, p.w[0], ws.dX, rows, 2 * d.D, H, H, K1, K1, nullptr, 0, nullptr, 0};
+        R3M_TRY((run_gemm<true, false>(gx, s)));
+      }
+    }
+    lang_scatter_kernel<<<rows, 256, 0, s>>>(ws.dX, perms, dE, d);
+    R3M_TRY(cudaGetLastError());
+  }
+#undef R3M_TRY
+  if (launches) *launches = n;
+  return cudaSuccess;
+}
+
+}  // namespace r3m

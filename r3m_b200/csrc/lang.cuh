@@ -1,0 +1,44 @@
+// Video-language alignment head of Trainer.update (reference r3m/trainer.py:63-118, LanguageReward MLP
+// r3m/models/models_language.py:37-55).  All 15 get_reward() evaluations of one update are batched into ONE
+// [15*B, 2D+768] pass (the reference runs 15 separate MLP calls, 75 small cuBLAS launches).  fp32 throughout: the
+// reference's Linear layers run in true fp32 (cuda.matmul.allow_tf32 == False) and the loss tolerance is 1e-4.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace r3m {
+
+struct LangDims {
+  int B = 0;   // clips
+  int D = 0;   // embedding dim
+  int L = 768; // sentence-embedding dim
+  int H = 0;   // hidden units
+  __host__ __device__ int rows() const { return 15 * B; }
+  __host__ __device__ int k1() const { return 2 * D + L; }
+};
+
+struct LangParams {  // device pointers into the flat parameter / gradient buffers
+  const float* w[5];
+  const float* b[5];
+  float* dw[5];
+  float* db[5];
+};
+
+struct LangWorkspace {  // device scratch, sized by lang_workspace_floats()
+  float* X;      // [rows][k1]
+  float* Hact[4];  // post-ReLU hidden activations [rows][H]
+  float* S;      // [rows] scores
+  float* dS;     // [rows]
+  float* dH[2];  // ping-pong [rows][H]
+  float* dX;     // [rows][k1]
+};
+size_t lang_workspace_floats(const LangDims& d);
+void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws);
+
+// Forward + InfoNCE loss (+ metrics).  When dE != null also the full backward: parameter gradients are WRITTEN to
+// p.dw / p.db and d(langw * rewloss)/dE is atomically accumulated into dE.  Returns the number of kernels launched
+// through *launches.
+cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWorkspace& ws, const float* E, float* dE,
+                          const int* perms, const float* lang_emb, const float* lang_mask, float langw,
+                          float* metrics, int* launches, cudaStream_t s);
+
+}  // namespace r3m

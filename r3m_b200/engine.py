@@ -127,6 +127,18 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_adam_step(self._h, lr, grad_scale, step, L.current_stream()))
 
+    FAMILIES = ("conv_igemm", "wgrad", "norm", "pool", "loss", "optim", "lang", "other")
+
+    def profile_update(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, lr, step):
+        """One instrumented step -> {family: {ms, flops, bytes, launches}} (see r3m_b200_engine_profile_update)."""
+        out = (ctypes.c_double * 32)()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_profile_update(self._h, L.ptr(obs), L.ptr(perms), L.ptr(lang_emb),
+                                                         L.ptr(lang_mask), l2w, l1w, langw, tcnw, lr, step, out,
+                                                         L.current_stream()))
+        return {name: {"ms": out[4 * i], "flops": out[4 * i + 1], "bytes": out[4 * i + 2],
+                       "launches": int(out[4 * i + 3])} for i, name in enumerate(self.FAMILIES)}
+
     def read_metrics(self):
         """ONE device->host copy of the 16-float metrics buffer (the reference does ~10 .item() syncs)."""
         p, n = self._region(7)

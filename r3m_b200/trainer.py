@@ -40,6 +40,7 @@ def draw_permutations(batch_size, langweight, tcnweight, num_negatives=3):
 class Trainer:
     def __init__(self, eval_freq):
         self.eval_freq = eval_freq
+        self.last_launches = 0  # kernels launched by the most recent update() (forward + losses + backward + Adam)
 
     def update(self, model, batch, step, eval=False, perms=None, lang_emb=None):
         """``perms`` / ``lang_emb`` are optional injection points for parity tests; by default they are produced the
@@ -77,6 +78,7 @@ class Trainer:
             mask_dev = torch.tensor([1.0 * (b != "") for b in b_lang], dtype=torch.float32).to(dev)  # trainer.py:108
         eng.update_grads(frames, perms_dev, emb_dev, mask_dev, float(m.l2weight), float(m.l1weight),
                          float(m.langweight), float(m.tcnweight), bool(eval))
+        self.last_launches = eng.launches()
         t5 = time.time()
         t6 = time.time()
         if not eval:
@@ -87,6 +89,7 @@ class Trainer:
 
                 dist.all_reduce(m._flat(1), op=dist.ReduceOp.SUM)  # the step's only collective
             m.encoder_opt.step(grad_scale=1.0 / world)
+            self.last_launches += eng.launches()
         vals = eng.read_metrics()
         for i, k in enumerate(METRIC_KEYS):
             if k.startswith("rew") and not m.langweight > 0:
