@@ -116,6 +116,12 @@ int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* pe
                                    const float* lang_mask, float l2weight, float l1weight, float langweight,
                                    float tcnweight, float lr, int step, double* out32, void* stream);
 
+/* Per-launch records of the last r3m_b200_engine_profile_update, in launch order: out[4*i + {0,1,2,3}] =
+ * {family, device ms, algorithmic FLOPs, algorithmic HBM bytes}.  out is HOST memory of 4*capacity_ops doubles. */
+int r3m_b200_engine_profile_ops(void* handle, double* out, int capacity_ops, int* num_ops);
+/* Human-readable label (layer / role) of launch `index` of the last profile. */
+int r3m_b200_engine_profile_label(void* handle, int index, char* out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

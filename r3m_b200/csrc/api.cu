@@ -277,6 +277,22 @@ int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* pe
   h.tcnweight = tcnweight;
   RETURN_STR(eng->profile_update(obs, perms, lang_emb, lang_mask, h, lr, step, out32, (cudaStream_t)stream));
 }
+int r3m_b200_engine_profile_ops(void* handle, double* out, int capacity_ops, int* num_ops) {
+  ENGINE_OR_FAIL(handle);
+  const std::vector<double>& v = eng->last_profile_ops();
+  const int n = (int)(v.size() / 4);
+  *num_ops = n;
+  for (int i = 0; i < n && i < capacity_ops; ++i)
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = v[4 * i + j];
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_profile_label(void* handle, int index, char* out, int capacity) {
+  ENGINE_OR_FAIL(handle);
+  const std::vector<std::string>& v = eng->last_profile_labels();
+  if (index < 0 || index >= (int)v.size()) return fail(R3M_B200_ERR_INVALID, "profile index out of range");
+  std::snprintf(out, capacity, "%s", v[index].c_str());
+  return R3M_B200_OK;
+}
 int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream) {
   ENGINE_OR_FAIL(handle);
   RETURN_STR(eng->adam_step(lr, grad_scale, step, (cudaStream_t)stream));

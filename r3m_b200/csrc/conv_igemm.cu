@@ -11,9 +11,12 @@
 //                            live in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //                            the main loop of tile i+1.
 //   warp 2    TMEM allocator.
-//   warps 4-7 epilogue     : tcgen05.ld -> bf16 -> swizzled smem staging -> (a) per-channel sum / sum-of-squares
-//                            for train-mode BatchNorm, accumulated per CTA in smem and flushed once with
-//                            atomics, (b) fully coalesced 128-byte row stores (dense or strided scatter).
+//   warps 4-11 epilogue    : two warps per TMEM lane quadrant, alternating 32-column units:
+//                            tcgen05.ld (next unit in flight) -> bf16 -> 64B-swizzled smem staging ->
+//                            (a) per-channel sum / sum-of-squares for train-mode BatchNorm, accumulated per CTA in
+//                            smem and flushed once with atomics, (b) dense outputs leave through TMA bulk tensor
+//                            stores (cp.reduce...add when accumulating into an existing gradient), strided scatter
+//                            outputs (stride-2 dgrad parity classes) through 64-byte row segments.
 //
 // The same kernel serves: every forward conv of ResNet-18/34/50 (ref: torchvision resnet.py conv1/conv2/conv3/
 // downsample and the 7x7 stem re-expressed as a 4x1-tap conv over a space-to-depth view), and every dgrad
@@ -29,7 +32,10 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kStagingBytes = 4 * 32 * 128;  // 4 epilogue warps x 32 rows x 64 bf16
+constexpr int kNumEpiWarps = 8;  // two warps per TMEM lane quadrant, alternating 32-column units
+constexpr int kThreads = 128 + kNumEpiWarps * 32;
+constexpr int kUnitBytes = 32 * 32 * 2;  // one epilogue unit: 32 rows x 32 columns bf16, 64B-swizzled rows
+constexpr int kStagingBytes = kNumEpiWarps * kUnitBytes;
 constexpr int kMaxStatC = 2048;
 
 template <int BN>
@@ -43,9 +49,9 @@ struct Cfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvKernelParams p) {
+                  const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -65,6 +71,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.out_mode == 0) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -73,7 +80,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kNumEpiWarps);
     }
     mbar_fence_init();
   }
@@ -178,80 +185,102 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
-    uint8_t* stg = staging + ew * (32 * 128);
+    // warp (q, h): TMEM lane quadrant q = warp % 4 (rows 32q..32q+31 of the tile), 32-column units u = h, h+2, ...
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    uint8_t* stg = staging + (warp - 4) * kUnitBytes;
     const uint32_t stg_u32 = smem_u32(stg);
+    const bool dense = (p.out_mode == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    bool ok = true;
     __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+    constexpr int kUnits = BN / 32;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int m0 = m_tile * kBlockM + ew * 32;
+      const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
-      // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
-      long long row_off[8];
+      long long row_off[4];
+      if (!dense) {
+        // element offsets of the 4 rows this lane stores (row = 8*i + lane/4 of the warp's 32 rows)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + 4 * i + (lane >> 3);
-        if (m >= p.M_total) {
-          row_off[i] = -1;
-        } else if (p.out_mode == 0) {
-          row_off[i] = static_cast<long long>(m) * p.ldo;
-        } else {
-          const int n_img = m / p.PQ;
-          const int rem = m - n_img * p.PQ;
-          const int pp = rem / p.Q;
-          const int qq = rem - pp * p.Q;
-          row_off[i] = ((static_cast<long long>(n_img) * p.oH + (pp * p.o_stride + p.o_h0)) * p.oW +
-                        (qq * p.o_stride + p.o_w0)) * p.ldo;
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + 8 * i + (lane >> 2);
+          if (m >= p.M_total) {
+            row_off[i] = -1;
+          } else {
+            const int n_img = m / p.PQ;
+            const int rem = m - n_img * p.PQ;
+            const int pp = rem / p.Q;
+            const int qq = rem - pp * p.Q;
+            row_off[i] = ((static_cast<long long>(n_img) * p.oH + (pp * p.o_stride + p.o_h0)) * p.oW +
+                          (qq * p.o_stride + p.o_w0)) * p.ldo;
+          }
         }
       }
       if (!mbar_wait(&tfull_bar[acc], acc_phase)) {
         if (lane == 0) atomicExch(p.error_flag, 4);
-        ok = false;
         break;
       }
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + h * 32, v);
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 64; ++chunk) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(t_row + chunk * 64, v0);
-        tmem_ld_32x32(t_row + chunk * 64 + 32, v1);
+      for (int u = h; u < kUnits; u += 2) {
         tc_wait_ld();
-        // thread = row `lane`; write 8 x 16B chunks, XOR-swizzled by row so that both the row-wise writes
-        // here and the transposed reads below are bank-conflict free
-        const uint32_t rbase = stg_u32 + lane * 128;
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a0 = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
-          const uint32_t a1 = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
-          const uint32_t a2 = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
-          const uint32_t a3 = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
-          const uint32_t addr = rbase + (((j) ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3)
-                       : "memory");
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        if (u + 2 < kUnits) {
+          tmem_ld_32x32(t_row + (u + 2) * 32, v);  // in flight while this unit is written out
+        } else {
+          // the accumulator stage is fully in registers: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a0 = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
-          const uint32_t a1 = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
-          const uint32_t a2 = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
-          const uint32_t a3 = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
-          const uint32_t addr = rbase + (((j + 4) ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3)
-                       : "memory");
-        }
+        // staging buffer must no longer be read by the previous unit's bulk store
+        if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
+        // thread = row `lane`: four 16-byte chunks, XOR-swizzled (== TMA SWIZZLE_64B) so that row-wise writes, the
+        // column-pair reads of the statistics and the bulk store all agree and are bank-conflict free
+        const uint32_t rbase = stg_u32 + lane * 64;
+        const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t addr = rbase + ((j ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                       "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        }
+        if (dense) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (dense && lane == 0) {
+          const int c0 = n0 + u * 32;
+          if (p.accumulate) {
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(stg_u32), "r"(c0), "r"(m0)
+                         : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(stg_u32), "r"(c0), "r"(m0)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         if (do_stats) {
-          // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk; rows beyond M_total are exact zeros
+          // lanes 0-15 take even rows, lanes 16-31 odd rows; each lane owns the column pair (2*cp, 2*cp+1).
+          // Rows beyond M_total are exact zeros (TMA zero fill), so they do not disturb the sums.
+          const int cp = lane & 15;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = 2 * rr + (lane >> 4);
             uint32_t w;
-            const uint32_t addr = stg_u32 + r * 128 + ((((lane >> 2)) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+            const uint32_t addr = stg_u32 + r * 64 + ((((cp >> 2)) ^ ((r >> 1) & 3)) << 4) + ((cp & 3) << 2);
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
             const float a = bf16lo(w), b = bf16hi(w);
             s0 += a;
@@ -259,48 +288,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             q0 = fmaf(a, a, q0);
             q1 = fmaf(b, b, q1);
           }
-          const int col = n0 + chunk * 64 + 2 * lane;
-          atomicAdd(&s_sum[col], s0);
-          atomicAdd(&s_sum[col + 1], s1);
-          atomicAdd(&s_sq[col], q0);
-          atomicAdd(&s_sq[col + 1], q1);
-        }
-        // coalesced stores: 8 lanes x 16 B = one 128-byte output row segment, 4 rows per instruction
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + (lane >> 3);
-          const int c = lane & 7;
-          uint32_t x0, x1, x2, x3;
-          const uint32_t addr = stg_u32 + r * 128 + ((c ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
-          if (row_off[i] >= 0) {
-            uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + chunk * 64 + c * 8);
-            if (p.accumulate) {
-              const uint4 o = *dst;
-              x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
-              x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
-              x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
-              x3 = pack_bf16x2(bf16lo(x3) + bf16lo(o.w), bf16hi(x3) + bf16hi(o.w));
-            }
-            *dst = make_uint4(x0, x1, x2, x3);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          if (lane < 16) {
+            const int col = n0 + u * 32 + 2 * cp;
+            atomicAdd(&s_sum[col], s0);
+            atomicAdd(&s_sum[col + 1], s1);
+            atomicAdd(&s_sq[col], q0);
+            atomicAdd(&s_sq[col + 1], q1);
           }
         }
-        __syncwarp();
+        if (!dense) {
+          // strided scatter (stride-2 dgrad parity classes): 4 lanes x 16 B = one 64-byte row segment
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            const int c = lane & 3;
+            uint32_t x0, x1, x2, x3;
+            const uint32_t addr = stg_u32 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+            if (row_off[i] >= 0) {
+              uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + u * 32 + c * 8);
+              if (p.accumulate) {
+                const uint4 o = *dst;
+                x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
+                x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
+                x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
+                x3 = pack_bf16x2(bf16lo(x3) + bf16lo(o.w), bf16hi(x3) + bf16hi(o.w));
+              }
+              *dst = make_uint4(x0, x1, x2, x3);
+            }
+          }
+          __syncwarp();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
-      // all four epilogue warps are done with every tile of this CTA -> flush the CTA partials
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 128; i < p.Cout; i += 128) {
-        const float s = s_sum[i], q = s_sq[i];
-        if (s != 0.f || q != 0.f) {
+      // all epilogue warps are done with every tile of this CTA -> flush the CTA partials
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < p.Cout; i += kNumEpiWarps * 32) {
+        const float s = s_sum[i], qv = s_sq[i];
+        if (s != 0.f || qv != 0.f) {
           atomicAdd(&p.stat_sum[i], s);
-          atomicAdd(&p.stat_sq[i], q);
+          atomicAdd(&p.stat_sq[i], qv);
         }
       }
     }
@@ -315,8 +350,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int grid,
-                      cudaStream_t stream) {
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                      const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -325,21 +360,21 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_igemm_kernel<BN><<<grid, 256, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  conv_igemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
-                              int grid, cudaStream_t stream) {
+cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                              const ConvKernelParams& p, int grid, cudaStream_t stream) {
   switch (bn) {
     case 64:
-      return launch_bn<64>(tmA, tmB, p, grid, stream);
+      return launch_bn<64>(tmA, tmB, tmC, p, grid, stream);
     case 128:
-      return launch_bn<128>(tmA, tmB, p, grid, stream);
+      return launch_bn<128>(tmA, tmB, tmC, p, grid, stream);
     case 256:
-      return launch_bn<256>(tmA, tmB, p, grid, stream);
+      return launch_bn<256>(tmA, tmB, tmC, p, grid, stream);
     default:
       return cudaErrorInvalidValue;
   }

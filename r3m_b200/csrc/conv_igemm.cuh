@@ -34,8 +34,8 @@ struct ConvKernelParams {
   int* error_flag;
 };
 
-cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
-                              int grid, cudaStream_t stream);
+cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                              const ConvKernelParams& p, int grid, cudaStream_t stream);
 
 struct WgradKernelParams {
   int M_total;

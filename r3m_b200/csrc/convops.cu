@@ -51,6 +51,13 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   if (!err.empty()) return err;
   ConvKernelParams& p = plan->p;
   p.M_total = g.N * g.P * g.Q;
+  if (g.out_mode == 0) {
+    err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * 2, 32, 32,
+                              /*swizzle_bytes=*/64);
+    if (!err.empty()) return err;
+  } else {
+    plan->tmC = plan->tmB;
+  }
   p.PQ = g.P * g.Q;
   p.Q = g.Q;
   p.stride = g.stride;
@@ -85,7 +92,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
 }
 
 cudaError_t run_conv(const ConvPlan& plan, cudaStream_t stream) {
-  return conv_igemm_launch(plan.bn, plan.tmA, plan.tmB, plan.p, plan.grid, stream);
+  return conv_igemm_launch(plan.bn, plan.tmA, plan.tmB, plan.tmC, plan.p, plan.grid, stream);
 }
 
 std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {

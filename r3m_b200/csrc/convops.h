@@ -28,7 +28,7 @@ struct GatherConv {
 };
 
 struct ConvPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;  // im2col activations, filter, dense output (unused for scatter outputs)
   ConvKernelParams p;
   int bn = 0;
   int grid = 0;

@@ -283,6 +283,7 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.save_rstd = saved + c.save_off + c.Cout;
   const double mc = (double)a.M * a.C * 2;
   ops.push_back(Op([a](cudaStream_t s) { return launch_bn_apply(a, s); }, kFamNorm, 0.0, mc * (residual ? 3 : 2)));
+  ops.back().label = "bn_apply " + c.bn + (residual ? " +res" : "");
 }
 
 std::string Engine::plan_all() {
@@ -303,7 +304,7 @@ std::string Engine::plan_all() {
   const int N = N_;
   std::string err;
 
-  auto push_conv = [&](std::vector<Op>& ops, const GatherConv& gc) {
+  auto push_conv = [&](std::vector<Op>& ops, const GatherConv& gc, const std::string& label) {
     ConvPlan plan;
     std::string e2 = plan_conv(gc, &plan);
     if (!e2.empty()) {
@@ -315,6 +316,7 @@ std::string Engine::plan_all() {
     const double m = (double)gc.N * gc.P * gc.Q;
     ops.push_back(Op([plan](cudaStream_t s) { return run_conv(plan, s); }, kFamConv, 2.0 * m * gc.Cout * kdim,
                      2.0 * ((double)gc.N * gc.H * gc.W * gc.C + m * gc.Cout * (gc.accumulate ? 2 : 1) + gc.Cout * kdim)));
+    ops.back().label = label;
   };
   auto fwd_geom = [&](const Conv& c, int train) {
     GatherConv gc;
@@ -359,7 +361,7 @@ std::string Engine::plan_all() {
     std::vector<Op>& ops = train ? fwd_train_ : fwd_eval_;
     ops.clear();
     Conv& st = *convs_[0];
-    push_conv(ops, fwd_geom(st, train));
+    push_conv(ops, fwd_geom(st, train), "fwd conv1 (stem 7x7 as 4x64)");
     {
       StemPoolArgs a;
       a.y = st.y;
@@ -385,7 +387,7 @@ std::string Engine::plan_all() {
       for (size_t i = 0; i < blk->main.size(); ++i) {
         Conv& c = *convs_[blk->main[i]];
         c.x = cur;
-        push_conv(ops, fwd_geom(c, train));
+        push_conv(ops, fwd_geom(c, train), "fwd " + c.name);
         if (i + 1 < blk->main.size()) {
           add_bn_apply(ops, c, nullptr, c.a, 1, train);
           cur = c.a;
@@ -396,7 +398,7 @@ std::string Engine::plan_all() {
       if (blk->ds >= 0) {
         Conv& d = *convs_[blk->ds];
         d.x = blk->x_in;
-        push_conv(ops, fwd_geom(d, train));
+        push_conv(ops, fwd_geom(d, train), "fwd " + d.name);
         add_bn_apply(ops, d, nullptr, d.a, 0, train);
         residual = d.a;
       }
@@ -434,6 +436,8 @@ std::string Engine::plan_all() {
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * (mask ? 3 : 2)));
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); }, kFamNorm, 0.0,
                       mc * ((mask ? 3 : 2) + 1 + (dz_out ? 1 : 0))));
+    bwd_[bwd_.size() - 2].label = "bn_bwd_reduce " + c.bn;
+    bwd_.back().label = "bn_bwd_apply " + c.bn;
   };
   auto push_wgrad = [&](const Conv& c, const bf16* dy) {
     WgradDesc d;
@@ -456,6 +460,7 @@ std::string Engine::plan_all() {
     const double kdim = (double)c.R * c.R * c.Cin;
     bwd_.push_back(Op([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad, 2.0 * m * c.Cout * kdim,
                       2.0 * (m * c.Cout + (double)N * c.H * c.W * c.Cin) + 4.0 * c.Cout * kdim));
+    bwd_.back().label = "wgrad " + c.name;
   };
   auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
@@ -494,7 +499,7 @@ std::string Engine::plan_all() {
         gc.o_w0 = k.pw;
       }
       gc.accumulate = accumulate;
-      push_conv(bwd_, gc);
+      push_conv(bwd_, gc, "dgrad " + c.name + (accumulate ? " (+=)" : "") + (c.stride > 1 ? " class " + std::to_string(k.ph) + std::to_string(k.pw) : ""));
       off += (size_t)c.Cin * k.ntaps * c.Cout;
     }
   };
@@ -627,6 +632,7 @@ cudaError_t Engine::launch(const Op& op, cudaStream_t stream) {
   prof_ops_family_.push_back(op.family);
   prof_flops_.push_back(op.flops);
   prof_bytes_.push_back(op.bytes);
+  prof_labels_run_.push_back(op.label);
   return e;
 }
 
@@ -637,16 +643,23 @@ std::string Engine::profile_update(const float* obs, const int* perms, const flo
   prof_ops_family_.clear();
   prof_flops_.clear();
   prof_bytes_.clear();
+  prof_labels_run_.clear();
   std::string err = update_grads(obs, perms, lang_emb, lang_mask, h, 0, stream);
   if (err.empty()) err = adam_step(lr, 1.0f, step, stream);
   profiling_ = false;
   cudaError_t e = cudaStreamSynchronize(stream);
   if (err.empty() && e != cudaSuccess) err = std::string("profile sync: ") + cudaGetErrorString(e);
   for (int i = 0; i < kNumFamilies * 4; ++i) out[i] = 0.0;
+  prof_last_.clear();
+  prof_labels_ = prof_labels_run_;
   for (size_t i = 0; i < prof_ops_family_.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, prof_events_[2 * i], prof_events_[2 * i + 1]);
     const int f = prof_ops_family_[i];
+    prof_last_.push_back(f);
+    prof_last_.push_back(ms);
+    prof_last_.push_back(prof_flops_[i]);
+    prof_last_.push_back(prof_bytes_[i]);
     out[f * 4 + 0] += ms;
     out[f * 4 + 1] += prof_flops_[i];
     out[f * 4 + 2] += prof_bytes_[i];

@@ -66,6 +66,9 @@ class Engine {
   // step: 1-based Adam step count (bias correction); the caller owns it because engines share a parameter block
   std::string adam_step(float lr, float grad_scale, int step, cudaStream_t stream);
   int launches_last_call() const { return launches_; }
+  // per-launch records of the last profile_update: {family, ms, flops, bytes} each
+  const std::vector<double>& last_profile_ops() const { return prof_last_; }
+  const std::vector<std::string>& last_profile_labels() const { return prof_labels_; }
   // Runs ONE update_grads + adam_step with a CUDA-event pair around every launch (serialises nothing: events are
   // recorded in-stream) and accumulates per-family device time.  out: [kNumFamilies][4] = {ms, flops, bytes, launches}.
   std::string profile_update(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
@@ -83,6 +86,7 @@ class Engine {
     int family = 0;      // OpFamily
     double flops = 0.0;  // algorithmic FLOPs (2*MAC) of the launch
     double bytes = 0.0;  // algorithmic HBM bytes (operands read once + results written once)
+    std::string label;   // what the launch is (layer / role), for the per-launch profile
     Op() {}
     template <class F>
     Op(F f, int fam = 0, double fl = 0.0, double by = 0.0) : fn(f), family(fam), flops(fl), bytes(by) {}
@@ -106,7 +110,8 @@ class Engine {
   bool profiling_ = false;
   std::vector<cudaEvent_t> prof_events_;
   std::vector<int> prof_ops_family_;
-  std::vector<double> prof_flops_, prof_bytes_;
+  std::vector<double> prof_flops_, prof_bytes_, prof_last_;
+  std::vector<std::string> prof_labels_, prof_labels_run_;
   cudaError_t launch(const Op& op, cudaStream_t stream);
 
   // arena offsets (bytes)

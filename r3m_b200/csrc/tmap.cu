@@ -70,7 +70,7 @@ std::string encode_im2col_map(CUtensorMap* out, const void* base, int C, int W, 
 }
 
 std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                                uint64_t row_stride_bytes, int box_inner, int box_outer) {
+                                uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes) {
   std::call_once(g_once, resolve);
   if (!g_tiled) return g_resolve_error;
   const cuuint64_t dims[2] = {inner, outer};
@@ -78,8 +78,9 @@ std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inn
   const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = g_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return "cuTensorMapEncodeTiled failed (CUresult " + std::to_string((int)r) + ") inner=" + std::to_string(inner) +
            " outer=" + std::to_string(outer) + " box=" + std::to_string(box_inner) + "x" + std::to_string(box_outer);

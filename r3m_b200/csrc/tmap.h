@@ -19,8 +19,9 @@ namespace r3m {
 std::string encode_im2col_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int lower_w, int lower_h,
                               int upper_w, int upper_h, int channels, int pixels, int trav_stride);
 
-// Row-major 2-D bf16 matrix [outer][inner] (inner contiguous), 128B-swizzled boxes of box_inner x box_outer.
+// Row-major 2-D bf16 matrix [outer][inner] (inner contiguous), swizzled boxes of box_inner x box_outer.
+// swizzle_bytes: 128 (box_inner * 2 <= 128) or 64 (box_inner * 2 <= 64).
 std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                                uint64_t row_stride_bytes, int box_inner, int box_outer);
+                                uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes = 128);
 
 }  // namespace r3m

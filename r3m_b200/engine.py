@@ -139,6 +139,20 @@ class Engine:
         return {name: {"ms": out[4 * i], "flops": out[4 * i + 1], "bytes": out[4 * i + 2],
                        "launches": int(out[4 * i + 3])} for i, name in enumerate(self.FAMILIES)}
 
+    def profile_ops(self):
+        """Per-launch (family, ms, flops, bytes) of the last profile_update, in launch order."""
+        cap = 4096
+        out = (ctypes.c_double * (4 * cap))()
+        n = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_profile_ops(self._h, out, cap, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(160)
+        rows = []
+        for i in range(min(n.value, cap)):
+            L.check(L.lib.r3m_b200_engine_profile_label(self._h, i, buf, 160))
+            rows.append((self.FAMILIES[int(out[4 * i])], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3],
+                         buf.value.decode()))
+        return rows
+
     def read_metrics(self):
         """ONE device->host copy of the 16-float metrics buffer (the reference does ~10 .item() syncs)."""
         p, n = self._region(7)

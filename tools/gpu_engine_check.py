@@ -108,9 +108,10 @@ def case_update(size, clips, seeds, frames_kind, golden=None, lang=False):
     leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     alles = O.r3m_forward(leaf, {k: v.clone() for k, v in buffers.items()}, frames.reshape(-1, 3, 224, 224), size, True)
     alles.backward(eng.embedding_grads().cpu())
-    vjp = {k: leaf[k].grad for k in o_grads}
-    gv = {k: rel(named[k].grad.cpu(), vjp[k]) for k in o_grads}
-    res["vjp_grad_global_rel"] = rel(cat({k: named[k].grad.cpu() for k in o_grads}), cat(vjp))
+    vjp = {k: leaf[k].grad for k in o_grads if leaf[k].grad is not None}
+    gv = {k: rel(named[k].grad.cpu(), vjp[k]) for k in vjp}
+    catv = lambda d: torch.cat([d[k].flatten().double() for k in vjp])  # noqa: E731
+    res["vjp_grad_global_rel"] = rel(catv({k: named[k].grad.cpu() for k in vjp}), catv(vjp))
     res["vjp_grad_worst"] = sorted(gv.items(), key=lambda kv: -kv[1])[:6]
     res["vjp_grad_by_layer"] = [(k, round(v, 4)) for k, v in gv.items() if k.endswith("conv1.weight") or k.endswith("bn1.weight") or "downsample" in k][:40]
     # the reference under the SAME storage policy (bf16 rounding at the points where the CUDA path stores bf16)
