@@ -54,6 +54,51 @@ int r3m_b200_conv_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, in
 int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                         int stride, int pad, void* stream);
 
+/* Input normalisation + stem re-layout (replaces aten::div/sub/div of models_r3m.py:97-98 fused with the layout the
+ * stem conv consumes).  obs fp32 NCHW [N,3,224,224] in [0,255] -> xs bf16 [N,112,112,64]; channel
+ * j = kw*16 + (dy*2+dx)*4 + c holds normalise(obs[n,c,2i+dy,2(q-2+kw)+dx]) (zero outside the image / for c == 3). */
+int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream);
+
+/* BatchNorm2d forward on a raw conv output (replaces aten::cudnn_batch_norm + relu_ [+ add_], tv resnet.py:89-105,
+ * 143-163).  y, a, residual: bf16 [M][C].  train != 0: batch statistics from (sum, sq) = per-channel sum / sum of
+ * squares of y; writes save_mean / save_rstd and updates running_mean / running_var (momentum 0.1, unbiased var).
+ * train == 0: running statistics.  a = [relu](gamma * xhat + beta [+ residual]). */
+int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
+                      const float* sq, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* save_mean, float* save_rstd, void* stream);
+
+/* BatchNorm2d backward (replaces aten::cudnn_batch_norm_backward + threshold_backward).  dA: gradient w.r.t. the
+ * activated output; a: activated output used as ReLU mask (NULL: no ReLU); y: raw conv output; sums: fp32 [2*C]
+ * scratch that must be zero on entry.  Writes dy (gradient w.r.t. y), optionally dz (masked gradient, the residual
+ * branch's share), dgamma, dbeta. */
+int r3m_b200_bn_backward(const void* dA, const void* a, const void* y, int M, int C, const float* mean,
+                         const float* rstd, const float* gamma, float* sums, void* dy, void* dz, float* dgamma,
+                         float* dbeta, void* stream);
+
+/* Stem tail: BN + ReLU + MaxPool2d(3,2,1) (tv resnet.py:198-200) and its backward.  y bf16 [N,H,W,C] ->
+ * a bf16 [N,H/2,W/2,C] plus the argmax code (0..8, scan order) per output element. */
+int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N, int H, int W, int C, int train,
+                                  const float* sum, const float* sq, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float* save_mean, float* save_rstd,
+                                  void* stream);
+int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
+                              void* stream);
+
+/* AdaptiveAvgPool2d((1,1)) + flatten (tv resnet.py:278-279) and its backward.  a bf16 [N,HW,C] <-> fp32 [N,C]. */
+int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream);
+int r3m_b200_avgpool_backward(const float* dE, void* dA, int N, int HW, int C, void* stream);
+
+/* Loss heads on embeddings E fp32 [5*B][D] (trainer.py:51-59 and :120-150).  metrics: fp32[16] accumulated into
+ * (zero it first); dE (may be NULL): loss_lp WRITES d/dE of the weighted penalty, loss_tcn ACCUMULATES on top. */
+int r3m_b200_loss_lp(const float* E, float* dE, int rows, int D, float l2weight, float l1weight, float* metrics,
+                     void* stream);
+int r3m_b200_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, float* metrics,
+                      void* stream);
+
+/* torch.optim.Adam step over a flat fp32 buffer (defaults beta 0.9/0.999, eps 1e-8), also emitting the bf16 copy. */
+int r3m_b200_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, int step,
+                  float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Engine: the whole hot path behind R3M.forward (r3m/models/models_r3m.py:84-100) and Trainer.update
  * (r3m/trainer.py:25-162) for one backbone size and one frame count.  The caller owns two device allocations

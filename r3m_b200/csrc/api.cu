@@ -9,6 +9,7 @@
 #include "convops.h"
 #include "elementwise.cuh"
 #include "engine.h"
+#include "loss.cuh"
 
 namespace r3m {
 thread_local std::string g_last_error;
@@ -157,6 +158,114 @@ int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, 
   return R3M_B200_OK;
 }
 
+
+#define CUDA_OR_FAIL(expr, what)                         \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return fail_cuda(_e, what);   \
+    return R3M_B200_OK;                                  \
+  } while (0)
+
+int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream) {
+  if (!obs || !xs || N < 1) return fail(R3M_B200_ERR_INVALID, "preprocess_stem: bad arguments");
+  CUDA_OR_FAIL(launch_preprocess_stem(obs, xs, N, (cudaStream_t)stream), "preprocess_stem");
+}
+
+int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
+                      const float* sq, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* save_mean, float* save_rstd, void* stream) {
+  BnApplyArgs g;
+  g.y = y;
+  g.a = a;
+  g.residual = residual;
+  g.M = M;
+  g.C = C;
+  g.relu = relu;
+  g.train = train;
+  g.sum = sum;
+  g.sq = sq;
+  g.gamma = gamma;
+  g.beta = beta;
+  g.running_mean = running_mean;
+  g.running_var = running_var;
+  g.save_mean = save_mean;
+  g.save_rstd = save_rstd;
+  CUDA_OR_FAIL(launch_bn_apply(g, (cudaStream_t)stream), "bn_apply");
+}
+
+int r3m_b200_bn_backward(const void* dA, const void* a, const void* y, int M, int C, const float* mean,
+                         const float* rstd, const float* gamma, float* sums, void* dy, void* dz, float* dgamma,
+                         float* dbeta, void* stream) {
+  BnBwdArgs g;
+  g.dA = dA;
+  g.a = a;
+  g.y = y;
+  g.M = M;
+  g.C = C;
+  g.mean = mean;
+  g.rstd = rstd;
+  g.gamma = gamma;
+  g.sums = sums;
+  g.dy = dy;
+  g.dz_out = dz;
+  g.dgamma = dgamma;
+  g.dbeta = dbeta;
+  cudaError_t e = launch_bn_bwd_reduce(g, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "bn_bwd_reduce");
+  CUDA_OR_FAIL(launch_bn_bwd_apply(g, (cudaStream_t)stream), "bn_bwd_apply");
+}
+
+int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N, int H, int W, int C, int train,
+                                  const float* sum, const float* sq, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float* save_mean, float* save_rstd,
+                                  void* stream) {
+  StemPoolArgs g;
+  g.y = y;
+  g.a = a;
+  g.argmax = argmax;
+  g.N = N;
+  g.H = H;
+  g.W = W;
+  g.C = C;
+  g.train = train;
+  g.sum = sum;
+  g.sq = sq;
+  g.gamma = gamma;
+  g.beta = beta;
+  g.running_mean = running_mean;
+  g.running_var = running_var;
+  g.save_mean = save_mean;
+  g.save_rstd = save_rstd;
+  CUDA_OR_FAIL(launch_stem_bn_relu_maxpool(g, (cudaStream_t)stream), "stem_bn_relu_maxpool");
+}
+
+int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
+                              void* stream) {
+  CUDA_OR_FAIL(launch_maxpool_bwd(dA, a, argmax, dz, N, H, W, C, (cudaStream_t)stream), "maxpool_backward");
+}
+
+int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream) {
+  CUDA_OR_FAIL(launch_avgpool_fwd(a, out, N, HW, C, (cudaStream_t)stream), "avgpool_forward");
+}
+int r3m_b200_avgpool_backward(const float* dE, void* dA, int N, int HW, int C, void* stream) {
+  CUDA_OR_FAIL(launch_avgpool_bwd(dE, dA, N, HW, C, (cudaStream_t)stream), "avgpool_backward");
+}
+
+int r3m_b200_loss_lp(const float* E, float* dE, int rows, int D, float l2weight, float l1weight, float* metrics,
+                     void* stream) {
+  CUDA_OR_FAIL(launch_loss_lp(E, dE, rows, D, l2weight, l1weight, metrics, (cudaStream_t)stream), "loss_lp");
+}
+int r3m_b200_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, float* metrics,
+                      void* stream) {
+  CUDA_OR_FAIL(launch_loss_tcn(E, dE, perms, B, D, tcnweight, metrics, (cudaStream_t)stream), "loss_tcn");
+}
+
+int r3m_b200_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, int step,
+                  float grad_scale, void* stream) {
+  if (step < 1) return fail(R3M_B200_ERR_INVALID, "Adam step count starts at 1");
+  CUDA_OR_FAIL(launch_adam(p, g, m, v, p_bf16, n, lr, 0.9f, 0.999f, 1e-8f, step, grad_scale, (cudaStream_t)stream),
+               "adam");
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // engine

@@ -24,6 +24,17 @@ def _world():
     return 1
 
 
+def allreduce_gradients(module):
+    """The step's ONLY collective: sum the flat fp32 gradient buffer over all ranks (NCCL over NVLink on GPUs; any
+    torch.distributed backend works).  Returns the factor Adam must apply to turn the sum into the mean."""
+    world = _world()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(module._flat(1), op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
 def draw_permutations(batch_size, langweight, tcnweight, num_negatives=3):
     """[15, B] int32 permutations drawn exactly as the reference draws them (same count, same order, global CPU
     generator): 3*num_neg for the language branch if it is on, then 2*num_neg for TCN if it is on."""
@@ -83,12 +94,7 @@ class Trainer:
         t6 = time.time()
         if not eval:
             m._nbt += 1
-            world = _world()
-            if world > 1:
-                import torch.distributed as dist
-
-                dist.all_reduce(m._flat(1), op=dist.ReduceOp.SUM)  # the step's only collective
-            m.encoder_opt.step(grad_scale=1.0 / world)
+            m.encoder_opt.step(grad_scale=allreduce_gradients(m))
             self.last_launches += eng.launches()
         vals = eng.read_metrics()
         for i, k in enumerate(METRIC_KEYS):

@@ -1,0 +1,205 @@
+"""End-to-end parity of R3M.forward / Trainer.update on the B200 against the golden fixtures (outputs of the real
+reference) and the CPU oracle.
+
+Tolerances (see DESIGN.md "Parity tiers"): the CUDA path stores activations / filters as bf16 with fp32 accumulation.
+  * eval-mode embeddings vs the fp32 reference: <= 5e-3 relative L2 (measured 2.7e-3);
+  * train-mode-BN embeddings: rounding is amplified by batch-stat BN at random init — the reference under the SAME
+    storage policy (oracle policy="bf16") deviates from fp32 by 1e-2 (RN18) ... 1e-1 (RN50); ours must not deviate more
+    than 1.5x that;
+  * loss heads on identical embeddings: <= 1e-4 relative (north star), measured ~1e-7;
+  * parameter gradients: the gradient of this network at random init is so ill-conditioned that rounding ONLY the
+    filters to bf16 moves it by 30 %; the check is that our deviation from the fp32 oracle stays within
+    1.5x of the bf16-policy oracle's own deviation, layer group by layer group, plus exact kernel-level tests in
+    test_kernels_gpu.py; Adam is checked exactly on OUR gradients."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HYPER = dict(l2weight=1e-5, l1weight=1e-5, tcnweight=1.0, lr=1e-4)
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _case(name):
+    from oracle import r3m_oracle as O
+
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    case = json.loads(bytes(z["case_json"]).decode())
+    gold_metrics = json.loads(bytes(z["metrics_json"]).decode())
+    sw, sf, sp, sl = case["seeds"]
+    lang = case["langweight"] > 0
+    params, buffers = O.init_state(case["size"], sw, lang=lang)
+    frames = (O.synthetic_frames if case["frames"] == "randint" else O.structured_frames)(case["clips"], sf)
+    perms = O.draw_permutations(case["clips"], sp)
+    lang_emb = O.stub_lang_embedding(case["clips"], sl) if lang else None
+    sentences = ["C does something %d" % i for i in range(case["clips"])]
+    if lang and case["clips"] >= 4:
+        sentences[1] = ""
+    if not lang:
+        sentences = [""] * case["clips"]
+    mask = torch.tensor([1.0 * (s != "") for s in sentences])
+    return z, case, gold_metrics, params, buffers, frames, perms, lang_emb, sentences, mask
+
+
+def _model(case, params, buffers, lang_emb):
+    import r3m_b200
+    from r3m_b200 import R3M
+
+    r3m_b200.set_lang_encoder_factory(lambda dev: (lambda s: lang_emb))
+    m = R3M("cuda", HYPER["lr"], 1024, size=case["size"], l2weight=HYPER["l2weight"], l1weight=HYPER["l1weight"],
+            langweight=case["langweight"], tcnweight=HYPER["tcnweight"])
+    sd = dict(params)
+    sd.update(buffers)
+    m.load_state_dict(sd)
+    return m, torch.nn.DataParallel(m).cuda()
+
+
+def test_eval_forward_c1_against_reference_golden():
+    """BASELINE.json configs[0] (load_r3m('resnet18') forward, batch 4), run on the GPU path."""
+    from oracle import r3m_oracle as O
+    from r3m_b200 import R3M
+
+    z = np.load(os.path.join(GOLD, "rn18_eval_b4.npz"))
+    params, buffers = O.init_state(18, 5)
+    g = torch.Generator().manual_seed(6)
+    for k in buffers:
+        if k.endswith("running_mean"):
+            buffers[k] = 0.1 * torch.randn(buffers[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            buffers[k] = 0.5 + torch.rand(buffers[k].shape, generator=g)
+    frames = O.synthetic_frames(1, 7)[0, :4]
+    m = R3M("cuda", 1e-4, 1024, size=18, langweight=0.0)
+    sd = dict(params)
+    sd.update(buffers)
+    m.load_state_dict(sd)
+    m = torch.nn.DataParallel(m).cuda()
+    m.eval()
+    with torch.no_grad():
+        out = m(frames.cuda())
+    assert out.shape == (4, 512) and out.dtype == torch.float32
+    assert rel(out, z["embeddings"]) < 5e-3
+    # uint8 frames are accepted like the reference (obs.float()), and eval leaves the running stats untouched
+    out2 = m(frames.to(torch.uint8).cuda())
+    assert rel(out2, out) < 1e-6
+    assert torch.equal(m.module.state_dict()["convnet.bn1.running_mean"].cpu(), buffers["convnet.bn1.running_mean"])
+
+
+@pytest.mark.parametrize("name", ["rn18_tcn", "rn34_tcn", "rn18_lang_b4", "rn50_lang"])
+def test_update_against_reference_golden(name):
+    from oracle import r3m_oracle as O
+    from r3m_b200 import Trainer
+
+    z, case, gold, params, buffers, frames, perms, lang_emb, sentences, mask = _case(name)
+    hyper = dict(HYPER, langweight=case["langweight"])
+    m, model = _model(case, params, buffers, lang_emb)
+    trainer = Trainer(eval_freq=100)
+    metrics, st = trainer.update(model, (frames.cuda(), sentences), 0, perms=perms, lang_emb=lang_emb)
+    assert set(metrics) == set(gold) and isinstance(st, str) and st.startswith("Load time")
+    eng = m._any_engine()
+    emb = eng.embeddings().cpu()
+
+    # ---- forward: vs the fp32 reference, calibrated by the reference under the same storage policy
+    b_params = {k: v.clone() for k, v in params.items()}
+    b_buffers = {k: v.clone() for k, v in buffers.items()}
+    b_metrics, b_grads, b_emb = O.update(b_params, b_buffers, O.new_opt_state(), frames, perms, hyper, case["size"],
+                                         lang_emb, mask, policy="bf16")
+    ours_dev, policy_dev = rel(emb, z["embeddings"]), rel(b_emb, z["embeddings"])
+    assert ours_dev < 1.5 * policy_dev + 1e-3, (ours_dev, policy_dev)
+    assert ours_dev < (0.15 if case["size"] == 50 else 0.04)
+    for k in ("l2loss", "l1loss", "l0loss"):
+        assert abs(metrics[k] - gold[k]) <= 5e-3 * abs(gold[k]), (k, metrics[k], gold[k])
+
+    # ---- loss heads on identical embeddings: the north star's 1e-4
+    e = emb.clone().requires_grad_(True)
+    lp = {k: v.clone().requires_grad_(True) for k, v in params.items() if k.startswith("lang_rew")}
+    full, same = O.losses(lp, e, perms, hyper, lang_emb, mask)
+    full.backward()
+    for k, v in same.items():
+        assert abs(metrics[k] - v) <= 1e-4 * max(abs(v), 1e-6), (k, metrics[k], v)
+    assert rel(eng.embedding_grads(), e.grad) < 1e-4
+    named = dict(m.named_parameters())
+    for k, v in lp.items():
+        if k.endswith("pred.8.bias"):
+            assert float((named[k].grad.cpu() - v.grad).abs().max()) < 1e-6  # true value cancels to ~eps
+        else:
+            assert rel(named[k].grad, v.grad) < 1e-3, k
+
+    # ---- backward through the network: deviation profile vs the same-policy oracle
+    o_params = {k: v.clone() for k, v in params.items()}
+    o_metrics, o_grads, _ = O.update(o_params, {k: v.clone() for k, v in buffers.items()}, O.new_opt_state(), frames,
+                                     perms, hyper, case["size"], lang_emb, mask)
+    conv_keys = [k for k in o_grads if k.startswith("convnet.")]
+    cat = lambda d, keys: torch.cat([d[k].detach().flatten().double().cpu() for k in keys])  # noqa: E731
+    ours = {k: named[k].grad for k in conv_keys}
+    for prefix in ("convnet.layer4", "convnet.layer3", "convnet.layer2", "convnet.layer1", "convnet."):
+        keys = [k for k in conv_keys if k.startswith(prefix)]
+        d_ours = rel(cat(ours, keys), cat(o_grads, keys))
+        d_pol = rel(cat(b_grads, keys), cat(o_grads, keys))
+        assert d_ours < 1.5 * d_pol + 0.02, (prefix, d_ours, d_pol)
+    assert all(torch.isfinite(named[k].grad).all() for k in conv_keys)
+
+    # ---- Adam, exactly, on OUR gradients (post-step weights == torch-formula step of the pre-step weights)
+    sd = m.state_dict()
+    for k in ("convnet.conv1.weight", "convnet.layer2.0.downsample.0.weight", "convnet.layer4.0.bn1.bias"):
+        gk = named[k].grad.cpu()
+        want = params[k] - HYPER["lr"] * gk / (gk.abs() + 1e-8)  # first Adam step: m/(sqrt(v)+eps) with bias corr.
+        assert rel(sd[k], want) < 1e-5, k
+    # ---- BN running statistics (momentum 0.1, unbiased variance) and the batch counter
+    assert rel(sd["convnet.bn1.running_mean"], z["post::convnet.bn1.running_mean"]) < 5e-3
+    assert rel(sd["convnet.bn1.running_var"], z["post::convnet.bn1.running_var"]) < 5e-3
+    assert int(sd["convnet.bn1.num_batches_tracked"]) == 1
+    assert trainer.last_launches > 100
+
+
+def test_eval_update_has_no_side_effects():
+    """trainer.py:28-29,155: eval=True -> eval-mode BN, no optimiser step; metrics still produced."""
+    from r3m_b200 import Trainer
+
+    z, case, gold, params, buffers, frames, perms, lang_emb, sentences, mask = _case("rn18_tcn")
+    m, model = _model(case, params, buffers, lang_emb)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    metrics, _ = Trainer(100).update(model, (frames.cuda(), sentences), 0, eval=True, perms=perms)
+    after = m.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    assert set(metrics) == set(gold) and np.isfinite(list(metrics.values())).all()
+
+
+def test_full_size_c3_step_properties():
+    """BASELINE c3 size (ResNet-50, 64 clips = 320 frames, TCN + language + L1/L2): properties that need no oracle —
+    finite metrics with the reference key set, loss decreasing on a fixed batch, embeddings non-negative
+    (post-ReLU average pool), state_dict round trip."""
+    import r3m_b200
+    from r3m_b200 import R3M, Trainer
+
+    B = 64
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(B, 768, generator=g)
+    r3m_b200.set_lang_encoder_factory(lambda dev: (lambda s: emb))
+    torch.manual_seed(0)
+    m = R3M("cuda", 1e-4, 1024, size=50, l2weight=1e-5, l1weight=1e-5, langweight=1.0, tcnweight=1.0)
+    model = torch.nn.DataParallel(m).cuda()
+    frames = torch.randint(0, 255, (B, 5, 3, 224, 224), device="cuda").float()
+    lang = ["" if i % 10 == 9 else "clip %d" % i for i in range(B)]
+    tr = Trainer(100)
+    hist = [tr.update(model, (frames, lang), i)[0] for i in range(6)]
+    keys = ["l2loss", "l1loss", "l0loss", "rewloss", "rewacc1", "rewacc2", "rewacc3", "tcnloss", "aligned", "full_loss"]
+    assert list(hist[0].keys()) == keys
+    assert all(np.isfinite(list(h.values())).all() for h in hist)
+    assert hist[-1]["full_loss"] < hist[0]["full_loss"]
+    e = m._any_engine().embeddings()
+    assert e.shape == (320, 2048) and float(e.min()) >= 0.0
+    sd = m.state_dict()
+    m2 = R3M("cuda", 1e-4, 1024, size=50, langweight=1.0).cuda()
+    m2.load_state_dict(sd)
+    m2.eval(), m.eval()
+    with torch.no_grad():
+        assert rel(m2(frames[0]), m(frames[0])) < 1e-6

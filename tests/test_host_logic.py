@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference surface (no GPU): state_dict contract, loader, permutation stream, config."""
+import os
+import sys
+
+import pytest
+import torch
+import torchvision
+
+import r3m_b200
+from r3m_b200 import R3M, Trainer
+from r3m_b200.trainer import draw_permutations
+
+
+class _StubEnc:
+    lang_size = 768
+
+    def __init__(self, device):
+        pass
+
+    def __call__(self, s):
+        return torch.zeros(len(s), 768)
+
+
+@pytest.mark.parametrize("size", [18, 34, 50])
+def test_state_dict_matches_torchvision(size):
+    """module.convnet.* keys, shapes, dtypes identical to torchvision's ResNet (SURVEY.md §5 checkpoint contract)."""
+    m = R3M("cpu", 1e-4, 1024, size=size, langweight=0.0)
+    tv = getattr(torchvision.models, f"resnet{size}")()
+    tv.fc = torch.nn.Identity()
+    want = {"convnet." + k: v for k, v in tv.state_dict().items()}
+    got = m.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
+        assert got[k].is_contiguous()
+    # reference checkpoints load (strict) and survive a round trip bit-exactly
+    m.load_state_dict(want)
+    back = m.state_dict()
+    assert all(torch.equal(back[k], want[k]) for k in want)
+    # and ours load into torchvision
+    tv.load_state_dict({k[len("convnet."):]: v for k, v in back.items()})
+    dp = torch.nn.DataParallel(m)
+    assert next(iter(dp.state_dict())).startswith("module.convnet.")
+
+
+def test_language_head_keys_and_init_laws():
+    r3m_b200.set_lang_encoder_factory(_StubEnc)
+    m = R3M("cpu", 1e-4, 1024, size=50, langweight=1.0)
+    sd = m.state_dict()
+    for i, shape in zip((0, 2, 4, 6, 8), ((1024, 4864), (1024, 1024), (1024, 1024), (1024, 1024), (1, 1024))):
+        assert sd[f"lang_rew.pred.{i}.weight"].shape == shape
+        assert sd[f"lang_rew.pred.{i}.bias"].shape == (shape[0],)
+    w = sd["convnet.layer1.0.conv2.weight"]  # kaiming_normal_(fan_out, relu): std = sqrt(2 / (Cout*k*k))
+    assert abs(float(w.std()) - (2.0 / (64 * 9)) ** 0.5) < 0.1 * (2.0 / (64 * 9)) ** 0.5
+    assert torch.all(sd["convnet.bn1.weight"] == 1) and torch.all(sd["convnet.bn1.bias"] == 0)
+    assert torch.all(sd["convnet.bn1.running_var"] == 1) and torch.all(sd["convnet.bn1.running_mean"] == 0)
+    b = 1.0 / 4864 ** 0.5
+    assert float(sd["lang_rew.pred.0.weight"].abs().max()) <= b
+    assert sum(p.numel() for p in m.parameters()) == 23508032 + 8131585
+    assert m.num_negatives == 3 and m.outdim == 2048
+
+
+def test_constructor_signature_and_attributes():
+    import inspect
+
+    sig = inspect.signature(R3M.__init__)
+    assert list(sig.parameters)[1:] == ["device", "lr", "hidden_dim", "size", "l2weight", "l1weight", "langweight",
+                                        "tcnweight", "l2dist", "bs"]  # models_r3m.py:22-23
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["size"], d["l2weight"], d["l1weight"], d["langweight"], d["tcnweight"], d["l2dist"], d["bs"]) == \
+        (34, 1.0, 1.0, 1.0, 0.0, True, 16)
+    with pytest.raises(NameError):
+        R3M("cpu", 1e-4, 1024, size=101, langweight=0.0)
+    m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0, tcnweight=1.0)
+    a, b = torch.randn(3, 8), torch.randn(3, 8)
+    assert torch.allclose(m.sim(a, b), -torch.linalg.norm(a - b, dim=-1))
+    assert hasattr(m.encoder_opt, "zero_grad") and hasattr(m.encoder_opt, "step")
+
+
+def test_parameters_alias_the_flat_block_and_survive_to():
+    m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
+    w = m.convnet.layer1._modules["0"].conv1.weight
+    flat = m._flat(0)
+    with torch.no_grad():
+        w[3, 5, 1, 2] = 42.0
+    assert (flat == 42.0).sum() == 1  # the OIHW view writes through to the KRSC master copy
+    assert w.grad is not None and w.grad.shape == w.shape
+    m.to("cpu")
+    m.float()
+    assert m.convnet.layer1._modules["0"].conv1.weight[3, 5, 1, 2] == 42.0
+
+
+def test_permutation_stream_matches_reference_draw_order():
+    """trainer.py:86-92 then :135-137: 9 language permutations (if on) then 6 TCN ones from the global CPU RNG."""
+    torch.manual_seed(7)
+    want = [torch.randperm(6) for _ in range(15)]
+    torch.manual_seed(7)
+    got = draw_permutations(6, 1.0, 1.0)
+    assert all(torch.equal(got[i].long(), want[i]) for i in range(15))
+    torch.manual_seed(7)
+    got = draw_permutations(6, 0.0, 1.0)  # language off: the TCN draws come first in the stream
+    assert all(torch.equal(got[9 + i].long(), want[i]) for i in range(6))
+    assert got.dtype == torch.int32 and got.shape == (15, 6)
+
+
+def test_load_r3m_offline_from_cache(tmp_path, monkeypatch):
+    """r3m/__init__.py:61-74: an existing ~/.r3m/<folder>/model.pt is used without downloading; the language head is
+    stripped; invalid ids raise NameError."""
+    monkeypatch.setenv("HOME", str(tmp_path))
+    folder = tmp_path / ".r3m" / "r3m_18"
+    folder.mkdir(parents=True)
+    src = torch.nn.DataParallel(R3M("cpu", 1e-4, 1024, size=18, langweight=0.0))
+    sd = src.state_dict()
+    sd["module.lang_rew.pred.0.weight"] = torch.zeros(3, 3)  # must be ignored (remove_language_head)
+    torch.save({"r3m": sd, "global_step": 5}, folder / "model.pt")
+    (folder / "config.yaml").write_text(
+        "agent:\n  _target_: r3m.R3M\n  device: cuda\n  lr: 0.0001\n  hidden_dim: 1024\n  size: 18\n  l2weight: 0.00001\n"
+        "  l1weight: 0.00001\n  tcnweight: 1.0\n  langweight: 1.0\n  l2dist: true\n  bs: 32\n  extra_key: 1\n")
+    rep = r3m_b200.load_r3m("resnet18")
+    assert isinstance(rep, torch.nn.DataParallel) and rep.module.langweight == 0
+    got = rep.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in src.state_dict().items())
+    with pytest.raises(NameError):
+        r3m_b200.load_r3m("resnet101")
+
+
+def test_trainer_contract_needs_gpu_but_keeps_signature():
+    import inspect
+
+    params = list(inspect.signature(Trainer.update).parameters)
+    assert params[:5] == ["self", "model", "batch", "step", "eval"]
+    assert Trainer(eval_freq=20000).eval_freq == 20000
