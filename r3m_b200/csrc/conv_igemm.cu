@@ -11,8 +11,8 @@
 //                            live in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //                            the main loop of tile i+1.
 //   warp 2    TMEM allocator.
-//   warps 4-11 epilogue    : two warps per TMEM lane quadrant, alternating 32-column units:
-//                            tcgen05.ld (next unit in flight) -> bf16 -> 64B-swizzled smem staging ->
+//   warps 4-11 epilogue    : two warps per TMEM lane quadrant, alternating 64-column units:
+//                            tcgen05.ld (next unit in flight) -> bf16 -> 128B-swizzled smem staging ->
 //                            (a) per-channel sum / sum-of-squares for train-mode BatchNorm, accumulated per CTA in
 //                            smem and flushed once with atomics, (b) dense outputs leave through TMA bulk tensor
 //                            stores (cp.reduce...add when accumulating into an existing gradient), strided scatter
@@ -32,31 +32,36 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kNumEpiWarps = 8;  // two warps per TMEM lane quadrant, alternating 32-column units
-constexpr int kThreads = 128 + kNumEpiWarps * 32;
-constexpr int kUnitBytes = 32 * 32 * 2;  // one epilogue unit: 32 rows x 32 columns bf16, 64B-swizzled rows
-constexpr int kStagingBytes = kNumEpiWarps * kUnitBytes;
+constexpr int kUnitCols = 64;  // one epilogue unit: 32 rows x 64 columns bf16 = 128-byte rows (TMA stores are paced per row)
+constexpr int kUnitBytes = 32 * kUnitCols * 2;
 constexpr int kMaxStatC = 2048;
 
-template <int BN>
+// STAGES: depth of the TMA->MMA operand ring.  BUFS: staging buffers per epilogue warp (bulk stores in flight).
+// Long-K tiles (3x3 convs) want the deep ring, short-K tiles (1x1 convs into wide outputs) are epilogue bound and want
+// several stores in flight; both fit the 227 KB budget only one at a time for BN = 256.
+// EPI: epilogue warps (4 or 8 = one or two per TMEM lane quadrant).
+template <int BN, int STAGES, int BUFS, int EPI>
 struct Cfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = STAGES;
+  static constexpr int kStagingBytes = EPI * BUFS * kUnitBytes;
+  static constexpr int kThreads = 128 + EPI * 32;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStagingBytes + 2 * kMaxStatC * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, int BUFS, int EPI>
+__global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, STAGES, BUFS, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
-  float* s_sum = reinterpret_cast<float*>(staging + kStagingBytes);
+  float* s_sum = reinterpret_cast<float*>(staging + C::kStagingBytes);
   float* s_sq = s_sum + kMaxStatC;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + kMaxStatC);
   uint64_t* empty_bar = full_bar + C::kStages;
@@ -80,7 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kNumEpiWarps);
+      mbar_init(&tempty_bar[i], EPI);
     }
     mbar_fence_init();
   }
@@ -188,24 +193,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // warp (q, h): TMEM lane quadrant q = warp % 4 (rows 32q..32q+31 of the tile), 32-column units u = h, h+2, ...
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
-    uint8_t* stg = staging + (warp - 4) * kUnitBytes;
-    const uint32_t stg_u32 = smem_u32(stg);
+    const uint32_t stg_base = smem_u32(staging + (warp - 4) * (BUFS * kUnitBytes));
+    int buf = 0;
     const bool dense = (p.out_mode == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-    constexpr int kUnits = BN / 32;
+    constexpr int kUnits = BN / kUnitCols;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
-      long long row_off[4];
+      long long row_off[8];
       if (!dense) {
-        // element offsets of the 4 rows this lane stores (row = 8*i + lane/4 of the warp's 32 rows)
+        // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = m0 + 8 * i + (lane >> 2);
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + 4 * i + (lane >> 3);
           if (m >= p.M_total) {
             row_off[i] = -1;
           } else {
@@ -224,104 +229,111 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + h * 32, v);
+      if (h >= kUnits) {
+        // BN == 64: a single unit per quadrant; the second warp of the pair has nothing to drain
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_row + h * kUnitCols, v0);
+        tmem_ld_32x32(t_row + h * kUnitCols + 32, v1);
 #pragma unroll 1
-      for (int u = h; u < kUnits; u += 2) {
-        tc_wait_ld();
-        uint32_t pk[16];
+        for (int u = h; u < kUnits; u += EPI / 4) {
+          tc_wait_ld();
+          uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        if (u + 2 < kUnits) {
-          tmem_ld_32x32(t_row + (u + 2) * 32, v);  // in flight while this unit is written out
-        } else {
-          // the accumulator stage is fully in registers: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        // staging buffer must no longer be read by the previous unit's bulk store
-        if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        // thread = row `lane`: four 16-byte chunks, XOR-swizzled (== TMA SWIZZLE_64B) so that row-wise writes, the
-        // column-pair reads of the statistics and the bulk store all agree and are bank-conflict free
-        const uint32_t rbase = stg_u32 + lane * 64;
-        const uint32_t sw = (lane >> 1) & 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t addr = rbase + ((j ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
-                       "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                       : "memory");
-        }
-        if (dense) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (dense && lane == 0) {
-          const int c0 = n0 + u * 32;
-          if (p.accumulate) {
-            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(stg_u32), "r"(c0), "r"(m0)
-                         : "memory");
+          for (int j = 0; j < 16; ++j) {
+            pk[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+            pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+          }
+          if (u + EPI / 4 < kUnits) {
+            tmem_ld_32x32(t_row + (u + EPI / 4) * kUnitCols, v0);  // in flight while this unit is written out
+            tmem_ld_32x32(t_row + (u + EPI / 4) * kUnitCols + 32, v1);
           } else {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(stg_u32), "r"(c0), "r"(m0)
+            // the accumulator stage is fully in registers: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          // the staging buffer about to be overwritten must no longer be read by the bulk store issued BUFS units ago
+          const uint32_t stg_u32 = stg_base + buf * kUnitBytes;
+          if (++buf == BUFS) buf = 0;
+          if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BUFS - 1) : "memory");
+          __syncwarp();
+          // thread = row `lane`: eight 16-byte chunks, XOR-swizzled by row (== TMA SWIZZLE_128B) so that the row-wise
+          // writes, the column-pair reads of the statistics and the bulk store agree and are bank-conflict free
+          const uint32_t rbase = stg_u32 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = rbase + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                         "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                          : "memory");
           }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        if (do_stats) {
-          // lanes 0-15 take even rows, lanes 16-31 odd rows; each lane owns the column pair (2*cp, 2*cp+1).
-          // Rows beyond M_total are exact zeros (TMA zero fill), so they do not disturb the sums.
-          const int cp = lane & 15;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) {
-            const int r = 2 * rr + (lane >> 4);
-            uint32_t w;
-            const uint32_t addr = stg_u32 + r * 64 + ((((cp >> 2)) ^ ((r >> 1) & 3)) << 4) + ((cp & 3) << 2);
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
-            const float a = bf16lo(w), b = bf16hi(w);
-            s0 += a;
-            s1 += b;
-            q0 = fmaf(a, a, q0);
-            q1 = fmaf(b, b, q1);
+          if (dense) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (dense && lane == 0) {
+            const int c0 = n0 + u * kUnitCols;
+            if (p.accumulate) {
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmC)),
+                  "r"(stg_u32), "r"(c0), "r"(m0)
+                  : "memory");
+            } else {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(stg_u32), "r"(c0), "r"(m0)
+                           : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
-          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-          if (lane < 16) {
-            const int col = n0 + u * 32 + 2 * cp;
+          if (do_stats) {
+            // lane owns columns (2*lane, 2*lane+1) of the unit; rows beyond M_total are exact zeros (TMA zero fill)
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              uint32_t w;
+              const uint32_t addr = stg_u32 + r * 128 + ((((lane >> 2)) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+              const float a = bf16lo(w), b = bf16hi(w);
+              s0 += a;
+              s1 += b;
+              q0 = fmaf(a, a, q0);
+              q1 = fmaf(b, b, q1);
+            }
+            const int col = n0 + u * kUnitCols + 2 * lane;
             atomicAdd(&s_sum[col], s0);
             atomicAdd(&s_sum[col + 1], s1);
             atomicAdd(&s_sq[col], q0);
             atomicAdd(&s_sq[col + 1], q1);
           }
-        }
-        if (!dense) {
-          // strided scatter (stride-2 dgrad parity classes): 4 lanes x 16 B = one 64-byte row segment
+          if (!dense) {
+            // strided scatter (stride-2 dgrad parity classes): 8 lanes x 16 B = one 128-byte row segment
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = 8 * i + (lane >> 2);
-            const int c = lane & 3;
-            uint32_t x0, x1, x2, x3;
-            const uint32_t addr = stg_u32 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
-            if (row_off[i] >= 0) {
-              uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + u * 32 + c * 8);
-              if (p.accumulate) {
-                const uint4 o = *dst;
-                x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
-                x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
-                x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
-                x3 = pack_bf16x2(bf16lo(x3) + bf16lo(o.w), bf16hi(x3) + bf16hi(o.w));
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3);
+              const int c = lane & 7;
+              uint32_t x0, x1, x2, x3;
+              const uint32_t addr = stg_u32 + r * 128 + ((c ^ (r & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                           : "r"(addr));
+              if (row_off[i] >= 0) {
+                uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + u * kUnitCols + c * 8);
+                if (p.accumulate) {
+                  const uint4 o = *dst;
+                  x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
+                  x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
+                  x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
+                  x3 = pack_bf16x2(bf16lo(x3) + bf16lo(o.w), bf16hi(x3) + bf16hi(o.w));
+                }
+                *dst = make_uint4(x0, x1, x2, x3);
               }
-              *dst = make_uint4(x0, x1, x2, x3);
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       acc ^= 1;
@@ -330,8 +342,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
       // all epilogue warps are done with every tile of this CTA -> flush the CTA partials
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = threadIdx.x - 128; i < p.Cout; i += kNumEpiWarps * 32) {
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
+      for (int i = threadIdx.x - 128; i < p.Cout; i += EPI * 32) {
         const float s = s_sum[i], qv = s_sq[i];
         if (s != 0.f || qv != 0.f) {
           atomicAdd(&p.stat_sum[i], s);
@@ -349,18 +361,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, int STAGES, int BUFS, int EPI>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, STAGES, BUFS, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_igemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  conv_igemm_kernel<BN, STAGES, BUFS, EPI><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 
@@ -368,13 +380,15 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 
 cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                               const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  const int num_kb = p.num_taps * p.cblocks;
   switch (bn) {
     case 64:
-      return launch_bn<64>(tmA, tmB, tmC, p, grid, stream);
+      return launch_bn<64, 6, 4, 4>(tmA, tmB, tmC, p, grid, stream);   // one unit per quadrant
     case 128:
-      return launch_bn<128>(tmA, tmB, tmC, p, grid, stream);
+      return launch_bn<128, 4, 2, 8>(tmA, tmB, tmC, p, grid, stream);
     case 256:
-      return launch_bn<256>(tmA, tmB, tmC, p, grid, stream);
+      if (num_kb >= 12) return launch_bn<256, 4, 1, 4>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
+      return launch_bn<256, 3, 2, 8>(tmA, tmB, tmC, p, grid, stream);                    // epilogue bound
     default:
       return cudaErrorInvalidValue;
   }

@@ -52,8 +52,8 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   ConvKernelParams& p = plan->p;
   p.M_total = g.N * g.P * g.Q;
   if (g.out_mode == 0) {
-    err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * 2, 32, 32,
-                              /*swizzle_bytes=*/64);
+    err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * 2, 64, 32,
+                              /*swizzle_bytes=*/128);
     if (!err.empty()) return err;
   } else {
     plan->tmC = plan->tmB;
