@@ -50,7 +50,8 @@ struct WgradKernelParams {
   int Cout;         // rows of dW
   int ldw;          // elements per dW row (= taps * Cin)
   int Cin;
-  int mblocks_total;      // ceil(M_total / 64)
+  int pix_block;          // reduction rows (pixels) per pipeline stage: 64 or 128
+  int mblocks_total;      // ceil(M_total / pix_block)
   int mblocks_per_split;
   int num_stages;
   float* dW;        // fp32, accumulated with red.add
@@ -59,6 +60,6 @@ struct WgradKernelParams {
 
 cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const WgradKernelParams& p, int splits,
                          int groups, int ktiles, cudaStream_t stream);
-int wgrad_smem_bytes(int group, int num_stages);
+int wgrad_smem_bytes(int group, int num_stages, int pix_block);
 
 }  // namespace r3m

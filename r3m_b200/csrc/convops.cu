@@ -1,6 +1,7 @@
 #include "convops.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "tmap.h"
@@ -100,11 +101,15 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   if (d.ntaps < 1 || d.ntaps > kMaxTaps) return "wgrad: tap count out of range";
   *plan = {};
   const int M = d.N * d.P * d.Q;
-  std::string err = encode_tiled_2d_map(&plan->tmDy, d.dy, (uint64_t)d.Cout, (uint64_t)M, (uint64_t)d.Cout * 2, 64, 64);
+  int pix = 128;
+  if (const char* e = getenv("R3M_WGRAD_PIX")) pix = atoi(e);  // tuning aid
+  if (pix != 64 && pix != 128) return "wgrad: pix_block must be 64 or 128";
+  std::string err =
+      encode_tiled_2d_map(&plan->tmDy, d.dy, (uint64_t)d.Cout, (uint64_t)M, (uint64_t)d.Cout * 2, 64, pix);
   if (!err.empty()) return err;
   const int upper_w = (d.Q - 1) * d.stride + 1 + d.base_w - d.W;
   const int upper_h = (d.P - 1) * d.stride + 1 + d.base_h - d.H;
-  err = encode_im2col_map(&plan->tmX, d.x, d.C, d.W, d.H, d.N, d.base_w, d.base_h, upper_w, upper_h, 64, 64, d.stride);
+  err = encode_im2col_map(&plan->tmX, d.x, d.C, d.W, d.H, d.N, d.base_w, d.base_h, upper_w, upper_h, 64, pix, d.stride);
   if (!err.empty()) return err;
   WgradKernelParams& p = plan->p;
   p.M_total = M;
@@ -115,7 +120,9 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   p.base_h = d.base_h;
   p.cblocks = d.C / 64;
   p.num_items = d.ntaps * p.cblocks;
-  p.group = std::min(4, p.num_items);
+  int group_pref = 5;  // largest group whose two pipeline stages of 128-pixel atoms fit in shared memory
+  if (const char* e = getenv("R3M_WGRAD_GROUP")) group_pref = atoi(e);  // tuning aid
+  p.group = std::min(group_pref, p.num_items);
   for (int t = 0; t < d.ntaps; ++t) {
     p.tap_w[t] = (uint16_t)d.tap_w[t];
     p.tap_h[t] = (uint16_t)d.tap_h[t];
@@ -123,15 +130,22 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   p.Cout = d.Cout;
   p.Cin = d.C;
   p.ldw = d.ntaps * d.C;
-  p.mblocks_total = (M + 63) / 64;
-  p.num_stages = std::min(6, (227 * 1024 - 2048) / ((2 + p.group) * 8192));
+  p.pix_block = pix;
+  p.mblocks_total = (M + pix - 1) / pix;
+  p.num_stages = std::min(6, (227 * 1024 - 2048) / ((2 + p.group) * pix * 128));
+  if (p.num_stages < 2) return "wgrad: group too large for the shared-memory budget";
+  if (const char* e = getenv("R3M_WGRAD_STAGES")) p.num_stages = std::min(p.num_stages, atoi(e));
   p.dW = d.dw;
   p.error_flag = device_error_flag();
   if (!p.error_flag) return "could not allocate the device error flag";
   plan->groups = (p.num_items + p.group - 1) / p.group;
   plan->ktiles = (d.Cout + 127) / 128;
   const int slabs = plan->groups * plan->ktiles;
-  int splits = (2 * device_sm_count() + slabs - 1) / slabs;
+  // split-K so that the grid is at most `waves` full waves of CTAs (rounding DOWN: a grid slightly above a multiple of
+  // the SM count pays a whole extra wave)
+  int waves = 1;
+  if (const char* e = getenv("R3M_WGRAD_WAVES")) waves = atoi(e);
+  int splits = (waves * device_sm_count()) / slabs;
   splits = std::max(1, std::min(splits, p.mblocks_total));
   p.mblocks_per_split = (p.mblocks_total + splits - 1) / splits;
   plan->splits = (p.mblocks_total + p.mblocks_per_split - 1) / p.mblocks_per_split;

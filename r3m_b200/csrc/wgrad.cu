@@ -17,15 +17,17 @@ namespace r3m {
 
 namespace {
 
-constexpr int kPixBlock = 64;          // reduction rows per stage
-constexpr int kAtomBytes = 64 * 128;   // one [64 pixels][64 channels] bf16 tile
 constexpr int kTmemCols = 512;
+// One "atom" = [pix_block pixels][64 channels] bf16, one TMA op.  The TMA unit retires roughly one op per ~300 cycles
+// per SM regardless of its size (measured), so the reduction block per stage is as tall as shared memory allows.
 
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
              const WgradKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kPixBlock = p.pix_block;
+  const int kAtomBytes = kPixBlock * 128;
   const int stage_bytes = (2 + p.group) * kAtomBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + 8;
@@ -117,7 +119,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + 2 * kAtomBytes;
-#pragma unroll
           for (int ks = 0; ks < kPixBlock / 16; ++ks) {
             const uint64_t da = make_smem_desc_sw128(a_addr + ks * 2048, lbo_a, 1024);
             // the items of a group are consecutive 64-wide N atoms (LBO apart), so up to four of them go into one
@@ -184,12 +185,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 
 }  // namespace
 
-int wgrad_smem_bytes(int group, int num_stages) { return num_stages * (2 + group) * kAtomBytes + 256 + 1024; }
+int wgrad_smem_bytes(int group, int num_stages, int pix_block) {
+  return num_stages * (2 + group) * pix_block * 128 + 256 + 1024;
+}
 
 cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const WgradKernelParams& p, int splits,
                          int groups, int ktiles, cudaStream_t stream) {
   static int configured_bytes = 0;
-  const int bytes = wgrad_smem_bytes(p.group, p.num_stages);
+  const int bytes = wgrad_smem_bytes(p.group, p.num_stages, p.pix_block);
   if (bytes > configured_bytes) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;

@@ -78,8 +78,39 @@ def convs():
         print(f"  wgrad: {ms:.4f} ms  {fl / ms / 1e9:.0f} TFLOP/s")
 
 
+def wgrads():
+    from r3m_b200 import _lib as L
+
+    N = 320
+    shapes = [(14, 256, 256, 3, 1, 1), (56, 64, 64, 3, 1, 1), (56, 64, 256, 1, 1, 0), (7, 512, 512, 3, 1, 1),
+              (28, 128, 128, 3, 1, 1), (14, 1024, 256, 1, 1, 0)]
+    s = L.current_stream()
+    out = []
+    for (H, Cin, Cout, R, stride, pad) in shapes:
+        x = torch.randn(N, H, H, Cin, device="cuda").bfloat16()
+        P = (H + 2 * pad - R) // stride + 1
+        dy = torch.randn(N, P, P, Cout, device="cuda").bfloat16()
+        dw = torch.zeros(Cout, R, R, Cin, device="cuda")
+        for _ in range(2):
+            L.check(L.lib.r3m_b200_conv_wgrad(L.ptr(dy), L.ptr(x), L.ptr(dw), N, H, H, Cin, Cout, R, R, stride, pad, s))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            L.check(L.lib.r3m_b200_conv_wgrad(L.ptr(dy), L.ptr(x), L.ptr(dw), N, H, H, Cin, Cout, R, R, stride, pad, s))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 2.0 * N * P * P * Cout * Cin * R * R
+        out.append(f"{H}/{Cin}/{Cout}/{R}: {ms:.4f}ms {fl / ms / 1e9:.0f}TF")
+    print(os.environ.get("R3M_WGRAD_GROUP"), os.environ.get("R3M_WGRAD_STAGES"), os.environ.get("R3M_WGRAD_WAVES"),
+          " | ".join(out))
+
+
 if __name__ == "__main__":
-    if "--convs" in sys.argv:
+    if "--wgrads" in sys.argv:
+        wgrads()
+    elif "--convs" in sys.argv:
         convs()
     else:
         step_ops()
