@@ -62,18 +62,26 @@ int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream);
 /* BatchNorm2d forward on a raw conv output (replaces aten::cudnn_batch_norm + relu_ [+ add_], tv resnet.py:89-105,
  * 143-163).  y, a, residual: bf16 [M][C].  train != 0: batch statistics from (sum, sq) = per-channel sum / sum of
  * squares of y; writes save_mean / save_rstd and updates running_mean / running_var (momentum 0.1, unbiased var).
- * train == 0: running statistics.  a = [relu](gamma * xhat + beta [+ residual]). */
+ * train == 0: running statistics.  a = [relu](gamma * xhat + beta [+ residual] [+ bn2(y2)]).
+ *   mask_out (optional, uint8 [M][C/8]): bit-packed (a > 0), the ReLU mask the backward pass consumes.
+ *   y2 ... save_rstd2 (optional, all NULL otherwise): a SECOND BatchNorm — the downsample branch of a residual
+ *   block — whose un-activated output is added before the ReLU without being materialised. */
 int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
                       const float* sq, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                      float* save_mean, float* save_rstd, void* stream);
+                      float* save_mean, float* save_rstd, uint8_t* mask_out, const void* y2, const float* sum2,
+                      const float* sq2, const float* gamma2, const float* beta2, float* running_mean2,
+                      float* running_var2, float* save_mean2, float* save_rstd2, void* stream);
 
 /* BatchNorm2d backward (replaces aten::cudnn_batch_norm_backward + threshold_backward).  dA: gradient w.r.t. the
- * activated output; a: activated output used as ReLU mask (NULL: no ReLU); y: raw conv output; sums: fp32 [2*C]
- * scratch that must be zero on entry.  Writes dy (gradient w.r.t. y), optionally dz (masked gradient, the residual
- * branch's share), dgamma, dbeta. */
-int r3m_b200_bn_backward(const void* dA, const void* a, const void* y, int M, int C, const float* mean,
-                         const float* rstd, const float* gamma, float* sums, void* dy, void* dz, float* dgamma,
-                         float* dbeta, void* stream);
+ * activated output; ReLU mask either from a (activated output, bf16) or from mask (bit-packed, as written by
+ * bn_apply); both NULL: no ReLU.  y: raw conv output; sums: fp32 [2*C] scratch that must be zero on entry.  Writes
+ * dy (gradient w.r.t. y), optionally dz (masked gradient, the residual branch's share), dgamma, dbeta.
+ *   y2 ... dbeta2 (optional): the second (downsample) BatchNorm fed by the same masked gradient; sums2 fp32 [C]
+ *   zeroed scratch, dy2 its data gradient. */
+int r3m_b200_bn_backward(const void* dA, const void* a, const uint8_t* mask, const void* y, int M, int C,
+                         const float* mean, const float* rstd, const float* gamma, float* sums, void* dy, void* dz,
+                         float* dgamma, float* dbeta, const void* y2, const float* mean2, const float* rstd2,
+                         const float* gamma2, float* sums2, void* dy2, float* dgamma2, float* dbeta2, void* stream);
 
 /* Stem tail: BN + ReLU + MaxPool2d(3,2,1) (tv resnet.py:198-200) and its backward.  y bf16 [N,H,W,C] ->
  * a bf16 [N,H/2,W/2,C] plus the argmax code (0..8, scan order) per output element. */

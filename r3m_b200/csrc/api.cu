@@ -173,7 +173,9 @@ int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream) {
 
 int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
                       const float* sq, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                      float* save_mean, float* save_rstd, void* stream) {
+                      float* save_mean, float* save_rstd, uint8_t* mask_out, const void* y2, const float* sum2,
+                      const float* sq2, const float* gamma2, const float* beta2, float* running_mean2,
+                      float* running_var2, float* save_mean2, float* save_rstd2, void* stream) {
   BnApplyArgs g;
   g.y = y;
   g.a = a;
@@ -190,15 +192,28 @@ int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C
   g.running_var = running_var;
   g.save_mean = save_mean;
   g.save_rstd = save_rstd;
+  g.mask_out = mask_out;
+  g.y2 = y2;
+  g.sum2 = sum2;
+  g.sq2 = sq2;
+  g.gamma2 = gamma2;
+  g.beta2 = beta2;
+  g.running_mean2 = running_mean2;
+  g.running_var2 = running_var2;
+  g.save_mean2 = save_mean2;
+  g.save_rstd2 = save_rstd2;
   CUDA_OR_FAIL(launch_bn_apply(g, (cudaStream_t)stream), "bn_apply");
 }
 
-int r3m_b200_bn_backward(const void* dA, const void* a, const void* y, int M, int C, const float* mean,
-                         const float* rstd, const float* gamma, float* sums, void* dy, void* dz, float* dgamma,
-                         float* dbeta, void* stream) {
+int r3m_b200_bn_backward(const void* dA, const void* a, const uint8_t* mask, const void* y, int M, int C,
+                         const float* mean, const float* rstd, const float* gamma, float* sums, void* dy, void* dz,
+                         float* dgamma, float* dbeta, const void* y2, const float* mean2, const float* rstd2,
+                         const float* gamma2, float* sums2, void* dy2, float* dgamma2, float* dbeta2, void* stream) {
+  if (a && mask) return fail(R3M_B200_ERR_INVALID, "bn_backward: give the ReLU mask as `a` or as `mask`, not both");
   BnBwdArgs g;
   g.dA = dA;
   g.a = a;
+  g.mask = mask;
   g.y = y;
   g.M = M;
   g.C = C;
@@ -210,6 +225,14 @@ int r3m_b200_bn_backward(const void* dA, const void* a, const void* y, int M, in
   g.dz_out = dz;
   g.dgamma = dgamma;
   g.dbeta = dbeta;
+  g.y2 = y2;
+  g.mean2 = mean2;
+  g.rstd2 = rstd2;
+  g.gamma2 = gamma2;
+  g.sums2 = sums2;
+  g.dy2 = dy2;
+  g.dgamma2 = dgamma2;
+  g.dbeta2 = dbeta2;
   cudaError_t e = launch_bn_bwd_reduce(g, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(e, "bn_bwd_reduce");
   CUDA_OR_FAIL(launch_bn_bwd_apply(g, (cudaStream_t)stream), "bn_bwd_apply");

@@ -126,14 +126,23 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
-  float sc[8], sh[8];
+  const bool dual = (a.y2 != nullptr);
+  float sc[8], sh[8], sc2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float mean, var;
     bn_coeffs(a.train, a.sum, a.sq, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
               mean, var);
+    sc2[j] = 0.f;
+    if (dual) {
+      float shift2;
+      bn_coeffs(a.train, a.sum2, a.sq2, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, chunk * 8 + j,
+                sc2[j], shift2, mean, var);
+      sh[j] += shift2;
+    }
   }
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
+  const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const bf16* __restrict__ res = reinterpret_cast<const bf16*>(a.residual);
   bf16* __restrict__ out = reinterpret_cast<bf16*>(a.a);
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
@@ -142,6 +151,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     F8 f = ld8(y + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
+    if (dual) {
+      const F8 t = ld8(y2 + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f.v[j] = fmaf(t.v[j], sc2[j], f.v[j]);
+    }
     if (res) {
       const F8 r = ld8(res + off);
 #pragma unroll
@@ -152,11 +166,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
       for (int j = 0; j < 8; ++j) f.v[j] = fmaxf(f.v[j], 0.f);
     }
     st8(out + off, f);
+    if (a.mask_out) {
+      // the mask must describe the STORED (bf16-rounded) activation: a tiny positive value that rounds to +0 is off
+      unsigned bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bits |= (__bfloat162float(__float2bfloat16_rn(f.v[j])) > 0.f ? 1u : 0u) << j;
+      a.mask_out[row * C8 + chunk] = (uint8_t)bits;
+    }
   }
   if (a.train && blockIdx.x == 0) {
     // every block has already read sum/sq into registers for its own coefficients; running stats are separate
     // buffers, so the in-place update below cannot race with other blocks
     bn_publish(a.C, a.M, a.sum, a.sq, a.save_mean, a.save_rstd, a.running_mean, a.running_var, a.update_running);
+    if (dual)
+      bn_publish(a.C, a.M, a.sum2, a.sq2, a.save_mean2, a.save_rstd2, a.running_mean2, a.running_var2,
+                 a.update_running);
   }
 }
 
@@ -310,48 +334,70 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ BN backward
+__device__ __forceinline__ void apply_relu_mask(F8& g, const bf16* act, const uint8_t* mask, long long off,
+                                                long long mask_idx) {
+  if (act) {
+    const F8 m = ld8(act + off);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = m.v[j] > 0.f ? g.v[j] : 0.f;
+  } else if (mask) {
+    const unsigned bits = mask[mask_idx];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = ((bits >> j) & 1u) ? g.v[j] : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
-  extern __shared__ float s_red[];  // [2][C]
+  extern __shared__ float s_red[];  // [3][C]: sum(dz), sum(dz*xhat), sum(dz*xhat2)
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
-  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
+  const bool dual = (a.y2 != nullptr);
+  for (int i = threadIdx.x; i < 3 * a.C; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
-  float mean[8], rstd[8], s1[8], s2[8];
+  float mean[8], rstd[8], mean2[8], rstd2[8], s1[8], s2[8], s3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mean[j] = a.mean[chunk * 8 + j];
     rstd[j] = a.rstd[chunk * 8 + j];
+    mean2[j] = dual ? a.mean2[chunk * 8 + j] : 0.f;
+    rstd2[j] = dual ? a.rstd2[chunk * 8 + j] : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
+    s3[j] = 0.f;
   }
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
   const bf16* __restrict__ act = reinterpret_cast<const bf16*>(a.a);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
+  const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
     F8 g = ld8(dA + off);
-    if (act) {
-      const F8 m = ld8(act + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = m.v[j] > 0.f ? g.v[j] : 0.f;
-    }
+    apply_relu_mask(g, act, a.mask, off, row * C8 + chunk);
     const F8 yy = ld8(y + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s1[j] += g.v[j];
       s2[j] = fmaf(g.v[j], (yy.v[j] - mean[j]) * rstd[j], s2[j]);
     }
+    if (dual) {
+      const F8 t = ld8(y2 + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s3[j] = fmaf(g.v[j], (t.v[j] - mean2[j]) * rstd2[j], s3[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(&s_red[chunk * 8 + j], s1[j]);
     atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j]);
+    if (dual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
+  if (dual)
+    for (int i = threadIdx.x; i < a.C; i += blockDim.x) atomicAdd(&a.sums2[i], s_red[2 * a.C + i]);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
@@ -360,7 +406,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
-  float mean[8], rstd[8], grs[8], mdz[8], mdzx[8];
+  const bool dual = (a.y2 != nullptr);
+  float mean[8], rstd[8], grs[8], mdz[8], mdzx[8], mean2[8], rstd2[8], grs2[8], mdzx2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
@@ -369,21 +416,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     grs[j] = a.gamma[c] * rstd[j];
     mdz[j] = a.sums[c] * inv_m;
     mdzx[j] = a.sums[a.C + c] * inv_m;
+    mean2[j] = dual ? a.mean2[c] : 0.f;
+    rstd2[j] = dual ? a.rstd2[c] : 0.f;
+    grs2[j] = dual ? a.gamma2[c] * rstd2[j] : 0.f;
+    mdzx2[j] = dual ? a.sums2[c] * inv_m : 0.f;
   }
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
   const bf16* __restrict__ act = reinterpret_cast<const bf16*>(a.a);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
+  const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   bf16* __restrict__ dy = reinterpret_cast<bf16*>(a.dy);
+  bf16* __restrict__ dy2 = reinterpret_cast<bf16*>(a.dy2);
   bf16* __restrict__ dzo = reinterpret_cast<bf16*>(a.dz_out);
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
     F8 g = ld8(dA + off);
-    if (act) {
-      const F8 m = ld8(act + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = m.v[j] > 0.f ? g.v[j] : 0.f;
-    }
+    apply_relu_mask(g, act, a.mask, off, row * C8 + chunk);
     if (dzo) st8(dzo + off, g);
     const F8 yy = ld8(y + off);
     F8 o;
@@ -393,11 +442,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
       o.v[j] = grs[j] * (g.v[j] - mdz[j] - xhat * mdzx[j]);
     }
     st8(dy + off, o);
+    if (dual) {
+      const F8 t = ld8(y2 + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (t.v[j] - mean2[j]) * rstd2[j];
+        o.v[j] = grs2[j] * (g.v[j] - mdz[j] - xhat * mdzx2[j]);
+      }
+      st8(dy2 + off, o);
+    }
   }
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = a.sums[c];
       if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+      if (dual) {
+        if (a.dbeta2) a.dbeta2[c] = a.sums[c];
+        if (a.dgamma2) a.dgamma2[c] = a.sums2[c];
+      }
     }
   }
 }
@@ -525,7 +587,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const int rows_per_iter = 256 / (a.C / 8);
   // several rows per thread so that the shared/global atomics are amortised
   const int blocks = grid_for((a.M + 15) / 16, rows_per_iter, 148 * 4);
-  bn_bwd_reduce_kernel<<<blocks, 256, 2 * a.C * sizeof(float), s>>>(a);
+  bn_bwd_reduce_kernel<<<blocks, 256, 3 * a.C * sizeof(float), s>>>(a);
   return cudaGetLastError();
 }
 

@@ -29,6 +29,18 @@ struct BnApplyArgs {
   float* save_mean = nullptr;   // [C] written in train mode (for backward)
   float* save_rstd = nullptr;
   int update_running = 1;
+  uint8_t* mask_out = nullptr;  // optional [M][C/8]: bit j of byte (row, chunk) = (a[row][8*chunk+j] > 0)
+  // optional second BatchNorm whose (un-activated) output is added before the ReLU: the downsample branch of a
+  // residual block, a = relu(bn(y) + bn2(y2))  (tv resnet.py:100-103, 155-161) without materialising bn2(y2)
+  const void* y2 = nullptr;
+  const float* sum2 = nullptr;
+  const float* sq2 = nullptr;
+  const float* gamma2 = nullptr;
+  const float* beta2 = nullptr;
+  float* running_mean2 = nullptr;
+  float* running_var2 = nullptr;
+  float* save_mean2 = nullptr;
+  float* save_rstd2 = nullptr;
 };
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s);
 
@@ -60,6 +72,7 @@ cudaError_t launch_avgpool_bwd(const float* dE, void* dA, int N, int HW, int C, 
 struct BnBwdArgs {
   const void* dA = nullptr;   // bf16 [M][C] gradient w.r.t. the layer's (activated) output
   const void* a = nullptr;    // bf16 [M][C] activated output (ReLU mask) or null when no ReLU follows / already masked
+  const uint8_t* mask = nullptr;  // alternative ReLU mask: bit-packed [M][C/8] as written by bn_apply (a must be null)
   const void* y = nullptr;    // bf16 [M][C] raw conv output
   int M = 0, C = 0;
   const float* mean = nullptr;
@@ -70,6 +83,15 @@ struct BnBwdArgs {
   void* dz_out = nullptr;     // optional bf16 [M][C]: masked gradient (feeds the residual branch)
   float* dgamma = nullptr;    // [C]
   float* dbeta = nullptr;
+  // optional second BatchNorm fed by the same masked gradient (the downsample branch): y2 raw output, dy2 result
+  const void* y2 = nullptr;
+  const float* mean2 = nullptr;
+  const float* rstd2 = nullptr;
+  const float* gamma2 = nullptr;
+  float* sums2 = nullptr;     // [C] workspace: sum(dz * xhat2); zeroed by the caller
+  void* dy2 = nullptr;
+  float* dgamma2 = nullptr;
+  float* dbeta2 = nullptr;
 };
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);

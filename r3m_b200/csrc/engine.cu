@@ -22,6 +22,8 @@ struct Engine::Conv {
   size_t save_off = 0;                            // saved batch statistics (floats): mean[C] rstd[C]
   size_t wd_off = 0;                              // dgrad-packed filters (bf16 elements)
   size_t y_off = 0, a_off = 0;                    // arena byte offsets of the raw / activated outputs
+  size_t mask_off = 0;                            // bit-packed ReLU mask of the activated output (train mode)
+  uint8_t* mask = nullptr;
   const bf16* x = nullptr;                        // input activation
   bf16* y = nullptr;
   bf16* a = nullptr;
@@ -143,7 +145,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
     c->beta_off = take(np, c->Cout, 128);
     c->rm_off = take(nb, c->Cout, 32);
     c->rv_off = take(nb, c->Cout, 32);
-    c->zero_off = take(nz, 4 * (size_t)c->Cout, 32);
+    c->zero_off = take(nz, 5 * (size_t)c->Cout, 32);  // sum, sq, bwd sums (2C), downsample-branch bwd sum
     c->save_off = take(ns, 2 * (size_t)c->Cout, 32);
     if (!c->stem) c->wd_off = take(nwd, wn, 128);
     TensorInfo t;
@@ -232,6 +234,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
       c->a_off = arena(N * 56 * 56 * 64 * 2);  // pooled
     else
       c->a_off = arena(c->out_elems(frames) * 2);
+    if (!c->stem) c->mask_off = arena(c->out_elems(frames) / 8);
   }
   e->off_E_ = arena(N * e->D_ * 4);
   e->off_dE_ = arena(N * e->D_ * 4);
@@ -255,12 +258,14 @@ std::string Engine::bind(void* params, size_t param_bytes, void* ws, size_t byte
   for (Conv* c : convs_) {
     c->y = reinterpret_cast<bf16*>(ws_ + c->y_off);
     c->a = reinterpret_cast<bf16*>(ws_ + c->a_off);
+    c->mask = c->stem ? nullptr : ws_ + c->mask_off;
   }
   bound_ = true;
   return plan_all();
 }
 
-void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train) {
+void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train,
+                          const Conv* second) {
   float* P = reinterpret_cast<float*>(pws_ + off_P_);
   float* buf = reinterpret_cast<float*>(pws_ + off_buf_);
   float* zero = reinterpret_cast<float*>(ws_ + off_zero_);
@@ -281,9 +286,24 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.running_var = buf + c.rv_off;
   a.save_mean = saved + c.save_off;
   a.save_rstd = saved + c.save_off + c.Cout;
+  if (train && relu) a.mask_out = c.mask;
+  if (second) {
+    // downsample branch folded in: a = relu(bn(y) + bn_ds(y_ds)), bn_ds(y_ds) is never materialised
+    const Conv& d = *second;
+    a.y2 = d.y;
+    a.sum2 = zero + d.zero_off;
+    a.sq2 = zero + d.zero_off + d.Cout;
+    a.gamma2 = P + d.gamma_off;
+    a.beta2 = P + d.beta_off;
+    a.running_mean2 = buf + d.rm_off;
+    a.running_var2 = buf + d.rv_off;
+    a.save_mean2 = saved + d.save_off;
+    a.save_rstd2 = saved + d.save_off + d.Cout;
+  }
   const double mc = (double)a.M * a.C * 2;
-  ops.push_back(Op([a](cudaStream_t s) { return launch_bn_apply(a, s); }, kFamNorm, 0.0, mc * (residual ? 3 : 2)));
-  ops.back().label = "bn_apply " + c.bn + (residual ? " +res" : "");
+  ops.push_back(Op([a](cudaStream_t s) { return launch_bn_apply(a, s); }, kFamNorm, 0.0,
+                   mc * (2 + (residual ? 1 : 0) + (second ? 1 : 0)) + (a.mask_out ? mc / 16 : 0.0)));
+  ops.back().label = "bn_apply " + c.bn + (residual ? " +res" : "") + (second ? " +" + second->bn : "");
 }
 
 std::string Engine::plan_all() {
@@ -389,20 +409,19 @@ std::string Engine::plan_all() {
         c.x = cur;
         push_conv(ops, fwd_geom(c, train), "fwd " + c.name);
         if (i + 1 < blk->main.size()) {
-          add_bn_apply(ops, c, nullptr, c.a, 1, train);
+          add_bn_apply(ops, c, nullptr, c.a, 1, train, nullptr);
           cur = c.a;
         }
       }
       Conv& last = *convs_[blk->main.back()];
-      const void* residual = blk->x_in;
       if (blk->ds >= 0) {
         Conv& d = *convs_[blk->ds];
         d.x = blk->x_in;
         push_conv(ops, fwd_geom(d, train), "fwd " + d.name);
-        add_bn_apply(ops, d, nullptr, d.a, 0, train);
-        residual = d.a;
+        add_bn_apply(ops, last, nullptr, last.a, 1, train, &d);
+      } else {
+        add_bn_apply(ops, last, blk->x_in, last.a, 1, train, nullptr);
       }
-      add_bn_apply(ops, last, residual, last.a, 1, train);
       blk->a_out = last.a;
       x = last.a;
     }
@@ -417,10 +436,11 @@ std::string Engine::plan_all() {
 
   // ------------------------------------------------------------------------------------------------ backward
   bwd_.clear();
-  auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const bf16* mask, bf16* dy, bf16* dz_out) {
+  auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const uint8_t* mask, bf16* dy, bf16* dz_out,
+                         const Conv* second, bf16* dy2) {
     BnBwdArgs a;
     a.dA = dA;
-    a.a = mask;
+    a.mask = mask;
     a.y = c.y;
     a.M = N * c.P * c.Q;
     a.C = c.Cout;
@@ -432,10 +452,22 @@ std::string Engine::plan_all() {
     a.dz_out = dz_out;
     a.dgamma = G + c.gamma_off;
     a.dbeta = G + c.beta_off;
+    if (second) {
+      const Conv& d = *second;
+      a.y2 = d.y;
+      a.mean2 = saved + d.save_off;
+      a.rstd2 = saved + d.save_off + d.Cout;
+      a.gamma2 = P + d.gamma_off;
+      a.sums2 = zero + c.zero_off + 4 * c.Cout;
+      a.dy2 = dy2;
+      a.dgamma2 = G + d.gamma_off;
+      a.dbeta2 = G + d.beta_off;
+    }
     const double mc = (double)a.M * a.C * 2;
-    bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * (mask ? 3 : 2)));
+    const double rd = 2 + (mask ? 1.0 / 16 : 0.0) + (second ? 1 : 0);
+    bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * rd));
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); }, kFamNorm, 0.0,
-                      mc * ((mask ? 3 : 2) + 1 + (dz_out ? 1 : 0))));
+                      mc * (rd + 1 + (dz_out ? 1 : 0) + (second ? 1 : 0))));
     bwd_[bwd_.size() - 2].label = "bn_bwd_reduce " + c.bn;
     bwd_.back().label = "bn_bwd_apply " + c.bn;
   };
@@ -519,8 +551,10 @@ std::string Engine::plan_all() {
     const int n = (int)blk->main.size();
     Conv& last = *convs_[blk->main[n - 1]];
     const bool has_ds = blk->ds >= 0;
-    // last BN of the residual branch: mask with the block output; the masked gradient also feeds the skip path
-    push_bn_bwd(last, d_out, blk->a_out, s1, has_ds ? s3 : d_in);
+    // last BN of the residual branch: masked by the block output's ReLU.  Identity blocks: the masked gradient is
+    // also the skip path's share and seeds d_in.  Downsample blocks: the same masked gradient drives the downsample
+    // BatchNorm's backward in the same two passes (dy_ds -> s3).
+    push_bn_bwd(last, d_out, last.mask, s1, has_ds ? nullptr : d_in, has_ds ? convs_[blk->ds] : nullptr, s3);
     const bf16* dy = s1;
     for (int i = n - 1; i >= 0; --i) {
       Conv& c = *convs_[blk->main[i]];
@@ -528,7 +562,7 @@ std::string Engine::plan_all() {
       if (i > 0) {
         Conv& prev = *convs_[blk->main[i - 1]];
         push_dgrad(c, dy, s2, 0);
-        push_bn_bwd(prev, s2, prev.a, s1, nullptr);
+        push_bn_bwd(prev, s2, prev.mask, s1, nullptr, nullptr, nullptr);
         dy = s1;
       } else {
         push_dgrad(c, dy, d_in, has_ds ? 0 : 1);
@@ -536,9 +570,8 @@ std::string Engine::plan_all() {
     }
     if (has_ds) {
       Conv& d = *convs_[blk->ds];
-      push_bn_bwd(d, s3, nullptr, s1, nullptr);
-      push_wgrad(d, s1);
-      push_dgrad(d, s1, d_in, 1);
+      push_wgrad(d, s3);
+      push_dgrad(d, s3, d_in, 1);
     }
     std::swap(d_out, d_in);
     if (!err.empty()) return err;
@@ -552,7 +585,7 @@ std::string Engine::plan_all() {
     bwd_.push_back(Op([dpool, apool, argmax, dz, N](cudaStream_t s) {
       return launch_maxpool_bwd(dpool, apool, argmax, dz, N, 112, 112, 64, s);
     }, kFamPool, 0.0, (double)N * 64 * (56.0 * 56 * 5 + 112.0 * 112 * 2)));
-    push_bn_bwd(st, s1, nullptr, s2, nullptr);
+    push_bn_bwd(st, s1, nullptr, s2, nullptr, nullptr, nullptr);
     WgradDesc d;
     d.dy = s2;
     d.x = xs;

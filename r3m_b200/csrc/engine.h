@@ -94,7 +94,8 @@ class Engine {
 
   std::string plan_all();
   std::string run(const std::vector<Op>& ops, cudaStream_t stream);
-  void add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train);
+  void add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* residual, void* dst, int relu, int train,
+                    const Conv* second);
 
   int size_ = 0, N_ = 0, D_ = 0, B_ = 0, lang_ = 0, hidden_ = 0;
   bool bottleneck_ = false;

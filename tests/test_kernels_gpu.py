@@ -128,6 +128,14 @@ def test_preprocess_matches_normalize(lib):
     assert float(xs.float()[..., 3::4].abs().max()) == 0.0  # padded 4th channel is exactly zero
 
 
+NULL9 = [None] * 9
+
+
+def _unpack_mask(mask, C):
+    bits = (mask.long()[..., None] >> torch.arange(8, device=mask.device)) & 1
+    return bits.reshape(mask.shape[0], C).bool()
+
+
 @pytest.mark.parametrize("C,M,res,relu", [(64, 1000, False, True), (256, 777, True, True), (2048, 98, True, True),
                                            (512, 300, False, False)])
 def test_bn_apply_train_and_eval(lib, C, M, res, relu):
@@ -141,10 +149,11 @@ def test_bn_apply_train_and_eval(lib, C, M, res, relu):
     ssum, ssq = yf.sum(0), (yf * yf).sum(0)
     sm, sr = torch.empty(C).cuda(), torch.empty(C).cuda()
     a = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    mask = torch.zeros(M, C // 8, device="cuda", dtype=torch.uint8)
     s = lib.current_stream()
     lib.check(lib.lib.r3m_b200_bn_apply(lib.ptr(y), lib.ptr(a), lib.ptr(r), M, C, int(relu), 1, lib.ptr(ssum),
                                         lib.ptr(ssq), lib.ptr(gamma), lib.ptr(beta), lib.ptr(rm), lib.ptr(rv),
-                                        lib.ptr(sm), lib.ptr(sr), s))
+                                        lib.ptr(sm), lib.ptr(sr), lib.ptr(mask), *NULL9, s))
     rm0, rv0 = torch.zeros(C).cuda(), torch.ones(C).cuda()
     ref = F.batch_norm(yf, rm0, rv0, gamma, beta, training=True, momentum=0.1, eps=1e-5)
     if res:
@@ -152,11 +161,13 @@ def test_bn_apply_train_and_eval(lib, C, M, res, relu):
     if relu:
         ref = ref.relu()
     assert rel(a.float(), ref) < 2.5e-3
+    assert torch.equal(_unpack_mask(mask, C), a.float() > 0)       # the bit mask describes the stored activation
     assert rel(rm, rm0) < 1e-4 and rel(rv, rv0) < 1e-4            # running stats: momentum 0.1, unbiased variance
     assert rel(sm, yf.mean(0)) < 1e-4 and rel(sr, 1 / (yf.var(0, unbiased=False) + 1e-5).sqrt()) < 1e-4
     # eval mode uses the running statistics
     lib.check(lib.lib.r3m_b200_bn_apply(lib.ptr(y), lib.ptr(a), lib.ptr(r), M, C, int(relu), 0, None, None,
-                                        lib.ptr(gamma), lib.ptr(beta), lib.ptr(rm), lib.ptr(rv), None, None, s))
+                                        lib.ptr(gamma), lib.ptr(beta), lib.ptr(rm), lib.ptr(rv), None, None, None,
+                                        *NULL9, s))
     ref = F.batch_norm(yf, rm, rv, gamma, beta, training=False, eps=1e-5)
     if res:
         ref = ref + r.float()
@@ -165,8 +176,55 @@ def test_bn_apply_train_and_eval(lib, C, M, res, relu):
     assert rel(a.float(), ref) < 2.5e-3
 
 
-@pytest.mark.parametrize("C,M,mask,want_dz", [(64, 2000, True, False), (256, 999, True, True), (1024, 196, False, False)])
-def test_bn_backward_matches_autograd(lib, C, M, mask, want_dz):
+@pytest.mark.parametrize("C,M", [(256, 1500), (2048, 147)])
+def test_dual_bn_forward_backward(lib, C, M):
+    """Downsample block tail: a = relu(bn3(y3) + bn_ds(y_ds)) in one pass, and both BatchNorm backwards fed by the same
+    masked gradient in one reduce + one apply pass (tv resnet.py:155-161)."""
+    g = torch.Generator().manual_seed(C)
+    y1 = (torch.randn(M, C, generator=g) * 1.3 + 0.2).cuda().bfloat16()
+    y2 = (torch.randn(M, C, generator=g) * 0.7 - 0.1).cuda().bfloat16()
+    g1 = (1 + 0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    b1 = (0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    g2 = (1 + 0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    b2 = (0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    dA = torch.randn(M, C, generator=g).cuda().bfloat16()
+    l1, l2 = y1.float().requires_grad_(True), y2.float().requires_grad_(True)
+    ref = (F.batch_norm(l1, None, None, g1, b1, training=True, eps=1e-5)
+           + F.batch_norm(l2, None, None, g2, b2, training=True, eps=1e-5)).relu()
+    ref.backward(dA.float())
+    stats = lambda t: (t.float().sum(0), (t.float() ** 2).sum(0))  # noqa: E731
+    (s1, q1), (s2, q2) = stats(y1), stats(y2)
+    bufs = [torch.zeros(C).cuda() for _ in range(8)]
+    rm1, rv1, sm1, sr1, rm2, rv2, sm2, sr2 = bufs
+    rv1.fill_(1), rv2.fill_(1)
+    a = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    mask = torch.zeros(M, C // 8, device="cuda", dtype=torch.uint8)
+    s = lib.current_stream()
+    lib.check(lib.lib.r3m_b200_bn_apply(lib.ptr(y1), lib.ptr(a), None, M, C, 1, 1, lib.ptr(s1), lib.ptr(q1),
+                                        lib.ptr(g1.detach()), lib.ptr(b1.detach()), lib.ptr(rm1), lib.ptr(rv1),
+                                        lib.ptr(sm1), lib.ptr(sr1), lib.ptr(mask), lib.ptr(y2), lib.ptr(s2), lib.ptr(q2),
+                                        lib.ptr(g2.detach()), lib.ptr(b2.detach()), lib.ptr(rm2), lib.ptr(rv2),
+                                        lib.ptr(sm2), lib.ptr(sr2), s))
+    assert rel(a.float(), ref.detach()) < 2.5e-3
+    assert rel(sm2, y2.float().mean(0)) < 1e-4 and rel(rm2, 0.1 * y2.float().mean(0)) < 1e-4
+    sums, sums2 = torch.zeros(2 * C, device="cuda"), torch.zeros(C, device="cuda")
+    dy1 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    dy2 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    dg1, db1, dg2, db2 = (torch.empty(C).cuda() for _ in range(4))
+    lib.check(lib.lib.r3m_b200_bn_backward(lib.ptr(dA), None, lib.ptr(mask), lib.ptr(y1), M, C, lib.ptr(sm1),
+                                           lib.ptr(sr1), lib.ptr(g1.detach()), lib.ptr(sums), lib.ptr(dy1), None,
+                                           lib.ptr(dg1), lib.ptr(db1), lib.ptr(y2), lib.ptr(sm2), lib.ptr(sr2),
+                                           lib.ptr(g2.detach()), lib.ptr(sums2), lib.ptr(dy2), lib.ptr(dg2),
+                                           lib.ptr(db2), s))
+    # the reference mask comes from the fp32 sum; ours from the bf16-stored activation: identical except at exact ties
+    assert rel(dy1.float(), l1.grad) < 6e-3 and rel(dy2.float(), l2.grad) < 6e-3
+    assert rel(dg1, g1.grad) < 2e-3 and rel(db1, b1.grad) < 2e-3
+    assert rel(dg2, g2.grad) < 2e-3 and rel(db2, b2.grad) < 2e-3
+
+
+@pytest.mark.parametrize("C,M,mask_kind,want_dz", [(64, 2000, "act", False), (256, 999, "bits", True),
+                                                   (1024, 196, "none", False)])
+def test_bn_backward_matches_autograd(lib, C, M, mask_kind, want_dz):
     g = torch.Generator().manual_seed(C)
     y = (torch.randn(M, C, generator=g) * 1.5 + 0.3).cuda().bfloat16()
     gamma = (1 + 0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
@@ -174,18 +232,23 @@ def test_bn_backward_matches_autograd(lib, C, M, mask, want_dz):
     dA = torch.randn(M, C, generator=g).cuda().bfloat16()
     yl = y.float().requires_grad_(True)
     z = F.batch_norm(yl, None, None, gamma, beta, training=True, eps=1e-5)
-    a = z.relu() if mask else z
+    a = z.relu() if mask_kind != "none" else z
     a.backward(dA.float())
     a_b = a.detach().bfloat16()
+    bits = None
+    if mask_kind == "bits":
+        on = (a_b.float() > 0).reshape(M, C // 8, 8).long()
+        bits = (on << torch.arange(8, device="cuda")).sum(-1).to(torch.uint8).contiguous()
     mean = y.float().mean(0)
     rstd = 1 / (y.float().var(0, unbiased=False) + 1e-5).sqrt()
     sums = torch.zeros(2 * C, device="cuda")
     dy = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
     dz = torch.empty(M, C, device="cuda", dtype=torch.bfloat16) if want_dz else None
     dg, db = torch.empty(C).cuda(), torch.empty(C).cuda()
-    lib.check(lib.lib.r3m_b200_bn_backward(lib.ptr(dA), lib.ptr(a_b) if mask else None, lib.ptr(y), M, C, lib.ptr(mean),
-                                           lib.ptr(rstd), lib.ptr(gamma.detach()), lib.ptr(sums), lib.ptr(dy),
-                                           lib.ptr(dz), lib.ptr(dg), lib.ptr(db), lib.current_stream()))
+    lib.check(lib.lib.r3m_b200_bn_backward(lib.ptr(dA), lib.ptr(a_b) if mask_kind == "act" else None, lib.ptr(bits),
+                                           lib.ptr(y), M, C, lib.ptr(mean), lib.ptr(rstd), lib.ptr(gamma.detach()),
+                                           lib.ptr(sums), lib.ptr(dy), lib.ptr(dz), lib.ptr(dg), lib.ptr(db),
+                                           *([None] * 8), lib.current_stream()))
     assert rel(dy.float(), yl.grad) < 4e-3
     assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-4
     if want_dz:
