@@ -21,7 +21,7 @@ struct F8 {
   float v[8];
 };
 __device__ __forceinline__ F8 ld8(const bf16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));  // every ld8 source is read-only within its kernel
   F8 f;
   f.v[0] = bf16lo(u.x);
   f.v[1] = bf16hi(u.x);
@@ -120,13 +120,14 @@ __global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------ BN apply
+template <bool kDual, bool kRes>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
-  const bool dual = (a.y2 != nullptr);
+  constexpr bool dual = kDual;
   float sc[8], sh[8], sc2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -145,21 +146,20 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const bf16* __restrict__ res = reinterpret_cast<const bf16*>(a.residual);
   bf16* __restrict__ out = reinterpret_cast<bf16*>(a.a);
+#pragma unroll 2
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
+    // all loads of the row first (no control flow between them)
     F8 f = ld8(y + off);
+    F8 t, r;
+    if (kDual) t = ld8(y2 + off);
+    if (kRes) r = ld8(res + off);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
-    if (dual) {
-      const F8 t = ld8(y2 + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f.v[j] = fmaf(t.v[j], sc2[j], f.v[j]);
-    }
-    if (res) {
-      const F8 r = ld8(res + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f.v[j] += r.v[j];
+    for (int j = 0; j < 8; ++j) {
+      f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
+      if (kDual) f.v[j] = fmaf(t.v[j], sc2[j], f.v[j]);
+      if (kRes) f.v[j] += r.v[j];
     }
     if (a.relu) {
 #pragma unroll
@@ -334,26 +334,28 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ BN backward
-__device__ __forceinline__ void apply_relu_mask(F8& g, const bf16* act, const uint8_t* mask, long long off,
-                                                long long mask_idx) {
-  if (act) {
-    const F8 m = ld8(act + off);
+// ReLU-mask source of the backward kernels (compile-time, so that the row loop has no control flow between its loads:
+// a branch between the loads serialises them and the kernels become latency bound — measured 3.8 vs 6.2 TB/s)
+enum { kMaskNone = 0, kMaskAct = 1, kMaskBits = 2 };
+
+template <int kMask>
+__device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bits) {
+  if (kMask == kMaskAct) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] = m.v[j] > 0.f ? g.v[j] : 0.f;
-  } else if (mask) {
-    const unsigned bits = mask[mask_idx];
+    for (int j = 0; j < 8; ++j) g.v[j] = act.v[j] > 0.f ? g.v[j] : 0.f;
+  } else if (kMask == kMaskBits) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) g.v[j] = ((bits >> j) & 1u) ? g.v[j] : 0.f;
   }
 }
 
+template <bool kDual, int kMask>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   extern __shared__ float s_red[];  // [3][C]: sum(dz), sum(dz*xhat), sum(dz*xhat2)
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
-  const bool dual = (a.y2 != nullptr);
   for (int i = threadIdx.x; i < 3 * a.C; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   float mean[8], rstd[8], mean2[8], rstd2[8], s1[8], s2[8], s3[8];
@@ -361,8 +363,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   for (int j = 0; j < 8; ++j) {
     mean[j] = a.mean[chunk * 8 + j];
     rstd[j] = a.rstd[chunk * 8 + j];
-    mean2[j] = dual ? a.mean2[chunk * 8 + j] : 0.f;
-    rstd2[j] = dual ? a.rstd2[chunk * 8 + j] : 0.f;
+    mean2[j] = kDual ? a.mean2[chunk * 8 + j] : 0.f;
+    rstd2[j] = kDual ? a.rstd2[chunk * 8 + j] : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
     s3[j] = 0.f;
@@ -371,42 +373,45 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const bf16* __restrict__ act = reinterpret_cast<const bf16*>(a.a);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
+  const uint8_t* __restrict__ mask = a.mask;
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
+    // all loads of the row first
     F8 g = ld8(dA + off);
-    apply_relu_mask(g, act, a.mask, off, row * C8 + chunk);
     const F8 yy = ld8(y + off);
+    F8 m, t;
+    unsigned bits = 0;
+    if (kMask == kMaskAct) m = ld8(act + off);
+    if (kMask == kMaskBits) bits = __ldg(mask + row * C8 + chunk);
+    if (kDual) t = ld8(y2 + off);
+    mask_gradient<kMask>(g, m, bits);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s1[j] += g.v[j];
       s2[j] = fmaf(g.v[j], (yy.v[j] - mean[j]) * rstd[j], s2[j]);
-    }
-    if (dual) {
-      const F8 t = ld8(y2 + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s3[j] = fmaf(g.v[j], (t.v[j] - mean2[j]) * rstd2[j], s3[j]);
+      if (kDual) s3[j] = fmaf(g.v[j], (t.v[j] - mean2[j]) * rstd2[j], s3[j]);
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(&s_red[chunk * 8 + j], s1[j]);
     atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j]);
-    if (dual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j]);
+    if (kDual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
-  if (dual)
+  if (kDual)
     for (int i = threadIdx.x; i < a.C; i += blockDim.x) atomicAdd(&a.sums2[i], s_red[2 * a.C + i]);
 }
 
+template <bool kDual, int kMask, bool kDz>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
-  const bool dual = (a.y2 != nullptr);
   float mean[8], rstd[8], grs[8], mdz[8], mdzx[8], mean2[8], rstd2[8], grs2[8], mdzx2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -416,15 +421,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     grs[j] = a.gamma[c] * rstd[j];
     mdz[j] = a.sums[c] * inv_m;
     mdzx[j] = a.sums[a.C + c] * inv_m;
-    mean2[j] = dual ? a.mean2[c] : 0.f;
-    rstd2[j] = dual ? a.rstd2[c] : 0.f;
-    grs2[j] = dual ? a.gamma2[c] * rstd2[j] : 0.f;
-    mdzx2[j] = dual ? a.sums2[c] * inv_m : 0.f;
+    mean2[j] = kDual ? a.mean2[c] : 0.f;
+    rstd2[j] = kDual ? a.rstd2[c] : 0.f;
+    grs2[j] = kDual ? a.gamma2[c] * rstd2[j] : 0.f;
+    mdzx2[j] = kDual ? a.sums2[c] * inv_m : 0.f;
   }
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
   const bf16* __restrict__ act = reinterpret_cast<const bf16*>(a.a);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
+  const uint8_t* __restrict__ mask = a.mask;
   bf16* __restrict__ dy = reinterpret_cast<bf16*>(a.dy);
   bf16* __restrict__ dy2 = reinterpret_cast<bf16*>(a.dy2);
   bf16* __restrict__ dzo = reinterpret_cast<bf16*>(a.dz_out);
@@ -432,9 +438,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
     F8 g = ld8(dA + off);
-    apply_relu_mask(g, act, a.mask, off, row * C8 + chunk);
-    if (dzo) st8(dzo + off, g);
     const F8 yy = ld8(y + off);
+    F8 m, t;
+    unsigned bits = 0;
+    if (kMask == kMaskAct) m = ld8(act + off);
+    if (kMask == kMaskBits) bits = __ldg(mask + row * C8 + chunk);
+    if (kDual) t = ld8(y2 + off);
+    mask_gradient<kMask>(g, m, bits);
+    if (kDz) st8(dzo + off, g);
     F8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -442,8 +453,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
       o.v[j] = grs[j] * (g.v[j] - mdz[j] - xhat * mdzx[j]);
     }
     st8(dy + off, o);
-    if (dual) {
-      const F8 t = ld8(y2 + off);
+    if (kDual) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xhat = (t.v[j] - mean2[j]) * rstd2[j];
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = a.sums[c];
       if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
-      if (dual) {
+      if (kDual) {
         if (a.dbeta2) a.dbeta2[c] = a.sums[c];
         if (a.dgamma2) a.dgamma2[c] = a.sums2[c];
       }
@@ -550,7 +560,14 @@ cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  bn_apply_kernel<<<grid_for(a.M, rows_per_iter, 148 * 8), 256, 0, s>>>(a);
+  const int blocks = grid_for(a.M, rows_per_iter, 148 * 8);
+  if (a.y2 && a.residual) return cudaErrorInvalidValue;  // a block tail has either an identity or a downsample branch
+  if (a.y2)
+    bn_apply_kernel<true, false><<<blocks, 256, 0, s>>>(a);
+  else if (a.residual)
+    bn_apply_kernel<false, true><<<blocks, 256, 0, s>>>(a);
+  else
+    bn_apply_kernel<false, false><<<blocks, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -582,19 +599,43 @@ cudaError_t launch_avgpool_bwd(const float* dE, void* dA, int N, int HW, int C, 
   return cudaGetLastError();
 }
 
+namespace {
+inline int mask_kind(const BnBwdArgs& a) { return a.a ? kMaskAct : (a.mask ? kMaskBits : kMaskNone); }
+}  // namespace
+
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
   // several rows per thread so that the shared/global atomics are amortised
   const int blocks = grid_for((a.M + 15) / 16, rows_per_iter, 148 * 4);
-  bn_bwd_reduce_kernel<<<blocks, 256, 3 * a.C * sizeof(float), s>>>(a);
+  const size_t smem = 3 * a.C * sizeof(float);
+  const bool dual = a.y2 != nullptr;
+#define R3M_LAUNCH(D, K) bn_bwd_reduce_kernel<D, K><<<blocks, 256, smem, s>>>(a)
+  switch (mask_kind(a)) {
+    case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
+    case kMaskBits: if (dual) R3M_LAUNCH(true, kMaskBits); else R3M_LAUNCH(false, kMaskBits); break;
+    default: if (dual) R3M_LAUNCH(true, kMaskNone); else R3M_LAUNCH(false, kMaskNone); break;
+  }
+#undef R3M_LAUNCH
   return cudaGetLastError();
 }
 
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  bn_bwd_apply_kernel<<<grid_for(a.M, rows_per_iter, 148 * 8), 256, 0, s>>>(a);
+  const int blocks = grid_for(a.M, rows_per_iter, 148 * 8);
+  const bool dual = a.y2 != nullptr, dz = a.dz_out != nullptr;
+#define R3M_LAUNCH(D, K)                                                  \
+  do {                                                                    \
+    if (dz) bn_bwd_apply_kernel<D, K, true><<<blocks, 256, 0, s>>>(a);    \
+    else bn_bwd_apply_kernel<D, K, false><<<blocks, 256, 0, s>>>(a);      \
+  } while (0)
+  switch (mask_kind(a)) {
+    case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
+    case kMaskBits: if (dual) R3M_LAUNCH(true, kMaskBits); else R3M_LAUNCH(false, kMaskBits); break;
+    default: if (dual) R3M_LAUNCH(true, kMaskNone); else R3M_LAUNCH(false, kMaskNone); break;
+  }
+#undef R3M_LAUNCH
   return cudaGetLastError();
 }
 
