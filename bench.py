@@ -39,41 +39,57 @@ def parse():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): one
+    streaming `nvidia-smi -lms 100` process, started before and stopped after the timed steps."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.proc, self.t0 = index, None, 0.0
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) == 7:
-                    self.rows.append(parts)
-            except Exception:  # noqa: BLE001 - sampling is best effort
-                pass
-            self._halt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.35)  # first sample is out before the timed region starts
+        except Exception:  # noqa: BLE001 - sampling is best effort
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+                out = ""
+            for line in out.splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) == 7:
+                    rows.append(parts)
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+
+        sm = sorted(v for v in (num(r[0]) for r in rows) if v is not None)
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        power = [v for v in (num(r[2]) for r in rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "power_w_max": max((float(r[2]) for r in self.rows), default=None),
-                "samples": len(self.rows), "reasons": sorted(reasons)}
+                "sm_max_mhz": num(rows[0][1]) if rows else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(rows), "reasons": sorted(reasons)}
 
 
 class StubLangEncoder:

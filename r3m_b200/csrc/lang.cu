@@ -260,14 +260,28 @@ __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restric
   }
 }
 
-// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  One thread per column; rows are coalesced.
-__global__ void __launch_bounds__(128) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
+// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 8 row-slices; rows are
+// strided over the slices and combined in shared memory (a one-thread-per-column loop over ~1000 rows was 70 us).
+__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
                                                       float* __restrict__ out, int rows, int cols) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
-  out[j] = acc;
+  if (j < cols)
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += 8 * gridDim.y)
+      acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += part[i][tx];
+    if (gridDim.y == 1)
+      out[j] = v;
+    else
+      atomicAdd(&out[j], v);
+  }
 }
 
 __global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
@@ -346,7 +360,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   R3M_TRY(cudaGetLastError());
   if (dE) {
     // ---- backward
-    col_sum_kernel<<<(H + 127) / 128, 128, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
     R3M_TRY(cudaGetLastError());
     vec_sum_kernel<<<1, 256, 0, s>>>(ws.dS, p.db[4], rows);
     R3M_TRY(cudaGetLastError());
@@ -358,7 +372,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
       const float* inl = (l == 0) ? ws.X : ws.Hact[l - 1];
       const int kl = (l == 0) ? K1 : H;
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * in[m][k]
-      col_sum_kernel<<<(H + 127) / 128, 128, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
+      col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
       GemmArgs gw{dHl, inl, p.dw[l], H, kl, rows, H, kl, kl, nullptr, 0, nullptr, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
