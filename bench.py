@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU)
     ap.add_argument("--lang", type=int, default=1, help="language head on (c3) / off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-debug", default="", help="diagnostic: 'nocopy' skips the H2D copy in the e2e loop")
     return ap.parse_args()
 
 
@@ -276,7 +277,8 @@ def run_ours(args):
     def prefetch(slot):
         copy_stream.wait_event(consumed[slot])  # the step that last read this slot has finished
         with torch.cuda.stream(copy_stream):
-            staging[slot].copy_(host, non_blocking=True)
+            if args.e2e_debug != "nocopy":
+                staging[slot].copy_(host, non_blocking=True)
             ready[slot].record(copy_stream)
 
     for ev in consumed:

@@ -27,36 +27,43 @@ __device__ __forceinline__ void eval_rows(int j, int b, const int* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256) lang_gather_kernel(const float* __restrict__ E, const float* __restrict__ Lemb,
-                                                          const int* __restrict__ perms, float* __restrict__ X,
+// H1[row] = relu(U[clip of e0] + V[e_t row] + Lc[b] + b1)
+__global__ void __launch_bounds__(256) lang_layer1_kernel(const float* __restrict__ U, const float* __restrict__ V,
+                                                          const float* __restrict__ Lc, const float* __restrict__ b1,
+                                                          const int* __restrict__ perms, float* __restrict__ H1,
                                                           LangDims d) {
   const int row = blockIdx.x;
   const int j = row / d.B, b = row - j * d.B;
   int r0, r1;
   eval_rows(j, b, perms, d.B, r0, r1);
-  float* x = X + (size_t)row * d.k1();
-  const float4* a = reinterpret_cast<const float4*>(E + (size_t)r0 * d.D);
-  const float4* c = reinterpret_cast<const float4*>(E + (size_t)r1 * d.D);
-  const float4* l = reinterpret_cast<const float4*>(Lemb + (size_t)b * d.L);
-  float4* x4 = reinterpret_cast<float4*>(x);
-  const int d4 = d.D / 4, l4 = d.L / 4;
-  for (int i = threadIdx.x; i < d4; i += blockDim.x) {
-    x4[i] = a[i];
-    x4[d4 + i] = c[i];
+  const float4* u = reinterpret_cast<const float4*>(U + (size_t)(r0 / 5) * d.H);
+  const float4* v = reinterpret_cast<const float4*>(V + (size_t)r1 * d.H);
+  const float4* l = reinterpret_cast<const float4*>(Lc + (size_t)b * d.H);
+  const float4* bias = reinterpret_cast<const float4*>(b1);
+  float4* out = reinterpret_cast<float4*>(H1 + (size_t)row * d.H);
+  for (int i = threadIdx.x; i < d.H / 4; i += blockDim.x) {
+    const float4 a = u[i], c = v[i], e = l[i], f = bias[i];
+    out[i] = make_float4(fmaxf(a.x + c.x + e.x + f.x, 0.f), fmaxf(a.y + c.y + e.y + f.y, 0.f),
+                         fmaxf(a.z + c.z + e.z + f.z, 0.f), fmaxf(a.w + c.w + e.w + f.w, 0.f));
   }
-  for (int i = threadIdx.x; i < l4; i += blockDim.x) x4[2 * d4 + i] = l[i];
 }
 
-__global__ void __launch_bounds__(256) lang_scatter_kernel(const float* __restrict__ dX, const int* __restrict__ perms,
-                                                           float* __restrict__ dE, LangDims d) {
+// dU[clip of e0] += dpre1[row];  dV[e_t row] += dpre1[row];  dLc[b] += dpre1[row]   (targets zeroed by the caller)
+__global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __restrict__ dpre, const int* __restrict__ perms,
+                                                              float* __restrict__ dU, float* __restrict__ dV,
+                                                              float* __restrict__ dLc, LangDims d) {
   const int row = blockIdx.x;
   const int j = row / d.B, b = row - j * d.B;
   int r0, r1;
   eval_rows(j, b, perms, d.B, r0, r1);
-  const float* x = dX + (size_t)row * d.k1();
-  for (int i = threadIdx.x; i < d.D; i += blockDim.x) {
-    atomicAdd(&dE[(size_t)r0 * d.D + i], x[i]);
-    atomicAdd(&dE[(size_t)r1 * d.D + i], x[d.D + i]);
+  const float* g = dpre + (size_t)row * d.H;
+  for (int i = threadIdx.x; i < d.H; i += blockDim.x) {
+    const float x = g[i];
+    if (x != 0.f) {
+      atomicAdd(&dU[(size_t)(r0 / 5) * d.H + i], x);
+      atomicAdd(&dV[(size_t)r1 * d.H + i], x);
+      atomicAdd(&dLc[(size_t)b * d.H + i], x);
+    }
   }
 }
 
@@ -75,6 +82,7 @@ struct GemmArgs {
   int relu;
   const float* mask;
   int ldm;
+  int accumulate;  // C += result
 };
 
 template <bool kAK, bool kBK>
@@ -183,7 +191,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       if (g.bias) v += g.bias[col];
       if (g.relu) v = fmaxf(v, 0.f);
       if (g.mask) v = g.mask[(size_t)row * g.ldm + col] > 0.f ? v : 0.f;
-      g.C[(size_t)row * g.ldc + col] = v;
+      float* dst = &g.C[(size_t)row * g.ldc + col];
+      *dst = g.accumulate ? *dst + v : v;
     }
   }
 }
@@ -303,17 +312,26 @@ __global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ 
 size_t lang_workspace_floats(const LangDims& d) {
   const size_t r = (size_t)d.rows();
   auto up = [](size_t v) { return (v + 63) / 64 * 64; };
-  return 2 * up(r * d.k1()) + 6 * up(r * d.H) + 2 * up(r);
+  return 2 * (2 * up((size_t)d.B * d.H) + up((size_t)5 * d.B * d.H)) + 6 * up(r * d.H) + 2 * up(r);
 }
 
 void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws) {
   const size_t r = (size_t)d.rows();
   auto up = [](size_t v) { return (v + 63) / 64 * 64; };
   float* p = base;
-  ws->X = p;
-  p += up(r * d.k1());
-  ws->dX = p;
-  p += up(r * d.k1());
+  // dU, dV, dLc are contiguous: one memset clears them
+  ws->dU = p;
+  p += up((size_t)d.B * d.H);
+  ws->dV = p;
+  p += up((size_t)5 * d.B * d.H);
+  ws->dLc = p;
+  p += up((size_t)d.B * d.H);
+  ws->U = p;
+  p += up((size_t)d.B * d.H);
+  ws->V = p;
+  p += up((size_t)5 * d.B * d.H);
+  ws->Lc = p;
+  p += up((size_t)d.B * d.H);
   for (int i = 0; i < 4; ++i) {
     ws->Hact[i] = p;
     p += up(r * d.H);
@@ -343,16 +361,22 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     }                            \
   } while (0)
 
-  lang_gather_kernel<<<rows, 256, 0, s>>>(E, lang_emb, perms, ws.X, d);
-  R3M_TRY(cudaGetLastError());
-  // ---- forward: 4 x (Linear + ReLU), then Linear(H -> 1)
-  const float* in = ws.X;
-  int kin = K1;
-  for (int l = 0; l < 4; ++l) {
-    GemmArgs g{in, p.w[l], ws.Hact[l], rows, H, kin, kin, kin, H, p.b[l], 1, nullptr, 0};
+  const int B = d.B, D = d.D;
+  // ---- forward layer 1 (factorised): U = E0 . W1a^T, V = E . W1b^T, Lc = L . W1c^T, then gather-add + bias + ReLU
+  {
+    GemmArgs gu{E, p.w[0], ws.U, B, H, D, 5 * D, K1, H, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<true, true>(gu, s)));
+    GemmArgs gv{E, p.w[0] + D, ws.V, 5 * B, H, D, D, K1, H, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<true, true>(gv, s)));
+    GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<true, true>(gl, s)));
+    lang_layer1_kernel<<<rows, 256, 0, s>>>(ws.U, ws.V, ws.Lc, p.b[0], perms, ws.Hact[0], d);
+    R3M_TRY(cudaGetLastError());
+  }
+  // ---- layers 2-4: Linear + ReLU, then Linear(H -> 1)
+  for (int l = 1; l < 4; ++l) {
+    GemmArgs g{ws.Hact[l - 1], p.w[l], ws.Hact[l], rows, H, H, H, H, H, p.b[l], 1, nullptr, 0, 0};
     R3M_TRY((run_gemm<true, true>(g, s)));
-    in = ws.Hact[l];
-    kin = H;
   }
   lang_score_kernel<<<rows, 256, 0, s>>>(ws.Hact[3], p.w[4], p.b[4], ws.S, H);
   R3M_TRY(cudaGetLastError());
@@ -367,28 +391,41 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     lang_dscore_kernel<<<148 * 4, 256, 0, s>>>(ws.dS, p.w[4], ws.Hact[3], ws.dH[0], rows, H);
     R3M_TRY(cudaGetLastError());
     int cur = 0;
-    for (int l = 3; l >= 0; --l) {
+    for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
-      const float* inl = (l == 0) ? ws.X : ws.Hact[l - 1];
-      const int kl = (l == 0) ? K1 : H;
-      // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * in[m][k]
+      // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
       col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
-      GemmArgs gw{dHl, inl, p.dw[l], H, kl, rows, H, kl, kl, nullptr, 0, nullptr, 0};
+      GemmArgs gw{dHl, ws.Hact[l - 1], p.dw[l], H, H, rows, H, H, H, nullptr, 0, nullptr, 0, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
-      // d(in)[m][k] = sum_n dH_l[m][n] * W_l[n][k], gated by ReLU of the layer below
-      if (l > 0) {
-        GemmArgs gx{dHl, p.w[l], ws.dH[cur ^ 1], rows, H, H, H, H, H, nullptr, 0, ws.Hact[l - 1], H};
-        R3M_TRY((run_gemm<true, false>(gx, s)));
-        cur ^= 1;
-      } else {
-        // only the two embedding slices of dX feed back into the network (the sentence embedding is frozen)
-        GemmArgs gx{dHl, p.w[0], ws.dX, rows, 2 * d.D, H, H, K1, K1, nullptr, 0, nullptr, 0};
-        R3M_TRY((run_gemm<true, false>(gx, s)));
-      }
+      // dH_{l-1}[m][k] = sum_n dH_l[m][n] * W_l[n][k], gated by ReLU of the layer below
+      GemmArgs gx{dHl, p.w[l], ws.dH[cur ^ 1], rows, H, H, H, H, H, nullptr, 0, ws.Hact[l - 1], H, 0};
+      R3M_TRY((run_gemm<true, false>(gx, s)));
+      cur ^= 1;
     }
-    lang_scatter_kernel<<<rows, 256, 0, s>>>(ws.dX, perms, dE, d);
+    // ---- layer 1 backward (factorised)
+    const float* dpre = ws.dH[cur];
+    col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(dpre, nullptr, p.db[0], rows, H);
     R3M_TRY(cudaGetLastError());
+    e = cudaMemsetAsync(ws.dU, 0, (size_t)((ws.U - ws.dU)) * sizeof(float), s);
+    if (e != cudaSuccess) {
+      if (launches) *launches = n;
+      return e;
+    }
+    lang_layer1_bwd_kernel<<<rows, 256, 0, s>>>(dpre, perms, ws.dU, ws.dV, ws.dLc, d);
+    R3M_TRY(cudaGetLastError());
+    // dW1 = [dU^T E0 | dV^T E | dLc^T L]   (column blocks of the [H][2D+768] gradient)
+    GemmArgs wa{ws.dU, E, p.dw[0], H, D, B, H, 5 * D, K1, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<false, false>(wa, s)));
+    GemmArgs wb{ws.dV, E, p.dw[0] + D, H, D, 5 * B, H, D, K1, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<false, false>(wb, s)));
+    GemmArgs wc{ws.dLc, lang_emb, p.dw[0] + 2 * D, H, d.L, B, H, d.L, K1, nullptr, 0, nullptr, 0, 0};
+    R3M_TRY((run_gemm<false, false>(wc, s)));
+    // dE0 += dU . W1a,  dE += dV . W1b   (the sentence embedding is frozen: no gradient through W1c's input)
+    GemmArgs ea{ws.dU, p.w[0], dE, B, D, H, H, K1, 5 * D, nullptr, 0, nullptr, 0, 1};
+    R3M_TRY((run_gemm<true, false>(ea, s)));
+    GemmArgs eb{ws.dV, p.w[0] + D, dE, 5 * B, D, H, H, K1, D, nullptr, 0, nullptr, 0, 1};
+    R3M_TRY((run_gemm<true, false>(eb, s)));
   }
 #undef R3M_TRY
   if (launches) *launches = n;

@@ -24,12 +24,19 @@ struct LangParams {  // device pointers into the flat parameter / gradient buffe
 };
 
 struct LangWorkspace {  // device scratch, sized by lang_workspace_floats()
-  float* X;      // [rows][k1]
+  // Layer 1 is factorised: cat([e0, e_t, l]) . W1^T = e0 . W1a^T + e_t . W1b^T + l . W1c^T, and only B distinct e0 rows,
+  // 5B distinct e_t rows and B distinct sentence rows exist among the 15B evaluations, so the three products are
+  // computed once per distinct row (3.4x fewer layer-1 FLOPs than the reference's 15 concatenated passes).
+  float* U;        // [B][H]   e0 . W1a^T
+  float* V;        // [5B][H]  e  . W1b^T
+  float* Lc;       // [B][H]   l  . W1c^T
+  float* dU;       // gradients of the three products (scatter-added from the 15B rows)
+  float* dV;
+  float* dLc;
   float* Hact[4];  // post-ReLU hidden activations [rows][H]
-  float* S;      // [rows] scores
-  float* dS;     // [rows]
-  float* dH[2];  // ping-pong [rows][H]
-  float* dX;     // [rows][k1]
+  float* S;        // [rows] scores
+  float* dS;       // [rows]
+  float* dH[2];    // ping-pong [rows][H]
 };
 size_t lang_workspace_floats(const LangDims& d);
 void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws);
