@@ -40,6 +40,13 @@ int r3m_b200_check_device_flag(void);
 int r3m_b200_conv_fwd(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int R, int S,
                       int stride, int pad, float* stat_sum, float* stat_sq, void* stream);
 
+/* Inference form of the forward convolution: BatchNorm folded into the epilogue (replaces cudnn_convolution +
+ * cudnn_batch_norm(eval) + add_ + relu_ of one residual-block stage, tv resnet.py:89-105,143-163).
+ *   y = [relu](conv(x, w) * scale[c] + shift[c] [+ residual]);  scale/shift fp32 [Cout], residual bf16 like y or NULL. */
+int r3m_b200_conv_fwd_affine(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int R, int S,
+                             int stride, int pad, const float* scale, const float* shift, const void* residual,
+                             int relu, void* stream);
+
 /* Re-pack a master filter fp32 [Cout,R,S,Cin] into the dgrad operand (bf16, Cout*R*S*Cin elements: one
  * [Cin][taps][Cout] block per output-parity class, classes in (ph,pw) row-major order). */
 int r3m_b200_pack_dgrad_filter(const float* w, void* w_dgrad, int Cout, int R, int S, int Cin, int stride, int pad,

@@ -47,6 +47,8 @@ def _sig(name, argtypes):
 _sig("r3m_b200_abi_version", [])
 _sig("r3m_b200_check_device_flag", [])
 _sig("r3m_b200_conv_fwd", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p, c_void_p])
+_sig("r3m_b200_conv_fwd_affine", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p, c_void_p, c_int,
+                                                                                c_void_p])
 _sig("r3m_b200_pack_dgrad_filter", [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p])
 _sig("r3m_b200_conv_dgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p])
 _sig("r3m_b200_conv_wgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p])

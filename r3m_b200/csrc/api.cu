@@ -68,6 +68,33 @@ int r3m_b200_conv_fwd(const void* x, const void* w, void* y, int N, int H, int W
   return R3M_B200_OK;
 }
 
+int r3m_b200_conv_fwd_affine(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int R, int S,
+                             int stride, int pad, const float* scale, const float* shift, const void* residual,
+                             int relu, void* stream) {
+  if (!scale || !shift) return fail(R3M_B200_ERR_INVALID, "conv_fwd_affine: scale and shift are required");
+  GatherConv g;
+  g.src = x;
+  g.N = N;
+  g.H = H;
+  g.W = W;
+  g.C = Cin;
+  fill_fwd_geometry(&g, R, S, stride, pad);
+  g.wpk = w;
+  g.Cout = Cout;
+  g.out = y;
+  g.ldo = Cout;
+  g.ep_scale = scale;
+  g.ep_shift = shift;
+  g.ep_res = residual;
+  g.ep_relu = relu;
+  ConvPlan plan;
+  std::string err = plan_conv(g, &plan);
+  if (!err.empty()) return fail(R3M_B200_ERR_INVALID, err);
+  cudaError_t e = run_conv(plan, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "conv_fwd_affine launch");
+  return R3M_B200_OK;
+}
+
 int r3m_b200_pack_dgrad_filter(const float* w, void* w_dgrad, int Cout, int R, int S, int Cin, int stride, int pad,
                                void* stream) {
   // H, W only set the class extents, which the packing does not depend on

@@ -90,10 +90,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  const bool do_affine = (p.ep_scale != nullptr);
   if (do_stats) {
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
       s_sum[i] = 0.f;
       s_sq[i] = 0.f;
+    }
+  } else if (do_affine) {
+    // the statistics arrays double as the per-channel scale / shift table of the fused inference epilogue
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      s_sum[i] = p.ep_scale[i];
+      s_sq[i] = p.ep_shift[i];
     }
   }
   tc_fence_before();
@@ -241,6 +248,41 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
         for (int u = h; u < kUnits; u += EPI / 4) {
           tc_wait_ld();
+          if (do_affine) {
+            // folded BatchNorm (+ residual) (+ ReLU) on the fp32 accumulators; thread = output row m0 + lane
+            const float* sc = s_sum + n0 + u * kUnitCols;
+            const float* sh = s_sq + n0 + u * kUnitCols;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v0[j] = __float_as_uint(fmaf(__uint_as_float(v0[j]), sc[j], sh[j]));
+              v1[j] = __float_as_uint(fmaf(__uint_as_float(v1[j]), sc[32 + j], sh[32 + j]));
+            }
+            if (p.ep_res != nullptr && m0 + lane < p.M_total) {
+              const uint4* rrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.ep_res) +
+                                                                 static_cast<long long>(m0 + lane) * p.ldo + n0 +
+                                                                 u * kUnitCols);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 r = __ldg(rrow + c);
+                uint32_t* dst = (c < 4) ? &v0[8 * c] : &v1[8 * (c - 4)];
+                dst[0] = __float_as_uint(__uint_as_float(dst[0]) + bf16lo(r.x));
+                dst[1] = __float_as_uint(__uint_as_float(dst[1]) + bf16hi(r.x));
+                dst[2] = __float_as_uint(__uint_as_float(dst[2]) + bf16lo(r.y));
+                dst[3] = __float_as_uint(__uint_as_float(dst[3]) + bf16hi(r.y));
+                dst[4] = __float_as_uint(__uint_as_float(dst[4]) + bf16lo(r.z));
+                dst[5] = __float_as_uint(__uint_as_float(dst[5]) + bf16hi(r.z));
+                dst[6] = __float_as_uint(__uint_as_float(dst[6]) + bf16lo(r.w));
+                dst[7] = __float_as_uint(__uint_as_float(dst[7]) + bf16hi(r.w));
+              }
+            }
+            if (p.ep_relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v0[j] = __float_as_uint(fmaxf(__uint_as_float(v0[j]), 0.f));
+                v1[j] = __float_as_uint(fmaxf(__uint_as_float(v1[j]), 0.f));
+              }
+            }
+          }
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {

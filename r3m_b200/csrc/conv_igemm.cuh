@@ -31,6 +31,12 @@ struct ConvKernelParams {
   // optional per-channel statistics of the (bf16-rounded) output
   float* stat_sum;
   float* stat_sq;
+  // optional fused epilogue (inference: BatchNorm folded into a per-channel affine): out = [relu](acc * ep_scale[c] +
+  // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.
+  const float* ep_scale;
+  const float* ep_shift;
+  const void* ep_res;  // bf16 [M][ldo] or null
+  int ep_relu;
   int* error_flag;
 };
 

@@ -85,6 +85,12 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.accumulate = g.accumulate;
   p.stat_sum = g.stat_sum;
   p.stat_sq = g.stat_sq;
+  if (g.ep_scale && (g.stat_sum || g.out_mode != 0 || g.accumulate))
+    return "gather conv: the fused affine epilogue needs a dense, non-accumulating output without statistics";
+  p.ep_scale = g.ep_scale;
+  p.ep_shift = g.ep_shift;
+  p.ep_res = g.ep_res;
+  p.ep_relu = g.ep_relu;
   p.error_flag = device_error_flag();
   if (!p.error_flag) return "could not allocate the device error flag";
   plan->bn = bn;

@@ -25,6 +25,11 @@ struct GatherConv {
   int accumulate = 0;  // out += result (read-modify-write)
   float* stat_sum = nullptr;  // optional per-channel sum / sum of squares of the stored (bf16) output
   float* stat_sq = nullptr;
+  // fused inference epilogue (see ConvKernelParams): per-channel affine (+ residual) (+ ReLU) on the accumulators
+  const float* ep_scale = nullptr;
+  const float* ep_shift = nullptr;
+  const void* ep_res = nullptr;
+  int ep_relu = 0;
 };
 
 struct ConvPlan {

@@ -184,6 +184,15 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   }
 }
 
+__global__ void bn_fold_kernel(const BnFoldEntry* __restrict__ table) {
+  const BnFoldEntry e = table[blockIdx.x];
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    const float sc = e.gamma[c] / sqrtf(e.running_var[c] + kBnEps);
+    e.scale[c] = sc;
+    e.shift[c] = e.beta[c] - e.running_mean[c] * sc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ stem pool
 __global__ void __launch_bounds__(256) stem_pool_kernel(const StemPoolArgs a) {
   const int C8 = a.C >> 3;
@@ -554,6 +563,11 @@ inline int grid_for(long long work_items, int threads, int max_blocks) {
 cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream_t s) {
   const long long total = (long long)N * 112 * 112 * 4;
   preprocess_stem_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(obs, reinterpret_cast<bf16*>(xs), N);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_fold(const BnFoldEntry* table_dev, int entries, cudaStream_t s) {
+  bn_fold_kernel<<<entries, 256, 0, s>>>(table_dev);
   return cudaGetLastError();
 }
 

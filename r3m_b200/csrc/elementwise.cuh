@@ -96,6 +96,18 @@ struct BnBwdArgs {
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
 
+// Inference: fold BatchNorm (running statistics) into a per-channel affine, for all layers in one launch.
+struct BnFoldEntry {
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float* scale;  // gamma / sqrt(var + eps)
+  float* shift;  // beta - mean * scale
+  int C;
+};
+cudaError_t launch_bn_fold(const BnFoldEntry* table_dev, int entries, cudaStream_t s);
+
 // Adam (torch.optim.Adam defaults, ref r3m/models/models_r3m.py:76): flat fp32 p/g/m/v, also emits the bf16 copy.
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, float beta1,
                         float beta2, float eps, int step, float grad_scale, cudaStream_t s);

@@ -240,6 +240,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   e->off_dE_ = arena(N * e->D_ * 4);
   for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
+  e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
   e->ws_bytes_ = align_up(cur, kAlign);
   *out = e;
   return std::string();
@@ -400,6 +401,29 @@ std::string Engine::plan_all() {
       ops.push_back(Op([a](cudaStream_t s) { return launch_stem_bn_relu_maxpool(a, s); }, kFamPool, 0.0,
                        (double)N * 64 * (112.0 * 112 * 2 + 56.0 * 56 * 3)));
     }
+    if (!train) {
+      // inference: every BatchNorm except the stem's is folded into its conv's epilogue (scale/shift live in the
+      // `saved` slots, which only training uses otherwise); one launch refreshes all of them from the running stats
+      std::vector<BnFoldEntry> table;
+      for (size_t i = 1; i < convs_.size(); ++i) {
+        const Conv& c = *convs_[i];
+        BnFoldEntry fe;
+        fe.gamma = P + c.gamma_off;
+        fe.beta = P + c.beta_off;
+        fe.running_mean = buf + c.rm_off;
+        fe.running_var = buf + c.rv_off;
+        fe.scale = saved + c.save_off;
+        fe.shift = saved + c.save_off + c.Cout;
+        fe.C = c.Cout;
+        table.push_back(fe);
+      }
+      BnFoldEntry* table_dev = reinterpret_cast<BnFoldEntry*>(ws_ + off_fold_);
+      cudaError_t ce = cudaMemcpy(table_dev, table.data(), table.size() * sizeof(BnFoldEntry), cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) return std::string("fold table upload: ") + cudaGetErrorString(ce);
+      const int entries = (int)table.size();
+      ops.push_back(Op([table_dev, entries](cudaStream_t s) { return launch_bn_fold(table_dev, entries, s); }, kFamNorm));
+      ops.back().label = "bn_fold (all layers)";
+    }
     const bf16* x = st.a;
     for (Block* blk : blocks_) {
       blk->x_in = x;
@@ -407,20 +431,52 @@ std::string Engine::plan_all() {
       for (size_t i = 0; i < blk->main.size(); ++i) {
         Conv& c = *convs_[blk->main[i]];
         c.x = cur;
-        push_conv(ops, fwd_geom(c, train), "fwd " + c.name);
-        if (i + 1 < blk->main.size()) {
-          add_bn_apply(ops, c, nullptr, c.a, 1, train, nullptr);
+        if (train) {
+          push_conv(ops, fwd_geom(c, train), "fwd " + c.name);
+          if (i + 1 < blk->main.size()) {
+            add_bn_apply(ops, c, nullptr, c.a, 1, train, nullptr);
+            cur = c.a;
+          }
+        } else if (i + 1 < blk->main.size()) {
+          GatherConv gc = fwd_geom(c, 0);
+          gc.out = c.a;
+          gc.ep_scale = saved + c.save_off;
+          gc.ep_shift = saved + c.save_off + c.Cout;
+          gc.ep_relu = 1;
+          push_conv(ops, gc, "fwd+bn+relu " + c.name);
           cur = c.a;
         }
       }
       Conv& last = *convs_[blk->main.back()];
-      if (blk->ds >= 0) {
-        Conv& d = *convs_[blk->ds];
-        d.x = blk->x_in;
-        push_conv(ops, fwd_geom(d, train), "fwd " + d.name);
-        add_bn_apply(ops, last, nullptr, last.a, 1, train, &d);
+      if (train) {
+        if (blk->ds >= 0) {
+          Conv& d = *convs_[blk->ds];
+          d.x = blk->x_in;
+          push_conv(ops, fwd_geom(d, train), "fwd " + d.name);
+          add_bn_apply(ops, last, nullptr, last.a, 1, train, &d);
+        } else {
+          add_bn_apply(ops, last, blk->x_in, last.a, 1, train, nullptr);
+        }
       } else {
-        add_bn_apply(ops, last, blk->x_in, last.a, 1, train, nullptr);
+        const void* residual = blk->x_in;
+        if (blk->ds >= 0) {
+          Conv& d = *convs_[blk->ds];
+          d.x = blk->x_in;
+          GatherConv gd = fwd_geom(d, 0);
+          gd.out = d.a;
+          gd.ep_scale = saved + d.save_off;
+          gd.ep_shift = saved + d.save_off + d.Cout;
+          gd.ep_relu = 0;
+          push_conv(ops, gd, "fwd+bn " + d.name);
+          residual = d.a;
+        }
+        GatherConv gl = fwd_geom(last, 0);
+        gl.out = last.a;
+        gl.ep_scale = saved + last.save_off;
+        gl.ep_shift = saved + last.save_off + last.Cout;
+        gl.ep_res = residual;
+        gl.ep_relu = 1;
+        push_conv(ops, gl, "fwd+bn+res+relu " + last.name);
       }
       blk->a_out = last.a;
       x = last.a;

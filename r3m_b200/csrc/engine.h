@@ -123,6 +123,7 @@ class Engine {
   // language head (optional)
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
   size_t off_lang_ws_ = 0;
+  size_t off_fold_ = 0;  // BnFoldEntry table (device) for the inference path
   LangDims lang_dims_;
 
   std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;

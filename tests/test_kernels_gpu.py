@@ -86,6 +86,30 @@ def test_conv_wgrad(lib, geom):
     assert rel(dw, ref) < 2e-5
 
 
+@pytest.mark.parametrize("geom,res,relu", [((2, 56, 64, 256, 1, 1, 0), True, True), ((3, 14, 256, 256, 3, 1, 1), False, True),
+                                            ((2, 28, 256, 512, 1, 2, 0), False, False), ((1, 7, 512, 2048, 1, 1, 0), True, True)])
+def test_conv_forward_folded_bn_epilogue(lib, geom, res, relu):
+    """Inference path: y = relu(conv * scale + shift + residual) in the conv epilogue == conv -> eval BN -> add -> relu."""
+    N, H, Cin, Cout, R, stride, pad = geom
+    x, w, _, P = _mk(geom, 7)
+    g = torch.Generator().manual_seed(3)
+    scale = (0.5 + torch.rand(Cout, generator=g)).cuda()
+    shift = torch.randn(Cout, generator=g).cuda()
+    r = torch.randn(N, P, P, Cout, generator=g).cuda().bfloat16() if res else None
+    xn, wk = x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).contiguous()
+    y = torch.full((N, P, P, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.lib.r3m_b200_conv_fwd_affine(lib.ptr(xn), lib.ptr(wk), lib.ptr(y), N, H, H, Cin, Cout, R, R, stride,
+                                               pad, lib.ptr(scale), lib.ptr(shift), lib.ptr(r), int(relu),
+                                               lib.current_stream()))
+    lib.check(lib.lib.r3m_b200_check_device_flag())
+    ref = F.conv2d(x.float(), w.float(), stride=stride, padding=pad).permute(0, 2, 3, 1) * scale + shift
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.relu()
+    assert rel(y.float(), ref) < 2.5e-3
+
+
 def test_conv_linearity_at_full_size(lib):
     """Size-independent property at BASELINE c2/c3 size (320 frames, layer3 3x3): conv(x1 + x2) == conv(x1) + conv(x2)
     up to output rounding — no oracle needed."""
