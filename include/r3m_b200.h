@@ -141,7 +141,8 @@ int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_ca
                                 int* ndim, int* dims4);
 /* which: 0 params, 1 grads, 2 Adam m, 3 Adam v (fp32, same flat layout), 4 BN buffers fp32, 5 embeddings fp32
  * [frames][D], 6 d(loss)/d(embeddings) fp32, 7 metrics fp32[16]
- * (l2loss,l1loss,l0loss,rewloss,rewacc1,rewacc2,rewacc3,tcnloss,aligned,full_loss). count = number of elements. */
+ * (slots 0-9: l2loss,l1loss,l0loss,rewloss,rewacc1,rewacc2,rewacc3,tcnloss,aligned,full_loss; slot 15: device-side
+ * pipeline-watchdog flag of the step, 0 = clean). count = number of elements. */
 int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
 /* what: 0 embedding dim, 1 frames, 2 kernels launched by the last engine call */
 int r3m_b200_engine_get_int(void* handle, int what, int* value);

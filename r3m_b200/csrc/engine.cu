@@ -853,9 +853,12 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
     int n_lang = 0;
     int* n_ptr = &n_lang;
     // the head is ~25 launches; it is charged to the "lang" family as one profiled unit
-    const double rows = ld.rows(), H = ld.H, K1 = ld.k1();
-    const double fwd_mac = rows * (K1 * H + 3 * H * H + H);
-    const double bwd_mac = rows * (K1 * H + 3 * H * H) + rows * (2.0 * ld.D * H + 3 * H * H);
+    // algorithmic MACs of the factorised head: layer 1 once per distinct row (B e0 rows, 5B e_t rows, B sentences),
+    // layers 2-4 over the 15B evaluations
+    const double rows = ld.rows(), H = ld.H, Bc = ld.B, Dd = ld.D, Ll = ld.L;
+    const double l1_mac = (6.0 * Bc * Dd + Bc * Ll) * H;
+    const double fwd_mac = l1_mac + rows * (3 * H * H + H);
+    const double bwd_mac = 2.0 * rows * 3 * H * H + (l1_mac + 6.0 * Bc * Dd * H);
     e = launch(Op([=](cudaStream_t s) {
                  return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s);
                },
@@ -867,6 +870,11 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
   if (!eval) {
     err = run(bwd_, stream);
     if (!err.empty()) return err;
+  }
+  {
+    const int* flag = device_error_flag();
+    e = launch(Op([flag, metrics](cudaStream_t s) { return launch_publish_flag(flag, metrics, s); }, kFamLoss), stream);
+    if (e != cudaSuccess) return std::string("publish_flag: ") + cudaGetErrorString(e);
   }
   return std::string();
 }

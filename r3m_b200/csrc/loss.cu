@@ -136,7 +136,16 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
   }
 }
 
+__global__ void publish_flag_kernel(const int* __restrict__ flag, float* __restrict__ metrics) {
+  metrics[kDeviceFlag] = (float)*flag;
+}
+
 }  // namespace
+
+cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s) {
+  publish_flag_kernel<<<1, 1, 0, s>>>(flag, metrics);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w, float l1w, float* metrics,
                            cudaStream_t s) {

@@ -7,7 +7,7 @@ namespace r3m {
 // slots of the device metrics buffer (fp32[16]); same key set as the reference's metrics dict
 enum Metric {
   kL2 = 0, kL1 = 1, kL0 = 2, kRewLoss = 3, kRewAcc1 = 4, kRewAcc2 = 5, kRewAcc3 = 6, kTcnLoss = 7, kAligned = 8,
-  kFullLoss = 9, kNumMetrics = 16
+  kFullLoss = 9, kDeviceFlag = 15 /* != 0: a tcgen05 pipeline watchdog fired during the step */, kNumMetrics = 16
 };
 constexpr float kLossEps = 1e-8f;  // r3m/trainer.py:18
 
@@ -21,5 +21,8 @@ cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w
 // reference's draw order (rows 9..14 are the TCN permutations: es0 then es2 per iteration).
 cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, float* metrics,
                             cudaStream_t s);
+
+// metrics[kDeviceFlag] = (float)*flag  — lets the single metrics read-back also carry the kernels' error flag
+cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s);
 
 }  // namespace r3m

@@ -159,7 +159,12 @@ class Engine:
         dev = _as_tensor(p, n, torch.float32, self.device)
         self._metrics_host.copy_(dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return self._metrics_host.tolist()
+        vals = self._metrics_host.tolist()
+        if vals[15] != 0.0:  # slot 15 carries the device-side pipeline watchdog flag of the step's tcgen05 kernels
+            L.lib.r3m_b200_check_device_flag()  # clears it
+            raise L.R3MB200Error(f"a tcgen05/TMA pipeline watchdog fired during the step (code {int(vals[15])}); "
+                                 "the step's results are invalid")
+        return vals
 
     def embeddings(self):
         p, n = self._region(5)
