@@ -34,36 +34,44 @@ constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kUnitCols = 64;  // one epilogue unit: 32 rows x 64 columns bf16 = 128-byte rows (TMA stores are paced per row)
 constexpr int kUnitBytes = 32 * kUnitCols * 2;
-constexpr int kMaxStatC = 2048;
+template <int BN>
+struct StatC {  // per-CTA statistics / affine table capacity (channels): narrow tiles only serve Cout <= 512
+  static constexpr int value = (BN == 256) ? 2048 : 512;
+};
 
 // STAGES: depth of the TMA->MMA operand ring.  BUFS: staging buffers per epilogue warp (bulk stores in flight).
 // Long-K tiles (3x3 convs) want the deep ring, short-K tiles (1x1 convs into wide outputs) are epilogue bound and want
 // several stores in flight; both fit the 227 KB budget only one at a time for BN = 256.
 // EPI: epilogue warps (4 or 8 = one or two per TMEM lane quadrant).
-template <int BN, int STAGES, int BUFS, int EPI>
+// KPS: 64-wide K blocks per pipeline stage.  The TMA-producer and MMA-issuer roles are single threads whose per-stage
+// bookkeeping (mbarrier try_wait ~90 cycles, expect_tx, descriptor math, op issue) costs ~450-600 cycles (measured:
+// per-stage time is flat in the number of MMAs and TMA ops), so a stage must carry at least that much tensor work:
+// 4 MMAs of N=256 (512 cycles) do, 4 MMAs of N=64 (128 cycles) do not -> narrow tiles put several K blocks in a stage.
+template <int BN, int STAGES, int BUFS, int EPI, int KPS>
 struct Cfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kKbBytes = kABytes + kBBytes;   // one K block: A sub-tile then B sub-tile
+  static constexpr int kStageBytes = KPS * kKbBytes;
   static constexpr int kStages = STAGES;
   static constexpr int kStagingBytes = EPI * BUFS * kUnitBytes;
   static constexpr int kThreads = 128 + EPI * 32;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kStagingBytes + 2 * kMaxStatC * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
+      kStages * kStageBytes + kStagingBytes + 2 * StatC<BN>::value * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, int BUFS, int EPI>
+template <int BN, int STAGES, int BUFS, int EPI, int KPS>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
-  using C = Cfg<BN, STAGES, BUFS, EPI>;
+  using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
   float* s_sum = reinterpret_cast<float*>(staging + C::kStagingBytes);
-  float* s_sq = s_sum + kMaxStatC;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + kMaxStatC);
+  float* s_sq = s_sum + StatC<BN>::value;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + StatC<BN>::value);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -128,20 +136,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int cw = p.base_w + qq * p.stride;
         const int ch = p.base_h + pp * p.stride;
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
           if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) {
             atomicExch(p.error_flag, 1);
             ok = false;
             break;
           }
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_tile * BN);
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++tap;
+          const int nk = min(KPS, num_kb - kb0);
+          uint8_t* st = smem + stage * C::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk * C::kKbBytes));
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              uint8_t* sa = st + j * C::kKbBytes;
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
+              tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, (kb0 + j) * kBlockK, n_tile * BN);
+              if (++cb == p.cblocks) {
+                cb = 0;
+                ++tap;
+              }
+            }
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -166,22 +180,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
           if (!mbar_wait(&full_bar[stage], phase)) {
             atomicExch(p.error_flag, 3);
             ok = false;
             break;
           }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr, 16, 1024);
+          const int nk = min(KPS, num_kb - kb0);
+          const uint32_t st_addr = smem_u32(smem + stage * C::kStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is >>4)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              const uint32_t a_addr = st_addr + j * C::kKbBytes;
+              const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is >>4)
+                umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                          (kb0 | j | k) != 0 ? 1u : 0u);
+              }
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
@@ -403,18 +423,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int STAGES, int BUFS, int EPI>
+template <int BN, int STAGES, int BUFS, int EPI, int KPS>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES, BUFS, EPI>;
+  using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_igemm_kernel<BN, STAGES, BUFS, EPI><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 
@@ -424,13 +444,17 @@ cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap&
                               const ConvKernelParams& p, int grid, cudaStream_t stream) {
   const int num_kb = p.num_taps * p.cblocks;
   switch (bn) {
-    case 64:
-      return launch_bn<64, 6, 4, 4>(tmA, tmB, tmC, p, grid, stream);   // one unit per quadrant
+    case 64:  // one unit per quadrant
+      if (p.Cout > StatC<64>::value) return cudaErrorInvalidValue;
+      if (num_kb >= 9) return launch_bn<64, 4, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3: two K blocks per stage
+      return launch_bn<64, 6, 4, 4, 1>(tmA, tmB, tmC, p, grid, stream);
     case 128:
-      return launch_bn<128, 4, 2, 8>(tmA, tmB, tmC, p, grid, stream);
+      if (p.Cout > StatC<128>::value) return cudaErrorInvalidValue;
+      if (num_kb >= 18) return launch_bn<128, 3, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3
+      return launch_bn<128, 4, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);
     case 256:
-      if (num_kb >= 12) return launch_bn<256, 4, 1, 4>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
-      return launch_bn<256, 3, 2, 8>(tmA, tmB, tmC, p, grid, stream);                    // epilogue bound
+      if (num_kb >= 12) return launch_bn<256, 4, 1, 4, 1>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
+      return launch_bn<256, 3, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);                    // epilogue bound
     default:
       return cudaErrorInvalidValue;
   }
