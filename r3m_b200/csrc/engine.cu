@@ -41,10 +41,12 @@ struct Engine::Block {
 namespace {
 constexpr size_t kAlign = 1024;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr size_t kMaxActPerFrame = 112 * 112 * 64;  // largest activation (stem output == layer1 bottleneck output)
+constexpr size_t kMaxActPerFrame = 112 * 112 * 64;
+constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are launch-latency bound -> CUDA graph  // largest activation (stem output == layer1 bottleneck output)
 }  // namespace
 
 Engine::~Engine() {
+  if (eval_graph_) cudaGraphExecDestroy(eval_graph_);
   for (Conv* c : convs_) delete c;
   for (Block* b : blocks_) delete b;
 }
@@ -241,6 +243,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
   e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
+  if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
   e->ws_bytes_ = align_up(cur, kAlign);
   *out = e;
   return std::string();
@@ -775,20 +778,60 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
   if (!bound_) return "engine has no workspace bound";
   launches_ = 0;
   cudaError_t e;
-  if (train) {
-    e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
-    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  std::string err;
+  if (!train && N_ <= kGraphMaxFrames && !profiling_) {
+    // Launch-latency-bound regime (load_r3m users, r3m/example.py: batch 1-4): ~25 kernels of a few microseconds.
+    // The frames are copied to a fixed staging buffer and the whole eval forward is replayed as one CUDA graph
+    // (captured on the second call, once every kernel's attributes have been configured by a plain first call).
+    float* stage = reinterpret_cast<float*>(ws_ + off_obs_stage_);
+    e = cudaMemcpyAsync(stage, obs, (size_t)N_ * 3 * 224 * 224 * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return std::string("stage frames: ") + cudaGetErrorString(e);
+    ++eval_calls_;
+    if (eval_graph_ == nullptr && eval_calls_ >= 2) {
+      // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+      cudaGraph_t graph = nullptr;
+      cudaStream_t cap = nullptr;
+      if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
+          cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        cudaError_t ce = launch_preprocess_stem(stage, ws_ + off_xs_, N_, cap);
+        std::string cerr = run(fwd_eval_, cap);
+        cudaError_t ee = cudaStreamEndCapture(cap, &graph);
+        if (ce == cudaSuccess && cerr.empty() && ee == cudaSuccess && graph != nullptr) {
+          if (cudaGraphInstantiate(&eval_graph_, graph, 0) != cudaSuccess) eval_graph_ = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+      }
+      if (cap) cudaStreamDestroy(cap);
+      launches_ = 0;
+    }
+    if (eval_graph_ != nullptr) {
+      e = cudaGraphLaunch(eval_graph_, stream);
+      if (e != cudaSuccess) return std::string("graph launch: ") + cudaGetErrorString(e);
+      launches_ = (int)fwd_eval_.size() + 1;
+    } else {
+      e = launch_preprocess_stem(stage, ws_ + off_xs_, N_, stream);
+      if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
+      ++launches_;
+      err = run(fwd_eval_, stream);
+      if (!err.empty()) return err;
+    }
+  } else {
+    if (train) {
+      e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+      if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+    }
+    {
+      void* xs = ws_ + off_xs_;
+      const int N = N_;
+      e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
+                    (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+                 stream);
+    }
+    if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
+    err = run(train ? fwd_train_ : fwd_eval_, stream);
+    if (!err.empty()) return err;
   }
-  {
-    void* xs = ws_ + off_xs_;
-    const int N = N_;
-    e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
-                  (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
-               stream);
-  }
-  if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
-  std::string err = run(train ? fwd_train_ : fwd_eval_, stream);
-  if (!err.empty()) return err;
   if (out) {
     e = cudaMemcpyAsync(out, ws_ + off_E_, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return std::string("copy out: ") + cudaGetErrorString(e);

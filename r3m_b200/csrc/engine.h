@@ -124,6 +124,10 @@ class Engine {
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
   size_t off_lang_ws_ = 0;
   size_t off_fold_ = 0;  // BnFoldEntry table (device) for the inference path
+  // small-batch inference: the eval forward is replayed as a CUDA graph from a fixed staging copy of the frames
+  size_t off_obs_stage_ = 0;
+  cudaGraphExec_t eval_graph_ = nullptr;
+  int eval_calls_ = 0;
   LangDims lang_dims_;
 
   std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;

@@ -130,3 +130,19 @@ def test_trainer_contract_needs_gpu_but_keeps_signature():
     params = list(inspect.signature(Trainer.update).parameters)
     assert params[:5] == ["self", "model", "batch", "step", "eval"]
     assert Trainer(eval_freq=20000).eval_freq == 20000
+
+
+def test_optimizer_state_roundtrip_for_exact_resume():
+    """the reference does not checkpoint Adam state; ours exposes it (encoder_opt.state_dict) so a
+    resumed run continues bit-exactly, while the model state_dict stays loadable by the reference."""
+    m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
+    m._flat(2).normal_()
+    m._flat(3).uniform_()
+    m.encoder_opt.steps = 7
+    sd = m.encoder_opt.state_dict()
+    m2 = R3M("cpu", 3e-4, 1024, size=18, langweight=0.0)
+    m2.encoder_opt.load_state_dict(sd)
+    assert m2.encoder_opt.steps == 7 and m2.encoder_opt.param_groups[0]["lr"] == 1e-4
+    assert torch.equal(m2._flat(2), m._flat(2)) and torch.equal(m2._flat(3), m._flat(3))
+    m.encoder_opt.zero_grad()
+    assert float(m._flat(1).abs().max()) == 0.0
