@@ -269,8 +269,9 @@ __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restric
   }
 }
 
-// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 8 row-slices; rows are
-// strided over the slices and combined in shared memory (a one-thread-per-column loop over ~1000 rows was 70 us).
+// out[j] += sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 8 row-slices, gridDim.y
+// row groups combined with atomics: `out` lives in the gradient buffer, which is zero at this point of the step
+// (a one-thread-per-column loop over ~1000 rows took 70 us per call).
 __global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
                                                       float* __restrict__ out, int rows, int cols) {
   __shared__ float part[8][33];
@@ -384,7 +385,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   R3M_TRY(cudaGetLastError());
   if (dE) {
     // ---- backward
-    col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
     R3M_TRY(cudaGetLastError());
     vec_sum_kernel<<<1, 256, 0, s>>>(ws.dS, p.db[4], rows);
     R3M_TRY(cudaGetLastError());
@@ -394,7 +395,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
-      col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
+      col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
       GemmArgs gw{dHl, ws.Hact[l - 1], p.dw[l], H, H, rows, H, H, H, nullptr, 0, nullptr, 0, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
@@ -405,7 +406,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     }
     // ---- layer 1 backward (factorised)
     const float* dpre = ws.dH[cur];
-    col_sum_kernel<<<dim3((H + 31) / 32, 1), 256, 0, s>>>(dpre, nullptr, p.db[0], rows, H);
+    col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(dpre, nullptr, p.db[0], rows, H);
     R3M_TRY(cudaGetLastError());
     e = cudaMemsetAsync(ws.dU, 0, (size_t)((ws.U - ws.dU)) * sizeof(float), s);
     if (e != cudaSuccess) {
