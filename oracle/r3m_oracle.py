@@ -222,17 +222,20 @@ def sim(a, b):
     return -torch.linalg.norm(a - b, dim=-1)
 
 
-def lang_reward(params, e0, eg, le):
-    """models_language.py:43-55: 5-layer MLP on cat([e0, eg, le])."""
+def lang_reward(params, e0, eg, le, taps=None):
+    """models_language.py:43-55: 5-layer MLP on cat([e0, eg, le]).  `taps` (a list) collects (layer, pre-activation)
+    of the four hidden layers — used by the tests to find ReLU inputs that sit on the kink to within round-off."""
     h = torch.cat([e0, eg, le], -1)
     for i in range(5):
         h = F.linear(h, params[f"lang_rew.pred.{2 * i}.weight"], params[f"lang_rew.pred.{2 * i}.bias"])
         if i < 4:
+            if taps is not None:
+                taps.append((i, h))
             h = F.relu(h)
     return h.squeeze(-1)
 
 
-def losses(params, alles, perms, hyper, lang_emb=None, lang_mask=None):
+def losses(params, alles, perms, hyper, lang_emb=None, lang_mask=None, lang_taps=None):
     """trainer.py:42-152 given the embeddings.  Returns (full_loss tensor, metrics dict of python floats)."""
     bs = alles.shape[0] // 5
     alle = alles.reshape(bs, 5, -1)
@@ -245,7 +248,7 @@ def losses(params, alles, perms, hyper, lang_emb=None, lang_mask=None):
     full = hyper["l2weight"] * l2loss + hyper["l1weight"] * l1loss
     pi = 0
     if hyper["langweight"] > 0:
-        G = lambda a, b: lang_reward(params, a, b, lang_emb)  # noqa: E731
+        G = lambda a, b: lang_reward(params, a, b, lang_emb, lang_taps)  # noqa: E731
         pos = [G(e0, eg), G(e0, es1), G(e0, es2)]
         negs = [[G(e0, e0)], [G(e0, es0)], [G(e0, es1)]]
         targets = [eg, es1, es2]

@@ -43,6 +43,80 @@ def mostly_close(a, b, rtol=1e-4, max_bad_rows=0.02):
     return float(bad.double().mean()), err
 
 
+def _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, metrics, nclips):
+    """Metrics, dE and the language-head gradients against the fp32 oracle evaluated on OUR embeddings.
+
+    The head is piecewise linear.  A hidden pre-activation that is zero to within fp32 round-off (about 1e-7 of the
+    layer's scale; expected count over 15*B*4096 units is ~0.1-0.5 per run, and it moves from run to run with the
+    atomics-ordered BN statistics) is 'on' in one summation order and 'off' in another; either side is a valid gradient
+    of the reference function, but the flip perturbs every gradient below that layer by ~1e-3.  So: compare as is;
+    if that fails, enumerate the sign choices of the (few) pre-activations inside the round-off band — forced through a
+    <=4e-6-relative bias nudge in the oracle — and require an exact match with ONE of them."""
+    import itertools
+
+    from oracle import r3m_oracle as O
+
+    lang_keys = [k for k in params if k.startswith("lang_rew")]
+
+    def evaluate(nudges):
+        e = emb.clone().requires_grad_(True)
+        lp = {k: params[k].clone() for k in lang_keys}
+        for (layer, unit), shift in nudges.items():
+            lp[f"lang_rew.pred.{2 * layer}.bias"][unit] += shift
+        for v in lp.values():
+            v.requires_grad_(True)
+        taps = []
+        full, same = O.losses(lp, e, perms, hyper, lang_emb, mask, lang_taps=taps)
+        full.backward()
+        return same, e.grad, {k: v.grad for k, v in lp.items()}, taps
+
+    def mismatches(same, e_grad, grads):
+        out = []
+        for k, v in same.items():
+            if k.startswith("rewacc") or k == "aligned":
+                # means of strict comparisons between scores: an exact tie-break may differ by one clip
+                if abs(metrics[k] - v) > 1.0 / nclips + 1e-6:
+                    out.append((k, metrics[k], v))
+            elif abs(metrics[k] - v) > 1e-4 * max(abs(v), 1e-6):
+                out.append((k, metrics[k], v))
+        bad, err = mostly_close(eng.embedding_grads(), e_grad)
+        if not (bad <= 0.25 and err < 1e-4):
+            out.append(("dE", bad, err))
+        for k, g in grads.items():
+            if k.endswith("pred.8.bias"):
+                d = float((named[k].grad.cpu() - g).abs().max())  # true value cancels to ~eps
+                if d >= 1e-6:
+                    out.append((k, d))
+            else:
+                bad, err = mostly_close(named[k].grad, g, rtol=1e-3)
+                if not (bad <= 0.02 and err < 1e-3):
+                    out.append((k, bad, err))
+        return out
+
+    same, e_grad, grads, taps = evaluate({})
+    first = mismatches(same, e_grad, grads)
+    if not first:
+        return
+    # pre-activations inside the round-off band (identical (e0, e_t) rows occur in several evaluations: dedupe)
+    band = 2e-6
+    cands = {}
+    for layer, pre in taps:
+        pre = pre.detach()
+        rms = float(pre.pow(2).mean().sqrt())
+        for b, j in (pre.abs() < band * rms).nonzero().tolist():
+            cands.setdefault((layer, j, round(float(pre[b, j]) / (rms * 1e-9))), (layer, j, float(pre[b, j]), rms))
+    cands = list(cands.values())
+    assert cands, ("loss heads differ from the oracle and no ReLU input is within round-off of its kink", first)
+    assert len(cands) <= 4, ("too many ReLU inputs on the kink to enumerate", len(cands), first)
+    for signs in itertools.product((1.0, -1.0), repeat=len(cands)):
+        nudges = {}
+        for (layer, j, pre, rms), sg in zip(cands, signs):
+            nudges[(layer, j)] = -pre + sg * 2.0 * band * rms
+        if not mismatches(*evaluate(nudges)[:3]):
+            return
+    raise AssertionError(("loss heads match the oracle on neither side of the near-kink ReLU inputs", cands, first))
+
+
 def _case(name):
     from oracle import r3m_oracle as O
 
@@ -133,26 +207,8 @@ def test_update_against_reference_golden(name):
         assert abs(metrics[k] - gold[k]) <= 5e-3 * abs(gold[k]), (k, metrics[k], gold[k])
 
     # ---- loss heads on identical embeddings: the north star's 1e-4
-    e = emb.clone().requires_grad_(True)
-    lp = {k: v.clone().requires_grad_(True) for k, v in params.items() if k.startswith("lang_rew")}
-    full, same = O.losses(lp, e, perms, hyper, lang_emb, mask)
-    full.backward()
-    nclips = case["clips"]
-    for k, v in same.items():
-        if k.startswith("rewacc") or k == "aligned":
-            # means of strict comparisons between scores: an exact tie-break may differ by one clip
-            assert abs(metrics[k] - v) <= 1.0 / nclips + 1e-6, (k, metrics[k], v)
-        else:
-            assert abs(metrics[k] - v) <= 1e-4 * max(abs(v), 1e-6), (k, metrics[k], v)
-    bad, err = mostly_close(eng.embedding_grads(), e.grad)
-    assert bad <= 0.25 and err < 1e-4, (bad, err)
     named = dict(m.named_parameters())
-    for k, v in lp.items():
-        if k.endswith("pred.8.bias"):
-            assert float((named[k].grad.cpu() - v.grad).abs().max()) < 1e-6  # true value cancels to ~eps
-        else:
-            bad, err = mostly_close(named[k].grad, v.grad, rtol=1e-3)
-            assert bad <= 0.02 and err < 1e-3, (k, bad, err)
+    _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, metrics, case["clips"])
 
     # ---- backward through the network: deviation profile vs the same-policy oracle
     o_params = {k: v.clone() for k, v in params.items()}
