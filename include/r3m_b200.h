@@ -91,13 +91,20 @@ int r3m_b200_bn_backward(const void* dA, const void* a, const uint8_t* mask, con
                          const float* gamma2, float* sums2, void* dy2, float* dgamma2, float* dbeta2, void* stream);
 
 /* Stem tail: BN + ReLU + MaxPool2d(3,2,1) (tv resnet.py:198-200) and its backward.  y bf16 [N,H,W,C] ->
- * a bf16 [N,H/2,W/2,C] plus the argmax code (0..8, scan order) per output element. */
+ * a bf16 [N,H/2,W/2,C] plus the argmax code per output element (0..8: scan-order window position of the maximum;
+ * 15: the maximum is 0, i.e. clipped by the ReLU, and carries no gradient).  maxpool_backward returns the gradient
+ * w.r.t. the BN output with the ReLU mask applied (`a` is unused and may be null).  stem_backward is the fused form
+ * the engine runs: aten::max_pool2d_with_indices_backward + threshold_backward + cudnn_batch_norm_backward in two
+ * passes that recompute the pooled gradient scatter on the fly (sums: fp32 [2*C] zeroed scratch). */
 int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N, int H, int W, int C, int train,
                                   const float* sum, const float* sq, const float* gamma, const float* beta,
                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd,
                                   void* stream);
 int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
                               void* stream);
+int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y, int N, int H, int W, int C,
+                           const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
+                           float* dgamma, float* dbeta, void* stream);
 
 /* AdaptiveAvgPool2d((1,1)) + flatten (tv resnet.py:278-279) and its backward.  a bf16 [N,HW,C] <-> fp32 [N,C]. */
 int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream);

@@ -291,7 +291,31 @@ int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N
 
 int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
                               void* stream) {
-  CUDA_OR_FAIL(launch_maxpool_bwd(dA, a, argmax, dz, N, H, W, C, (cudaStream_t)stream), "maxpool_backward");
+  (void)a;  // the argmax codes mark ReLU-clipped maxima themselves (code 15); kept in the signature for ABI stability
+  CUDA_OR_FAIL(launch_maxpool_bwd(dA, argmax, dz, N, H, W, C, (cudaStream_t)stream), "maxpool_backward");
+}
+
+int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y, int N, int H, int W, int C,
+                           const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
+                           float* dgamma, float* dbeta, void* stream) {
+  if (!dA || !argmax || !y || !mean || !rstd || !gamma || !sums || !dy)
+    return fail(R3M_B200_ERR_INVALID, "stem_backward: null argument");
+  StemBwdArgs g;
+  g.dA = dA;
+  g.argmax = argmax;
+  g.y = y;
+  g.N = N;
+  g.H = H;
+  g.W = W;
+  g.C = C;
+  g.mean = mean;
+  g.rstd = rstd;
+  g.gamma = gamma;
+  g.sums = sums;
+  g.dy = dy;
+  g.dgamma = dgamma;
+  g.dbeta = dbeta;
+  CUDA_OR_FAIL(launch_stem_bwd(g, (cudaStream_t)stream), "stem_backward");
 }
 
 int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream) {

@@ -23,6 +23,7 @@
 // (stride-1: rotated/transposed filter; stride-2: one launch per output-parity class with scatter stores).
 #include "conv_igemm.cuh"
 
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace r3m {
@@ -98,6 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  pdl_sync();  // everything above is CTA-local; global memory is first touched below
   const bool do_affine = (p.ep_scale != nullptr);
   if (do_stats) {
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
@@ -163,6 +165,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      pdl_done();  // all loads of this CTA are issued
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -434,7 +437,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 

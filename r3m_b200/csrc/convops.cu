@@ -4,9 +4,19 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "launch.h"
 #include "tmap.h"
 
 namespace r3m {
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = std::getenv("R3M_PDL");
+    on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
 
 int device_sm_count() {
   static int sms = 0;

@@ -8,7 +8,9 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace r3m {
@@ -77,6 +79,7 @@ __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const
 // ------------------------------------------------------------------------------------------------ preprocess
 __global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __restrict__ obs, bf16* __restrict__ xs,
                                                               int N) {
+  pdl_sync();
   const long long total = (long long)N * 112 * 112 * 4;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float istd[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------ BN apply
 template <bool kDual, bool kRes>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  pdl_sync();
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
       a.mask_out[row * C8 + chunk] = (uint8_t)bits;
     }
   }
+  pdl_done();
   if (a.train && blockIdx.x == 0) {
     // every block has already read sum/sq into registers for its own coefficients; running stats are separate
     // buffers, so the in-place update below cannot race with other blocks
@@ -185,6 +190,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 }
 
 __global__ void bn_fold_kernel(const BnFoldEntry* __restrict__ table) {
+  pdl_sync();
   const BnFoldEntry e = table[blockIdx.x];
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
     const float sc = e.gamma[c] / sqrtf(e.running_var[c] + kBnEps);
@@ -194,115 +200,294 @@ __global__ void bn_fold_kernel(const BnFoldEntry* __restrict__ table) {
 }
 
 // ------------------------------------------------------------------------------------------------ stem pool
-__global__ void __launch_bounds__(256) stem_pool_kernel(const StemPoolArgs a) {
+// argmax code per pooled element: scan-order index 0..8 of the window position that holds the maximum, or
+// kPoolDead when the maximum is 0 (every input of the window was clipped by the ReLU: no gradient flows).
+constexpr int kPoolDead = 15;
+
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) {
+  __nv_bfloat162 r;
+  *reinterpret_cast<uint32_t*>(&r) = v;
+  return r;
+}
+__device__ __forceinline__ uint32_t as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// The first version ran BN + ReLU in fp32 on all nine taps (700 instructions per 8-channel output; instruction bound
+// at 1.7 TB/s).  relu(sc*y + sh) is monotone in y (increasing for sc >= 0, decreasing for sc < 0), so the window
+// maximum of the activation is the activation of the window maximum of y (minimum for sc < 0: the sign bit of y is
+// flipped for those channels).  The search therefore runs on the raw bf16 pairs with packed compare / max (exact),
+// tracking the first maximum in scan order like ATen's max_pool2d, and the affine + ReLU is applied once.
+__global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
+  pdl_sync();
   const int C8 = a.C >> 3;
   const int P = a.H / 2, Q = a.W / 2;
-  const long long total = (long long)a.N * P * Q * C8;
   const float inv_m = 1.0f / ((float)a.N * a.H * a.W);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   bf16* __restrict__ out = reinterpret_cast<bf16*>(a.a);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(idx % C8);
-    long long t = idx / C8;
-    const int q = (int)(t % Q);
-    t /= Q;
-    const int p = (int)(t % P);
-    const int n = (int)(t / P);
-    float sc[8], sh[8];
+  // One block iteration = one pooled row (n, p); threads stride over (q, chunk) with 32-bit arithmetic only.  blockDim
+  // is a multiple of C8, so a thread keeps its 8-channel chunk and the coefficients are hoisted.
+  const int chunk = threadIdx.x % C8;
+  float sc[8], sh[8];
+  uint32_t flip[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float mean, var;
-      bn_coeffs(a.train, a.sum, a.sq, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j],
-                sh[j], mean, var);
-    }
-    float best[8];
-    int code[8];
+  for (int j = 0; j < 8; ++j) {
+    float mean, var;
+    bn_coeffs(a.train, a.sum, a.sq, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
+              mean, var);
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -1.f;
-      code[j] = 0;
-    }
+  for (int w = 0; w < 4; ++w) flip[w] = (sc[2 * w] < 0.f ? 0x8000u : 0u) | (sc[2 * w + 1] < 0.f ? 0x80000000u : 0u);
+  constexpr uint32_t kNegInf2 = 0xFF80FF80u;
+  for (int row = blockIdx.x; row < a.N * P; row += gridDim.x) {
+    const int n = row / P, p = row - n * P;
+    for (int i = threadIdx.x; i < Q * C8; i += blockDim.x) {
+      const int q = i / C8;
+      const long long idx = (long long)row * (Q * C8) + i;
+      // all nine loads first, from clamped coordinates
+      uint4 f[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * p - 1 + r;
-      if (h < 0 || h >= a.H) continue;
+      for (int r = 0; r < 3; ++r) {
+        const int hc = max(2 * p - 1 + r, 0);  // 2p+1 <= H-1 always (H even)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = 2 * q - 1 + s;
-        if (w < 0 || w >= a.W) continue;
-        const F8 f = ld8(y + (((long long)n * a.H + h) * a.W + w) * a.C + chunk * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = fmaxf(fmaf(f.v[j], sc[j], sh[j]), 0.f);
-          if (v > best[j]) {  // strict: the first maximum in scan order wins, as in ATen's max_pool2d
-            best[j] = v;
-            code[j] = r * 3 + s;
-          }
+        for (int t = 0; t < 3; ++t) {
+          const int wc = max(2 * q - 1 + t, 0);
+          f[r * 3 + t] = __ldg(reinterpret_cast<const uint4*>(y + (((long long)n * a.H + hc) * a.W + wc) * a.C + chunk * 8));
         }
       }
-    }
-    F8 o;
+      uint32_t best[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
+      uint32_t code[4] = {0u, 0u, 0u, 0u};  // one 16-bit code per channel, packed like the values
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
-    st8(out + idx * 8, o);
-    if (a.argmax) {
-      uint2 packed;
-      packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
-      packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
-      *reinterpret_cast<uint2*>(a.argmax + idx * 8) = packed;
+      for (int k = 0; k < 9; ++k) {
+        const bool valid = !((k < 3 && p == 0) || (k % 3 == 0 && q == 0));  // taps at h = -1 / w = -1
+        const uint32_t word[4] = {f[k].x, f[k].y, f[k].z, f[k].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t v = valid ? (word[w] ^ flip[w]) : kNegInf2;
+          const uint32_t gt = __hgt2_mask(as_bf162(v), as_bf162(best[w]));  // strict: the first maximum wins
+          best[w] = as_u32(__hmax2(as_bf162(best[w]), as_bf162(v)));
+          code[w] = (code[w] & ~gt) | ((uint32_t)(k | (k << 16)) & gt);
+        }
+      }
+      F8 o;
+      int cd[8];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t yb = best[w] ^ flip[w];
+        o.v[2 * w] = fmaxf(fmaf(bf16lo(yb), sc[2 * w], sh[2 * w]), 0.f);
+        o.v[2 * w + 1] = fmaxf(fmaf(bf16hi(yb), sc[2 * w + 1], sh[2 * w + 1]), 0.f);
+        cd[2 * w] = (int)(code[w] & 0xFFu);
+        cd[2 * w + 1] = (int)(code[w] >> 16);
+      }
+      st8(out + idx * 8, o);
+      if (a.argmax) {
+        // "dead" must describe the STORED (bf16-rounded) activation, like the ReLU masks of bn_apply
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(__bfloat162float(__float2bfloat16_rn(o.v[j])) > 0.f)) cd[j] = kPoolDead;
+        uint2 packed;
+        packed.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
+        packed.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+        *reinterpret_cast<uint2*>(a.argmax + idx * 8) = packed;
+      }
     }
   }
+  pdl_done();
   if (a.train && blockIdx.x == 0) {
     bn_publish(a.C, a.N * a.H * a.W, a.sum, a.sq, a.save_mean, a.save_rstd, a.running_mean, a.running_var,
                a.update_running);
   }
 }
 
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ a,
+// Gradient w.r.t. the stem's BatchNorm output (ReLU mask applied) of one 8-channel chunk at conv-output pixel (h, w):
+// the sum over the (up to four) pooling windows that cover the pixel of dA[window] where the window's argmax is (h, w).
+// All eight loads (clamped coordinates) are issued before any use.
+struct PoolGather {
+  const bf16* dA;
+  const uint8_t* argmax;
+  int H, W, P, Q, C;
+};
+__device__ __forceinline__ F8 pool_gather(const PoolGather& g, int n, int h, int w, int chunk) {
+  const int p0 = h >> 1, p1 = (h + 1) >> 1;  // windows p with 2p-1 <= h <= 2p+1
+  const int q0 = w >> 1, q1 = (w + 1) >> 1;
+  const int pc[2] = {p0, min(p1, g.P - 1)};
+  const int qc[2] = {q0, min(q1, g.Q - 1)};
+  const bool pv[2] = {true, p1 != p0 && p1 < g.P};
+  const bool qv[2] = {true, q1 != q0 && q1 < g.Q};
+  uint2 codes[4];
+  F8 gr[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long o = (((long long)n * g.P + pc[i]) * g.Q + qc[k]) * g.C + chunk * 8;
+      codes[i * 2 + k] = __ldg(reinterpret_cast<const uint2*>(g.argmax + o));
+      gr[i * 2 + k] = ld8(g.dA + o);
+    }
+  F8 acc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      // position of (h, w) inside window (p, q); an invalid window can match no code
+      const int my = (pv[i] && qv[k]) ? (h - (2 * pc[i] - 1)) * 3 + (w - (2 * qc[k] - 1)) : 255;
+      const uint2 cd = codes[i * 2 + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cj = (j < 4 ? (cd.x >> (8 * j)) : (cd.y >> (8 * (j - 4)))) & 0xFF;
+        acc.v[j] += (cj == my) ? gr[i * 2 + k].v[j] : 0.f;
+      }
+    }
+  return acc;
+}
+
+__global__ void __launch_bounds__(224) maxpool_bwd_kernel(const bf16* __restrict__ dA,
                                                           const uint8_t* __restrict__ argmax, bf16* __restrict__ dz,
                                                           int N, int H, int W, int C) {
+  pdl_sync();
   const int C8 = C >> 3;
-  const int P = H / 2, Q = W / 2;
-  const long long total = (long long)N * H * W * C8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(idx % C8);
-    long long t = idx / C8;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    F8 acc;
+  const PoolGather g{dA, argmax, H, W, H / 2, W / 2, C};
+  const int chunk = threadIdx.x % C8;  // blockDim is a multiple of C8
+  for (int row = blockIdx.x; row < N * H; row += gridDim.x)
+    for (int i = threadIdx.x; i < W * C8; i += blockDim.x) {
+      const int n = row / H, h = row - n * H;
+      st8(dz + ((long long)row * (W * C8) + i) * 8, pool_gather(g, n, h, i / C8, chunk));
+    }
+}
+
+// Stem backward, fused: maxpool backward + ReLU mask are recomputed on the fly from (dA_pool, argmax) inside both
+// passes of the BatchNorm backward, so the [N,112,112,64] masked gradient is never written or re-read.
+//   pass 1 (kApply = false): sums[c] += dz, sums[C + c] += dz * xhat
+//   pass 2 (kApply = true) : dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); block 0 publishes dgamma, dbeta
+// A thread owns the 2x2 input quad (2k+dh, 2m+dw) of one 8-channel chunk.  Exactly the four pooling windows
+// (k+i, m+j), i, j in {0, 1}, cover the quad, and the argmax code that selects pixel (dh, dw) from window (i, j) is the
+// compile-time constant (dh + 1 - 2i) * 3 + (dw + 1 - 2j): nine (window, pixel) pairs per channel instead of sixteen
+// per-pixel gathers, and the window loads are shared by the four pixels (the per-pixel gather was instruction bound:
+// 360 instructions per 8 channels, 1.5 TB/s).
+template <bool kApply>
+__global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
+  pdl_sync();
+  __shared__ float s_red[2 * 256];  // C <= 256
+  const int C8 = a.C >> 3;
+  const int P = a.H / 2, Q = a.W / 2;
+  const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
+  const uint8_t* __restrict__ am = a.argmax;
+  const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
+  bf16* __restrict__ dy = reinterpret_cast<bf16*>(a.dy);
+  const int chunk = threadIdx.x % C8;  // blockDim is a multiple of C8
+  const float inv_m = 1.0f / ((float)a.N * a.H * a.W);
+  float c0[8], c1[8], c2[8];  // reduce: mean, s1, s2;  apply: cA, cB, cC
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-    // windows p with 2p-1 <= h <= 2p+1
-    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;
-    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
-    for (int p = p_lo; p <= p_hi; ++p) {
-      if (p >= P) continue;
-      const int r = h - (2 * p - 1);
-      for (int q = q_lo; q <= q_hi; ++q) {
-        if (q >= Q) continue;
-        const int s = w - (2 * q - 1);
-        const int my = r * 3 + s;
-        const long long o = (((long long)n * P + p) * Q + q) * C + chunk * 8;
-        const uint2 codes = *reinterpret_cast<const uint2*>(argmax + o);
-        const F8 g = ld8(dA + o);
-        const F8 act = ld8(a + o);
+  for (int j = 0; j < 8; ++j) {
+    const int c = chunk * 8 + j;
+    if (kApply) {
+      const float mean = a.mean[c], rstd = a.rstd[c];
+      const float mdz = a.sums[c] * inv_m, mdzx = a.sums[a.C + c] * inv_m;
+      c0[j] = a.gamma[c] * rstd;
+      c1[j] = -c0[j] * rstd * mdzx;
+      c2[j] = -c0[j] * mdz - c1[j] * mean;
+    } else {
+      c0[j] = a.mean[c];
+      c1[j] = 0.f;
+      c2[j] = 0.f;
+    }
+  }
+  if (!kApply) {
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+  }
+  for (int row = blockIdx.x; row < a.N * P; row += gridDim.x) {
+    const int n = row / P, k = row - n * P;
+    for (int it = threadIdx.x; it < Q * C8; it += blockDim.x) {
+      const int m = it / C8;
+      // ---- all loads first: 4 input pixels, 4 windows (clamped; out-of-range windows are disabled below)
+      const int k1 = min(k + 1, P - 1), m1 = min(m + 1, Q - 1);
+      const long long ybase = (((long long)n * a.H + 2 * k) * a.W + 2 * m) * a.C + chunk * 8;
+      uint4 yv[4];
+      yv[0] = __ldg(reinterpret_cast<const uint4*>(y + ybase));
+      yv[1] = __ldg(reinterpret_cast<const uint4*>(y + ybase + a.C));
+      yv[2] = __ldg(reinterpret_cast<const uint4*>(y + ybase + (long long)a.W * a.C));
+      yv[3] = __ldg(reinterpret_cast<const uint4*>(y + ybase + (long long)a.W * a.C + a.C));
+      const long long w00 = (((long long)n * P + k) * Q + m) * a.C + chunk * 8;
+      const long long w01 = (((long long)n * P + k) * Q + m1) * a.C + chunk * 8;
+      const long long w10 = (((long long)n * P + k1) * Q + m) * a.C + chunk * 8;
+      const long long w11 = (((long long)n * P + k1) * Q + m1) * a.C + chunk * 8;
+      uint2 cw[4];
+      uint4 gw[4];
+      cw[0] = __ldg(reinterpret_cast<const uint2*>(am + w00));
+      cw[1] = __ldg(reinterpret_cast<const uint2*>(am + w01));
+      cw[2] = __ldg(reinterpret_cast<const uint2*>(am + w10));
+      cw[3] = __ldg(reinterpret_cast<const uint2*>(am + w11));
+      gw[0] = __ldg(reinterpret_cast<const uint4*>(dA + w00));
+      gw[1] = __ldg(reinterpret_cast<const uint4*>(dA + w01));
+      gw[2] = __ldg(reinterpret_cast<const uint4*>(dA + w10));
+      gw[3] = __ldg(reinterpret_cast<const uint4*>(dA + w11));
+      // a window beyond the last pooled row / column selects nothing: 0xFF matches no code
+      if (m + 1 >= Q) cw[1] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (k + 1 >= P) cw[2] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (m + 1 >= Q || k + 1 >= P) cw[3] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      // ---- masked gradient of the four pixels: dz[dh * 2 + dw][channel]
+      float dz[4][8];
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        const int i = wi >> 1, jw = wi & 1;
+        const uint32_t gwords[4] = {gw[wi].x, gw[wi].y, gw[wi].z, gw[wi].w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int cj = (j < 4 ? (codes.x >> (8 * j)) : (codes.y >> (8 * (j - 4)))) & 0xFF;
-          if (cj == my && act.v[j] > 0.f) acc.v[j] += g.v[j];
+          const uint32_t cj = ((j < 4 ? cw[wi].x : cw[wi].y) >> (8 * (j & 3))) & 0xFFu;
+          const float g = (j & 1) ? bf16hi(gwords[j >> 1]) : bf16lo(gwords[j >> 1]);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const int dh = px >> 1, dw = px & 1;
+            const int r = dh + 1 - 2 * i, t = dw + 1 - 2 * jw;  // position of the pixel inside the window
+            if (wi == 0) dz[px][j] = 0.f;
+            if (r >= 0 && t >= 0) dz[px][j] += (cj == (uint32_t)(r * 3 + t)) ? g : 0.f;
+          }
+        }
+      }
+      // ---- consume
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const uint32_t ywords[4] = {yv[px].x, yv[px].y, yv[px].z, yv[px].w};
+        if (kApply) {
+          F8 o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float yy = (j & 1) ? bf16hi(ywords[j >> 1]) : bf16lo(ywords[j >> 1]);
+            o.v[j] = fmaf(c0[j], dz[px][j], fmaf(c1[j], yy, c2[j]));
+          }
+          st8(dy + ybase + (long long)(px >> 1) * a.W * a.C + (px & 1) * a.C, o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float yy = (j & 1) ? bf16hi(ywords[j >> 1]) : bf16lo(ywords[j >> 1]);
+            c1[j] += dz[px][j];
+            c2[j] = fmaf(dz[px][j], yy - c0[j], c2[j]);
+          }
         }
       }
     }
-    st8(dz + idx * 8, acc);
+  }
+  pdl_done();
+  if (!kApply) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_red[chunk * 8 + j], c1[j]);
+      atomicAdd(&s_red[a.C + chunk * 8 + j], c2[j] * a.rstd[chunk * 8 + j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
+  } else if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      if (a.dbeta) a.dbeta[c] = a.sums[c];
+      if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ avg pool
 __global__ void avgpool_fwd_kernel(const bf16* __restrict__ a, float* __restrict__ out, int HW, int C) {
+  pdl_sync();
   const int n = blockIdx.x;
   const float inv = 1.0f / (float)HW;
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
@@ -320,6 +505,7 @@ __global__ void avgpool_fwd_kernel(const bf16* __restrict__ a, float* __restrict
 
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dE, bf16* __restrict__ dA, int N,
                                                           int HW, int C) {
+  pdl_sync();
   const int C8 = C >> 3;
   const long long total = (long long)N * HW * C8;
   const float inv = 1.0f / (float)HW;
@@ -360,6 +546,7 @@ __device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bit
 
 template <bool kDual, int kMask>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  pdl_sync();
   extern __shared__ float s_red[];  // [3][C]: sum(dz), sum(dz*xhat), sum(dz*xhat2)
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
@@ -367,13 +554,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const int r0 = threadIdx.x / C8;
   for (int i = threadIdx.x; i < 3 * a.C; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
-  float mean[8], rstd[8], mean2[8], rstd2[8], s1[8], s2[8], s3[8];
+  // s2 / s3 accumulate sum(dz * (y - mean)); the 1/std factor is applied once at the end
+  float mean[8], mean2[8], s1[8], s2[8], s3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mean[j] = a.mean[chunk * 8 + j];
-    rstd[j] = a.rstd[chunk * 8 + j];
     mean2[j] = kDual ? a.mean2[chunk * 8 + j] : 0.f;
-    rstd2[j] = kDual ? a.rstd2[chunk * 8 + j] : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
     s3[j] = 0.f;
@@ -383,6 +569,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const uint8_t* __restrict__ mask = a.mask;
+#pragma unroll 2
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
@@ -398,15 +585,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s1[j] += g.v[j];
-      s2[j] = fmaf(g.v[j], (yy.v[j] - mean[j]) * rstd[j], s2[j]);
-      if (kDual) s3[j] = fmaf(g.v[j], (t.v[j] - mean2[j]) * rstd2[j], s3[j]);
+      s2[j] = fmaf(g.v[j], yy.v[j] - mean[j], s2[j]);
+      if (kDual) s3[j] = fmaf(g.v[j], t.v[j] - mean2[j], s3[j]);
     }
   }
+  pdl_done();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(&s_red[chunk * 8 + j], s1[j]);
-    atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j]);
-    if (kDual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j]);
+    atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j] * a.rstd[chunk * 8 + j]);
+    if (kDual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j] * a.rstd2[chunk * 8 + j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
@@ -416,24 +604,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
 
 template <bool kDual, int kMask, bool kDz>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  pdl_sync();
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
-  float mean[8], rstd[8], grs[8], mdz[8], mdzx[8], mean2[8], rstd2[8], grs2[8], mdzx2[8];
+  // dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat)),  xhat = (y - mean) * rstd
+  //    = cA * dz + cB * y + cC   with per-channel constants (three registers per channel instead of five)
+  float cA[8], cB[8], cC[8], cA2[8], cB2[8], cC2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    mean[j] = a.mean[c];
-    rstd[j] = a.rstd[c];
-    grs[j] = a.gamma[c] * rstd[j];
-    mdz[j] = a.sums[c] * inv_m;
-    mdzx[j] = a.sums[a.C + c] * inv_m;
-    mean2[j] = kDual ? a.mean2[c] : 0.f;
-    rstd2[j] = kDual ? a.rstd2[c] : 0.f;
-    grs2[j] = kDual ? a.gamma2[c] * rstd2[j] : 0.f;
-    mdzx2[j] = kDual ? a.sums2[c] * inv_m : 0.f;
+    const float mean = a.mean[c], rstd = a.rstd[c];
+    const float mdz = a.sums[c] * inv_m, mdzx = a.sums[a.C + c] * inv_m;
+    cA[j] = a.gamma[c] * rstd;
+    cB[j] = -cA[j] * rstd * mdzx;
+    cC[j] = -cA[j] * mdz - cB[j] * mean;
+    if (kDual) {
+      const float mean2 = a.mean2[c], rstd2 = a.rstd2[c];
+      const float mdzx2 = a.sums2[c] * inv_m;
+      cA2[j] = a.gamma2[c] * rstd2;
+      cB2[j] = -cA2[j] * rstd2 * mdzx2;
+      cC2[j] = -cA2[j] * mdz - cB2[j] * mean2;
+    } else {
+      cA2[j] = cB2[j] = cC2[j] = 0.f;
+    }
   }
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
   const bf16* __restrict__ act = reinterpret_cast<const bf16*>(a.a);
@@ -443,6 +639,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   bf16* __restrict__ dy = reinterpret_cast<bf16*>(a.dy);
   bf16* __restrict__ dy2 = reinterpret_cast<bf16*>(a.dy2);
   bf16* __restrict__ dzo = reinterpret_cast<bf16*>(a.dz_out);
+#pragma unroll 2
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
@@ -457,20 +654,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     if (kDz) st8(dzo + off, g);
     F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (yy.v[j] - mean[j]) * rstd[j];
-      o.v[j] = grs[j] * (g.v[j] - mdz[j] - xhat * mdzx[j]);
-    }
+    for (int j = 0; j < 8; ++j) o.v[j] = fmaf(cA[j], g.v[j], fmaf(cB[j], yy.v[j], cC[j]));
     st8(dy + off, o);
     if (kDual) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xhat = (t.v[j] - mean2[j]) * rstd2[j];
-        o.v[j] = grs2[j] * (g.v[j] - mdz[j] - xhat * mdzx2[j]);
-      }
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(cA2[j], g.v[j], fmaf(cB2[j], t.v[j], cC2[j]));
       st8(dy2 + off, o);
     }
   }
+  pdl_done();
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = a.sums[c];
@@ -488,6 +680,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    bf16* __restrict__ pb, size_t n, float lr, float beta1, float beta2,
                                                    float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  pdl_sync();
   const float step_size = lr / bc1;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -504,6 +697,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
                                                         size_t n) {
+  pdl_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -514,6 +708,7 @@ struct TapList {
 };
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int T, int Cin, int nt,
                                   TapList taps) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int src = taps.t[t];
@@ -538,6 +733,7 @@ __device__ __forceinline__ bool stem_map(int k, int rr, int j, int& oihw) {
   return true;
 }
 __global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp) {
+  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 64 * 4 * 64) return;
   const int j = idx & 63, rr = (idx >> 6) & 3, k = idx >> 8;
@@ -545,6 +741,7 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__
   wp[idx] = __float2bfloat16_rn(stem_map(k, rr, j, o) ? w[o] : 0.f);
 }
 __global__ void stem_unpack_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
+  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 64 * 4 * 64) return;
   const int j = idx & 63, rr = (idx >> 6) & 3, k = idx >> 8;
@@ -558,58 +755,94 @@ inline int grid_for(long long work_items, int threads, int max_blocks) {
   return (int)std::min<long long>(b, max_blocks);
 }
 
+// Grid-stride kernels run as ONE resident wave: SMs x (CTAs per SM the kernel's registers / shared memory allow).  A
+// fixed cap of 8 CTAs per SM gave 72-120-register kernels 2.7-4 unequal waves (measured 4.0 vs 5.5 TB/s).
+// R3M_GRID_WAVES (experiments) scales the wave count.
+template <auto Kernel>
+int resident_blocks(int threads, size_t smem = 0) {
+  static int blocks = 0;
+  if (blocks == 0) {
+    int occ = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    const char* e = std::getenv("R3M_GRID_WAVES");
+    const int waves = e ? std::max(1, atoi(e)) : 1;
+    blocks = occ * sms * waves;
+  }
+  return blocks;
+}
+
 }  // namespace
 
 cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream_t s) {
   const long long total = (long long)N * 112 * 112 * 4;
-  preprocess_stem_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(obs, reinterpret_cast<bf16*>(xs), N);
+  launch_kernel(preprocess_stem_kernel, grid_for(total, 256, 148 * 16), 256, 0, s, obs, reinterpret_cast<bf16*>(xs), N);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bn_fold(const BnFoldEntry* table_dev, int entries, cudaStream_t s) {
-  bn_fold_kernel<<<entries, 256, 0, s>>>(table_dev);
+  launch_kernel(bn_fold_kernel, entries, 256, 0, s, table_dev);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  const int blocks = grid_for(a.M, rows_per_iter, 148 * 8);
   if (a.y2 && a.residual) return cudaErrorInvalidValue;  // a block tail has either an identity or a downsample branch
+#define R3M_LAUNCH(D, R)                                                                              \
+  launch_kernel(bn_apply_kernel<D, R>, grid_for(a.M, rows_per_iter, resident_blocks<bn_apply_kernel<D, R>>(256)), \
+                256, 0, s, a)
   if (a.y2)
-    bn_apply_kernel<true, false><<<blocks, 256, 0, s>>>(a);
+    R3M_LAUNCH(true, false);
   else if (a.residual)
-    bn_apply_kernel<false, true><<<blocks, 256, 0, s>>>(a);
+    R3M_LAUNCH(false, true);
   else
-    bn_apply_kernel<false, false><<<blocks, 256, 0, s>>>(a);
+    R3M_LAUNCH(false, false);
+#undef R3M_LAUNCH
   return cudaGetLastError();
 }
+
+// Stem kernels: 224 threads = 28 pixels x 8 chunks, so a 112-pixel row is exactly 4 (56: 2) block iterations.
+constexpr int kStemThreads = 224;
 
 cudaError_t launch_stem_bn_relu_maxpool(const StemPoolArgs& a, cudaStream_t s) {
-  if (a.C % 8 != 0 || (a.H & 1) || (a.W & 1)) return cudaErrorInvalidValue;
-  const long long total = (long long)a.N * (a.H / 2) * (a.W / 2) * (a.C / 8);
-  stem_pool_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(a);
+  if (a.C % 8 != 0 || kStemThreads % (a.C / 8) != 0 || (a.H & 1) || (a.W & 1)) return cudaErrorInvalidValue;
+  const int rows = a.N * (a.H / 2);
+  launch_kernel(stem_pool_kernel, std::min(rows, resident_blocks<stem_pool_kernel>(kStemThreads)), kStemThreads, 0, s, a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_maxpool_bwd(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W,
-                               int C, cudaStream_t s) {
-  const long long total = (long long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(dA), reinterpret_cast<const bf16*>(a), argmax, reinterpret_cast<bf16*>(dz), N, H, W,
-      C);
+cudaError_t launch_maxpool_bwd(const void* dA, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
+                               cudaStream_t s) {
+  if (C % 8 != 0 || kStemThreads % (C / 8) != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  launch_kernel(maxpool_bwd_kernel, std::min(N * H, resident_blocks<maxpool_bwd_kernel>(kStemThreads)), kStemThreads, 0,
+                s, reinterpret_cast<const bf16*>(dA), argmax, reinterpret_cast<bf16*>(dz), N, H, W, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s) {
+  if (a.C % 8 != 0 || a.C > 256 || kStemThreads % (a.C / 8) != 0 || (a.H & 1) || (a.W & 1))
+    return cudaErrorInvalidValue;
+  const int rows = a.N * (a.H / 2);  // one block iteration = one row of 2x2 quads
+  launch_kernel(stem_bwd_kernel<false>, std::min(rows, resident_blocks<stem_bwd_kernel<false>>(kStemThreads)),
+                kStemThreads, 0, s, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  launch_kernel(stem_bwd_kernel<true>, std::min(rows, resident_blocks<stem_bwd_kernel<true>>(kStemThreads)),
+                kStemThreads, 0, s, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_avgpool_fwd(const void* a, float* out, int N, int HW, int C, cudaStream_t s) {
   const int threads = std::min(1024, std::max(32, C / 2));
-  avgpool_fwd_kernel<<<N, threads, 0, s>>>(reinterpret_cast<const bf16*>(a), out, HW, C);
+  launch_kernel(avgpool_fwd_kernel, N, threads, 0, s, reinterpret_cast<const bf16*>(a), out, HW, C);
   return cudaGetLastError();
 }
 
 cudaError_t launch_avgpool_bwd(const float* dE, void* dA, int N, int HW, int C, cudaStream_t s) {
   const long long total = (long long)N * HW * (C / 8);
-  avgpool_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(dE, reinterpret_cast<bf16*>(dA), N, HW, C);
+  launch_kernel(avgpool_bwd_kernel, grid_for(total, 256, 148 * 16), 256, 0, s, dE, reinterpret_cast<bf16*>(dA), N, HW, C);
   return cudaGetLastError();
 }
 
@@ -620,11 +853,13 @@ inline int mask_kind(const BnBwdArgs& a) { return a.a ? kMaskAct : (a.mask ? kMa
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  // several rows per thread so that the shared/global atomics are amortised
-  const int blocks = grid_for((a.M + 15) / 16, rows_per_iter, 148 * 4);
+  // at least two rows per thread (the loop is unrolled by two), otherwise one resident wave
   const size_t smem = 3 * a.C * sizeof(float);
   const bool dual = a.y2 != nullptr;
-#define R3M_LAUNCH(D, K) bn_bwd_reduce_kernel<D, K><<<blocks, 256, smem, s>>>(a)
+#define R3M_LAUNCH(D, K)                                                                     \
+  launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                  \
+                grid_for((a.M + 1) / 2, rows_per_iter, resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem)), 256, \
+                smem, s, a)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
     case kMaskBits: if (dual) R3M_LAUNCH(true, kMaskBits); else R3M_LAUNCH(false, kMaskBits); break;
@@ -637,12 +872,14 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  const int blocks = grid_for(a.M, rows_per_iter, 148 * 8);
   const bool dual = a.y2 != nullptr, dz = a.dz_out != nullptr;
-#define R3M_LAUNCH(D, K)                                                  \
-  do {                                                                    \
-    if (dz) bn_bwd_apply_kernel<D, K, true><<<blocks, 256, 0, s>>>(a);    \
-    else bn_bwd_apply_kernel<D, K, false><<<blocks, 256, 0, s>>>(a);      \
+#define R3M_LAUNCH1(D, K, Z)                                                                                      \
+  launch_kernel(bn_bwd_apply_kernel<D, K, Z>,                                                                     \
+                grid_for(a.M, rows_per_iter, resident_blocks<bn_bwd_apply_kernel<D, K, Z>>(256)), 256, 0, s, a)
+#define R3M_LAUNCH(D, K)            \
+  do {                              \
+    if (dz) R3M_LAUNCH1(D, K, true); \
+    else R3M_LAUNCH1(D, K, false);  \
   } while (0)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
@@ -650,6 +887,7 @@ cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
     default: if (dual) R3M_LAUNCH(true, kMaskNone); else R3M_LAUNCH(false, kMaskNone); break;
   }
 #undef R3M_LAUNCH
+#undef R3M_LAUNCH1
   return cudaGetLastError();
 }
 
@@ -657,13 +895,13 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf
                         float beta2, float eps, int step, float grad_scale, cudaStream_t s) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid_for((long long)n, 256, 148 * 16), 256, 0, s>>>(p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, lr,
+  launch_kernel(adam_kernel, grid_for((long long)n, 256, 148 * 16), 256, 0, s, p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, lr,
                                                                     beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
   return cudaGetLastError();
 }
 
 cudaError_t launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t s) {
-  cast_bf16_kernel<<<grid_for((long long)n, 256, 148 * 16), 256, 0, s>>>(src, reinterpret_cast<bf16*>(dst), n);
+  launch_kernel(cast_bf16_kernel, grid_for((long long)n, 256, 148 * 16), 256, 0, s, src, reinterpret_cast<bf16*>(dst), n);
   return cudaGetLastError();
 }
 
@@ -673,17 +911,17 @@ cudaError_t launch_pack_dgrad(const float* w, void* out, int Cout, int T, int Ci
   TapList taps;
   for (int i = 0; i < 16; ++i) taps.t[i] = i < nt ? src_tap[i] : 0;
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, nt);
-  pack_dgrad_kernel<<<grid, dim3(32, 8), 0, s>>>(w, reinterpret_cast<bf16*>(out), Cout, T, Cin, nt, taps);
+  launch_kernel(pack_dgrad_kernel, grid, dim3(32, 8), 0, s, w, reinterpret_cast<bf16*>(out), Cout, T, Cin, nt, taps);
   return cudaGetLastError();
 }
 
 cudaError_t launch_stem_pack(const float* w_oihw, void* wp_bf16, cudaStream_t s) {
-  stem_pack_kernel<<<64, 256, 0, s>>>(w_oihw, reinterpret_cast<bf16*>(wp_bf16));
+  launch_kernel(stem_pack_kernel, 64, 256, 0, s, w_oihw, reinterpret_cast<bf16*>(wp_bf16));
   return cudaGetLastError();
 }
 
 cudaError_t launch_stem_unpack_grad(const float* dwp, float* dw_oihw, cudaStream_t s) {
-  stem_unpack_grad_kernel<<<64, 256, 0, s>>>(dwp, dw_oihw);
+  launch_kernel(stem_unpack_grad_kernel, 64, 256, 0, s, dwp, dw_oihw);
   return cudaGetLastError();
 }
 

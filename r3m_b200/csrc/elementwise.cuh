@@ -62,9 +62,26 @@ struct StemPoolArgs {
   int update_running = 1;
 };
 cudaError_t launch_stem_bn_relu_maxpool(const StemPoolArgs& a, cudaStream_t s);
-// dz[n,h,w,c] = sum over pooling windows whose argmax is (h,w) of dA[window] * (a[window] > 0)
-cudaError_t launch_maxpool_bwd(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W,
-                               int C, cudaStream_t s);
+// dz[n,h,w,c] = sum over pooling windows whose argmax is (h,w) of dA[window]   (dead maxima carry code 15: no match)
+cudaError_t launch_maxpool_bwd(const void* dA, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
+                               cudaStream_t s);
+
+// Stem backward in two launches: maxpool backward + ReLU mask recomputed from (dA, argmax) inside the BatchNorm
+// backward's reduce and apply passes (the masked [N,H,W,C] gradient is never materialised).
+struct StemBwdArgs {
+  const void* dA = nullptr;        // bf16 [N,H/2,W/2,C] gradient w.r.t. the pooled output
+  const uint8_t* argmax = nullptr; // [N,H/2,W/2,C] codes written by launch_stem_bn_relu_maxpool
+  const void* y = nullptr;         // bf16 [N,H,W,C] raw stem conv output
+  int N = 0, H = 112, W = 112, C = 64;
+  const float* mean = nullptr;
+  const float* rstd = nullptr;
+  const float* gamma = nullptr;
+  float* sums = nullptr;           // [2][C] zeroed scratch
+  void* dy = nullptr;              // bf16 [N,H,W,C]
+  float* dgamma = nullptr;
+  float* dbeta = nullptr;
+};
+cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s);
 
 cudaError_t launch_avgpool_fwd(const void* a, float* out, int N, int HW, int C, cudaStream_t s);
 cudaError_t launch_avgpool_bwd(const float* dE, void* dA, int N, int HW, int C, cudaStream_t s);

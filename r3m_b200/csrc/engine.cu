@@ -636,15 +636,25 @@ std::string Engine::plan_all() {
     if (!err.empty()) return err;
   }
   {
-    // stem: maxpool backward (+ReLU mask) -> BN backward -> filter gradient (no data gradient needed)
+    // stem: maxpool backward + ReLU mask + BN backward fused in two passes -> filter gradient (no data gradient)
     Conv& st = *convs_[0];
-    const bf16* dpool = d_out;
-    const bf16* apool = st.a;
-    bf16* dz = s1;
-    bwd_.push_back(Op([dpool, apool, argmax, dz, N](cudaStream_t s) {
-      return launch_maxpool_bwd(dpool, apool, argmax, dz, N, 112, 112, 64, s);
-    }, kFamPool, 0.0, (double)N * 64 * (56.0 * 56 * 5 + 112.0 * 112 * 2)));
-    push_bn_bwd(st, s1, nullptr, s2, nullptr, nullptr, nullptr);
+    StemBwdArgs sb;
+    sb.dA = d_out;
+    sb.argmax = argmax;
+    sb.y = st.y;
+    sb.N = N;
+    sb.mean = saved + st.save_off;
+    sb.rstd = saved + st.save_off + 64;
+    sb.gamma = P + st.gamma_off;
+    sb.sums = zero + st.zero_off + 2 * 64;
+    sb.dy = s2;
+    sb.dgamma = G + st.gamma_off;
+    sb.dbeta = G + st.beta_off;
+    // algorithmic bytes: y read twice, pooled gradient + argmax codes read twice, dy written once
+    bwd_.push_back(Op([sb](cudaStream_t s) { return launch_stem_bwd(sb, s); }, kFamNorm, 0.0,
+                      (double)N * 64 * (112.0 * 112 * 6 + 56.0 * 56 * 6)));
+    bwd_.back().label = "stem_bwd (maxpool + relu + bn1 backward, 2 launches)";
+    bwd_.back().nlaunch = 2;
     WgradDesc d;
     d.dy = s2;
     d.x = xs;
@@ -711,7 +721,7 @@ std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
 }
 
 cudaError_t Engine::launch(const Op& op, cudaStream_t stream) {
-  ++launches_;
+  launches_ += op.nlaunch;
   if (!profiling_) return op.fn(stream);
   cudaEvent_t a, b;
   cudaEventCreate(&a);

@@ -87,6 +87,7 @@ class Engine {
     double flops = 0.0;  // algorithmic FLOPs (2*MAC) of the launch
     double bytes = 0.0;  // algorithmic HBM bytes (operands read once + results written once)
     std::string label;   // what the launch is (layer / role), for the per-launch profile
+    int nlaunch = 1;     // kernels the op launches (fused two-pass ops count both)
     Op() {}
     template <class F>
     Op(F f, int fam = 0, double fl = 0.0, double by = 0.0) : fn(f), family(fam), flops(fl), bytes(by) {}

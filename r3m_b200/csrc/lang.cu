@@ -1,6 +1,7 @@
 #include "lang.cuh"
 
 #include "loss.cuh"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace r3m {
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(256) lang_layer1_kernel(const float* __restric
                                                           const float* __restrict__ Lc, const float* __restrict__ b1,
                                                           const int* __restrict__ perms, float* __restrict__ H1,
                                                           LangDims d) {
+  pdl_sync();
   const int row = blockIdx.x;
   const int j = row / d.B, b = row - j * d.B;
   int r0, r1;
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(256) lang_layer1_kernel(const float* __restric
 __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __restrict__ dpre, const int* __restrict__ perms,
                                                               float* __restrict__ dU, float* __restrict__ dV,
                                                               float* __restrict__ dLc, LangDims d) {
+  pdl_sync();
   const int row = blockIdx.x;
   const int j = row / d.B, b = row - j * d.B;
   int r0, r1;
@@ -87,6 +90,7 @@ struct GemmArgs {
 
 template <bool kAK, bool kBK>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  pdl_sync();
   __shared__ __align__(16) float As[16][64 + 4];
   __shared__ __align__(16) float Bs[16][64 + 4];
   const int t = threadIdx.x;
@@ -200,13 +204,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 template <bool kAK, bool kBK>
 cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-  sgemm_kernel<kAK, kBK><<<grid, 256, 0, s>>>(g);
+  launch_kernel(sgemm_kernel<kAK, kBK>, grid, 256, 0, s, g);
   return cudaGetLastError();
 }
 
 // S[row] = H4[row,:] . w5 + b5
 __global__ void __launch_bounds__(256) lang_score_kernel(const float* __restrict__ H4, const float* __restrict__ w5,
                                                          const float* __restrict__ b5, float* __restrict__ S, int H) {
+  pdl_sync();
   __shared__ float red[32];
   const int row = blockIdx.x;
   float acc = 0.f;
@@ -224,6 +229,7 @@ __global__ void __launch_bounds__(256) lang_score_kernel(const float* __restrict
 // InfoNCE over 1 positive + 4 negatives, 3 targets per clip (trainer.py:93-117); one thread per clip.
 __global__ void lang_loss_kernel(const float* __restrict__ S, const float* __restrict__ mask, float* __restrict__ dS,
                                  int B, float langw, float* __restrict__ metrics) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float invB = 1.0f / (float)B;
@@ -262,6 +268,7 @@ __global__ void lang_loss_kernel(const float* __restrict__ S, const float* __res
 __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restrict__ dS, const float* __restrict__ w5,
                                                           const float* __restrict__ H4, float* __restrict__ dH4,
                                                           int rows, int H) {
+  pdl_sync();
   const size_t total = (size_t)rows * H;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / H), j = (int)(i - (size_t)row * H);
@@ -274,6 +281,7 @@ __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restric
 // (a one-thread-per-column loop over ~1000 rows took 70 us per call).
 __global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
                                                       float* __restrict__ out, int rows, int cols) {
+  pdl_sync();
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ 
 }
 
 __global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
+  pdl_sync();
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
@@ -371,7 +380,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     R3M_TRY((run_gemm<true, true>(gv, s)));
     GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0};
     R3M_TRY((run_gemm<true, true>(gl, s)));
-    lang_layer1_kernel<<<rows, 256, 0, s>>>(ws.U, ws.V, ws.Lc, p.b[0], perms, ws.Hact[0], d);
+    launch_kernel(lang_layer1_kernel, rows, 256, 0, s, ws.U, ws.V, ws.Lc, p.b[0], perms, ws.Hact[0], d);
     R3M_TRY(cudaGetLastError());
   }
   // ---- layers 2-4: Linear + ReLU, then Linear(H -> 1)
@@ -379,23 +388,23 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     GemmArgs g{ws.Hact[l - 1], p.w[l], ws.Hact[l], rows, H, H, H, H, H, p.b[l], 1, nullptr, 0, 0};
     R3M_TRY((run_gemm<true, true>(g, s)));
   }
-  lang_score_kernel<<<rows, 256, 0, s>>>(ws.Hact[3], p.w[4], p.b[4], ws.S, H);
+  launch_kernel(lang_score_kernel, rows, 256, 0, s, ws.Hact[3], p.w[4], p.b[4], ws.S, H);
   R3M_TRY(cudaGetLastError());
-  lang_loss_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.S, lang_mask, dE ? ws.dS : nullptr, d.B, langw, metrics);
+  launch_kernel(lang_loss_kernel, (d.B + 127) / 128, 128, 0, s, ws.S, lang_mask, dE ? ws.dS : nullptr, d.B, langw, metrics);
   R3M_TRY(cudaGetLastError());
   if (dE) {
     // ---- backward
-    col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
     R3M_TRY(cudaGetLastError());
-    vec_sum_kernel<<<1, 256, 0, s>>>(ws.dS, p.db[4], rows);
+    launch_kernel(vec_sum_kernel, 1, 256, 0, s, ws.dS, p.db[4], rows);
     R3M_TRY(cudaGetLastError());
-    lang_dscore_kernel<<<148 * 4, 256, 0, s>>>(ws.dS, p.w[4], ws.Hact[3], ws.dH[0], rows, H);
+    launch_kernel(lang_dscore_kernel, 148 * 4, 256, 0, s, ws.dS, p.w[4], ws.Hact[3], ws.dH[0], rows, H);
     R3M_TRY(cudaGetLastError());
     int cur = 0;
     for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
-      col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(dHl, nullptr, p.db[l], rows, H);
+      launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
       GemmArgs gw{dHl, ws.Hact[l - 1], p.dw[l], H, H, rows, H, H, H, nullptr, 0, nullptr, 0, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
@@ -406,14 +415,14 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     }
     // ---- layer 1 backward (factorised)
     const float* dpre = ws.dH[cur];
-    col_sum_kernel<<<dim3((H + 31) / 32, 16), 256, 0, s>>>(dpre, nullptr, p.db[0], rows, H);
+    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, dpre, nullptr, p.db[0], rows, H);
     R3M_TRY(cudaGetLastError());
     e = cudaMemsetAsync(ws.dU, 0, (size_t)((ws.U - ws.dU)) * sizeof(float), s);
     if (e != cudaSuccess) {
       if (launches) *launches = n;
       return e;
     }
-    lang_layer1_bwd_kernel<<<rows, 256, 0, s>>>(dpre, perms, ws.dU, ws.dV, ws.dLc, d);
+    launch_kernel(lang_layer1_bwd_kernel, rows, 256, 0, s, dpre, perms, ws.dU, ws.dV, ws.dLc, d);
     R3M_TRY(cudaGetLastError());
     // dW1 = [dU^T E0 | dV^T E | dLc^T L]   (column blocks of the [H][2D+768] gradient)
     GemmArgs wa{ws.dU, E, p.dw[0], H, D, B, H, 5 * D, K1, nullptr, 0, nullptr, 0, 0};

@@ -3,6 +3,7 @@
 // -log term (:144-145), mean over clips, zero gradient at zero distance (torch.linalg.norm backward) and sign(0) = 0.
 #include "loss.cuh"
 
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace r3m {
@@ -29,6 +30,7 @@ __device__ __forceinline__ void block_sum(float (&v)[kN], float* smem /* [kN][32
 
 __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ E, float* __restrict__ dE, int rows,
                                                       int D, float l2w, float l1w, float* __restrict__ metrics) {
+  pdl_sync();
   __shared__ float red[3 * 32];
   const int row = blockIdx.x;
   const float* e = E + (size_t)row * D;
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__ E, float* __restrict__ dE,
                                                        const int* __restrict__ perms, int B, int D, float tcnw,
                                                        float* __restrict__ metrics) {
+  pdl_sync();
   __shared__ float red[9 * 32];
   __shared__ float coef[9];
   __shared__ int urow[9], vrow[9];
@@ -137,25 +140,26 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
 }
 
 __global__ void publish_flag_kernel(const int* __restrict__ flag, float* __restrict__ metrics) {
+  pdl_sync();
   metrics[kDeviceFlag] = (float)*flag;
 }
 
 }  // namespace
 
 cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s) {
-  publish_flag_kernel<<<1, 1, 0, s>>>(flag, metrics);
+  launch_kernel(publish_flag_kernel, 1, 1, 0, s, flag, metrics);
   return cudaGetLastError();
 }
 
 cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w, float l1w, float* metrics,
                            cudaStream_t s) {
-  loss_lp_kernel<<<rows, 256, 0, s>>>(E, dE, rows, D, l2w, l1w, metrics);
+  launch_kernel(loss_lp_kernel, rows, 256, 0, s, E, dE, rows, D, l2w, l1w, metrics);
   return cudaGetLastError();
 }
 
 cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, float* metrics,
                             cudaStream_t s) {
-  loss_tcn_kernel<<<B, 256, 0, s>>>(E, dE, perms, B, D, tcnw, metrics);
+  launch_kernel(loss_tcn_kernel, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,24 @@ namespace r3m {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Programmatic dependent launch (launch.h): wait until the preceding grid has completed and its memory is visible, then
+// let the following grid's CTAs be scheduled behind this one.  First statement of every kernel (the tcgen05 kernels
+// run their barrier / TMEM prologue first: it touches no global memory).
+#ifndef R3M_PDL_TRIGGER
+#define R3M_PDL_TRIGGER 0  // 0: never (dependents start at completion; measured best: -0.8 ms per RN50 step), 1: right after the wait (+0.5 ms), 2: at pdl_done() (+-0)
+#endif
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if R3M_PDL_TRIGGER == 1
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// after the kernel's main loop: the CTA has issued all its bulk work
+__device__ __forceinline__ void pdl_done() {
+#if R3M_PDL_TRIGGER == 2
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

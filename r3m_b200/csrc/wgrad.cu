@@ -11,6 +11,7 @@
 // vectorised red.global.add.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue.
 #include "conv_igemm.cuh"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace r3m {
@@ -58,6 +59,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_sync();  // everything above is CTA-local; global memory is first touched below
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,6 +102,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
             phase ^= 1u;
           }
         }
+        pdl_done();  // all loads of this CTA are issued
       }
     } else if (warp == 1) {
       if (lane == 0) {
@@ -198,7 +201,7 @@ cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const 
     if (e != cudaSuccess) return e;
     configured_bytes = bytes;
   }
-  wgrad_kernel<<<dim3(splits, groups, ktiles), 256, bytes, stream>>>(tmDy, tmX, p);
+  launch_kernel(wgrad_kernel, dim3(splits, groups, ktiles), 256, bytes, stream, tmDy, tmX, p);
   return cudaGetLastError();
 }
 

@@ -306,6 +306,25 @@ def test_stem_pool_forward_backward(lib):
     # gradient w.r.t. the BN output (ReLU mask applied): compare with autograd's grad at z, masked
     want = (z.grad * (z.detach() > 0)).permute(0, 2, 3, 1)
     assert rel(dz.float(), want) < 4e-3
+    # argmax codes: 0..8 = window position of the maximum, 15 = maximum clipped by the ReLU (no gradient)
+    codes = am.cpu()
+    assert bool(((codes <= 8) | (codes == 15)).all())
+    assert bool(((codes == 15) == (a.float().cpu() == 0)).all())
+
+    # fused form the engine runs: maxpool backward + ReLU mask + BatchNorm backward in two passes -> dy, dgamma, dbeta
+    sums = torch.zeros(2 * C, device="cuda")
+    dy = torch.empty(N, H, H, C, device="cuda", dtype=torch.bfloat16)
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    lib.check(lib.lib.r3m_b200_stem_backward(lib.ptr(dA), lib.ptr(am), lib.ptr(y), N, H, H, C, lib.ptr(sm), lib.ptr(sr),
+                                             lib.ptr(gamma), lib.ptr(sums), lib.ptr(dy), lib.ptr(dgamma),
+                                             lib.ptr(dbeta), s))
+    # reference: autograd through BatchNorm, ReLU and the pooling (x.grad), and BatchNorm's parameter gradients
+    # driven by the exact fp32 masked gradient (the fused kernel never rounds it to bf16)
+    x2 = yf.permute(0, 3, 1, 2).detach().requires_grad_(True)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.batch_norm(x2, None, None, g2, b2, training=True, eps=1e-5).backward(want.permute(0, 3, 1, 2).contiguous())
+    assert rel(dy.float(), x2.grad.permute(0, 2, 3, 1)) < 4e-3
+    assert rel(dgamma, g2.grad) < 1e-4 and rel(dbeta, b2.grad) < 1e-4
 
 
 def test_avgpool_forward_backward(lib):
