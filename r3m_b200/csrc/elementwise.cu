@@ -547,13 +547,12 @@ __device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bit
 template <bool kDual, int kMask>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   pdl_sync();
-  extern __shared__ float s_red[];  // [3][C]: sum(dz), sum(dz*xhat), sum(dz*xhat2)
+  extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * C / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
+  constexpr int kQ = kDual ? 3 : 2;
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
-  for (int i = threadIdx.x; i < 3 * a.C; i += blockDim.x) s_red[i] = 0.f;
-  __syncthreads();
   // s2 / s3 accumulate sum(dz * (y - mean)); the 1/std factor is applied once at the end
   float mean[8], mean2[8], s1[8], s2[8], s3[8];
 #pragma unroll
@@ -569,7 +568,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const uint8_t* __restrict__ mask = a.mask;
-#pragma unroll 2
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
@@ -590,16 +588,38 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     }
   }
   pdl_done();
+  // Block reduction without shared-memory atomics (fp32 shared atomics are CAS loops; with up to 32 row-threads per
+  // channel they dominated the small layers): every thread parks its partials, then one thread per four outputs adds
+  // the rows_per_iter copies and issues ONE vector atomic to global memory.
+  const int q4 = kQ * a.C / 4;  // float4 slots per partial row
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&s_red[chunk * 8 + j], s1[j]);
-    atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j] * a.rstd[chunk * 8 + j]);
-    if (kDual) atomicAdd(&s_red[2 * a.C + chunk * 8 + j], s3[j] * a.rstd2[chunk * 8 + j]);
+    s2[j] *= a.rstd[chunk * 8 + j];
+    if (kDual) s3[j] *= a.rstd2[chunk * 8 + j];
+  }
+  float4* mine = s_part + (size_t)r0 * q4 + chunk * 2;
+  mine[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  mine[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
+  mine[a.C / 4] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  mine[a.C / 4 + 1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+  if (kDual) {
+    mine[a.C / 2] = make_float4(s3[0], s3[1], s3[2], s3[3]);
+    mine[a.C / 2 + 1] = make_float4(s3[4], s3[5], s3[6], s3[7]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
-  if (kDual)
-    for (int i = threadIdx.x; i < a.C; i += blockDim.x) atomicAdd(&a.sums2[i], s_red[2 * a.C + i]);
+  for (int i = threadIdx.x; i < q4; i += blockDim.x) {
+    float4 acc = s_part[i];
+    for (int r = 1; r < rows_per_iter; ++r) {
+      const float4 v = s_part[(size_t)r * q4 + i];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    // slots [0, C/2) -> sums[0 .. 2C), slots [C/2, 3C/4) -> sums2[0 .. C)
+    float4* dst = (i < a.C / 2) ? reinterpret_cast<float4*>(a.sums) + i : reinterpret_cast<float4*>(a.sums2) + (i - a.C / 2);
+    atomicAdd(dst, acc);
+  }
 }
 
 template <bool kDual, int kMask, bool kDz>
@@ -853,12 +873,14 @@ inline int mask_kind(const BnBwdArgs& a) { return a.a ? kMaskAct : (a.mask ? kMa
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
-  // at least two rows per thread (the loop is unrolled by two), otherwise one resident wave
-  const size_t smem = 3 * a.C * sizeof(float);
+  // several rows per thread so that the block reduction and the global atomics are amortised; at most one resident wave
   const bool dual = a.y2 != nullptr;
-#define R3M_LAUNCH(D, K)                                                                     \
-  launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                  \
-                grid_for((a.M + 1) / 2, rows_per_iter, resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem)), 256, \
+  const size_t smem = (size_t)rows_per_iter * (dual ? 3 : 2) * a.C * sizeof(float);  // = 16 / 24 KB for every C
+  if ((reinterpret_cast<uintptr_t>(a.sums) & 15) != 0 || (dual && (reinterpret_cast<uintptr_t>(a.sums2) & 15) != 0))
+    return cudaErrorInvalidValue;
+#define R3M_LAUNCH(D, K)                                                                      \
+  launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                   \
+                grid_for((a.M + 15) / 16, rows_per_iter, resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem)), 256, \
                 smem, s, a)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
