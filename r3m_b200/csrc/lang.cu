@@ -1,5 +1,7 @@
 #include "lang.cuh"
 
+#include <algorithm>
+
 #include "loss.cuh"
 #include "launch.h"
 #include "ptx.cuh"
@@ -71,9 +73,14 @@ __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fp32 SIMT GEMM, 64x64x16 tiles, 4x4 per thread.  C[M,N] = A . B with selectable operand storage:
+// fp32 SIMT GEMM (exact fp32: the reference's nn.Linear runs in true fp32, torch.backends.cuda.matmul.allow_tf32 is
+// False).  C[M,N] = A . B with selectable operand storage:
 //   kAK: A stored [M][K] (K contiguous) else [K][M];   kBK: B stored [N][K] (K contiguous) else [K][N].
-// Epilogue: + bias[col], ReLU, or gating by mask[row][col] > 0 (ReLU backward).
+// Epilogue: + bias[col], ReLU, or gating by mask[row][col] > 0 (ReLU backward), optional C += result.
+// Tile 64 x 128 x 16, 128 threads, 8 x 8 outputs per thread (two 4-row groups x two 4-column groups, so that every
+// fragment read is one LDS.128 and the 64 FMAs per k step are fed by four of them), shared-memory double buffering with
+// the next tile's global loads held in registers.  The head's GEMMs are 960 x 1024 x 1024: 120 CTAs, one wave.
+// Vector loads need the contiguous dimension of each operand to be a multiple of 4 floats (checked by the launcher).
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmArgs {
   const float* A;
@@ -86,125 +93,164 @@ struct GemmArgs {
   const float* mask;
   int ldm;
   int accumulate;  // C += result
+  int kchunk = 0;  // split-K (gridDim.z > 1): K range per z slice, a multiple of kTK; the slices add into C atomically
+};
+
+constexpr int kTM = 64, kTN = 128, kTK = 16;
+
+// one operand tile [kTK][ROWS] (k-major in shared memory) <- global, through registers
+template <int ROWS, bool kKContig>
+struct TileLoader {
+  static constexpr int kVecs = ROWS * kTK / 4 / 128;  // float4 per thread
+  float4 v[kVecs];
+  __device__ __forceinline__ void load(const float* __restrict__ src, int ld, int row0, int rows, int k0, int K) {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int f = threadIdx.x + i * 128;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kKContig) {
+        const int r = f >> 2, kq = (f & 3) * 4;  // vector along k
+        if (row0 + r < rows && k0 + kq < K) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + kq));
+      } else {
+        const int k = f / (ROWS / 4), rq = (f % (ROWS / 4)) * 4;  // vector along the row index
+        if (k0 + k < K && row0 + rq < rows) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * ld + row0 + rq));
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float (*dst)[ROWS + 4]) const {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int f = threadIdx.x + i * 128;
+      if (kKContig) {
+        const int r = f >> 2, kq = (f & 3) * 4;
+        dst[kq + 0][r] = v[i].x;
+        dst[kq + 1][r] = v[i].y;
+        dst[kq + 2][r] = v[i].z;
+        dst[kq + 3][r] = v[i].w;
+      } else {
+        const int k = f / (ROWS / 4), rq = (f % (ROWS / 4)) * 4;
+        *reinterpret_cast<float4*>(&dst[k][rq]) = v[i];
+      }
+    }
+  }
 };
 
 template <bool kAK, bool kBK>
-__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(128) sgemm_kernel(const GemmArgs g) {
   pdl_sync();
-  __shared__ __align__(16) float As[16][64 + 4];
-  __shared__ __align__(16) float Bs[16][64 + 4];
+  __shared__ __align__(16) float As[2][kTK][kTM + 4];
+  __shared__ __align__(16) float Bs[2][kTK][kTN + 4];
   const int t = threadIdx.x;
-  const int ty = t >> 4, tx = t & 15;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  const int ty = t >> 4, tx = t & 15;  // rows {4ty.., 32+4ty..}, columns {4tx.., 64+4tx..}
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < g.K; k0 += 16) {
-    // ---- A tile -> As[k][m]
-    if (kAK) {
-      const int row = t >> 2, kq = (t & 3) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + row < g.M) {
-        const float* src = g.A + (size_t)(m0 + row) * g.lda + k0 + kq;
-        if (k0 + kq + 3 < g.K) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (k0 + kq + 0 < g.K) v.x = src[0];
-          if (k0 + kq + 1 < g.K) v.y = src[1];
-          if (k0 + kq + 2 < g.K) v.z = src[2];
-        }
-      }
-      As[kq + 0][row] = v.x;
-      As[kq + 1][row] = v.y;
-      As[kq + 2][row] = v.z;
-      As[kq + 3][row] = v.w;
-    } else {
-      const int k = t >> 4, mq = (t & 15) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < g.K) {
-        const float* src = g.A + (size_t)(k0 + k) * g.lda + m0 + mq;
-        if (m0 + mq + 3 < g.M) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (m0 + mq + 0 < g.M) v.x = src[0];
-          if (m0 + mq + 1 < g.M) v.y = src[1];
-          if (m0 + mq + 2 < g.M) v.z = src[2];
-        }
-      }
-      *reinterpret_cast<float4*>(&As[k][mq]) = v;
+  const bool split = gridDim.z > 1;
+  const int kbeg = split ? blockIdx.z * g.kchunk : 0;
+  const int kend = split ? min(g.K, kbeg + g.kchunk) : g.K;
+  TileLoader<kTM, kAK> la;
+  TileLoader<kTN, kBK> lb;
+  la.load(g.A, g.lda, m0, g.M, kbeg, kend);
+  lb.load(g.B, g.ldb, n0, g.N, kbeg, kend);
+  la.store(As[0]);
+  lb.store(Bs[0]);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += kTK) {
+    const bool more = k0 + kTK < kend;
+    if (more) {
+      la.load(g.A, g.lda, m0, g.M, k0 + kTK, kend);
+      lb.load(g.B, g.ldb, n0, g.N, k0 + kTK, kend);
     }
-    // ---- B tile -> Bs[k][n]
-    if (kBK) {
-      const int col = t >> 2, kq = (t & 3) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + col < g.N) {
-        const float* src = g.B + (size_t)(n0 + col) * g.ldb + k0 + kq;
-        if (k0 + kq + 3 < g.K) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (k0 + kq + 0 < g.K) v.x = src[0];
-          if (k0 + kq + 1 < g.K) v.y = src[1];
-          if (k0 + kq + 2 < g.K) v.z = src[2];
-        }
-      }
-      Bs[kq + 0][col] = v.x;
-      Bs[kq + 1][col] = v.y;
-      Bs[kq + 2][col] = v.z;
-      Bs[kq + 3][col] = v.w;
-    } else {
-      const int k = t >> 4, nq = (t & 15) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < g.K) {
-        const float* src = g.B + (size_t)(k0 + k) * g.ldb + n0 + nq;
-        if (n0 + nq + 3 < g.N) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (n0 + nq + 0 < g.N) v.x = src[0];
-          if (n0 + nq + 1 < g.N) v.y = src[1];
-          if (n0 + nq + 2 < g.N) v.z = src[2];
-        }
-      }
-      *reinterpret_cast<float4*>(&Bs[k][nq]) = v;
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][32 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    if (more) {
+      la.store(As[buf ^ 1]);
+      lb.store(Bs[buf ^ 1]);
+      __syncthreads();
+      buf ^= 1;
     }
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i < 4 ? ty * 4 + i : 32 + ty * 4 + (i - 4));
     if (row >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tx * 4 + j;
-      if (col >= g.N) continue;
-      float v = acc[i][j];
-      if (g.bias) v += g.bias[col];
-      if (g.relu) v = fmaxf(v, 0.f);
-      if (g.mask) v = g.mask[(size_t)row * g.ldm + col] > 0.f ? v : 0.f;
+    for (int jh = 0; jh < 2; ++jh) {
+      const int col = n0 + jh * 64 + tx * 4;
+      if (col >= g.N) continue;  // N is a multiple of 4 whenever it is the contiguous dimension of C
+      float v[4] = {acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col + j >= g.N) {
+          v[j] = 0.f;
+          continue;
+        }
+        if (g.bias) v[j] += g.bias[col + j];
+        if (g.relu) v[j] = fmaxf(v[j], 0.f);
+        if (g.mask) v[j] = g.mask[(size_t)row * g.ldm + col + j] > 0.f ? v[j] : 0.f;
+      }
       float* dst = &g.C[(size_t)row * g.ldc + col];
-      *dst = g.accumulate ? *dst + v : v;
+      if (split) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < g.N) atomicAdd(&dst[j], v[j]);
+      } else if (col + 3 < g.N && (g.ldc & 3) == 0) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (g.accumulate) {
+          const float4 c = *reinterpret_cast<const float4*>(dst);
+          o.x += c.x;
+          o.y += c.y;
+          o.z += c.z;
+          o.w += c.w;
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < g.N) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+      }
     }
   }
 }
 
 template <bool kAK, bool kBK>
 cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
-  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-  launch_kernel(sgemm_kernel<kAK, kBK>, grid, 256, 0, s, g);
+  // contiguous dimensions must be whole float4s, and every operand base 16-byte aligned
+  if ((kAK ? g.K : g.M) % 4 != 0 || (kBK ? g.K : g.N) % 4 != 0 || g.lda % 4 != 0 || g.ldb % 4 != 0 ||
+      ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B) | reinterpret_cast<uintptr_t>(g.C)) & 15) != 0)
+    return cudaErrorInvalidValue;
+  dim3 grid((g.N + kTN - 1) / kTN, (g.M + kTM - 1) / kTM);
+  GemmArgs a = g;
+  // Few-tile GEMMs with a long K (the M = clips rows of the factorised first layer) are split along K so that they
+  // fill the machine; their slices add into C atomically, so C must be pre-zeroed or `accumulate`, without epilogue.
+  const int tiles = grid.x * grid.y;
+  if (a.kchunk < 0) {
+    a.kchunk = 0;
+    if (tiles < 100 && !a.bias && !a.relu && !a.mask) {
+      int splits = std::min((148 + tiles - 1) / tiles, a.K / 64);
+      if (splits > 1) {
+        a.kchunk = ((a.K + splits - 1) / splits + kTK - 1) / kTK * kTK;
+        grid.z = (a.K + a.kchunk - 1) / a.kchunk;
+      }
+    }
+  }
+  launch_kernel(sgemm_kernel<kAK, kBK>, grid, 128, 0, s, a);
   return cudaGetLastError();
 }
 
@@ -374,11 +420,14 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   const int B = d.B, D = d.D;
   // ---- forward layer 1 (factorised): U = E0 . W1a^T, V = E . W1b^T, Lc = L . W1c^T, then gather-add + bias + ReLU
   {
-    GemmArgs gu{E, p.w[0], ws.U, B, H, D, 5 * D, K1, H, nullptr, 0, nullptr, 0, 0};
+    // U, V, Lc are contiguous and zeroed by one memset: their GEMMs are split along K (kchunk = -1: automatic)
+    e = cudaMemsetAsync(ws.U, 0, (size_t)(ws.Hact[0] - ws.U) * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    GemmArgs gu{E, p.w[0], ws.U, B, H, D, 5 * D, K1, H, nullptr, 0, nullptr, 0, 0, -1};
     R3M_TRY((run_gemm<true, true>(gu, s)));
-    GemmArgs gv{E, p.w[0] + D, ws.V, 5 * B, H, D, D, K1, H, nullptr, 0, nullptr, 0, 0};
+    GemmArgs gv{E, p.w[0] + D, ws.V, 5 * B, H, D, D, K1, H, nullptr, 0, nullptr, 0, 0, -1};
     R3M_TRY((run_gemm<true, true>(gv, s)));
-    GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0};
+    GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0, -1};
     R3M_TRY((run_gemm<true, true>(gl, s)));
     launch_kernel(lang_layer1_kernel, rows, 256, 0, s, ws.U, ws.V, ws.Lc, p.b[0], perms, ws.Hact[0], d);
     R3M_TRY(cudaGetLastError());
@@ -432,9 +481,9 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     GemmArgs wc{ws.dLc, lang_emb, p.dw[0] + 2 * D, H, d.L, B, H, d.L, K1, nullptr, 0, nullptr, 0, 0};
     R3M_TRY((run_gemm<false, false>(wc, s)));
     // dE0 += dU . W1a,  dE += dV . W1b   (the sentence embedding is frozen: no gradient through W1c's input)
-    GemmArgs ea{ws.dU, p.w[0], dE, B, D, H, H, K1, 5 * D, nullptr, 0, nullptr, 0, 1};
+    GemmArgs ea{ws.dU, p.w[0], dE, B, D, H, H, K1, 5 * D, nullptr, 0, nullptr, 0, 1, -1};
     R3M_TRY((run_gemm<true, false>(ea, s)));
-    GemmArgs eb{ws.dV, p.w[0] + D, dE, 5 * B, D, H, H, K1, D, nullptr, 0, nullptr, 0, 1};
+    GemmArgs eb{ws.dV, p.w[0] + D, dE, 5 * B, D, H, H, K1, D, nullptr, 0, nullptr, 0, 1, -1};
     R3M_TRY((run_gemm<true, false>(eb, s)));
   }
 #undef R3M_TRY
