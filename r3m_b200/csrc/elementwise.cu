@@ -744,6 +744,33 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict_
   }
 }
 
+// all dgrad re-packs of a network in one launch: the block index is mapped to (entry, tile) through block_begin
+__global__ void pack_dgrad_multi_kernel(const PackDgradEntry* __restrict__ table, int entries) {
+  pdl_sync();
+  __shared__ float tile[32][33];
+  int lo = 0, hi = entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackDgradEntry& e = table[lo];
+  const int local = blockIdx.x - e.block_begin;
+  const int gx = (e.Cin + 31) / 32, gy = (e.Cout + 31) / 32;
+  const int bx = local % gx, by = (local / gx) % gy, t = local / (gx * gy);
+  const int src = e.taps[t];
+  const int c0 = bx * 32, k0 = by * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int k = k0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (k < e.Cout && c < e.Cin) ? e.w[((size_t)k * e.T + src) * e.Cin + c] : 0.f;
+  }
+  __syncthreads();
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(e.out);
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, k = k0 + threadIdx.x;
+    if (c < e.Cin && k < e.Cout) out[((size_t)c * e.nt + t) * e.Cout + k] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
 __device__ __forceinline__ bool stem_map(int k, int rr, int j, int& oihw) {
   const int kw = j >> 4, sub = (j >> 2) & 3, c = j & 3;
   const int dy = sub >> 1, dx = sub & 1;
@@ -934,6 +961,12 @@ cudaError_t launch_pack_dgrad(const float* w, void* out, int Cout, int T, int Ci
   for (int i = 0; i < 16; ++i) taps.t[i] = i < nt ? src_tap[i] : 0;
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, nt);
   launch_kernel(pack_dgrad_kernel, grid, dim3(32, 8), 0, s, w, reinterpret_cast<bf16*>(out), Cout, T, Cin, nt, taps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_dgrad_multi(const PackDgradEntry* table_dev, int entries, int total_blocks, cudaStream_t s) {
+  if (entries < 1 || total_blocks < 1) return cudaErrorInvalidValue;
+  launch_kernel(pack_dgrad_multi_kernel, total_blocks, dim3(32, 8), 0, s, table_dev, entries);
   return cudaGetLastError();
 }
 

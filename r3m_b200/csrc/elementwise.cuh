@@ -133,6 +133,16 @@ cudaError_t launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t
 // dgrad filter: out[c][t][k] = w[k][src_tap[t]][c]   (w fp32 [Cout][T][Cin] -> bf16 [Cin][nt][Cout])
 cudaError_t launch_pack_dgrad(const float* w, void* out, int Cout, int T, int Cin, int nt, const int* src_tap,
                               cudaStream_t s);
+// the same for every filter of a network in ONE launch (61 launches of a few microseconds each otherwise); the table
+// lives in device memory, block_begin is the running sum of ceil(Cin/32) * ceil(Cout/32) * nt
+struct PackDgradEntry {
+  const float* w;
+  void* out;
+  int Cout, T, Cin, nt;
+  int taps[16];
+  int block_begin;
+};
+cudaError_t launch_pack_dgrad_multi(const PackDgradEntry* table_dev, int entries, int total_blocks, cudaStream_t s);
 // stem filter OIHW fp32 [64,3,7,7] <-> packed [64][4][64] (bf16 forward operand / fp32 gradient)
 cudaError_t launch_stem_pack(const float* w_oihw, void* wp_bf16, cudaStream_t s);
 cudaError_t launch_stem_unpack_grad(const float* dwp, float* dw_oihw, cudaStream_t s);

@@ -42,6 +42,7 @@ namespace {
 constexpr size_t kAlign = 1024;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr size_t kMaxActPerFrame = 112 * 112 * 64;
+constexpr size_t kMaxPackEntries = 128;  // dgrad re-pack table: one entry per (conv, output-parity class)
 constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are launch-latency bound -> CUDA graph  // largest activation (stem output == layer1 bottleneck output)
 }  // namespace
 
@@ -243,6 +244,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
   e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
+  e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
   if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
   e->ws_bytes_ = align_up(cur, kAlign);
   *out = e;
@@ -685,6 +687,8 @@ std::string Engine::plan_all() {
 
   // ------------------------------------------------------------------------------------------------ re-packs
   repack_.clear();
+  std::vector<PackDgradEntry> packs;
+  int pack_blocks = 0;
   for (Conv* cp : convs_) {
     const Conv& c = *cp;
     if (c.stem) {
@@ -696,18 +700,30 @@ std::string Engine::plan_all() {
     size_t off = 0;
     for (const DgradClass& k : cls) {
       if (k.ntaps == 0) continue;
-      struct Taps {
-        int t[kMaxTaps];
-      } taps;
-      for (int t = 0; t < kMaxTaps; ++t) taps.t[t] = t < k.ntaps ? k.src_r[t] * c.R + k.src_s[t] : 0;
-      const float* w = P + c.w_off;
-      bf16* dst = wd + c.wd_off + off;
-      const int Cout = c.Cout, T = c.R * c.R, Cin = c.Cin, nt = k.ntaps;
-      repack_.push_back(Op(
-          [w, dst, Cout, T, Cin, nt, taps](cudaStream_t s) { return launch_pack_dgrad(w, dst, Cout, T, Cin, nt, taps.t, s); },
-          kFamOptim, 0.0, 6.0 * Cin * nt * Cout));
-      off += (size_t)Cin * nt * Cout;
+      PackDgradEntry pe;
+      pe.w = P + c.w_off;
+      pe.out = wd + c.wd_off + off;
+      pe.Cout = c.Cout;
+      pe.T = c.R * c.R;
+      pe.Cin = c.Cin;
+      pe.nt = k.ntaps;
+      for (int t = 0; t < 16; ++t) pe.taps[t] = t < k.ntaps ? k.src_r[t] * c.R + k.src_s[t] : 0;
+      pe.block_begin = pack_blocks;
+      pack_blocks += ((c.Cin + 31) / 32) * ((c.Cout + 31) / 32) * k.ntaps;
+      packs.push_back(pe);
+      off += (size_t)c.Cin * k.ntaps * c.Cout;
     }
+  }
+  if (!packs.empty()) {
+    if (packs.size() > kMaxPackEntries) return "too many dgrad re-pack entries";
+    PackDgradEntry* table_dev = reinterpret_cast<PackDgradEntry*>(ws_ + off_pack_);
+    cudaError_t ce = cudaMemcpy(table_dev, packs.data(), packs.size() * sizeof(PackDgradEntry), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) return std::string("pack table upload: ") + cudaGetErrorString(ce);
+    const int entries = (int)packs.size(), blocks = pack_blocks;
+    repack_.push_back(Op([table_dev, entries, blocks](cudaStream_t s) {
+      return launch_pack_dgrad_multi(table_dev, entries, blocks, s);
+    }, kFamOptim, 0.0, 6.0 * (double)nwd_));
+    repack_.back().label = "pack_dgrad (all filters)";
   }
   return err;
 }

@@ -125,6 +125,7 @@ class Engine {
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
   size_t off_lang_ws_ = 0;
   size_t off_fold_ = 0;  // BnFoldEntry table (device) for the inference path
+  size_t off_pack_ = 0;  // PackDgradEntry table (device): all dgrad filter re-packs in one launch
   // small-batch inference: the eval forward is replayed as a CUDA graph from a fixed staging copy of the frames
   size_t off_obs_stage_ = 0;
   cudaGraphExec_t eval_graph_ = nullptr;

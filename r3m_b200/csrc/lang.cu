@@ -166,14 +166,26 @@ __global__ void __launch_bounds__(128) sgemm_kernel(const GemmArgs g) {
       la.load(g.A, g.lda, m0, g.M, k0 + kTK, kend);
       lb.load(g.B, g.ldb, n0, g.N, k0 + kTK, kend);
     }
+    // fragments of step kk + 1 are fetched while the 64 FMAs of step kk issue (one warp per scheduler: an exposed
+    // shared-memory round trip per step cost a third of the FMA rate)
+    float4 fa[2][2], fb[2][2];
+    fa[0][0] = *reinterpret_cast<const float4*>(&As[buf][0][ty * 4]);
+    fa[0][1] = *reinterpret_cast<const float4*>(&As[buf][0][32 + ty * 4]);
+    fb[0][0] = *reinterpret_cast<const float4*>(&Bs[buf][0][tx * 4]);
+    fb[0][1] = *reinterpret_cast<const float4*>(&Bs[buf][0][64 + tx * 4]);
 #pragma unroll
     for (int kk = 0; kk < kTK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][32 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk + 1 < kTK) {
+        fa[nxt][0] = *reinterpret_cast<const float4*>(&As[buf][kk + 1][ty * 4]);
+        fa[nxt][1] = *reinterpret_cast<const float4*>(&As[buf][kk + 1][32 + ty * 4]);
+        fb[nxt][0] = *reinterpret_cast<const float4*>(&Bs[buf][kk + 1][tx * 4]);
+        fb[nxt][1] = *reinterpret_cast<const float4*>(&Bs[buf][kk + 1][64 + tx * 4]);
+      }
+      const float av[8] = {fa[cur][0].x, fa[cur][0].y, fa[cur][0].z, fa[cur][0].w,
+                           fa[cur][1].x, fa[cur][1].y, fa[cur][1].z, fa[cur][1].w};
+      const float bv[8] = {fb[cur][0].x, fb[cur][0].y, fb[cur][0].z, fb[cur][0].w,
+                           fb[cur][1].x, fb[cur][1].y, fb[cur][1].z, fb[cur][1].w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
