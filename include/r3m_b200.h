@@ -106,6 +106,12 @@ int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y,
                            const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
                            float* dgamma, float* dbeta, void* stream);
 
+/* Side-band upload of the step's small host inputs (replaces the `.cuda()` calls of r3m/trainer.py:108 and the index
+ * tensors of :86-92,135-137): dst (device) <- host_pinned (page-locked host memory, device-accessible under unified
+ * addressing), copied by a kernel on `stream` instead of the H2D copy engine, so it never queues behind a bulk frame
+ * upload.  bytes must be a multiple of 16 and both pointers 16-byte aligned. */
+int r3m_b200_pull_host(const void* host_pinned, void* dst, size_t bytes, void* stream);
+
 /* AdaptiveAvgPool2d((1,1)) + flatten (tv resnet.py:278-279) and its backward.  a bf16 [N,HW,C] <-> fp32 [N,C]. */
 int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream);
 int r3m_b200_avgpool_backward(const float* dE, void* dA, int N, int HW, int C, void* stream);

@@ -318,6 +318,11 @@ int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y,
   CUDA_OR_FAIL(launch_stem_bwd(g, (cudaStream_t)stream), "stem_backward");
 }
 
+int r3m_b200_pull_host(const void* host_pinned, void* dst, size_t bytes, void* stream) {
+  if (!host_pinned || !dst) return fail(R3M_B200_ERR_INVALID, "pull_host: null argument");
+  CUDA_OR_FAIL(launch_pull_host(host_pinned, dst, bytes, (cudaStream_t)stream), "pull_host");
+}
+
 int r3m_b200_avgpool_forward(const void* a, float* out, int N, int HW, int C, void* stream) {
   CUDA_OR_FAIL(launch_avgpool_fwd(a, out, N, HW, C, (cudaStream_t)stream), "avgpool_forward");
 }

@@ -722,6 +722,15 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// the step's small host-side inputs (permutations, sentence mask / embedding) are pulled from mapped pinned host memory
+// by the SMs: a cudaMemcpyAsync would queue behind the NEXT batch's 193 MB frame upload on the H2D copy engine
+__global__ void __launch_bounds__(256) pull_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                        size_t n16) {
+  pdl_sync();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------------------------------------ filter packers
 struct TapList {
   int t[16];
@@ -946,6 +955,15 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf
   const float bc2 = 1.f - powf(beta2, (float)step);
   launch_kernel(adam_kernel, grid_for((long long)n, 256, 148 * 16), 256, 0, s, p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, lr,
                                                                     beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pull_host(const void* host_mapped, void* dst, size_t bytes, cudaStream_t s) {
+  if (bytes == 0 || (bytes & 15) != 0 ||
+      ((reinterpret_cast<uintptr_t>(host_mapped) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0)
+    return cudaErrorInvalidValue;
+  launch_kernel(pull_host_kernel, grid_for((long long)(bytes / 16), 256, 148), 256, 0, s,
+                reinterpret_cast<const uint4*>(host_mapped), reinterpret_cast<uint4*>(dst), bytes / 16);
   return cudaGetLastError();
 }
 

@@ -129,6 +129,9 @@ cudaError_t launch_bn_fold(const BnFoldEntry* table_dev, int entries, cudaStream
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, float beta1,
                         float beta2, float eps, int step, float grad_scale, cudaStream_t s);
 cudaError_t launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+// dst (device) <- host_mapped (pinned host memory, device-accessible under unified addressing), copied by a kernel so
+// that it does not share the H2D copy engine's queue with bulk uploads.  bytes: a multiple of 16; both 16-byte aligned.
+cudaError_t launch_pull_host(const void* host_mapped, void* dst, size_t bytes, cudaStream_t s);
 
 // dgrad filter: out[c][t][k] = w[k][src_tap[t]][c]   (w fp32 [Cout][T][Cin] -> bf16 [Cin][nt][Cout])
 cudaError_t launch_pack_dgrad(const float* w, void* out, int Cout, int T, int Cin, int nt, const int* src_tap,
