@@ -173,7 +173,9 @@ int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* ou
 /* Trainer.update up to (and excluding) the optimiser step: forward, LP / TCN / language losses, backward.
  *   perms: int32 [15][clips] permutations in the reference's draw order (9 language, then 6 TCN; trainer.py:86-92,
  *   135-137); lang_emb fp32 [clips][768] sentence embeddings and lang_mask fp32 [clips] (both may be NULL when
- *   langweight == 0).  eval != 0: eval-mode BN, no gradients (trainer.py:28-29,155).  Metrics land in region 7. */
+ *   langweight == 0).  eval != 0: eval-mode BN, no gradients (trainer.py:28-29,155).  Metrics land in region 7.
+ *   obs == NULL (training only): the forward pass was already enqueued with r3m_b200_engine_forward(obs, train = 1,
+ *   out = NULL) on the same stream, so the host may prepare perms / lang inputs while it runs. */
 int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
                                  const float* lang_mask, float l2weight, float l1weight, float langweight,
                                  float tcnweight, int eval, void* stream);

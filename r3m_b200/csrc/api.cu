@@ -445,7 +445,7 @@ int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perm
                                  const float* lang_mask, float l2weight, float l1weight, float langweight,
                                  float tcnweight, int eval, void* stream) {
   ENGINE_OR_FAIL(handle);
-  if (!obs || !perms) return fail(R3M_B200_ERR_INVALID, "null observation / permutation pointer");
+  if (!perms) return fail(R3M_B200_ERR_INVALID, "null permutation pointer");
   Hyper h;
   h.l2weight = l2weight;
   h.l1weight = l1weight;

@@ -857,6 +857,8 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
     if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
     err = run(train ? fwd_train_ : fwd_eval_, stream);
     if (!err.empty()) return err;
+    fwd_train_valid_ = train != 0;
+    fwd_launches_ = launches_;
   }
   if (out) {
     e = cudaMemcpyAsync(out, ws_ + off_E_, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
@@ -872,22 +874,33 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
   if (h.langweight > 0.f && !lang_) return "engine was created without the language head";
   if (h.langweight > 0.f && (!lang_emb || !lang_mask)) return "language head needs lang_emb and lang_mask";
   launches_ = 0;
-  cudaError_t e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
-  if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  cudaError_t e;
+  std::string err;
+  if (obs != nullptr) {
+    e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+    {
+      void* xs = ws_ + off_xs_;
+      const int N = N_;
+      e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
+                    (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+                 stream);
+    }
+    if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
+    err = run(eval ? fwd_eval_ : fwd_train_, stream);
+    if (!err.empty()) return err;
+  } else {
+    // obs == NULL: the caller has already enqueued forward(obs, train) on this stream (the activations, batch
+    // statistics and embeddings of that call are in place), so that its host-side preparation of perms / lang inputs
+    // overlaps the forward pass instead of delaying the step's first kernel
+    if (eval || !fwd_train_valid_) return "update_grads(obs = NULL) needs a preceding train-mode forward() on this engine";
+    launches_ = fwd_launches_;
+  }
+  fwd_train_valid_ = false;
   if (!eval) {
     e = cudaMemsetAsync(pws_ + off_G_, 0, nparams_ * 4, stream);
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   }
-  {
-    void* xs = ws_ + off_xs_;
-    const int N = N_;
-    e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
-                  (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
-               stream);
-  }
-  if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
-  std::string err = run(eval ? fwd_eval_ : fwd_train_, stream);
-  if (!err.empty()) return err;
   const float* E = reinterpret_cast<const float*>(ws_ + off_E_);
   float* dE = eval ? nullptr : reinterpret_cast<float*>(ws_ + off_dE_);
   float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);

@@ -109,6 +109,8 @@ class Engine {
   uint8_t* pws_ = nullptr;
   bool bound_ = false;
   int launches_ = 0;
+  bool fwd_train_valid_ = false;  // a train-mode forward() has run since the last update_grads (see obs == NULL there)
+  int fwd_launches_ = 0;
   bool profiling_ = false;
   std::vector<cudaEvent_t> prof_events_;
   std::vector<int> prof_ops_family_;

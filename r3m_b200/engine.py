@@ -115,8 +115,16 @@ class Engine:
             L.check(L.lib.r3m_b200_engine_forward(self._h, L.ptr(obs), int(train), L.ptr(out), L.current_stream()))
         return out
 
-    def update_grads(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, eval_mode):
+    def forward_train_async(self, obs):
+        """Enqueue the train-mode forward only (embeddings stay in the engine); pair with update_grads(obs=None)."""
         assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.frames * 3 * 224 * 224
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_forward(self._h, L.ptr(obs), 1, None, L.current_stream()))
+
+    def update_grads(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, eval_mode):
+        """obs None: the forward pass was enqueued with forward_train_async(obs) (training only)."""
+        assert obs is None or (obs.dtype == torch.float32 and obs.is_contiguous()
+                               and obs.numel() == self.frames * 3 * 224 * 224)
         assert perms.dtype == torch.int32 and perms.is_cuda and perms.is_contiguous()
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_update_grads(self._h, L.ptr(obs), L.ptr(perms), L.ptr(lang_emb),
