@@ -3,7 +3,9 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 
 #include "elementwise.cuh"
 #include "loss.cuh"
@@ -48,6 +50,8 @@ constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are
 
 Engine::~Engine() {
   if (eval_graph_) cudaGraphExecDestroy(eval_graph_);
+  for (cudaEvent_t ev : evs_) cudaEventDestroy(ev);
+  if (side_) cudaStreamDestroy(side_);
   for (Conv* c : convs_) delete c;
   for (Block* b : blocks_) delete b;
 }
@@ -241,7 +245,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   }
   e->off_E_ = arena(N * e->D_ * 4);
   e->off_dE_ = arena(N * e->D_ * 4);
-  for (int i = 0; i < 5; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
+  for (int i = 0; i < 7; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
   e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
   e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
@@ -325,8 +329,8 @@ std::string Engine::plan_all() {
   bf16* xs = reinterpret_cast<bf16*>(ws_ + off_xs_);
   uint8_t* argmax = ws_ + off_argmax_;
   float* E = reinterpret_cast<float*>(ws_ + off_E_);
-  bf16* g[5];
-  for (int i = 0; i < 5; ++i) g[i] = reinterpret_cast<bf16*>(ws_ + off_g_[i]);
+  bf16* g[7];
+  for (int i = 0; i < 7; ++i) g[i] = reinterpret_cast<bf16*>(ws_ + off_g_[i]);
   const int N = N_;
   std::string err;
 
@@ -497,6 +501,37 @@ std::string Engine::plan_all() {
 
   // ------------------------------------------------------------------------------------------------ backward
   bwd_.clear();
+  // Cross-stream schedule.  Every wgrad goes to the side stream and is released by the NEXT BatchNorm-backward reduce
+  // pass of the main chain:   dgrad(c) | bn_bwd_reduce(below) | wgrad(c) on the side stream || bn_bwd_apply(below) | ...
+  // A wgrad CTA takes a whole SM's shared memory, so it can only share the SM with kernels that use none: the apply
+  // pass (HBM bound) co-runs with it, the reduce pass (16-24 KB of shared memory) and the dgrad cannot.  The dy buffer
+  // a wgrad reads rotates over three buffers; before the main stream overwrites one, it waits for its last reader.
+  int n_events = 0;
+  std::vector<Op> held_wgrads;                 // created, not yet placed: released by the next reduce pass
+  std::vector<int> deferred;                   // waits to attach to the next main-stream op
+  std::map<const void*, int> pending_reader;   // dy buffer -> event of the side-stream wgrad that reads it
+  auto attach_deferred = [&](size_t first_new_op) {
+    if (deferred.empty() || first_new_op >= bwd_.size()) return;
+    for (int ev : deferred) bwd_[first_new_op].wait.push_back(ev);
+    deferred.clear();
+  };
+  auto guard_write = [&](const void* buf) {  // the next main op may overwrite `buf`
+    auto it = pending_reader.find(buf);
+    if (it != pending_reader.end()) {
+      deferred.push_back(it->second);
+      pending_reader.erase(it);
+    }
+  };
+  auto release_wgrads = [&]() {  // place the held filter gradients behind the main-stream op pushed last
+    if (held_wgrads.empty()) return;
+    if (bwd_.back().record < 0) bwd_.back().record = n_events++;
+    const int after_main = bwd_.back().record;
+    for (Op& w : held_wgrads) {
+      w.wait.push_back(after_main);
+      bwd_.push_back(w);
+    }
+    held_wgrads.clear();
+  };
   auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const uint8_t* mask, bf16* dy, bf16* dz_out,
                          const Conv* second, bf16* dy2) {
     BnBwdArgs a;
@@ -526,10 +561,15 @@ std::string Engine::plan_all() {
     }
     const double mc = (double)a.M * a.C * 2;
     const double rd = 2 + (mask ? 1.0 / 16 : 0.0) + (second ? 1 : 0);
+    guard_write(dy);
+    if (dy2) guard_write(dy2);
+    const size_t first = bwd_.size();
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * rd));
+    bwd_.back().label = "bn_bwd_reduce " + c.bn;
+    attach_deferred(first);
+    release_wgrads();
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); }, kFamNorm, 0.0,
                       mc * (rd + 1 + (dz_out ? 1 : 0) + (second ? 1 : 0))));
-    bwd_[bwd_.size() - 2].label = "bn_bwd_reduce " + c.bn;
     bwd_.back().label = "bn_bwd_apply " + c.bn;
   };
   auto push_wgrad = [&](const Conv& c, const bf16* dy) {
@@ -551,9 +591,13 @@ std::string Engine::plan_all() {
     }
     const double m = (double)N * c.P * c.Q;
     const double kdim = (double)c.R * c.R * c.Cin;
-    bwd_.push_back(Op([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad, 2.0 * m * c.Cout * kdim,
-                      2.0 * (m * c.Cout + (double)N * c.H * c.W * c.Cin) + 4.0 * c.Cout * kdim));
-    bwd_.back().label = "wgrad " + c.name;
+    Op w([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad, 2.0 * m * c.Cout * kdim,
+         2.0 * (m * c.Cout + (double)N * c.H * c.W * c.Cin) + 4.0 * c.Cout * kdim);
+    w.label = "wgrad " + c.name;
+    w.side = true;
+    w.record = n_events++;
+    pending_reader[dy] = w.record;
+    held_wgrads.push_back(w);
   };
   auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
@@ -599,7 +643,13 @@ std::string Engine::plan_all() {
 
   bf16* d_out = g[0];
   bf16* d_in = g[1];
-  bf16 *s1 = g[2], *s2 = g[3], *s3 = g[4];
+  bf16 *s2 = g[3], *s3 = g[4];
+  bf16* dy_ring[3] = {g[2], g[5], g[6]};
+  int dy_slot = 0;
+  auto next_dy = [&]() {
+    dy_slot = (dy_slot + 1) % 3;
+    return dy_ring[dy_slot];
+  };
   {
     const float* dE = reinterpret_cast<const float*>(ws_ + off_dE_);
     bf16* dst = d_out;
@@ -615,30 +665,34 @@ std::string Engine::plan_all() {
     // last BN of the residual branch: masked by the block output's ReLU.  Identity blocks: the masked gradient is
     // also the skip path's share and seeds d_in.  Downsample blocks: the same masked gradient drives the downsample
     // BatchNorm's backward in the same two passes (dy_ds -> s3).
-    push_bn_bwd(last, d_out, last.mask, s1, has_ds ? nullptr : d_in, has_ds ? convs_[blk->ds] : nullptr, s3);
-    const bf16* dy = s1;
+    bf16* dy = next_dy();
+    push_bn_bwd(last, d_out, last.mask, dy, has_ds ? nullptr : d_in, has_ds ? convs_[blk->ds] : nullptr, s3);
     for (int i = n - 1; i >= 0; --i) {
       Conv& c = *convs_[blk->main[i]];
-      push_wgrad(c, dy);
+      // data gradient first (main stream), then the filter gradient of the same layer on the side stream
       if (i > 0) {
         Conv& prev = *convs_[blk->main[i - 1]];
         push_dgrad(c, dy, s2, 0);
-        push_bn_bwd(prev, s2, prev.mask, s1, nullptr, nullptr, nullptr);
-        dy = s1;
+        push_wgrad(c, dy);
+        bf16* dy_prev = next_dy();
+        push_bn_bwd(prev, s2, prev.mask, dy_prev, nullptr, nullptr, nullptr);
+        dy = dy_prev;
       } else {
         push_dgrad(c, dy, d_in, has_ds ? 0 : 1);
+        push_wgrad(c, dy);
       }
     }
     if (has_ds) {
       Conv& d = *convs_[blk->ds];
-      push_wgrad(d, s3);
       push_dgrad(d, s3, d_in, 1);
+      push_wgrad(d, s3);
     }
     std::swap(d_out, d_in);
     if (!err.empty()) return err;
   }
   {
     // stem: maxpool backward + ReLU mask + BN backward fused in two passes -> filter gradient (no data gradient)
+    release_wgrads();  // layer1.0's filter gradients: behind its last dgrad
     Conv& st = *convs_[0];
     StemBwdArgs sb;
     sb.dA = d_out;
@@ -683,6 +737,20 @@ std::string Engine::plan_all() {
                       2.0 * N * 112.0 * 112 * 64 * 147, 2.0 * N * 112.0 * 112 * 128));
     float* dst = G + st.w_off;
     bwd_.push_back(Op([stem_dwp, dst](cudaStream_t s) { return launch_stem_unpack_grad(stem_dwp, dst, s); }, kFamOptim));
+    // join: the step's last backward op waits for every filter gradient still running on the side stream
+    for (auto& kv : pending_reader) bwd_.back().wait.push_back(kv.second);
+    pending_reader.clear();
+  }
+
+  while ((int)evs_.size() < n_events) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return "cudaEventCreate failed";
+    evs_.push_back(ev);
+  }
+  if (!side_ && cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking) != cudaSuccess) return "side stream creation failed";
+  {
+    const char* env = std::getenv("R3M_WGRAD_STREAM");
+    use_side_ = !(env && env[0] == '0');
   }
 
   // ------------------------------------------------------------------------------------------------ re-packs
@@ -729,9 +797,21 @@ std::string Engine::plan_all() {
 }
 
 std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
+  // profiling (an event pair around every launch) keeps everything on one stream so that per-family times add up
+  const bool two_streams = use_side_ && !profiling_ && side_ != nullptr;
   for (const Op& op : ops) {
-    cudaError_t e = launch(op, stream);
+    cudaStream_t s = (two_streams && op.side) ? side_ : stream;
+    if (two_streams)
+      for (int ev : op.wait) {
+        cudaError_t we = cudaStreamWaitEvent(s, evs_[ev], 0);
+        if (we != cudaSuccess) return std::string("stream wait failed: ") + cudaGetErrorString(we);
+      }
+    cudaError_t e = launch(op, s);
     if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
+    if (two_streams && op.record >= 0) {
+      cudaError_t re = cudaEventRecord(evs_[op.record], s);
+      if (re != cudaSuccess) return std::string("event record failed: ") + cudaGetErrorString(re);
+    }
   }
   return std::string();
 }

@@ -88,6 +88,10 @@ class Engine {
     double bytes = 0.0;  // algorithmic HBM bytes (operands read once + results written once)
     std::string label;   // what the launch is (layer / role), for the per-launch profile
     int nlaunch = 1;     // kernels the op launches (fused two-pass ops count both)
+    // cross-stream schedule of the backward pass: ops with side = true run on the engine's second stream
+    bool side = false;
+    std::vector<int> wait;  // event ids the op's stream waits on before the launch
+    int record = -1;        // event id recorded on the op's stream after the launch
     Op() {}
     template <class F>
     Op(F f, int fam = 0, double fl = 0.0, double by = 0.0) : fn(f), family(fam), flops(fl), bytes(by) {}
@@ -121,7 +125,7 @@ class Engine {
   // arena offsets (bytes)
   size_t off_P_ = 0, off_G_ = 0, off_M_ = 0, off_V_ = 0, off_Pb_ = 0, off_buf_ = 0, off_saved_ = 0, off_zero_ = 0,
          zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0,
-         off_E_ = 0, off_dE_ = 0, off_g_[5] = {0, 0, 0, 0, 0};
+         off_E_ = 0, off_dE_ = 0, off_g_[7] = {0, 0, 0, 0, 0, 0, 0};
   size_t nsaved_ = 0, nwd_ = 0;
   // language head (optional)
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
@@ -135,6 +139,11 @@ class Engine {
   LangDims lang_dims_;
 
   std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;
+  // Filter gradients run on a second stream: nothing in the backward chain consumes them, and a wgrad CTA (tensor /
+  // L2 bound, one per SM) co-resides with the HBM-bound BatchNorm-backward CTAs of the layer below.
+  cudaStream_t side_ = nullptr;
+  std::vector<cudaEvent_t> evs_;
+  bool use_side_ = true;
 };
 
 }  // namespace r3m

@@ -280,3 +280,39 @@ def test_full_size_c3_step_properties():
     m2.eval(), m.eval()
     with torch.no_grad():
         assert rel(m2(frames[0]), m(frames[0])) < 1e-6
+
+
+@pytest.mark.parametrize("size,clips", [(50, 12), (34, 6)])
+def test_side_stream_schedule_matches_single_stream(size, clips, monkeypatch):
+    """The backward pass runs the filter gradients on a second stream (released by the next BatchNorm-backward reduce
+    pass, dy buffers rotating over three slots).  The same step with everything on one stream (R3M_WGRAD_STREAM=0, read
+    when an engine is planned) must give the same gradients: a missing dependency would corrupt whole filters, while
+    the only legitimate difference is the ordering of fp32 atomics in the BatchNorm statistics (amplified by the
+    network's conditioning at random init to ~1e-3 on single tensors)."""
+    import r3m_b200
+    from r3m_b200 import R3M, Trainer
+    from oracle import r3m_oracle as O
+
+    lang_emb = O.stub_lang_embedding(clips, 3)
+    r3m_b200.set_lang_encoder_factory(lambda dev: (lambda s: lang_emb))
+    params, buffers = O.init_state(size, 1, lang=True)
+    frames = O.structured_frames(clips, 2).cuda()
+    perms = O.draw_permutations(clips, 4)
+    grads = []
+    for flag in ("0", "1", "1"):
+        monkeypatch.setenv("R3M_WGRAD_STREAM", flag)
+        m = R3M("cuda", 1e-4, 1024, size=size, l2weight=1e-5, l1weight=1e-5, langweight=1.0, tcnweight=1.0)
+        sd = dict(params)
+        sd.update(buffers)
+        m.load_state_dict(sd)
+        model = torch.nn.DataParallel(m).cuda()
+        tr = Trainer(100)
+        for _ in range(2):  # twice: the second step re-uses every event and ring slot
+            tr.update(model, (frames, ["x"] * clips), 0, perms=perms)
+        grads.append({k: v.grad.detach().clone() for k, v in m.named_parameters()})
+    noise = max(rel(grads[2][k], grads[1][k]) for k in grads[1] if k.endswith("conv1.weight") or "conv" in k)
+    for k in grads[0]:
+        if grads[0][k].numel() < 64:
+            continue
+        d = rel(grads[1][k], grads[0][k])
+        assert d < max(2e-2, 10 * noise), (k, d, noise)
