@@ -190,6 +190,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def conv_traffic(args, clips):
+    """DRAM bytes per conv_igemm launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 114 launches of
+    one step) from the committed ncu capture of this exact workload (profiles/r1_conv_traffic.json, produced by
+    tools/ncu_per_kernel.py); None for any other workload.  Algorithmic bytes per launch are ~267 MB: the measured
+    traffic is below them because gradients written by the preceding BatchNorm-backward kernel are still in L2."""
+    if args.size != 50 or clips != 64 or not args.lang:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def workload_config(args, clips_override=None):
     clips = clips_override or args.clips
     return {"workload": f"c3/c5: full Trainer.update(): ResNet-{args.size}, 5 frames/clip, {clips} clips per GPU, "
@@ -358,7 +372,8 @@ def run_ours(args):
                 "achieved": conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else None,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "peak_source": pk["source"] + ", of measured",
                 "launches_per_step": conv["launches"], "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
-                "share_of_step": conv["ms"] / total_ms if total_ms else None, "traffic": None,
+                "share_of_step": conv["ms"] / total_ms if total_ms else None,
+                "traffic": conv_traffic(args, B),
                 "dominant_family": dom,
                 "families": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None,

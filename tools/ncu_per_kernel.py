@@ -1,0 +1,69 @@
+"""Turn an `ncu --csv` log of ONE training step into (a) a per-kernel markdown table and (b) the conv_igemm family's
+DRAM traffic per launch (bench.py's roofline.traffic).  Usage (on the GPU box, then here):
+
+  ncu --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
+gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,\
+launch__registers_per_thread -s <launches of the warm-up steps> -c <launches of one step> --csv \
+--log-file gpurun_out/per_kernel.csv python tools/profile_step.py
+  python tools/ncu_per_kernel.py gpurun_out/per_kernel.csv profiles/<round>_ncu_per_kernel.md profiles/<round>_conv_traffic.json
+"""
+import collections
+import csv
+import json
+import re
+import sys
+
+
+def to_float(v):
+    return float(v.replace(",", "")) if v not in ("", "n/a") else 0.0
+
+
+def main(src, md, js):
+    rows = [r for r in csv.reader(open(src, errors="replace")) if len(r) > 10]
+    hdr = rows[0]
+    col = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        d = per.setdefault(r[col["ID"]], {"kernel": r[col["Kernel Name"]]})
+        unit, val = r[col["Metric Unit"]], to_float(r[col["Metric Value"]])
+        name = r[col["Metric Name"]]
+        if name.startswith("dram__bytes"):
+            val *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        if name == "gpu__time_duration.sum":
+            val *= {"ns": 1e-3, "us": 1, "ms": 1e3}.get(unit, 1)
+        d[name] = val
+    agg = collections.OrderedDict()
+    for d in per.values():
+        k = re.sub(r"^void ", "", d["kernel"])
+        k = re.sub(r"\(.*$", "", k).replace("<unnamed>::", "").replace("unnamed>::", "").replace("r3m::", "")
+        a = agg.setdefault(k, collections.defaultdict(float))
+        a["n"] += 1
+        t = d.get("gpu__time_duration.sum", 0.0)
+        a["us"] += t
+        a["rd"] += d.get("dram__bytes_read.sum", 0.0)
+        a["wr"] += d.get("dram__bytes_write.sum", 0.0)
+        a["tensor_t"] += t * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
+        a["dram_t"] += t * d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0.0)
+        a["regs"] = max(a["regs"], d.get("launch__registers_per_thread", 0.0))
+    total = sum(a["us"] for a in agg.values())
+    with open(md, "w") as f:
+        f.write(f"captured {int(sum(a['n'] for a in agg.values()))} launches, {total / 1e3:.2f} ms (serialised, cold cache: "
+                "compare shares)\n\n| kernel | launches | total us | share | dram read MB | dram write MB | HBM GB/s | "
+                "of 6532 | dram % (ncu) | tensor % | regs |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+            gbs = (a["rd"] + a["wr"]) / a["us"] / 1e3 if a["us"] else 0
+            f.write(f"| `{k}` | {int(a['n'])} | {a['us']:.0f} | {100 * a['us'] / total:.1f} % | {a['rd'] / 1e6:.0f} | "
+                    f"{a['wr'] / 1e6:.0f} | {gbs:.0f} | {gbs / 6532:.2f} | {a['dram_t'] / a['us']:.0f} | "
+                    f"{a['tensor_t'] / a['us']:.1f} | {int(a['regs'])} |\n")
+    conv = [a for k, a in agg.items() if k.startswith("conv_igemm_kernel")]
+    n = sum(a["n"] for a in conv)
+    out = {"kernel": "conv_igemm_kernel (all instantiations)", "launches": int(n),
+           "dram_bytes_per_launch": (sum(a["rd"] + a["wr"] for a in conv) / n) if n else None,
+           "dram_bytes_per_step": sum(a["rd"] + a["wr"] for a in conv),
+           "us_under_ncu": sum(a["us"] for a in conv), "source": src}
+    json.dump(out, open(js, "w"), indent=1)
+    print(out)
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:4])
