@@ -26,6 +26,10 @@
 #include "launch.h"
 #include "ptx.cuh"
 
+#ifndef R3M_STATS_REGS
+#define R3M_STATS_REGS 1  // BatchNorm statistics of the conv epilogue accumulate in registers across tiles (0: per-unit shared atomics)
+#endif
+
 namespace r3m {
 
 namespace {
@@ -230,11 +234,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     constexpr int kUnits = BN / kUnitCols;
+    // BatchNorm statistics: a lane owns two columns of each unit its warp drains.  The partial sums stay in registers
+    // for as long as the CTA's tiles keep the same column block (always, when gridDim is a multiple of num_n_tiles)
+    // and reach the CTA's shared-memory table once; shared-memory fp32 atomics are CAS loops, and four of them per
+    // unit were ~20 % of the epilogue's issue slots (ncu source view of the 64 -> 256 1x1 conv).
+    constexpr int kUPW = (kUnits + EPI / 4 - 1) / (EPI / 4);  // units per warp per tile
+    float racc[kUPW][4];
+#pragma unroll
+    for (int i = 0; i < kUPW; ++i) racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
+    int acc_ntile = -1;
+    auto flush_stats = [&](int nt) {
+#pragma unroll
+      for (int i = 0; i < kUPW; ++i) {
+        const int u = h + i * (EPI / 4);
+        if (u < kUnits) {
+          const int col = nt * BN + u * kUnitCols + 2 * lane;
+          atomicAdd(&s_sum[col], racc[i][0]);
+          atomicAdd(&s_sum[col + 1], racc[i][1]);
+          atomicAdd(&s_sq[col], racc[i][2]);
+          atomicAdd(&s_sq[col + 1], racc[i][3]);
+        }
+        racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
+      }
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
+#if R3M_STATS_REGS
+      if (do_stats && n_tile != acc_ntile) {
+        if (acc_ntile >= 0) flush_stats(acc_ntile);
+        acc_ntile = n_tile;
+      }
+#endif
       long long row_off[8];
       if (!dense) {
         // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
@@ -268,8 +301,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(t_row + h * kUnitCols, v0);
         tmem_ld_32x32(t_row + h * kUnitCols + 32, v1);
+        int ui = 0;
 #pragma unroll 1
-        for (int u = h; u < kUnits; u += EPI / 4) {
+        for (int u = h; u < kUnits; u += EPI / 4, ++ui) {
           tc_wait_ld();
           if (do_affine) {
             // folded BatchNorm (+ residual) (+ ReLU) on the fp32 accumulators; thread = output row m0 + lane
@@ -368,11 +402,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               q0 = fmaf(a, a, q0);
               q1 = fmaf(b, b, q1);
             }
+#if R3M_STATS_REGS
+#pragma unroll
+            for (int i = 0; i < kUPW; ++i)
+              if (i == ui) {
+                racc[i][0] += s0;
+                racc[i][1] += s1;
+                racc[i][2] += q0;
+                racc[i][3] += q1;
+              }
+#else
             const int col = n0 + u * kUnitCols + 2 * lane;
             atomicAdd(&s_sum[col], s0);
             atomicAdd(&s_sum[col + 1], s1);
             atomicAdd(&s_sq[col], q0);
             atomicAdd(&s_sq[col + 1], q1);
+#endif
           }
           if (!dense) {
             // strided scatter (stride-2 dgrad parity classes): 8 lanes x 16 B = one 128-byte row segment
@@ -406,6 +451,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
+#if R3M_STATS_REGS
+      if (acc_ntile >= 0) flush_stats(acc_ntile);
+#endif
       // all epilogue warps are done with every tile of this CTA -> flush the CTA partials
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
       for (int i = threadIdx.x - 128; i < p.Cout; i += EPI * 32) {
