@@ -66,7 +66,10 @@ struct Cfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int STAGES, int BUFS, int EPI, int KPS>
+// STATS: the launch accumulates BatchNorm statistics (training forward convs; always dense outputs).  A compile-time
+// switch because the statistics' register accumulators and the scatter path's row offsets do not fit together: with
+// both compiled in, the 8-epilogue-warp configurations (170-register budget) spilled and the stride-2 dgrads lost 30 %.
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, bool STATS>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
@@ -84,7 +87,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool do_stats = (p.stat_sum != nullptr);
+  constexpr bool do_stats = STATS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -104,7 +107,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
   pdl_sync();  // everything above is CTA-local; global memory is first touched below
-  const bool do_affine = (p.ep_scale != nullptr);
+  const bool do_affine = !STATS && (p.ep_scale != nullptr);
   if (do_stats) {
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
       s_sum[i] = 0.f;
@@ -229,7 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int h = (warp - 4) >> 2;
     const uint32_t stg_base = smem_u32(staging + (warp - 4) * (BUFS * kUnitBytes));
     int buf = 0;
-    const bool dense = (p.out_mode == 0);
+    const bool dense = STATS || (p.out_mode == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -238,7 +241,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // for as long as the CTA's tiles keep the same column block (always, when gridDim is a multiple of num_n_tiles)
     // and reach the CTA's shared-memory table once; shared-memory fp32 atomics are CAS loops, and four of them per
     // unit were ~20 % of the epilogue's issue slots (ncu source view of the 64 -> 256 1x1 conv).
-    constexpr int kUPW = (kUnits + EPI / 4 - 1) / (EPI / 4);  // units per warp per tile
+    constexpr int kUPW = STATS ? (kUnits + EPI / 4 - 1) / (EPI / 4) : 1;  // units per warp per tile
     float racc[kUPW][4];
 #pragma unroll
     for (int i = 0; i < kUPW; ++i) racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
@@ -262,13 +265,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
-#if R3M_STATS_REGS
-      if (do_stats && n_tile != acc_ntile) {
-        if (acc_ntile >= 0) flush_stats(acc_ntile);
-        acc_ntile = n_tile;
+      if constexpr (STATS && R3M_STATS_REGS) {
+        if (n_tile != acc_ntile) {
+          if (acc_ntile >= 0) flush_stats(acc_ntile);
+          acc_ntile = n_tile;
+        }
       }
-#endif
-      long long row_off[8];
+      long long row_off[STATS ? 1 : 8];
       if (!dense) {
         // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
 #pragma unroll
@@ -474,19 +477,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int STAGES, int BUFS, int EPI, int KPS>
-cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                      const ConvKernelParams& p, int grid, cudaStream_t stream) {
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, bool STATS>
+cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, STATS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB, tmC, p);
+  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, STATS>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB,
+                tmC, p);
   return cudaGetLastError();
+}
+
+template <int BN, int STAGES, int BUFS, int EPI, int KPS>
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                      const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  if (p.stat_sum != nullptr) {
+    if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr) return cudaErrorInvalidValue;
+    return launch_cfg<BN, STAGES, BUFS, EPI, KPS, true>(tmA, tmB, tmC, p, grid, stream);
+  }
+  return launch_cfg<BN, STAGES, BUFS, EPI, KPS, false>(tmA, tmB, tmC, p, grid, stream);
 }
 
 }  // namespace
