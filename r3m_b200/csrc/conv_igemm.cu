@@ -66,10 +66,13 @@ struct Cfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-// STATS: the launch accumulates BatchNorm statistics (training forward convs; always dense outputs).  A compile-time
-// switch because the statistics' register accumulators and the scatter path's row offsets do not fit together: with
-// both compiled in, the 8-epilogue-warp configurations (170-register budget) spilled and the stride-2 dgrads lost 30 %.
-template <int BN, int STAGES, int BUFS, int EPI, int KPS, bool STATS>
+// MODE (compile time, because the three epilogues' register needs do not fit together in the 170-register budget of
+// the 8-epilogue-warp configurations: compiled into one kernel they spilled and the stride-2 dgrads lost 30 %):
+//   kModeDense   dense output (TMA bulk stores / reduce-add), optional folded-BN epilogue
+//   kModeStats   dense output + BatchNorm statistics (training forward convs)
+//   kModeScatter strided scatter output with optional read-modify-write (stride-2 dgrad parity classes)
+enum { kModeDense = 0, kModeStats = 1, kModeScatter = 2 };
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
@@ -87,6 +90,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool STATS = (MODE == kModeStats);
   constexpr bool do_stats = STATS;
 
   if (warp == 0 && lane == 0) {
@@ -232,7 +236,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int h = (warp - 4) >> 2;
     const uint32_t stg_base = smem_u32(staging + (warp - 4) * (BUFS * kUnitBytes));
     int buf = 0;
-    const bool dense = STATS || (p.out_mode == 0);
+    constexpr bool dense = (MODE != kModeScatter);
     int acc = 0;
     uint32_t acc_phase = 0;
     __nv_bfloat16* __restrict__ outp = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -271,8 +275,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           acc_ntile = n_tile;
         }
       }
-      long long row_off[STATS ? 1 : 8];
-      if (!dense) {
+      long long row_off[dense ? 1 : 8];
+      if constexpr (!dense) {
         // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -422,8 +426,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             atomicAdd(&s_sq[col + 1], q1);
 #endif
           }
-          if (!dense) {
-            // strided scatter (stride-2 dgrad parity classes): 8 lanes x 16 B = one 128-byte row segment
+          if constexpr (!dense) {
+            // strided scatter (stride-2 dgrad parity classes): 8 lanes x 16 B = one 128-byte row segment.  When
+            // accumulating, the eight read-modify-write loads of the lane are issued together (one global round trip per
+            // unit instead of eight dependent ones).
+            uint4 prev[8];
+            if (p.accumulate) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                prev[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (row_off[i] >= 0)
+                  prev[i] = *reinterpret_cast<const uint4*>(outp + row_off[i] + n0 + u * kUnitCols + (lane & 7) * 8);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = 4 * i + (lane >> 3);
@@ -436,7 +451,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (row_off[i] >= 0) {
                 uint4* dst = reinterpret_cast<uint4*>(outp + row_off[i] + n0 + u * kUnitCols + c * 8);
                 if (p.accumulate) {
-                  const uint4 o = *dst;
+                  const uint4 o = prev[i];
                   x0 = pack_bf16x2(bf16lo(x0) + bf16lo(o.x), bf16hi(x0) + bf16hi(o.x));
                   x1 = pack_bf16x2(bf16lo(x1) + bf16lo(o.y), bf16hi(x1) + bf16hi(o.y));
                   x2 = pack_bf16x2(bf16lo(x2) + bf16lo(o.z), bf16hi(x2) + bf16hi(o.z));
@@ -477,18 +492,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int STAGES, int BUFS, int EPI, int KPS, bool STATS>
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE>
 cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, STATS>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, STATS>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB,
+  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB,
                 tmC, p);
   return cudaGetLastError();
 }
@@ -498,9 +513,18 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
   if (p.stat_sum != nullptr) {
     if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr) return cudaErrorInvalidValue;
-    return launch_cfg<BN, STAGES, BUFS, EPI, KPS, true>(tmA, tmB, tmC, p, grid, stream);
+    return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeStats>(tmA, tmB, tmC, p, grid, stream);
   }
-  return launch_cfg<BN, STAGES, BUFS, EPI, KPS, false>(tmA, tmB, tmC, p, grid, stream);
+  if (p.out_mode != 0) {
+    // the scatter epilogue keeps 8 row offsets + 8 prefetched 16-byte words per lane: 4 epilogue warps (254 registers)
+    if constexpr (EPI == 4) {
+      if (p.ep_scale != nullptr) return cudaErrorInvalidValue;
+      return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeScatter>(tmA, tmB, tmC, p, grid, stream);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
+  return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense>(tmA, tmB, tmC, p, grid, stream);
 }
 
 }  // namespace
@@ -508,6 +532,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                               const ConvKernelParams& p, int grid, cudaStream_t stream) {
   const int num_kb = p.num_taps * p.cblocks;
+  const bool scatter = p.out_mode != 0;
   switch (bn) {
     case 64:  // one unit per quadrant
       if (p.Cout > StatC<64>::value) return cudaErrorInvalidValue;
@@ -515,10 +540,10 @@ cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap&
       return launch_bn<64, 6, 4, 4, 1>(tmA, tmB, tmC, p, grid, stream);
     case 128:
       if (p.Cout > StatC<128>::value) return cudaErrorInvalidValue;
-      if (num_kb >= 18) return launch_bn<128, 3, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3
+      if (num_kb >= 18 || scatter) return launch_bn<128, 3, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3
       return launch_bn<128, 4, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);
     case 256:
-      if (num_kb >= 12) return launch_bn<256, 4, 1, 4, 1>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
+      if (num_kb >= 12 || scatter) return launch_bn<256, 4, 1, 4, 1>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
       return launch_bn<256, 3, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);                    // epilogue bound
     default:
       return cudaErrorInvalidValue;
