@@ -398,10 +398,18 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    # the first communicator is created), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+    # saved original descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
