@@ -95,14 +95,16 @@ int r3m_b200_bn_backward(const void* dA, const void* a, const uint8_t* mask, con
  * 15: the maximum is 0, i.e. clipped by the ReLU, and carries no gradient).  maxpool_backward returns the gradient
  * w.r.t. the BN output with the ReLU mask applied (`a` is unused and may be null).  stem_backward is the fused form
  * the engine runs: aten::max_pool2d_with_indices_backward + threshold_backward + cudnn_batch_norm_backward in two
- * passes that recompute the pooled gradient scatter on the fly (sums: fp32 [2*C] zeroed scratch). */
-int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N, int H, int W, int C, int train,
+ * passes that recompute the pooled gradient scatter on the fly (sums: fp32 [2*C] zeroed scratch).  ymax (optional in both
+ * calls): bf16 [N,H/2,W/2,C], the RAW conv output at each window's argmax; when given, the backward's reduce pass runs
+ * over the pooled elements only. */
+int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, void* ymax, int N, int H, int W, int C, int train,
                                   const float* sum, const float* sq, const float* gamma, const float* beta,
                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd,
                                   void* stream);
 int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argmax, void* dz, int N, int H, int W, int C,
                               void* stream);
-int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y, int N, int H, int W, int C,
+int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* ymax, const void* y, int N, int H, int W, int C,
                            const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
                            float* dgamma, float* dbeta, void* stream);
 

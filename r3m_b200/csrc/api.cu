@@ -265,7 +265,7 @@ int r3m_b200_bn_backward(const void* dA, const void* a, const uint8_t* mask, con
   CUDA_OR_FAIL(launch_bn_bwd_apply(g, (cudaStream_t)stream), "bn_bwd_apply");
 }
 
-int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N, int H, int W, int C, int train,
+int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, void* ymax, int N, int H, int W, int C, int train,
                                   const float* sum, const float* sq, const float* gamma, const float* beta,
                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd,
                                   void* stream) {
@@ -273,6 +273,7 @@ int r3m_b200_stem_bn_relu_maxpool(const void* y, void* a, uint8_t* argmax, int N
   g.y = y;
   g.a = a;
   g.argmax = argmax;
+  g.ymax = ymax;
   g.N = N;
   g.H = H;
   g.W = W;
@@ -295,7 +296,7 @@ int r3m_b200_maxpool_backward(const void* dA, const void* a, const uint8_t* argm
   CUDA_OR_FAIL(launch_maxpool_bwd(dA, argmax, dz, N, H, W, C, (cudaStream_t)stream), "maxpool_backward");
 }
 
-int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y, int N, int H, int W, int C,
+int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* ymax, const void* y, int N, int H, int W, int C,
                            const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
                            float* dgamma, float* dbeta, void* stream) {
   if (!dA || !argmax || !y || !mean || !rstd || !gamma || !sums || !dy)
@@ -303,6 +304,7 @@ int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* y,
   StemBwdArgs g;
   g.dA = dA;
   g.argmax = argmax;
+  g.ymax = ymax;
   g.y = y;
   g.N = N;
   g.H = H;

@@ -278,6 +278,9 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
         cd[2 * w + 1] = (int)(code[w] >> 16);
       }
       st8(out + idx * 8, o);
+      if (a.ymax)
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.ymax) + idx * 8) =
+            make_uint4(best[0] ^ flip[0], best[1] ^ flip[1], best[2] ^ flip[2], best[3] ^ flip[3]);
       if (a.argmax) {
         // "dead" must describe the STORED (bf16-rounded) activation, like the ReLU masks of bn_apply
 #pragma unroll
@@ -483,6 +486,50 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
       if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
     }
   }
+}
+
+// Reduce pass of the stem backward over the POOLED elements (needs ymax from the forward): every live window routes its
+// gradient to exactly one conv-output pixel, whose raw value is ymax, so
+//   sum_pixels dz = sum_windows dA * live,   sum_pixels dz * (y - mean) = sum_windows dA * live * (ymax - mean).
+// Reads 320 MB instead of the 706 MB (and the 2x2-quad matching) of the per-pixel formulation.
+__global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemBwdArgs a) {
+  pdl_sync();
+  __shared__ float s_red[2 * 256];
+  const int C8 = a.C >> 3;
+  const int chunk = threadIdx.x % C8;  // the grid stride is a multiple of C8
+  const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
+  const bf16* __restrict__ ym = reinterpret_cast<const bf16*>(a.ymax);
+  const size_t total = (size_t)a.N * (a.H / 2) * (a.W / 2) * C8;
+  float mean[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = a.mean[chunk * 8 + j];
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+#pragma unroll 2
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const F8 g = ld8(dA + idx * 8);
+    const F8 y = ld8(ym + idx * 8);
+    const uint2 cd = __ldg(reinterpret_cast<const uint2*>(a.argmax + idx * 8));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cj = ((j < 4 ? cd.x : cd.y) >> (8 * (j & 3))) & 0xFFu;
+      const float gj = (cj != (uint32_t)kPoolDead) ? g.v[j] : 0.f;
+      s1[j] += gj;
+      s2[j] = fmaf(gj, y.v[j] - mean[j], s2[j]);
+    }
+  }
+  pdl_done();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[chunk * 8 + j], s1[j]);
+    atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j] * a.rstd[chunk * 8 + j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ avg pool
@@ -881,8 +928,14 @@ cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 256 || kStemThreads % (a.C / 8) != 0 || (a.H & 1) || (a.W & 1))
     return cudaErrorInvalidValue;
   const int rows = a.N * (a.H / 2);  // one block iteration = one row of 2x2 quads
-  launch_kernel(stem_bwd_kernel<false>, std::min(rows, resident_blocks<stem_bwd_kernel<false>>(kStemThreads)),
-                kStemThreads, 0, s, a);
+  if (a.ymax != nullptr && 256 % (a.C / 8) == 0) {
+    const long long total = (long long)a.N * (a.H / 2) * (a.W / 2) * (a.C / 8);
+    launch_kernel(stem_bwd_reduce_pooled_kernel,
+                  grid_for((total + 3) / 4, 256, resident_blocks<stem_bwd_reduce_pooled_kernel>(256)), 256, 0, s, a);
+  } else {
+    launch_kernel(stem_bwd_kernel<false>, std::min(rows, resident_blocks<stem_bwd_kernel<false>>(kStemThreads)),
+                  kStemThreads, 0, s, a);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   launch_kernel(stem_bwd_kernel<true>, std::min(rows, resident_blocks<stem_bwd_kernel<true>>(kStemThreads)),

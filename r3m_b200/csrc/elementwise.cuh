@@ -49,6 +49,7 @@ struct StemPoolArgs {
   const void* y = nullptr;
   void* a = nullptr;
   uint8_t* argmax = nullptr;  // may be null (eval)
+  void* ymax = nullptr;       // optional bf16 [N,H/2,W/2,C]: the RAW conv output at the argmax (for the backward reduce)
   int N = 0, H = 112, W = 112, C = 64;
   int train = 1;
   const float* sum = nullptr;
@@ -71,6 +72,9 @@ cudaError_t launch_maxpool_bwd(const void* dA, const uint8_t* argmax, void* dz, 
 struct StemBwdArgs {
   const void* dA = nullptr;        // bf16 [N,H/2,W/2,C] gradient w.r.t. the pooled output
   const uint8_t* argmax = nullptr; // [N,H/2,W/2,C] codes written by launch_stem_bn_relu_maxpool
+  // optional bf16 [N,H/2,W/2,C] raw conv output at each window's argmax (same launch): the reduce pass then runs over
+  // the pooled elements only (sum dz = sum over live windows of dA, sum dz*xhat likewise with xhat taken at ymax)
+  const void* ymax = nullptr;
   const void* y = nullptr;         // bf16 [N,H,W,C] raw stem conv output
   int N = 0, H = 112, W = 112, C = 64;
   const float* mean = nullptr;

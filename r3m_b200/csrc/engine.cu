@@ -235,6 +235,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   e->off_stem_dwp_ = e->off_metrics_ + kNumMetrics * 4;
   e->off_xs_ = arena(N * 112 * 112 * 64 * 2);
   e->off_argmax_ = arena(N * 56 * 56 * 64);
+  e->off_ymax_ = arena(N * 56 * 56 * 64 * 2);
   for (Conv* c : e->convs_) {
     c->y_off = arena(c->out_elems(frames) * 2);
     if (c->stem)
@@ -328,6 +329,7 @@ std::string Engine::plan_all() {
   float* stem_dwp = reinterpret_cast<float*>(ws_ + off_stem_dwp_);
   bf16* xs = reinterpret_cast<bf16*>(ws_ + off_xs_);
   uint8_t* argmax = ws_ + off_argmax_;
+  bf16* ymax = reinterpret_cast<bf16*>(ws_ + off_ymax_);
   float* E = reinterpret_cast<float*>(ws_ + off_E_);
   bf16* g[7];
   for (int i = 0; i < 7; ++i) g[i] = reinterpret_cast<bf16*>(ws_ + off_g_[i]);
@@ -397,6 +399,7 @@ std::string Engine::plan_all() {
       a.y = st.y;
       a.a = st.a;
       a.argmax = train ? argmax : nullptr;
+      a.ymax = train ? ymax : nullptr;
       a.N = N;
       a.train = train;
       a.sum = zero + st.zero_off;
@@ -408,7 +411,7 @@ std::string Engine::plan_all() {
       a.save_mean = saved + st.save_off;
       a.save_rstd = saved + st.save_off + 64;
       ops.push_back(Op([a](cudaStream_t s) { return launch_stem_bn_relu_maxpool(a, s); }, kFamPool, 0.0,
-                       (double)N * 64 * (112.0 * 112 * 2 + 56.0 * 56 * 3)));
+                       (double)N * 64 * (112.0 * 112 * 2 + 56.0 * 56 * (train ? 5 : 2))));
     }
     if (!train) {
       // inference: every BatchNorm except the stem's is folded into its conv's epilogue (scale/shift live in the
@@ -697,6 +700,7 @@ std::string Engine::plan_all() {
     StemBwdArgs sb;
     sb.dA = d_out;
     sb.argmax = argmax;
+    sb.ymax = ymax;
     sb.y = st.y;
     sb.N = N;
     sb.mean = saved + st.save_off;
@@ -706,9 +710,10 @@ std::string Engine::plan_all() {
     sb.dy = s2;
     sb.dgamma = G + st.gamma_off;
     sb.dbeta = G + st.beta_off;
-    // algorithmic bytes: y read twice, pooled gradient + argmax codes read twice, dy written once
+    // algorithmic bytes: reduce pass over the pooled elements (dA, ymax, codes); apply pass y + pooled gradient + codes
+    // read, dy written
     bwd_.push_back(Op([sb](cudaStream_t s) { return launch_stem_bwd(sb, s); }, kFamNorm, 0.0,
-                      (double)N * 64 * (112.0 * 112 * 6 + 56.0 * 56 * 6)));
+                      (double)N * 64 * (112.0 * 112 * 4 + 56.0 * 56 * 8)));
     bwd_.back().label = "stem_bwd (maxpool + relu + bn1 backward, 2 launches)";
     bwd_.back().nlaunch = 2;
     WgradDesc d;

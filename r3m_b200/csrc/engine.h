@@ -124,7 +124,7 @@ class Engine {
 
   // arena offsets (bytes)
   size_t off_P_ = 0, off_G_ = 0, off_M_ = 0, off_V_ = 0, off_Pb_ = 0, off_buf_ = 0, off_saved_ = 0, off_zero_ = 0,
-         zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0,
+         zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0, off_ymax_ = 0,
          off_E_ = 0, off_dE_ = 0, off_g_[7] = {0, 0, 0, 0, 0, 0, 0};
   size_t nsaved_ = 0, nwd_ = 0;
   // language head (optional)

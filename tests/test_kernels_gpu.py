@@ -290,8 +290,9 @@ def test_stem_pool_forward_backward(lib):
     rm, rv, sm, sr = torch.zeros(C).cuda(), torch.ones(C).cuda(), torch.empty(C).cuda(), torch.empty(C).cuda()
     a = torch.empty(N, H // 2, H // 2, C, device="cuda", dtype=torch.bfloat16)
     am = torch.empty(N, H // 2, H // 2, C, device="cuda", dtype=torch.uint8)
+    ymax = torch.empty(N, H // 2, H // 2, C, device="cuda", dtype=torch.bfloat16)
     s = lib.current_stream()
-    lib.check(lib.lib.r3m_b200_stem_bn_relu_maxpool(lib.ptr(y), lib.ptr(a), lib.ptr(am), N, H, H, C, 1, lib.ptr(ssum),
+    lib.check(lib.lib.r3m_b200_stem_bn_relu_maxpool(lib.ptr(y), lib.ptr(a), lib.ptr(am), lib.ptr(ymax), N, H, H, C, 1, lib.ptr(ssum),
                                                     lib.ptr(ssq), lib.ptr(gamma), lib.ptr(beta), lib.ptr(rm),
                                                     lib.ptr(rv), lib.ptr(sm), lib.ptr(sr), s))
     x = yf.permute(0, 3, 1, 2).requires_grad_(True)
@@ -312,12 +313,22 @@ def test_stem_pool_forward_backward(lib):
     assert bool(((codes == 15) == (a.float().cpu() == 0)).all())
 
     # fused form the engine runs: maxpool backward + ReLU mask + BatchNorm backward in two passes -> dy, dgamma, dbeta
-    sums = torch.zeros(2 * C, device="cuda")
-    dy = torch.empty(N, H, H, C, device="cuda", dtype=torch.bfloat16)
-    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
-    lib.check(lib.lib.r3m_b200_stem_backward(lib.ptr(dA), lib.ptr(am), lib.ptr(y), N, H, H, C, lib.ptr(sm), lib.ptr(sr),
-                                             lib.ptr(gamma), lib.ptr(sums), lib.ptr(dy), lib.ptr(dgamma),
-                                             lib.ptr(dbeta), s))
+    # ymax = the raw conv output at each window's argmax
+    zmax = F.max_pool2d(F.batch_norm(yf.permute(0, 3, 1, 2), None, None, gamma, beta, training=True, eps=1e-5).relu(), 3, 2, 1)
+    live = (zmax > 0).permute(0, 2, 3, 1)
+    recon = (ymax.float() - sm) * sr * gamma + beta  # BN of ymax must reproduce the pooled activation where it is live
+    assert rel(recon[live], a.float()[live]) < 5e-3
+    for use_ymax in (True, False):  # reduce pass over the pooled elements / over 2x2 quads of conv-output pixels
+        sums = torch.zeros(2 * C, device="cuda")
+        dy = torch.empty(N, H, H, C, device="cuda", dtype=torch.bfloat16)
+        dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        lib.check(lib.lib.r3m_b200_stem_backward(lib.ptr(dA), lib.ptr(am), lib.ptr(ymax) if use_ymax else None, lib.ptr(y),
+                                                 N, H, H, C, lib.ptr(sm), lib.ptr(sr), lib.ptr(gamma), lib.ptr(sums),
+                                                 lib.ptr(dy), lib.ptr(dgamma), lib.ptr(dbeta), s))
+        _check_stem_backward(dy, dgamma, dbeta, yf, gamma, beta, want)
+
+
+def _check_stem_backward(dy, dgamma, dbeta, yf, gamma, beta, want):
     # reference: autograd through BatchNorm, ReLU and the pooling (x.grad), and BatchNorm's parameter gradients
     # driven by the exact fp32 masked gradient (the fused kernel never rounds it to bf16)
     x2 = yf.permute(0, 3, 1, 2).detach().requires_grad_(True)
