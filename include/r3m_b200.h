@@ -124,6 +124,10 @@ int r3m_b200_loss_lp(const float* E, float* dE, int rows, int D, float l2weight,
                      void* stream);
 int r3m_b200_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, float* metrics,
                       void* stream);
+/* The same head with the similarity of R3M.sim selectable (models_r3m.py:102-107): l2dist != 0 negative L2 distance
+ * (what r3m_b200_loss_tcn computes), l2dist == 0 nn.CosineSimilarity(dim=1). */
+int r3m_b200_loss_tcn_sim(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, int l2dist,
+                          float* metrics, void* stream);
 
 /* torch.optim.Adam step over a flat fp32 buffer (defaults beta 0.9/0.999, eps 1e-8), also emitting the bf16 copy. */
 int r3m_b200_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, int step,
@@ -161,6 +165,8 @@ int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_ca
 int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
 /* what: 0 embedding dim, 1 frames, 2 kernels launched by the last engine call */
 int r3m_b200_engine_get_int(void* handle, int what, int* value);
+/* what: 0 similarity of the TCN head: value != 0 negative L2 distance (default; R3M(l2dist=True)), 0 cosine */
+int r3m_b200_engine_set_int(void* handle, int what, int value);
 /* Byte offsets of {params, grads, Adam m, Adam v, BN buffers} inside the parameter block, and the element counts of
  * the flat parameter buffer / the BN-buffer region.  Valid before bind (pure layout query; no GPU needed). */
 int r3m_b200_engine_param_block_layout(void* handle, size_t* offsets5, size_t* num_params, size_t* num_buffer_floats);

@@ -125,7 +125,45 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def pin_cosine_sim(out_dir):
+    """R3M(l2dist=False): the reference's sim() is nn.CosineSimilarity(1) (models_r3m.py:37,105-107).  Pins the
+    oracle's sim(..., l2dist=False) and the TCN head built on it against the reference module's own method
+    (`python oracle/make_golden.py --cos-only` updates pinning.json in place)."""
+    R3M, _, _ = import_reference()
+    model = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0, l2dist=False)
+    g = torch.Generator().manual_seed(11)
+    a, b = torch.randn(16, 512, generator=g).relu(), torch.randn(16, 512, generator=g).relu()
+    a[3] = b[3]
+    d = rel(O.sim(a, b, False), model.sim(a, b))
+    # the reference's TCN head (trainer.py:120-150) evaluated with the reference model's sim on fixed embeddings
+    B = 8
+    alles = torch.randn(5 * B, 512, generator=g).relu() * 0.1
+    perms = O.draw_permutations(B, 12)
+    _, m = O.losses({}, alles, perms, dict(l2weight=0.0, l1weight=0.0, tcnweight=1.0, langweight=0.0, l2dist=False))
+    alle = alles.reshape(B, 5, -1)
+    es0, es1, es2 = alle[:, 2], alle[:, 3], alle[:, 4]
+    eps = 1e-8
+    s02, s12, s01 = model.sim(es2, es0), model.sim(es2, es1), model.sim(es1, es0)
+    neg0 = torch.stack([model.sim(es0, es0[perms[9 + 2 * i]]) for i in range(3)], -1)
+    neg2 = torch.stack([model.sim(es2, es2[perms[10 + 2 * i]]) for i in range(3)], -1)
+    sm1 = -torch.log(eps + torch.exp(s12) / (eps + torch.exp(s02) + torch.exp(s12) + torch.exp(neg2).sum(-1)))
+    sm2 = -torch.log(eps + torch.exp(s01) / (eps + torch.exp(s01) + torch.exp(s02) + torch.exp(neg0).sum(-1)))
+    ref_tcn = float(((sm1 + sm2) / 2.0).mean())
+    out = {"sim_rel": d, "tcnloss_rel": abs(m["tcnloss"] - ref_tcn) / abs(ref_tcn)}
+    print("cosine_sim", out)
+    assert out["sim_rel"] < 1e-6 and out["tcnloss_rel"] < 1e-6, out
+    path = os.path.join(out_dir, "pinning.json")
+    with open(path) as f:
+        pin = json.load(f)
+    pin["oracle_vs_reference"]["cosine_sim"] = out
+    with open(path, "w") as f:
+        json.dump(pin, f, indent=1)
+
+
 def main():
+    if "--cos-only" in sys.argv:
+        pin_cosine_sim(os.path.join(ROOT, "tests", "golden"))
+        return
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     pin = {}
@@ -202,6 +240,7 @@ def main():
     with open(os.path.join(out_dir, "pinning.json"), "w") as f:
         json.dump({"reference_commit": "b2334e726887fa0206962d7984c69c5fb09cceab", "torch": torch.__version__,
                    "oracle_vs_reference": pin}, f, indent=1)
+    pin_cosine_sim(out_dir)
 
 
 if __name__ == "__main__":

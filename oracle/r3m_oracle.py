@@ -217,9 +217,11 @@ def r3m_forward(params, buffers, obs, size, train, taps=None, policy="fp32"):
     return resnet_forward(params, buffers, x, size, train, taps, policy)
 
 
-def sim(a, b):
-    """models_r3m.py:102-104 (l2dist=True): negative L2 distance."""
-    return -torch.linalg.norm(a - b, dim=-1)
+def sim(a, b, l2dist=True):
+    """models_r3m.py:102-107: negative L2 distance (l2dist=True, the default) or nn.CosineSimilarity(dim=1)."""
+    if l2dist:
+        return -torch.linalg.norm(a - b, dim=-1)
+    return F.cosine_similarity(a, b, dim=1, eps=1e-08)
 
 
 def lang_reward(params, e0, eg, le, taps=None):
@@ -271,11 +273,12 @@ def losses(params, alles, perms, hyper, lang_emb=None, lang_mask=None, lang_taps
     else:
         pi = 9
     if hyper["tcnweight"] > 0:
-        s02, s12, s01 = sim(es2, es0), sim(es2, es1), sim(es1, es0)
+        l2d = hyper.get("l2dist", True)
+        s02, s12, s01 = sim(es2, es0, l2d), sim(es2, es1, l2d), sim(es1, es0, l2d)
         neg0, neg2 = [], []
         for _ in range(3):
-            neg0.append(sim(es0, es0[perms[pi]]))
-            neg2.append(sim(es2, es2[perms[pi + 1]]))
+            neg0.append(sim(es0, es0[perms[pi]], l2d))
+            neg2.append(sim(es2, es2[perms[pi + 1]], l2d))
             pi += 2
         neg0, neg2 = torch.stack(neg0, -1), torch.stack(neg2, -1)
         sm1 = -torch.log(EPSILON + torch.exp(s12) / (EPSILON + torch.exp(s02) + torch.exp(s12) + torch.exp(neg2).sum(-1)))

@@ -338,7 +338,11 @@ int r3m_b200_loss_lp(const float* E, float* dE, int rows, int D, float l2weight,
 }
 int r3m_b200_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, float* metrics,
                       void* stream) {
-  CUDA_OR_FAIL(launch_loss_tcn(E, dE, perms, B, D, tcnweight, metrics, (cudaStream_t)stream), "loss_tcn");
+  CUDA_OR_FAIL(launch_loss_tcn(E, dE, perms, B, D, tcnweight, 1, metrics, (cudaStream_t)stream), "loss_tcn");
+}
+int r3m_b200_loss_tcn_sim(const float* E, float* dE, const int* perms, int B, int D, float tcnweight, int l2dist,
+                          float* metrics, void* stream) {
+  CUDA_OR_FAIL(launch_loss_tcn(E, dE, perms, B, D, tcnweight, l2dist, metrics, (cudaStream_t)stream), "loss_tcn");
 }
 
 int r3m_b200_adam(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr, int step,
@@ -424,6 +428,14 @@ int r3m_b200_engine_get_int(void* handle, int what, int* value) {
     case 1: *value = eng->frames(); break;
     case 2: *value = eng->launches_last_call(); break;
     default: return fail(R3M_B200_ERR_INVALID, "unknown query");
+  }
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_set_int(void* handle, int what, int value) {
+  ENGINE_OR_FAIL(handle);
+  switch (what) {
+    case 0: eng->set_l2dist(value != 0); break;
+    default: return fail(R3M_B200_ERR_INVALID, "unknown setting");
   }
   return R3M_B200_OK;
 }

@@ -997,7 +997,8 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
                stream);
     if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
     if (tcnw > 0.f) {
-      e = launch(Op([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, metrics, s); }, kFamLoss, 0.0,
+      const int l2dist = l2dist_ ? 1 : 0;
+      e = launch(Op([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, l2dist, metrics, s); }, kFamLoss, 0.0,
                     (double)B * 18 * D * 4 * 2),
                  stream);
       if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);

@@ -57,6 +57,7 @@ class Engine {
   // 6: d(loss)/d(embeddings) fp32, 7: metrics fp32[16]
   void* region(int which) const;
   int embed_dim() const { return D_; }
+  void set_l2dist(bool v) { l2dist_ = v; }
   int frames() const { return N_; }
 
   std::string sync_weights(cudaStream_t stream);  // params fp32 -> bf16 operands (+ dgrad / stem re-packs)
@@ -104,6 +105,7 @@ class Engine {
 
   int size_ = 0, N_ = 0, D_ = 0, B_ = 0, lang_ = 0, hidden_ = 0;
   bool bottleneck_ = false;
+  bool l2dist_ = true;  // R3M.sim: negative L2 distance (default) or cosine similarity
   std::vector<Conv*> convs_;
   std::vector<Block*> blocks_;
   std::vector<TensorInfo> tensors_;

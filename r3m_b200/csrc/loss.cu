@@ -62,11 +62,15 @@ __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ 
   }
 }
 
+// kCos = false: sim(a, b) = -||a - b||_2 (l2dist=True, the default, models_r3m.py:102-104);
+// kCos = true : sim(a, b) = nn.CosineSimilarity(dim=1)(a, b) = a.b / (max(||a||, 1e-8) * max(||b||, 1e-8))  (:105-107)
+template <bool kCos>
 __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__ E, float* __restrict__ dE,
                                                        const int* __restrict__ perms, int B, int D, float tcnw,
                                                        float* __restrict__ metrics) {
   pdl_sync();
-  __shared__ float red[9 * 32];
+  constexpr int kAcc = kCos ? 27 : 9;
+  __shared__ float red[kAcc * 32];
   __shared__ float coef[9];
   __shared__ int urow[9], vrow[9];
   const int b = blockIdx.x;
@@ -80,27 +84,48 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
     }
   }
   __syncthreads();
-  float acc[9];
+  float acc[kAcc];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float diff = E[(size_t)urow[k] * D + d] - E[(size_t)vrow[k] * D + d];
-      acc[k] = fmaf(diff, diff, acc[k]);
+      const float u = E[(size_t)urow[k] * D + d], v = E[(size_t)vrow[k] * D + d];
+      if (kCos) {
+        acc[k] = fmaf(u, v, acc[k]);
+        acc[9 + k] = fmaf(u, u, acc[9 + k]);
+        acc[18 + k] = fmaf(v, v, acc[18 + k]);
+      } else {
+        const float diff = u - v;
+        acc[k] = fmaf(diff, diff, acc[k]);
+      }
     }
   }
-  block_sum<9>(acc, red);
-  float dist[9];
+  block_sum<kAcc>(acc, red);
+  // sim[k], and the coefficients of  d sim / du = ca * v - cb * u  (cos)  |  -(u - v) / dist  (l2)
+  float sim[9], ca[9], cb[9], cc[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) dist[k] = sqrtf(acc[k]);
+  for (int k = 0; k < 9; ++k) {
+    if (kCos) {
+      const float n1 = fmaxf(sqrtf(acc[9 + k]), 1e-8f), n2 = fmaxf(sqrtf(acc[18 + k]), 1e-8f);
+      sim[k] = acc[k] / (n1 * n2);
+      ca[k] = 1.0f / (n1 * n2);
+      cb[k] = sim[k] / (n1 * n1);
+      cc[k] = sim[k] / (n2 * n2);
+    } else {
+      const float dist = sqrtf(acc[k]);
+      sim[k] = -dist;
+      ca[k] = dist > 0.f ? 1.0f / dist : 0.f;  // zero gradient at zero distance (torch.linalg.norm backward)
+      cb[k] = cc[k] = 0.f;
+    }
+  }
   if (threadIdx.x == 0) {
-    const float s02 = -dist[0], s12 = -dist[1], s01 = -dist[2];
+    const float s02 = sim[0], s12 = sim[1], s01 = sim[2];
     const float e02 = expf(s02), e12 = expf(s12), e01 = expf(s01);
     float en0[3], en2[3], sum0 = 0.f, sum2 = 0.f;
     for (int j = 0; j < 3; ++j) {
-      en0[j] = expf(-dist[3 + j]);
-      en2[j] = expf(-dist[6 + j]);
+      en0[j] = expf(sim[3 + j]);
+      en2[j] = expf(sim[6 + j]);
       sum0 += en0[j];
       sum2 += en2[j];
     }
@@ -124,17 +149,22 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
   }
   __syncthreads();
   if (!dE) return;
-  float scale[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) scale[k] = dist[k] > 0.f ? coef[k] / dist[k] : 0.f;  // ds/du = -(u-v)/dist
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      if (scale[k] == 0.f) continue;
-      const float diff = E[(size_t)urow[k] * D + d] - E[(size_t)vrow[k] * D + d];
-      const float g = -scale[k] * diff;
-      atomicAdd(&dE[(size_t)urow[k] * D + d], g);
-      atomicAdd(&dE[(size_t)vrow[k] * D + d], -g);
+      const float w = coef[k];
+      if (w == 0.f || (!kCos && ca[k] == 0.f)) continue;
+      const float u = E[(size_t)urow[k] * D + d], v = E[(size_t)vrow[k] * D + d];
+      float gu, gv;
+      if (kCos) {
+        gu = w * (ca[k] * v - cb[k] * u);
+        gv = w * (ca[k] * u - cc[k] * v);
+      } else {
+        gu = -w * ca[k] * (u - v);
+        gv = -gu;
+      }
+      atomicAdd(&dE[(size_t)urow[k] * D + d], gu);
+      atomicAdd(&dE[(size_t)vrow[k] * D + d], gv);
     }
   }
 }
@@ -157,9 +187,12 @@ cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w
   return cudaGetLastError();
 }
 
-cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, float* metrics,
-                            cudaStream_t s) {
-  launch_kernel(loss_tcn_kernel, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
+cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, int l2dist,
+                            float* metrics, cudaStream_t s) {
+  if (l2dist)
+    launch_kernel(loss_tcn_kernel<false>, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
+  else
+    launch_kernel(loss_tcn_kernel<true>, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
   return cudaGetLastError();
 }
 

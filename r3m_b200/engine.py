@@ -67,7 +67,7 @@ def _aligned_empty(nbytes, device, zero):
 class Engine:
     """One launch schedule: (model parameter block, frame count)."""
 
-    def __init__(self, size, frames, param_block, lang_head=False, hidden_dim=1024):
+    def __init__(self, size, frames, param_block, lang_head=False, hidden_dim=1024, l2dist=True):
         if not param_block.is_cuda:
             raise L.R3MB200Error("r3m_b200 computes on an sm_100 GPU only; the parameter block is on "
                                  f"{param_block.device} (there is no CPU path)")
@@ -86,6 +86,7 @@ class Engine:
         d = ctypes.c_int()
         L.check(L.lib.r3m_b200_engine_get_int(self._h, 0, ctypes.byref(d)))
         self.embed_dim = d.value
+        L.check(L.lib.r3m_b200_engine_set_int(self._h, 0, int(bool(l2dist))))  # R3M.sim: -L2 distance or cosine
         self._metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
 
     def __del__(self):

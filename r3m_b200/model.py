@@ -188,7 +188,7 @@ class R3M(nn.Module):
         if eng is None:
             while len(self._engines) >= 3:
                 self._engines.popitem(last=False)
-            eng = Engine(self.size, frames, self._block, self._has_lang, self.hidden_dim)
+            eng = Engine(self.size, frames, self._block, self._has_lang, self.hidden_dim, l2dist=self.l2dist)
             self._engines[frames] = eng
         else:
             self._engines.move_to_end(frames)

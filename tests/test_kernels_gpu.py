@@ -380,6 +380,39 @@ def test_loss_heads_match_oracle(lib, B, D):
     assert torch.isfinite(dE).all()
 
 
+@pytest.mark.parametrize("B,D", [(6, 512), (16, 2048)])
+def test_tcn_head_with_cosine_similarity(lib, B, D):
+    """R3M(l2dist=False): sim = nn.CosineSimilarity(dim=1) (models_r3m.py:105-107) in the fused TCN head, against the
+    oracle (torch autograd through F.cosine_similarity) on identical embeddings."""
+    from oracle import r3m_oracle as O
+
+    g = torch.Generator().manual_seed(100 + B)
+    E = torch.randn(5 * B, D, generator=g).relu() * 0.05
+    perms = O.draw_permutations(B, 6)
+    perms[10] = torch.arange(B)                  # es2 against itself: cosine 1, gradient exactly zero
+    hyper = dict(l2weight=0.0, l1weight=0.0, tcnweight=0.7, langweight=0.0, l2dist=False)
+    e = E.clone().requires_grad_(True)
+    full, m = O.losses({}, e, perms, hyper)
+    full.backward()
+    Ed = E.cuda()
+    dE = torch.zeros(5 * B, D, device="cuda")
+    metrics = torch.zeros(16, device="cuda")
+    pd = perms.to(torch.int32).cuda()
+    s = lib.current_stream()
+    lib.check(lib.lib.r3m_b200_loss_tcn_sim(lib.ptr(Ed), lib.ptr(dE), lib.ptr(pd), B, D, 0.7, 0, lib.ptr(metrics), s))
+    got = metrics.cpu().tolist()
+    assert abs(got[7] - m["tcnloss"]) <= 1e-4 * abs(m["tcnloss"]), (got[7], m["tcnloss"])
+    assert abs(got[8] - m["aligned"]) <= 1.0 / B + 1e-6
+    assert abs(got[9] - 0.7 * m["tcnloss"]) <= 1e-4 * abs(0.7 * m["tcnloss"])
+    assert rel(dE.cpu(), e.grad) < 1e-4
+    # and the L2 flavour through the same entry point equals r3m_b200_loss_tcn
+    d1, d2 = torch.zeros_like(dE), torch.zeros_like(dE)
+    m1, m2 = torch.zeros(16, device="cuda"), torch.zeros(16, device="cuda")
+    lib.check(lib.lib.r3m_b200_loss_tcn_sim(lib.ptr(Ed), lib.ptr(d1), lib.ptr(pd), B, D, 0.7, 1, lib.ptr(m1), s))
+    lib.check(lib.lib.r3m_b200_loss_tcn(lib.ptr(Ed), lib.ptr(d2), lib.ptr(pd), B, D, 0.7, lib.ptr(m2), s))
+    assert rel(d1, d2) < 1e-6 and abs(float(m1[7]) - float(m2[7])) < 1e-6
+
+
 def test_adam_matches_torch(lib):
     n = 100003
     g = torch.Generator().manual_seed(9)
