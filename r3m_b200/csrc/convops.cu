@@ -136,9 +136,17 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   p.base_h = d.base_h;
   p.cblocks = d.C / 64;
   p.num_items = d.ntaps * p.cblocks;
-  int group_pref = 5;  // largest group whose two pipeline stages of 128-pixel atoms fit in shared memory
-  if (const char* e = getenv("R3M_WGRAD_GROUP")) group_pref = atoi(e);  // tuning aid
-  p.group = std::min(group_pref, p.num_items);
+  // 5 is the largest group whose two pipeline stages of 128-pixel atoms fit in shared memory; the items are spread
+  // evenly over ceil(items / 5) groups (16 items -> 4 x 4, not 5 + 5 + 5 + 1: the CTAs of a short group idle while the
+  // others finish; measured 4.49 -> 4.37 ms over the 53 wgrads of ResNet-50).
+  int group_pref = -5;
+  if (const char* e = getenv("R3M_WGRAD_GROUP")) group_pref = atoi(e);  // tuning aid (positive: fixed group size)
+  if (group_pref < 0) {
+    const int groups = (p.num_items - group_pref - 1) / (-group_pref);
+    p.group = (p.num_items + groups - 1) / groups;
+  } else {
+    p.group = std::min(group_pref, p.num_items);
+  }
   for (int t = 0; t < d.ntaps; ++t) {
     p.tap_w[t] = (uint16_t)d.tap_w[t];
     p.tap_h[t] = (uint16_t)d.tap_h[t];
