@@ -13,6 +13,15 @@
 #include "launch.h"
 #include "ptx.cuh"
 
+#define R3M_PRAGMA_(x) _Pragma(#x)
+#define R3M_UNROLL(n) R3M_PRAGMA_(unroll n)
+#ifndef R3M_BN_APPLY_UNROLL
+#define R3M_BN_APPLY_UNROLL 2
+#endif
+#ifndef R3M_BN_BWD_UNROLL
+#define R3M_BN_BWD_UNROLL 2
+#endif
+
 namespace r3m {
 
 namespace {
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const bf16* __restrict__ res = reinterpret_cast<const bf16*>(a.residual);
   bf16* __restrict__ out = reinterpret_cast<bf16*>(a.a);
-#pragma unroll 2
+R3M_UNROLL(R3M_BN_APPLY_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
@@ -706,7 +715,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   bf16* __restrict__ dy = reinterpret_cast<bf16*>(a.dy);
   bf16* __restrict__ dy2 = reinterpret_cast<bf16*>(a.dy2);
   bf16* __restrict__ dzo = reinterpret_cast<bf16*>(a.dz_out);
-#pragma unroll 2
+R3M_UNROLL(R3M_BN_BWD_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
