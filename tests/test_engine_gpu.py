@@ -316,3 +316,39 @@ def test_side_stream_schedule_matches_single_stream(size, clips, monkeypatch):
             continue
         d = rel(grads[1][k], grads[0][k])
         assert d < max(2e-2, 10 * noise), (k, d, noise)
+
+
+def test_get_reward_sim_and_cosine_update():
+    """R3M.get_reward / R3M.sim (models_r3m.py:78-81,102-107) against the oracle, and Trainer.update of a model built
+    with l2dist=False (cosine similarity in the fused TCN head) against the oracle's losses on OUR embeddings."""
+    import r3m_b200
+    from oracle import r3m_oracle as O
+    from r3m_b200 import R3M, Trainer
+
+    clips = 6
+    lang_emb = O.stub_lang_embedding(clips, 5)
+    r3m_b200.set_lang_encoder_factory(lambda dev: (lambda s: lang_emb))
+    params, buffers = O.init_state(18, 2, lang=True)
+    m = R3M("cuda", 1e-4, 1024, size=18, l2weight=1e-5, l1weight=1e-5, langweight=1.0, tcnweight=1.0, l2dist=False)
+    sd = dict(params)
+    sd.update(buffers)
+    m.load_state_dict(sd)
+    model = torch.nn.DataParallel(m).cuda()
+    g = torch.Generator().manual_seed(1)
+    e0, es = torch.randn(clips, 512, generator=g).relu(), torch.randn(clips, 512, generator=g).relu()
+    r, _ = m.get_reward(e0.cuda(), es.cuda(), ["x"] * clips)
+    assert rel(r.detach().cpu(), O.lang_reward(params, e0, es, lang_emb)) < 1e-5
+    assert rel(m.sim(e0.cuda(), es.cuda()).cpu(), O.sim(e0, es, False)) < 1e-6
+    m.l2dist = True
+    assert rel(m.sim(e0.cuda(), es.cuda()).cpu(), O.sim(e0, es, True)) < 1e-6
+    m.l2dist = False
+    frames = O.structured_frames(clips, 3)
+    perms = O.draw_permutations(clips, 4)
+    sentences = ["s%d" % i for i in range(clips)]
+    metrics, _ = Trainer(100).update(model, (frames.cuda(), sentences), 0, perms=perms)
+    emb = m._any_engine().embeddings().cpu()
+    hyper = dict(HYPER, langweight=1.0, l2dist=False)
+    _, want = O.losses(params, emb, perms, hyper, lang_emb, torch.ones(clips))
+    for k in ("tcnloss", "rewloss", "full_loss", "l2loss", "l1loss"):
+        assert abs(metrics[k] - want[k]) <= 1e-4 * max(abs(want[k]), 1e-6), (k, metrics[k], want[k])
+    assert abs(metrics["aligned"] - want["aligned"]) <= 1.0 / clips + 1e-6

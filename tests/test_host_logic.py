@@ -146,3 +146,17 @@ def test_optimizer_state_roundtrip_for_exact_resume():
     assert torch.equal(m2._flat(2), m._flat(2)) and torch.equal(m2._flat(3), m._flat(3))
     m.encoder_opt.zero_grad()
     assert float(m._flat(1).abs().max()) == 0.0
+
+
+def test_resize_center_crop_branch_matches_torchvision():
+    """models_r3m.py:85-90: frames that are not 3x224x224 go through transforms.Resize(256) + CenterCrop(224)."""
+    tv_t = pytest.importorskip("torchvision.transforms")
+    from r3m_b200.model import _resize256_center_crop224
+
+    ref = tv_t.Compose([tv_t.Resize(256), tv_t.CenterCrop(224)])
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2, 3, 240, 320), (1, 3, 480, 300), (3, 3, 256, 256)):
+        x = torch.rand(shape, generator=g) * 255
+        got = _resize256_center_crop224(x)
+        assert got.shape == (shape[0], 3, 224, 224)
+        assert torch.allclose(got, ref(x), atol=1e-4)
