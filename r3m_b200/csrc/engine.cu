@@ -43,9 +43,9 @@ struct Engine::Block {
 namespace {
 constexpr size_t kAlign = 1024;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr size_t kMaxActPerFrame = 112 * 112 * 64;
+constexpr size_t kMaxActPerFrame = 112 * 112 * 64;  // largest activation (stem output == layer1 bottleneck output)
 constexpr size_t kMaxPackEntries = 128;  // dgrad re-pack table: one entry per (conv, output-parity class)
-constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are launch-latency bound -> CUDA graph  // largest activation (stem output == layer1 bottleneck output)
+constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are launch-latency bound -> CUDA graph
 }  // namespace
 
 Engine::~Engine() {
