@@ -13,6 +13,9 @@
 #include "launch.h"
 #include "ptx.cuh"
 
+#ifndef R3M_STREAM_HINTS
+#define R3M_STREAM_HINTS 0  // bit 0: evict-first loads, bit 1: streaming stores in the HBM-bound kernels (A/B knob)
+#endif
 #define R3M_PRAGMA_(x) _Pragma(#x)
 #define R3M_UNROLL(n) R3M_PRAGMA_(unroll n)
 #ifndef R3M_BN_APPLY_UNROLL
@@ -32,7 +35,11 @@ struct F8 {
   float v[8];
 };
 __device__ __forceinline__ F8 ld8(const bf16* p) {
+#if R3M_STREAM_HINTS & 1
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));  // streaming (evict-first) read
+#else
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));  // every ld8 source is read-only within its kernel
+#endif
   F8 f;
   f.v[0] = bf16lo(u.x);
   f.v[1] = bf16hi(u.x);
@@ -44,13 +51,37 @@ __device__ __forceinline__ F8 ld8(const bf16* p) {
   f.v[7] = bf16hi(u.w);
   return f;
 }
+// last-use read: the line is marked evict-first so that it does not displace data the next kernels will read
+// (R3M_STREAM_HINTS bit 2; used by the BatchNorm apply passes, whose inputs are not touched again before the backward /
+// at all)
+__device__ __forceinline__ F8 ld8_last(const bf16* p) {
+#if R3M_STREAM_HINTS & 4
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+  F8 f;
+  f.v[0] = bf16lo(u.x);
+  f.v[1] = bf16hi(u.x);
+  f.v[2] = bf16lo(u.y);
+  f.v[3] = bf16hi(u.y);
+  f.v[4] = bf16lo(u.z);
+  f.v[5] = bf16hi(u.z);
+  f.v[6] = bf16lo(u.w);
+  f.v[7] = bf16hi(u.w);
+  return f;
+#else
+  return ld8(p);
+#endif
+}
 __device__ __forceinline__ void st8(bf16* p, const F8& f) {
   uint4 u;
   u.x = pack_bf16x2(f.v[0], f.v[1]);
   u.y = pack_bf16x2(f.v[2], f.v[3]);
   u.z = pack_bf16x2(f.v[4], f.v[5]);
   u.w = pack_bf16x2(f.v[6], f.v[7]);
+#if R3M_STREAM_HINTS & 2
+  __stcs(reinterpret_cast<uint4*>(p), u);
+#else
   *reinterpret_cast<uint4*>(p) = u;
+#endif
 }
 
 __device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, float inv_m, const float* gamma,
@@ -164,10 +195,10 @@ R3M_UNROLL(R3M_BN_APPLY_UNROLL)
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
     // all loads of the row first (no control flow between them)
-    F8 f = ld8(y + off);
+    F8 f = ld8_last(y + off);
     F8 t, r;
-    if (kDual) t = ld8(y2 + off);
-    if (kRes) r = ld8(res + off);
+    if (kDual) t = ld8_last(y2 + off);
+    if (kRes) r = ld8_last(res + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
@@ -719,13 +750,13 @@ R3M_UNROLL(R3M_BN_BWD_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
     const long long off = row * a.C + chunk * 8;
-    F8 g = ld8(dA + off);
-    const F8 yy = ld8(y + off);
+    F8 g = ld8_last(dA + off);
+    const F8 yy = ld8_last(y + off);
     F8 m, t;
     unsigned bits = 0;
     if (kMask == kMaskAct) m = ld8(act + off);
     if (kMask == kMaskBits) bits = __ldg(mask + row * C8 + chunk);
-    if (kDual) t = ld8(y2 + off);
+    if (kDual) t = ld8_last(y2 + off);
     mask_gradient<kMask>(g, m, bits);
     if (kDz) st8(dzo + off, g);
     F8 o;
