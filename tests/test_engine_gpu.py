@@ -51,7 +51,7 @@ def _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, met
     atomics-ordered BN statistics) is 'on' in one summation order and 'off' in another; either side is a valid gradient
     of the reference function, but the flip perturbs every gradient below that layer by ~1e-3.  So: compare as is;
     if that fails, enumerate the sign choices of the (few) pre-activations inside the round-off band — forced through a
-    <=4e-6-relative bias nudge in the oracle — and require an exact match with ONE of them."""
+    <=1e-5-relative bias nudge in the oracle — and require an exact match with ONE of them."""
     import itertools
 
     from oracle import r3m_oracle as O
@@ -98,7 +98,7 @@ def _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, met
     if not first:
         return
     # pre-activations inside the round-off band (identical (e0, e_t) rows occur in several evaluations: dedupe)
-    band = 2e-6
+    band = 4e-6
     cands = {}
     for layer, pre in taps:
         pre = pre.detach()
@@ -107,7 +107,7 @@ def _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, met
             cands.setdefault((layer, j, round(float(pre[b, j]) / (rms * 1e-9))), (layer, j, float(pre[b, j]), rms))
     cands = list(cands.values())
     assert cands, ("loss heads differ from the oracle and no ReLU input is within round-off of its kink", first)
-    assert len(cands) <= 4, ("too many ReLU inputs on the kink to enumerate", len(cands), first)
+    assert len(cands) <= 6, ("too many ReLU inputs on the kink to enumerate", len(cands), first)
     for signs in itertools.product((1.0, -1.0), repeat=len(cands)):
         nudges = {}
         for (layer, j, pre, rms), sg in zip(cands, signs):
