@@ -802,6 +802,33 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// four parameters per thread: 16-byte loads / stores of p, g, m, v and one 8-byte store of the bf16 copy
+__global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                        float4* __restrict__ m, float4* __restrict__ v,
+                                                        uint2* __restrict__ pb, size_t n4, float lr, float beta1,
+                                                        float beta2, float eps, float bc1, float bc2_sqrt,
+                                                        float grad_scale) {
+  pdl_sync();
+  const float step_size = lr / bc1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 g4 = g[i];
+    float4 m4 = m[i], v4 = v[i], p4 = p[i];
+    const float gs[4] = {g4.x * grad_scale, g4.y * grad_scale, g4.z * grad_scale, g4.w * grad_scale};
+    float ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // the same operation order as adam_kernel: results are bit-identical
+      ms[k] = beta1 * ms[k] + (1.f - beta1) * gs[k];
+      vs[k] = beta2 * vs[k] + (1.f - beta2) * gs[k] * gs[k];
+      const float denom = sqrtf(vs[k]) / bc2_sqrt + eps;
+      ps[k] = ps[k] - step_size * (ms[k] / denom);
+    }
+    m[i] = make_float4(ms[0], ms[1], ms[2], ms[3]);
+    v[i] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    p[i] = make_float4(ps[0], ps[1], ps[2], ps[3]);
+    if (pb) pb[i] = make_uint2(pack_bf16x2(ps[0], ps[1]), pack_bf16x2(ps[2], ps[3]));
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
                                                         size_t n) {
   pdl_sync();
@@ -1046,8 +1073,20 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, void* p_bf
                         float beta2, float eps, int step, float grad_scale, cudaStream_t s) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  launch_kernel(adam_kernel, grid_for((long long)n, 256, 148 * 16), 256, 0, s, p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, lr,
-                                                                    beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  const uintptr_t align = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                          reinterpret_cast<uintptr_t>(v) | (reinterpret_cast<uintptr_t>(p_bf16) << 1);
+  const size_t n4 = (align & 15) == 0 ? n / 4 : 0;  // vector body when every buffer allows 16-byte accesses
+  if (n4 > 0)
+    launch_kernel(adam_vec4_kernel, grid_for((long long)n4, 256, resident_blocks<adam_vec4_kernel>(256)), 256, 0, s,
+                  reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+                  reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p_bf16), n4, lr, beta1, beta2, eps, bc1,
+                  sqrtf(bc2), grad_scale);
+  if (n4 * 4 < n) {  // scalar tail (or everything, for unaligned buffers)
+    const size_t o = n4 * 4;
+    launch_kernel(adam_kernel, grid_for((long long)(n - o), 256, 148 * 16), 256, 0, s, p + o, g + o, m + o, v + o,
+                  p_bf16 ? reinterpret_cast<bf16*>(p_bf16) + o : nullptr, n - o, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
+                  grad_scale);
+  }
   return cudaGetLastError();
 }
 
