@@ -187,6 +187,20 @@ int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* ou
 int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
                                  const float* lang_mask, float l2weight, float l1weight, float langweight,
                                  float tcnweight, int eval, void* stream);
+/* The backward pass alone (what `full_loss.backward()` of r3m/trainer.py:157 runs below the embeddings), for hosts
+ * that compute the loss themselves — the reference's own Trainer through torch.autograd:
+ *   dE fp32 [frames][D] = d(loss)/d(embeddings) of the preceding r3m_b200_engine_forward(train = 1) on this engine.
+ * Filter gradients are ACCUMULATED into region 1 (zero it for a fresh gradient), BatchNorm gradients are written. */
+int r3m_b200_engine_backward(void* handle, const float* dE, void* stream);
+
+/* Test hooks for the block-level backward parity test: the bf16 NHWC buffers of residual block `block`
+ * (0 .. r3m_b200_engine_num_blocks()-1, forward order) — what: 0 input activation, 1 output activation, 2 incoming
+ * gradient (read by the block's backward), 3 outgoing gradient (written) — and a run of ONLY that block's backward
+ * kernels (BatchNorm backward, dgrad, wgrad of its convs; tv resnet.py:89-105,143-163) after a train-mode forward. */
+int r3m_b200_engine_num_blocks(void* handle, int* count);
+int r3m_b200_engine_debug_block(void* handle, int block, int what, void** ptr, size_t* count);
+int r3m_b200_engine_debug_run_block_backward(void* handle, int block, void* stream);
+
 /* torch.optim.Adam step (models_r3m.py:76, defaults) on grads * grad_scale, then refresh of the bf16 operands.
  * step is the 1-based step count (bias correction).  Between update_grads and adam_step the caller may all-reduce
  * region 1 across ranks (trainer DDP path: ONE NCCL all-reduce per step). */

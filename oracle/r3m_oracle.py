@@ -93,6 +93,19 @@ def init_state(size, seed, hidden_dim=1024, lang=False, lang_dim=768):
     return params, buffers
 
 
+def eval_fixture_state(size):
+    """The state of the eval-forward goldens (tests/golden/rn{18,50}_eval_b4.npz): seeded init with NON-trivial running
+    statistics, so that eval-mode BatchNorm is exercised."""
+    params, buffers = init_state(size, 5)
+    g = torch.Generator().manual_seed(6)
+    for k in buffers:
+        if k.endswith("running_mean"):
+            buffers[k] = 0.1 * torch.randn(buffers[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            buffers[k] = 0.5 + torch.rand(buffers[k].shape, generator=g)
+    return params, buffers
+
+
 def synthetic_frames(num_clips, seed):
     """[B,5,3,224,224] float frames with integer values in [0,255) (mirrors r3m/example.py:29 randint(0,255))."""
     g = torch.Generator().manual_seed(seed)
@@ -106,6 +119,28 @@ def structured_frames(num_clips, seed):
     up = F.interpolate(low, size=(224, 224), mode="bilinear", align_corners=False)
     x = 255.0 * (0.9 * up + 0.1 * torch.rand(num_clips * 5, 3, 224, 224, generator=g))
     return x.round().clamp(0, 255).reshape(num_clips, 5, 3, 224, 224)
+
+
+def varied_frames(num_clips, seed):
+    """``structured_frames`` with a per-frame, per-colour gain in [0.1, 1.5): frames (hence embeddings) differ from each
+    other by much more than the bf16 storage noise — half of what makes the "well-conditioned" parity fixtures."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    gain = torch.rand(num_clips, 5, 3, 1, 1, generator=g) * 1.4 + 0.1
+    return (structured_frames(num_clips, seed) * gain).clamp(0, 255).round()
+
+
+def scale_last_gamma(params, size, value):
+    """Sets the weight of the LAST BatchNorm of every residual block (bn3 of a Bottleneck, bn2 of a BasicBlock) to
+    ``value`` — torchvision's ``zero_init_residual`` option (tv resnet.py:214-220) with a small non-zero value.  At the
+    default init (1.0) the residual stream of a random-init ResNet-50 is dominated by a per-channel constant, a
+    1x1 conv's output then has |mean| >> std, and storing it in bf16 before the BatchNorm loses the signal: the fp32
+    gradient moves by >100 % under ANY bf16 storage policy (DESIGN.md "noise floor").  With 0.1 every conv sees
+    relu(N(0,1))-like inputs and the same comparison is conditioned to a few per cent."""
+    tail = "bn3.weight" if _CFG[size][0] == "bottleneck" else "bn2.weight"
+    for k in params:
+        if k.startswith("convnet.layer") and k.endswith(tail):
+            params[k] = torch.full_like(params[k], value)
+    return params
 
 
 def draw_permutations(batch, seed):
@@ -137,12 +172,29 @@ class _RoundBf16(torch.autograd.Function):
         return g.bfloat16().float()
 
 
+class _RoundBf16Forward(torch.autograd.Function):
+    """Filters: the CUDA path reads a bf16 copy of the fp32 master filter but accumulates the filter gradient in fp32,
+    so only the VALUE is rounded (straight-through gradient)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def _policy_round(policy):
     if policy == "fp32":
         return lambda t: t
     if policy == "bf16":
         return _RoundBf16.apply
     raise ValueError(policy)
+
+
+def _policy_round_weight(policy):
+    return (lambda t: t) if policy == "fp32" else _RoundBf16Forward.apply
 
 
 def _bn(x, params, buffers, name, train):
@@ -166,14 +218,15 @@ def _bn(x, params, buffers, name, train):
 def resnet_forward(params, buffers, x, size, train, taps=None, policy="fp32"):
     """tv resnet.py:266-282 with fc = Identity (models_r3m.py:62).  ``taps`` (optional dict) collects intermediate
     activations keyed by layer name for per-layer parity.  ``policy="bf16"`` rounds exactly the tensors the CUDA path
-    stores as bf16 (network input, filters, raw conv outputs, post-ReLU activations, the downsample BN output)."""
+    stores as bf16 (network input, filters, raw conv outputs, post-ReLU activations)."""
     kind, layers = _CFG[size]
     P = lambda k: params["convnet." + k]  # noqa: E731
     q = _policy_round(policy)
+    qw = _policy_round_weight(policy)
     x = q(x)
 
     def conv(t, name, stride, pad):
-        return q(F.conv2d(t, q(P(name + ".weight")), None, stride, pad))
+        return q(F.conv2d(t, qw(P(name + ".weight")), None, stride, pad))
 
     def bn(t, name):
         return _bn(t, params, buffers, "convnet." + name, train)
@@ -200,7 +253,8 @@ def resnet_forward(params, buffers, x, size, train, taps=None, policy="fp32"):
                 out = q(F.relu(bn(conv(out, f"{pre}.conv2", stride, 1), f"{pre}.bn2")))
                 out = bn(conv(out, f"{pre}.conv3", 1, 0), f"{pre}.bn3")
             if b == 0 and (stride != 1 or inplanes != planes * expansion):
-                identity = q(bn(conv(x, f"{pre}.downsample.0", stride, 0), f"{pre}.downsample.1"))
+                # the CUDA path never materialises the downsample BatchNorm's output (it is folded into the block tail)
+                identity = bn(conv(x, f"{pre}.downsample.0", stride, 0), f"{pre}.downsample.1")
             x = q(F.relu(out + identity))
             if taps is not None:
                 taps[pre] = x
@@ -211,8 +265,8 @@ def resnet_forward(params, buffers, x, size, train, taps=None, policy="fp32"):
 def r3m_forward(params, buffers, obs, size, train, taps=None, policy="fp32"):
     """models_r3m.py:84-100 for obs_shape == [3,224,224]: obs.float()/255 -> Normalize -> convnet."""
     x = obs.float() / 255.0
-    mean = torch.tensor(MEAN, dtype=x.dtype)[None, :, None, None]
-    std = torch.tensor(STD, dtype=x.dtype)[None, :, None, None]
+    mean = torch.tensor(MEAN, dtype=x.dtype, device=x.device)[None, :, None, None]
+    std = torch.tensor(STD, dtype=x.dtype, device=x.device)[None, :, None, None]
     x = (x - mean) / std
     return resnet_forward(params, buffers, x, size, train, taps, policy)
 

@@ -48,6 +48,52 @@ def remove_language_head(state_dict):
     return state_dict
 
 
+def load_config(path):
+    """``OmegaConf.load`` (r3m/__init__.py:68) for the checkpoint's config.yaml without omegaconf: PyYAML plus the two
+    things it does not do — hydra interpolations ``${key}`` / ``${a.b}`` resolved against the top-level config, and
+    numbers written like ``1e-4`` (a string for YAML 1.1) coerced."""
+    import re
+
+    import yaml
+
+    with open(path) as f:
+        cfg = yaml.safe_load(f)
+
+    def lookup(dotted):
+        node = cfg
+        for part in dotted.split("."):
+            node = node[part]
+        return node
+
+    def resolve(v, depth=0):
+        if isinstance(v, dict):
+            return {k: resolve(x, depth) for k, x in v.items()}
+        if isinstance(v, list):
+            return [resolve(x, depth) for x in v]
+        if isinstance(v, str):
+            m = re.fullmatch(r"\$\{([^}]+)\}", v.strip())
+            if m and depth < 8:
+                try:
+                    return resolve(lookup(m.group(1)), depth + 1)
+                except (KeyError, TypeError):
+                    raise ValueError(f"{path}: cannot resolve interpolation {v!r}") from None
+            try:
+                return int(v) if re.fullmatch(r"[+-]?\d+", v.strip()) else float(v)
+            except ValueError:
+                return v
+        return v
+
+    cfg = resolve(cfg)
+    agent = cfg.get("agent", {})
+    for key, typ in (("lr", float), ("hidden_dim", int), ("size", int)):
+        if key in agent:
+            try:
+                agent[key] = typ(agent[key])
+            except (TypeError, ValueError):
+                raise ValueError(f"{path}: agent.{key} = {agent[key]!r} is not a {typ.__name__}") from None
+    return cfg
+
+
 def _load(table, modelid):
     if modelid not in table:
         raise NameError("Invalid Model ID")  # r3m/__init__.py:59
@@ -64,15 +110,14 @@ def _load(table, modelid):
                                f"config.yaml there, or install gdown") from e
         gdown.download("https://drive.google.com/uc?id=" + model_id, modelpath, quiet=False)
         gdown.download("https://drive.google.com/uc?id=" + config_id, configpath, quiet=False)
-    import yaml
-
-    with open(configpath) as f:
-        modelcfg = yaml.safe_load(f)
-    cfg = cleanup_config(modelcfg["agent"])
+    cfg = cleanup_config(load_config(configpath)["agent"])
     device = "cuda" if torch.cuda.is_available() else "cpu"
     cfg["device"] = device
     rep = R3M(**cfg)
-    rep = torch.nn.DataParallel(rep)
+    # one GPU per process: with the default device_ids DataParallel would scatter a batch over every visible GPU and
+    # replicate a module whose parameters alias ONE device block
+    ids = [torch.cuda.current_device()] if device == "cuda" else None
+    rep = torch.nn.DataParallel(rep.to(device), device_ids=ids)
     payload = torch.load(modelpath, map_location=torch.device(device), weights_only=False)["r3m"]
     rep.load_state_dict(remove_language_head(payload))
     return rep

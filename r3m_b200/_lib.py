@@ -86,6 +86,10 @@ _sig("r3m_b200_engine_forward", [c_void_p, c_void_p, c_int, c_void_p, c_void_p])
 _sig("r3m_b200_engine_update_grads", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                       c_float, c_int, c_void_p])
 _sig("r3m_b200_engine_adam_step", [c_void_p, c_float, c_float, c_int, c_void_p])
+_sig("r3m_b200_engine_backward", [c_void_p, c_void_p, c_void_p])
+_sig("r3m_b200_engine_num_blocks", [c_void_p, c_int_p])
+_sig("r3m_b200_engine_debug_block", [c_void_p, c_int, c_int, c_void_pp, c_size_p])
+_sig("r3m_b200_engine_debug_run_block_backward", [c_void_p, c_int, c_void_p])
 _sig("r3m_b200_engine_profile_ops", [c_void_p, ctypes.POINTER(ctypes.c_double), c_int, c_int_p])
 _sig("r3m_b200_engine_profile_label", [c_void_p, c_int, ctypes.c_char_p, c_int])
 _sig("r3m_b200_engine_profile_update", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,

@@ -495,6 +495,25 @@ int r3m_b200_engine_profile_label(void* handle, int index, char* out, int capaci
   std::snprintf(out, capacity, "%s", v[index].c_str());
   return R3M_B200_OK;
 }
+int r3m_b200_engine_backward(void* handle, const float* dE, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  if (!dE) return fail(R3M_B200_ERR_INVALID, "null gradient pointer");
+  RETURN_STR(eng->backward(dE, (cudaStream_t)stream));
+}
+int r3m_b200_engine_num_blocks(void* handle, int* count) {
+  ENGINE_OR_FAIL(handle);
+  *count = eng->num_blocks();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_debug_block(void* handle, int block, int what, void** ptr, size_t* count) {
+  ENGINE_OR_FAIL(handle);
+  if (!ptr || !count) return fail(R3M_B200_ERR_INVALID, "null pointer");
+  RETURN_STR(eng->debug_block(block, what, ptr, count));
+}
+int r3m_b200_engine_debug_run_block_backward(void* handle, int block, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  RETURN_STR(eng->debug_run_block_backward(block, (cudaStream_t)stream));
+}
 int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step, void* stream) {
   ENGINE_OR_FAIL(handle);
   RETURN_STR(eng->adam_step(lr, grad_scale, step, (cudaStream_t)stream));

@@ -38,6 +38,8 @@ struct Engine::Block {
   const bf16* x_in = nullptr;
   bf16* a_out = nullptr;
   int Hin = 0, Win = 0, Cin = 0;
+  bf16* d_out = nullptr;  // backward: gradient w.r.t. the block's output (read) ...
+  bf16* d_in = nullptr;   // ... and w.r.t. its input (written); the two swap from block to block
 };
 
 namespace {
@@ -75,7 +77,6 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   if (size != 18 && size != 34 && size != 50) return "size must be 18, 34 or 50 (r3m/models/models_r3m.py:44-52)";
   if (frames < 1) return "frames must be positive";
   if (lang_head && (hidden_dim < 64 || hidden_dim % 64 != 0)) return "hidden_dim must be a positive multiple of 64";
-  if (lang_head && frames % 5 != 0) return "the language head needs frames == 5 * clips";
   Engine* e = new Engine();
   e->size_ = size;
   e->N_ = frames;
@@ -247,7 +248,8 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   e->off_E_ = arena(N * e->D_ * 4);
   e->off_dE_ = arena(N * e->D_ * 4);
   for (int i = 0; i < 7; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
-  if (lang_head) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
+  // a model with a language head still embeds any number of frames (R3M.forward); only update() needs 5 * clips
+  if (lang_head && e->B_ > 0) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
   e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
   e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
   if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
@@ -510,6 +512,7 @@ std::string Engine::plan_all() {
   // pass (HBM bound) co-runs with it, the reduce pass (16-24 KB of shared memory) and the dgrad cannot.  The dy buffer
   // a wgrad reads rotates over three buffers; before the main stream overwrites one, it waits for its last reader.
   int n_events = 0;
+  int cur_block = -1;                          // residual block the ops being pushed belong to (debug_run_block_backward)
   std::vector<Op> held_wgrads;                 // created, not yet placed: released by the next reduce pass
   std::vector<int> deferred;                   // waits to attach to the next main-stream op
   std::map<const void*, int> pending_reader;   // dy buffer -> event of the side-stream wgrad that reads it
@@ -569,11 +572,13 @@ std::string Engine::plan_all() {
     const size_t first = bwd_.size();
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * rd));
     bwd_.back().label = "bn_bwd_reduce " + c.bn;
+    bwd_.back().block = cur_block;
     attach_deferred(first);
     release_wgrads();
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_apply(a, s); }, kFamNorm, 0.0,
                       mc * (rd + 1 + (dz_out ? 1 : 0) + (second ? 1 : 0))));
     bwd_.back().label = "bn_bwd_apply " + c.bn;
+    bwd_.back().block = cur_block;
   };
   auto push_wgrad = [&](const Conv& c, const bf16* dy) {
     WgradDesc d;
@@ -597,6 +602,7 @@ std::string Engine::plan_all() {
     Op w([plan](cudaStream_t s) { return run_wgrad(plan, s); }, kFamWgrad, 2.0 * m * c.Cout * kdim,
          2.0 * (m * c.Cout + (double)N * c.H * c.W * c.Cin) + 4.0 * c.Cout * kdim);
     w.label = "wgrad " + c.name;
+    w.block = cur_block;
     w.side = true;
     w.record = n_events++;
     pending_reader[dy] = w.record;
@@ -640,10 +646,15 @@ std::string Engine::plan_all() {
       }
       gc.accumulate = accumulate;
       push_conv(bwd_, gc, "dgrad " + c.name + (accumulate ? " (+=)" : "") + (c.stride > 1 ? " class " + std::to_string(k.ph) + std::to_string(k.pw) : ""));
+      if (err.empty()) bwd_.back().block = cur_block;
       off += (size_t)c.Cin * k.ntaps * c.Cout;
     }
   };
 
+  // R3M_TEST_MUTATION=drop_skip_add deliberately breaks the schedule (the skip path's gradient is overwritten): the
+  // parity tests assert that they catch it (tests/test_block_backward_gpu.py::test_mutation_is_caught)
+  const char* mut_env = std::getenv("R3M_TEST_MUTATION");
+  const bool mutate_drop_skip_add = mut_env && std::string(mut_env) == "drop_skip_add";
   bf16* d_out = g[0];
   bf16* d_in = g[1];
   bf16 *s2 = g[3], *s3 = g[4];
@@ -662,6 +673,9 @@ std::string Engine::plan_all() {
   }
   for (int bi = (int)blocks_.size() - 1; bi >= 0; --bi) {
     Block* blk = blocks_[bi];
+    cur_block = bi;
+    blk->d_out = d_out;
+    blk->d_in = d_in;
     const int n = (int)blk->main.size();
     Conv& last = *convs_[blk->main[n - 1]];
     const bool has_ds = blk->ds >= 0;
@@ -681,7 +695,9 @@ std::string Engine::plan_all() {
         push_bn_bwd(prev, s2, prev.mask, dy_prev, nullptr, nullptr, nullptr);
         dy = dy_prev;
       } else {
-        push_dgrad(c, dy, d_in, has_ds ? 0 : 1);
+        // identity blocks: the masked gradient of the block output (written to d_in by the BatchNorm backward above)
+        // is the skip path's share, the first conv's data gradient is added on top
+        push_dgrad(c, dy, d_in, (has_ds || mutate_drop_skip_add) ? 0 : 1);
         push_wgrad(c, dy);
       }
     }
@@ -696,6 +712,7 @@ std::string Engine::plan_all() {
   {
     // stem: maxpool backward + ReLU mask + BN backward fused in two passes -> filter gradient (no data gradient)
     release_wgrads();  // layer1.0's filter gradients: behind its last dgrad
+    cur_block = -1;
     Conv& st = *convs_[0];
     StemBwdArgs sb;
     sb.dA = d_out;
@@ -890,6 +907,9 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
   launches_ = 0;
   cudaError_t e;
   std::string err;
+  // an eval forward overwrites the activations and the saved-statistics slots (BN fold coefficients) that a pending
+  // update_grads(obs = NULL) / backward() would read
+  if (!train) fwd_train_valid_ = false;
   if (!train && N_ <= kGraphMaxFrames && !profiling_) {
     // Launch-latency-bound regime (load_r3m users, r3m/example.py: batch 1-4): ~25 kernels of a few microseconds.
     // The frames are copied to a fixed staging buffer and the whole eval forward is replayed as one CUDA graph
@@ -948,6 +968,10 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
   if (out) {
     e = cudaMemcpyAsync(out, ws_ + off_E_, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return std::string("copy out: ") + cudaGetErrorString(e);
+    const int* flag = device_error_flag();
+    const size_t n = (size_t)N_ * D_;
+    e = launch(Op([flag, out, n](cudaStream_t s) { return launch_poison_on_flag(flag, out, n, s); }, kFamLoss), stream);
+    if (e != cudaSuccess) return std::string("poison_on_flag: ") + cudaGetErrorString(e);
   }
   return std::string();
 }
@@ -1045,6 +1069,68 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
     if (e != cudaSuccess) return std::string("publish_flag: ") + cudaGetErrorString(e);
   }
   return std::string();
+}
+
+std::string Engine::backward(const float* dE, cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  if (!fwd_train_valid_) return "backward() needs a preceding train-mode forward() on this engine (its activations are gone)";
+  launches_ = 0;
+  fwd_train_valid_ = false;
+  cudaError_t e = cudaMemcpyAsync(ws_ + off_dE_, dE, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return std::string("copy dE: ") + cudaGetErrorString(e);
+  std::string err = run(bwd_, stream);
+  if (!err.empty()) return err;
+  const int* flag = device_error_flag();
+  float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
+  e = launch(Op([flag, metrics](cudaStream_t s) { return launch_publish_flag(flag, metrics, s); }, kFamLoss), stream);
+  if (e != cudaSuccess) return std::string("publish_flag: ") + cudaGetErrorString(e);
+  return std::string();
+}
+
+int Engine::num_blocks() const { return (int)blocks_.size(); }
+
+std::string Engine::debug_block(int block, int what, void** ptr, size_t* count) const {
+  if (!bound_) return "engine has no workspace bound";
+  if (block < 0 || block >= (int)blocks_.size()) return "block index out of range";
+  const Block& b = *blocks_[block];
+  const Conv& last = *convs_[b.main.back()];
+  const size_t in_elems = (size_t)N_ * b.Hin * b.Win * b.Cin, out_elems = last.out_elems(N_);
+  switch (what) {
+    case 0: *ptr = const_cast<bf16*>(b.x_in); *count = in_elems; break;
+    case 1: *ptr = b.a_out; *count = out_elems; break;
+    case 2: *ptr = b.d_out; *count = out_elems; break;
+    case 3: *ptr = b.d_in; *count = in_elems; break;
+    default: return "unknown block buffer";
+  }
+  return std::string();
+}
+
+std::string Engine::debug_run_block_backward(int block, cudaStream_t stream) {
+  if (!bound_) return "engine has no workspace bound";
+  if (block < 0 || block >= (int)blocks_.size()) return "block index out of range";
+  launches_ = 0;
+  // the BatchNorm-backward sums of the block's layers are accumulated into: clear them (a full step clears the whole
+  // zeroed region once, before its forward pass)
+  const Block& b = *blocks_[block];
+  std::vector<int> cs(b.main);
+  if (b.ds >= 0) cs.push_back(b.ds);
+  for (int ci : cs) {
+    const Conv& c = *convs_[ci];
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<float*>(ws_ + off_zero_) + c.zero_off + 2 * c.Cout, 0,
+                                    3 * (size_t)c.Cout * 4, stream);
+    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
+  }
+  const bool saved = profiling_;
+  profiling_ = false;
+  const bool side = use_side_;
+  use_side_ = false;  // one stream: the ops of a block are in dependency order inside bwd_
+  std::vector<Op> ops;
+  for (const Op& op : bwd_)
+    if (op.block == block) ops.push_back(op);
+  std::string err = run(ops, stream);
+  use_side_ = side;
+  profiling_ = saved;
+  return err;
 }
 
 std::string Engine::adam_step(float lr, float grad_scale, int step, cudaStream_t stream) {

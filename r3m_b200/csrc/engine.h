@@ -64,6 +64,16 @@ class Engine {
   std::string forward(const float* obs, int train, float* out, cudaStream_t stream);
   std::string update_grads(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                            const Hyper& h, int eval, cudaStream_t stream);
+  // Backward pass alone, for callers that compute the loss themselves (the reference's own Trainer through
+  // torch.autograd): dE = d(loss)/d(embeddings) fp32 [frames][D] of the preceding train-mode forward().  Filter
+  // gradients are ACCUMULATED into the gradient region, BatchNorm gradients written.
+  std::string backward(const float* dE, cudaStream_t stream);
+  // Test hooks (tests/test_block_backward_gpu.py): the buffers of residual block `block` (what: 0 input activation,
+  // 1 output activation, 2 incoming gradient, 3 outgoing gradient; all bf16 NHWC) and a run of ONLY that block's
+  // backward ops on one stream, after a train-mode forward.
+  int num_blocks() const;
+  std::string debug_block(int block, int what, void** ptr, size_t* count) const;
+  std::string debug_run_block_backward(int block, cudaStream_t stream);
   // step: 1-based Adam step count (bias correction); the caller owns it because engines share a parameter block
   std::string adam_step(float lr, float grad_scale, int step, cudaStream_t stream);
   int launches_last_call() const { return launches_; }
@@ -89,6 +99,7 @@ class Engine {
     double bytes = 0.0;  // algorithmic HBM bytes (operands read once + results written once)
     std::string label;   // what the launch is (layer / role), for the per-launch profile
     int nlaunch = 1;     // kernels the op launches (fused two-pass ops count both)
+    int block = -1;      // backward ops: index of the residual block they belong to (-1: head / stem)
     // cross-stream schedule of the backward pass: ops with side = true run on the engine's second stream
     bool side = false;
     std::vector<int> wait;  // event ids the op's stream waits on before the launch

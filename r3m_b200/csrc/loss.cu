@@ -174,7 +174,19 @@ __global__ void publish_flag_kernel(const int* __restrict__ flag, float* __restr
   metrics[kDeviceFlag] = (float)*flag;
 }
 
+// forward-only calls have no metrics read-back: if a pipeline watchdog fired, the returned embeddings become NaN
+__global__ void poison_on_flag_kernel(const int* __restrict__ flag, float* __restrict__ out, size_t n) {
+  pdl_sync();
+  if (*flag == 0) return;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = __int_as_float(0x7fc00000);
+}
+
 }  // namespace
+
+cudaError_t launch_poison_on_flag(const int* flag, float* out, size_t n, cudaStream_t s) {
+  launch_kernel(poison_on_flag_kernel, 1, 256, 0, s, flag, out, n);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s) {
   launch_kernel(publish_flag_kernel, 1, 1, 0, s, flag, metrics);

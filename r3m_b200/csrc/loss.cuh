@@ -25,5 +25,7 @@ cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, 
 
 // metrics[kDeviceFlag] = (float)*flag  — lets the single metrics read-back also carry the kernels' error flag
 cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s);
+// out[0 .. n) <- NaN when the device-side pipeline watchdog flag is set (forward-only calls: no metrics read-back)
+cudaError_t launch_poison_on_flag(const int* flag, float* out, size_t n, cudaStream_t s);
 
 }  // namespace r3m

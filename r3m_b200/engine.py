@@ -136,6 +136,32 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_adam_step(self._h, lr, grad_scale, step, L.current_stream()))
 
+    def backward(self, dE):
+        """Backward pass alone: dE float32 [frames, D] = d(loss)/d(embeddings) of the preceding train-mode forward.
+        Accumulates filter gradients into the gradient region (see r3m_b200_engine_backward)."""
+        assert dE.dtype == torch.float32 and dE.is_cuda and dE.is_contiguous()
+        assert dE.numel() == self.frames * self.embed_dim
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_backward(self._h, L.ptr(dE), L.current_stream()))
+
+    # ---- test hooks (tests/test_block_backward_gpu.py)
+    def num_blocks(self):
+        v = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_num_blocks(self._h, ctypes.byref(v)))
+        return v.value
+
+    def block_buffer(self, block, what):
+        """bf16 alias of a residual block's buffer: 0 input, 1 output, 2 incoming gradient, 3 outgoing gradient."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        L.check(L.lib.r3m_b200_engine_debug_block(self._h, block, what, ctypes.byref(p), ctypes.byref(n)))
+        with torch.cuda.device(self.device):
+            raw = torch.as_tensor(_CudaArrayView(p.value, int(n.value), "<u2"), device=self.device)
+        return raw.view(torch.bfloat16)
+
+    def run_block_backward(self, block):
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_engine_debug_run_block_backward(self._h, block, L.current_stream()))
+
     FAMILIES = ("conv_igemm", "wgrad", "norm", "pool", "loss", "optim", "lang", "other")
 
     def profile_update(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, lr, step):

@@ -58,6 +58,34 @@ class _FusedAdam:
         self.param_groups = sd["param_groups"]
 
 
+class _EncodeFn(torch.autograd.Function):
+    """Train-mode ``R3M.forward`` as an autograd node, so that a host that builds the loss itself — the reference's own
+    ``Trainer.update`` (r3m/trainer.py:41,155-158: ``alles = model(b_im_r)`` ... ``full_loss.backward()``) or a
+    fine-tuning user of ``load_r3m`` — back-propagates through the sm_100a engine.  ``anchor`` is a parameter passed
+    only so that the output requires grad; parameter gradients are written by the engine straight into the flat
+    gradient region that every ``param.grad`` aliases, with autograd's accumulate semantics."""
+
+    @staticmethod
+    def forward(ctx, model, eng, x, anchor):
+        out = eng.forward(x, True)
+        eng._fwd_ticket = getattr(eng, "_fwd_ticket", 0) + 1
+        ctx.model, ctx.eng, ctx.ticket = model, eng, eng._fwd_ticket
+        return out
+
+    @staticmethod
+    def backward(ctx, dE):
+        model, eng = ctx.model, ctx.eng
+        if eng._fwd_ticket != ctx.ticket:
+            raise L.R3MB200Error("backward through an R3M.forward whose saved activations were overwritten by a later "
+                                 "forward of the same frame count (one outstanding train-mode forward per engine)")
+        G = model._flat(1)
+        stash = G.clone()  # whatever autograd / earlier backward passes have accumulated so far (language head included)
+        G.zero_()
+        eng.backward(dE.contiguous().float())
+        G.add_(stash)
+        return None, None, None, None
+
+
 class R3M(nn.Module):
     def __init__(self, device, lr, hidden_dim, size=34, l2weight=1.0, l1weight=1.0, langweight=1.0, tcnweight=0.0,
                  l2dist=True, bs=16):
@@ -212,14 +240,25 @@ class R3M(nn.Module):
             x = _resize256_center_crop224(x)  # transforms.Resize(256) + CenterCrop(224), models_r3m.py:85-90
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
             raise ValueError(f"expected [N, 3, 224, 224] frames, got {tuple(x.shape)}")
-        if not x.is_cuda:
+        if x.device != self._block.device:  # one GPU per process: inputs always follow the parameter block
             x = x.to(self._block.device)
         x = x.contiguous()
         eng = self._engine(x.shape[0])
-        out = eng.forward(x, self.training)
+        if self.training and torch.is_grad_enabled():
+            out = _EncodeFn.apply(self, eng, x, self._anchor())
+        else:
+            out = eng.forward(x, self.training)
         if self.training:
             self._nbt += 1
         return out
+
+    def _anchor(self):
+        return self.convnet.conv1._parameters["weight"]
+
+    def _replicate_for_data_parallel(self):
+        raise L.R3MB200Error("r3m_b200.R3M cannot be replicated by nn.DataParallel: its parameters are views into one "
+                             "flat device block.  Run one process per GPU (torchrun) and wrap with "
+                             "nn.DataParallel(model, device_ids=[torch.cuda.current_device()]) — a direct call")
 
     def sim(self, tensor1, tensor2):
         """models_r3m.py:102-107."""

@@ -148,7 +148,7 @@ def _model(case, params, buffers, lang_emb):
     sd = dict(params)
     sd.update(buffers)
     m.load_state_dict(sd)
-    return m, torch.nn.DataParallel(m).cuda()
+    return m, torch.nn.DataParallel(m.cuda(), device_ids=[0])
 
 
 def test_eval_forward_c1_against_reference_golden():
@@ -169,7 +169,7 @@ def test_eval_forward_c1_against_reference_golden():
     sd = dict(params)
     sd.update(buffers)
     m.load_state_dict(sd)
-    m = torch.nn.DataParallel(m).cuda()
+    m = torch.nn.DataParallel(m.cuda(), device_ids=[0])
     m.eval()
     with torch.no_grad():
         out = m(frames.cuda())
@@ -263,7 +263,7 @@ def test_full_size_c3_step_properties():
     r3m_b200.set_lang_encoder_factory(lambda dev: (lambda s: emb))
     torch.manual_seed(0)
     m = R3M("cuda", 1e-4, 1024, size=50, l2weight=1e-5, l1weight=1e-5, langweight=1.0, tcnweight=1.0)
-    model = torch.nn.DataParallel(m).cuda()
+    model = torch.nn.DataParallel(m.cuda(), device_ids=[0])
     frames = torch.randint(0, 255, (B, 5, 3, 224, 224), device="cuda").float()
     lang = ["" if i % 10 == 9 else "clip %d" % i for i in range(B)]
     tr = Trainer(100)
@@ -305,7 +305,7 @@ def test_side_stream_schedule_matches_single_stream(size, clips, monkeypatch):
         sd = dict(params)
         sd.update(buffers)
         m.load_state_dict(sd)
-        model = torch.nn.DataParallel(m).cuda()
+        model = torch.nn.DataParallel(m.cuda(), device_ids=[0])
         tr = Trainer(100)
         for _ in range(2):  # twice: the second step re-uses every event and ring slot
             tr.update(model, (frames, ["x"] * clips), 0, perms=perms)
@@ -333,7 +333,7 @@ def test_get_reward_sim_and_cosine_update():
     sd = dict(params)
     sd.update(buffers)
     m.load_state_dict(sd)
-    model = torch.nn.DataParallel(m).cuda()
+    model = torch.nn.DataParallel(m.cuda(), device_ids=[0])
     g = torch.Generator().manual_seed(1)
     e0, es = torch.randn(clips, 512, generator=g).relu(), torch.randn(clips, 512, generator=g).relu()
     r, _ = m.get_reward(e0.cuda(), es.cuda(), ["x"] * clips)

@@ -160,3 +160,31 @@ def test_resize_center_crop_branch_matches_torchvision():
         got = _resize256_center_crop224(x)
         assert got.shape == (shape[0], 3, 224, 224)
         assert torch.allclose(got, ref(x), atol=1e-4)
+
+
+def test_load_config_resolves_hydra_interpolations(tmp_path):
+    """The checkpoints' config.yaml is written by hydra (r3m/cfgs/config_rep.yaml:30-41: ``lr: ${lr}``,
+    ``bs: ${batch_size}``); without omegaconf the interpolations and YAML-1.1 floats like 1e-4 must still resolve."""
+    path = tmp_path / "config.yaml"
+    path.write_text("lr: 1e-4\nbatch_size: 32\ndevice: cuda\nouter:\n  hd: 512\nagent:\n  _target_: r3m.R3M\n"
+                    "  device: ${device}\n  lr: ${lr}\n  hidden_dim: ${outer.hd}\n  size: 34\n  bs: ${batch_size}\n"
+                    "  l2dist: true\n")
+    cfg = r3m_b200.load_config(str(path))["agent"]
+    assert cfg["lr"] == 1e-4 and isinstance(cfg["lr"], float)
+    assert cfg["hidden_dim"] == 512 and cfg["bs"] == 32 and cfg["device"] == "cuda" and cfg["l2dist"] is True
+    path.write_text("agent:\n  lr: ${missing}\n")
+    with pytest.raises(ValueError):
+        r3m_b200.load_config(str(path))
+    path.write_text("agent:\n  lr: fast\n")
+    with pytest.raises(ValueError):
+        r3m_b200.load_config(str(path))
+
+
+def test_data_parallel_replication_is_refused():
+    """One GPU per process: the parameters are views into one flat block, so nn.DataParallel's replicate
+    must fail loudly instead of sharing one engine between device threads."""
+    from r3m_b200._lib import R3MB200Error
+
+    m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
+    with pytest.raises(R3MB200Error):
+        m._replicate_for_data_parallel()

@@ -37,7 +37,7 @@ def case_eval18():
     assert abs(float(frames.double().sum()) - float(gold["frames_checksum"][0])) < 1e-3
     m = R3M("cuda", 1e-4, 1024, size=18, langweight=0.0)
     load_oracle_state(m, params, buffers)
-    m = torch.nn.DataParallel(m).cuda()
+    m = torch.nn.DataParallel(m.cuda(), device_ids=[0])
     m.eval()
     with torch.no_grad():
         out = m(frames.cuda())
@@ -68,7 +68,7 @@ def case_update(size, clips, seeds, frames_kind, golden=None, lang=False):
     m = R3M("cuda", hyper["lr"], 1024, size=size, l2weight=1e-5, l1weight=1e-5, langweight=hyper["langweight"],
             tcnweight=1.0)
     load_oracle_state(m, params, buffers)
-    model = torch.nn.DataParallel(m).cuda()
+    model = torch.nn.DataParallel(m.cuda(), device_ids=[0])
     res = {}
     # train-mode forward parity first (also exercises running-stat updates on a scratch copy of the buffers)
     o_params = {k: v.clone() for k, v in params.items()}

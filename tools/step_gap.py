@@ -13,7 +13,7 @@ from r3m_b200 import R3M, Trainer  # noqa: E402
 
 r3m_b200.set_lang_encoder_factory(bench.StubLangEncoder)
 m = R3M("cuda", 1e-4, 1024, size=50, l2weight=1e-5, l1weight=1e-5, langweight=1.0, tcnweight=1.0)
-model = torch.nn.DataParallel(m).cuda()
+model = torch.nn.DataParallel(m.cuda(), device_ids=[0])
 tr = Trainer(10 ** 9)
 B = 64
 frames = torch.randint(0, 255, (B, 5, 3, 224, 224), device="cuda").float()
