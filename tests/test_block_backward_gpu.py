@@ -2,8 +2,14 @@
 the buffer one residual block's backward reads, ONLY that block's backward kernels are run (BatchNorm backward, dgrad,
 wgrad, with their accumulate flags, the dual-BatchNorm tail of downsample blocks, the dy ring), and dX, dW, dgamma,
 dbeta are compared with torch autograd of the same block (tv resnet.py:89-105 BasicBlock, :143-163 Bottleneck)
-evaluated in fp32 on the SAME bf16-rounded block input, rounding where the CUDA path stores bf16.  Because both sides
-start from the same block input, the only noise is bf16 rounding inside one block: tolerance 1e-2 (relative L2)."""
+evaluated in fp32 on the SAME bf16-rounded block input, rounding where the CUDA path stores bf16.
+
+Tolerance 3e-2 (relative L2).  Measured on the B200 (gpurun_out/r2_block_backward.jsonl -> profiles/): 1.2e-3 .. 2.5e-3 in
+layer1, 4e-3 .. 7e-3 in layer2, ~1e-2 in layer3, 1.4e-2 .. 2.3e-2 in layer4 — the deeper the block, the longer its
+fp32 reductions (K up to 4608), the more bf16 roundings of an intermediate land on the other side in the two
+implementations, and each flipped ReLU-mask bit moves the random-walk sums over the injected gradient (even dbeta of the
+LAST BatchNorm, which depends on nothing but the injected gradient and the mask, moves by 1.4e-2 there).  A wiring
+error is two orders of magnitude away: dropping the skip-path accumulation gives dX = 0.96 (test_mutation_is_caught)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -51,7 +57,7 @@ def _block_forward(x, P, pre, kind, stride, has_ds):
     return F.relu(out + identity)
 
 
-def check_block(size, block, frames=6, seed=0, tol=1e-2):
+def check_block(size, block, frames=6, seed=0, tol=3e-2):
     """Returns {name: relative error}; raises AssertionError when any exceeds `tol`."""
     from r3m_b200 import R3M
 
@@ -92,6 +98,14 @@ def check_block(size, block, frames=6, seed=0, tol=1e-2):
     errs["dX"] = rel(d_in, xr.grad)
     for k in keys:
         errs[k[len("convnet."):]] = rel(named[k].grad, P[k].grad)
+    import json
+    import os
+
+    rep = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(rep):
+        with open(os.path.join(rep, "r2_block_backward.jsonl"), "a") as f:
+            f.write(json.dumps({"size": size, "block": pre, "frames": frames, "seed": seed,
+                                "mutation": os.environ.get("R3M_TEST_MUTATION", ""), "errors": errs}) + "\n")
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, (size, block, bad, errs)
     return errs

@@ -42,12 +42,14 @@ def test_reference_style_trainer_drives_r3m_through_autograd(size, lang):
             assert abs(metrics1[k] - metrics2[k]) <= 1.0 / clips + 1e-6
         else:
             assert abs(metrics1[k] - metrics2[k]) <= 1e-3 * abs(metrics2[k]) + 1e-6, (k, metrics1[k], metrics2[k])
-    # same engine kernels below the embeddings; dE comes from torch autograd instead of the fused loss kernels, and
-    # the BatchNorm statistics' atomics reorder from run to run
+    # Same engine kernels below the embeddings, but dE comes from torch autograd instead of the fused loss kernels:
+    # it differs in the last fp32 bits, some bf16 roundings of the stored gradients then land on the other side, and
+    # the cascade saturates at the bf16 tier's own noise floor (3-5 % on this state, see test_fullsize_gpu.py) — the
+    # two paths are as close to each other as either is to the fp32 reference.
     dist = group_distances(g2, g1)
-    assert all(d < 2e-2 for d in dist.values()), dist
+    assert all(d < 0.1 for d in dist.values()), dist
     if lang:
-        assert group_distances(g2, g1, ("lang_rew",))["lang_rew"] < 2e-2
+        assert group_distances(g2, g1, ("lang_rew",))["lang_rew"] < 0.1
     # the optimiser stepped: weights moved by ~lr along -sign(g), identically (up to that noise) on both paths
     sd1, sd2 = m1.state_dict(), m2.state_dict()
     k = "convnet.layer1.0.conv1.weight"
@@ -73,7 +75,7 @@ def test_autograd_accumulates_and_detects_stale_activations():
     e = m(x)
     e.sum().backward()  # no zero_grad: torch semantics accumulate
     g2 = m.convnet.layer1._modules["0"].conv1.weight.grad
-    assert rel(g2, 2 * g1) < 1e-2
+    assert torch.equal(g2, 2 * g1)  # deterministic kernels: the second pass repeats the first bit for bit
     # a second forward of the same frame count overwrites the saved activations of the first
     e_old = m(x)
     m(x)
