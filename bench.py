@@ -13,7 +13,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +34,7 @@ def parse():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU)
     ap.add_argument("--lang", type=int, default=1, help="language head on (c3) / off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--e2e-debug", default="", help="diagnostic: 'nocopy' skips the H2D copy in the e2e loop")
     return ap.parse_args()
 
@@ -148,7 +148,10 @@ def cpu_step_runner(size, clips, lang):
     return step
 
 
-def cpu_baseline(size, lang, clips=2, steps=3):
+CPU_SAMPLE_CLIPS = 8  # bounded sample of the 64-clip workload: 8 clips = 40 frames per step (~10-25 s of host work in all)
+
+
+def cpu_baseline(size, lang, clips=CPU_SAMPLE_CLIPS, steps=2):
     step = cpu_step_runner(size, clips, lang)
     step()
     t0 = time.time()
@@ -167,7 +170,7 @@ def run_reference(args):
     if rank != 0:
         return
     lang = bool(args.lang)
-    clips = 2  # bounded sample of the 64-clip workload (2 clips/step measured faster per frame than 4 on the host)
+    clips = CPU_SAMPLE_CLIPS
     step = cpu_step_runner(args.size, clips, lang)
     for _ in range(max(args.warmup, 1)):
         step()
@@ -190,18 +193,68 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def conv_traffic(args, clips):
-    """DRAM bytes per conv_igemm launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 114 launches of
-    one step) from the committed ncu capture of this exact workload (profiles/r1_conv_traffic.json, produced by
-    tools/ncu_per_kernel.py); None for any other workload.  Algorithmic bytes per launch are ~267 MB: the measured
-    traffic is below them because gradients written by the preceding BatchNorm-backward kernel are still in L2."""
+def family_traffic(args, clips, family):
+    """DRAM bytes per launch of a kernel family (dram__bytes_read.sum + dram__bytes_write.sum averaged over the family's
+    launches of one step) from the committed ncu capture of this exact workload (profiles/r2_traffic.json, produced by
+    tools/ncu_per_kernel.py from an `ncu` pass over tools/profile_step.py); None when no capture of this workload /
+    family is committed — DRAM counters cannot be read outside a profiler, and a number taken under one is never a
+    bench value, so the live part of the roofline is `achieved` (CUDA events) and this is the profiler's part."""
     if args.size != 50 or clips != 64 or not args.lang:
-        return None
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
+        with open(path) as f:
+            rec = json.load(f)["families"][family]
+        return rec["dram_bytes_per_launch"], "profiles/r2_traffic.json (ncu, same workload)"
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
+
+
+FAMILY_KERNELS = {
+    "conv_igemm": "conv_igemm_kernel (tcgen05 implicit GEMM: forward convs + dgrad)",
+    "wgrad": "wgrad_kernel (tcgen05 filter gradients, fp32 split-K)",
+    "norm": "BatchNorm family: bn_apply / bn_bwd_reduce / bn_bwd_apply / stem_bwd / preprocess_stem (HBM streaming)",
+    "pool": "stem BN+ReLU+maxpool, average pool",
+    "loss": "fused LP / TCN loss heads",
+    "optim": "fused Adam + filter re-packs",
+    "lang": "language-reward head (fp32 SIMT GEMM chain)",
+}
+TENSOR_FAMILIES = ("conv_igemm", "wgrad", "lang")
+
+
+def family_entry(name, f, pk, total_ms):
+    tensor = name in TENSOR_FAMILIES
+    ms = f["ms"]
+    achieved = None
+    if ms > 0:
+        achieved = (f["flops"] / (ms * 1e-3) / 1e12) if tensor else (f["bytes"] / (ms * 1e-3) / 1e9)
+    peak = pk["tflops"] if tensor else pk["hbm_gbs"]
+    return {"kernel": FAMILY_KERNELS.get(name, name), "family": name, "bound": "tensor" if tensor else "hbm",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s",
+            "frac": (achieved / peak) if achieved else None, "launches_per_step": f["launches"],
+            "avg_launch_ms": ms / max(f["launches"], 1), "share_of_step": ms / total_ms if total_ms else None,
+            "algorithmic_gbytes_per_step": f["bytes"] / 1e9, "algorithmic_tflop_per_step": f["flops"] / 1e12}
+
+
+def gpu_reference(args, clips, lang, dev):
+    """The survey's bar (SURVEY.md §8d "Reference timed beside it (2)"): the reference pipeline on THIS GPU through
+    torch / torchvision / cuDNN at the same config — as written (fp32 API, cudnn.benchmark, TF32 convs allowed) and in
+    its strongest fair form (bf16 autocast + channels_last).  Device-timed like `value`; frames resident."""
+    import torch
+    from oracle import torch_reference as T
+
+    out = {"what": "oracle/torch_reference.py: torchvision ResNet + the reference's update step, same clips per step",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "variants": {}}
+    torch.cuda.empty_cache()
+    for variant in ("as_written", "bf16_channels_last"):
+        try:
+            r = T.time_update(args.size, clips, variant, dev, lang=lang, steps=6, warmup=3)
+            out["variants"][variant] = {"value": r["frames_per_s"], "unit": "frames/s", "ms_per_step": r["ms_per_step"]}
+        except Exception as e:  # noqa: BLE001 - a reported side measurement must not sink the bench line
+            out["variants"][variant] = {"error": repr(e)[:200]}
+    T.configure("as_written")
+    torch.backends.cudnn.benchmark = False
+    return out
 
 
 def workload_config(args, clips_override=None):
@@ -277,76 +330,43 @@ def run_ours(args):
     frames_per_step = B * 5 * world
     value = frames_per_step * args.steps / (ms / 1e3)
 
-    # ---- end to end: pinned host frames -> H2D -> update -> metrics D2H, every step.  The H2D copy of step i+1 is
-    # issued on a copy stream while step i computes (what a pin_memory DataLoader + non_blocking .cuda() gives the
-    # reference's train loop, train_representation.py:102-104); every step still moves its own 193 MB.
-    host = torch.empty(frames.shape, dtype=torch.float32).pin_memory()
-    host.copy_(frames)
-    staging = [torch.empty_like(frames), torch.empty_like(frames)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0}
+    # ---- end to end through the public API: pinned HOST frames -> r3m_b200.FrameFeeder (H2D on a copy stream, two
+    # slots: the upload of batch i+1 overlaps the step on batch i, what a pin_memory DataLoader + non_blocking .cuda()
+    # gives the reference's loop, train_representation.py:102-104) -> Trainer.update -> metrics D2H, every step.
+    # Headline: uint8 frames, the input pipeline's native format (r3m_b200/data.py; the reference's decoder also
+    # yields uint8, data_loaders.py:30-32).  The fp32 batches the reference's loader would hand over are timed beside.
+    from r3m_b200 import FrameFeeder
 
-    def prefetch(slot):
-        copy_stream.wait_event(consumed[slot])  # the step that last read this slot has finished
-        with torch.cuda.stream(copy_stream):
-            if args.e2e_debug != "nocopy":
-                staging[slot].copy_(host, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def endless(host):
+        while True:
+            yield host, b_lang
 
-    for ev in consumed:
-        ev.record()
-    prefetch(0)
+    def time_e2e(host):
+        feeder = FrameFeeder(endless(host), dev, as_uint8=False)
 
-    def step_e2e():
-        slot = state["i"] & 1
-        torch.cuda.current_stream().wait_event(ready[slot])
-        prefetch(slot ^ 1)
-        metrics_box["m"], _ = trainer.update(model, (staging[slot], b_lang), 0)
-        consumed[slot].record()
-        state["i"] += 1
+        def step():
+            batch, lang_b = next(feeder)
+            metrics_box["m"], _ = trainer.update(model, (batch, lang_b), 0)
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e = {"value": frames_per_step * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
-           "h2d_bytes_per_step": int(host.numel() * 4 + 15 * B * 4 + (B * 769 * 4 if lang else 0)),
-           "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e / args.steps,
-           "api": "r3m_b200.Trainer.update(DataParallel(R3M), (frames, sentences), step); fp32 frames from pinned "
-                  "host memory, double-buffered H2D on a copy stream"}
+        for _ in range(2):
+            step()
+        return timed(step, args.steps)
 
-    # ---- the same loop with uint8 host frames (R3M.forward / Trainer.update accept any dtype, like the reference's
-    # obs.float(), models_r3m.py:97): 4x fewer PCIe bytes.  Reported as extra information; the headline e2e above
-    # uses the fp32 frames the reference's loader emits (r3m/utils/data_loaders.py:98-104).
     host8 = torch.empty(frames.shape, dtype=torch.uint8).pin_memory()
     host8.copy_(frames.to(torch.uint8))
-    staging8 = [torch.empty(frames.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-    state["i"] = 0
-
-    def prefetch8(slot):
-        copy_stream.wait_event(consumed[slot])
-        with torch.cuda.stream(copy_stream):
-            staging8[slot].copy_(host8, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def step_e2e8():
-        slot = state["i"] & 1
-        torch.cuda.current_stream().wait_event(ready[slot])
-        prefetch8(slot ^ 1)
-        metrics_box["m"], _ = trainer.update(model, (staging8[slot], b_lang), 0)
-        consumed[slot].record()
-        state["i"] += 1
-
-    torch.cuda.synchronize()
-    for ev in consumed:
-        ev.record()
-    prefetch8(0)
-    for _ in range(2):
-        step_e2e8()
-    ms_e2e8 = timed(step_e2e8, args.steps)
-    e2e["uint8_frames"] = {"value": frames_per_step * args.steps / (ms_e2e8 / 1e3), "unit": "frames/s",
-                           "h2d_bytes_per_step": int(host8.numel()), "ms_per_step": ms_e2e8 / args.steps}
+    ms_e2e = time_e2e(host8)
+    small = 15 * B * 4 + (B * 769 * 4 if lang else 0)  # permutations (+ sentence embedding and mask): side-band pull
+    e2e = {"value": frames_per_step * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+           "h2d_bytes_per_step": int(host8.numel() + small), "d2h_bytes_per_step": 64,
+           "ms_per_step": ms_e2e / args.steps,
+           "api": "for frames, sentences in r3m_b200.FrameFeeder(loader, device): r3m_b200.Trainer.update("
+                  "DataParallel(R3M), (frames, sentences), step) - uint8 frames from pinned host memory"}
+    host32 = torch.empty(frames.shape, dtype=torch.float32).pin_memory()
+    host32.copy_(frames)
+    ms_e2e32 = time_e2e(host32)
+    e2e["fp32_frames"] = {"value": frames_per_step * args.steps / (ms_e2e32 / 1e3), "unit": "frames/s",
+                          "h2d_bytes_per_step": int(host32.numel() * 4 + small), "ms_per_step": ms_e2e32 / args.steps}
+    del host32
 
     # ---- roofline of the dominant kernel family, measured live with in-stream CUDA events
     m = model.module
@@ -366,22 +386,28 @@ def run_ours(args):
                                  m.encoder_opt.steps)
     pk = peaks()
     total_ms = sum(f["ms"] for f in fam.values())
+    # the roofline subject is the family that takes the most device time in the step (not a hard-coded kernel)
     dom = max(fam, key=lambda k: fam[k]["ms"])
-    conv = fam["conv_igemm"]
-    roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: forward convs + dgrad)", "bound": "tensor",
-                "achieved": conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else None,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "peak_source": pk["source"] + ", of measured",
-                "launches_per_step": conv["launches"], "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
-                "share_of_step": conv["ms"] / total_ms if total_ms else None,
-                "traffic": conv_traffic(args, B),
-                "dominant_family": dom,
-                "families": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
-                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None,
-                                 "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
-                             for k, v in fam.items() if v["launches"]},
-                "whole_step_fraction_of_tensor_peak": value / world * TRAIN_GFLOP_PER_FRAME / 1e3 / pk["tflops"]
-                if args.size == 50 else None}
-    roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["achieved"] else None
+    roofline = family_entry(dom, fam[dom], pk, total_ms)
+    roofline["peak_source"] = pk["source"]
+    roofline["traffic"], roofline["traffic_source"] = family_traffic(args, B, dom)
+    roofline["dominant_family"] = dom
+    roofline["secondary"] = [family_entry(k, fam[k], pk, total_ms) for k in ("conv_igemm", "wgrad", "norm")
+                             if k != dom and fam[k]["launches"]]
+    for sec in roofline["secondary"]:
+        sec["traffic"], sec["traffic_source"] = family_traffic(args, B, sec["family"])
+    roofline["families"] = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None,
+                                "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                            for k, v in fam.items() if v["launches"]}
+    # layer-wise roofline of the step: every launch at max(tensor time, HBM time) of its algorithmic work
+    ops = eng.profile_ops()
+    layerwise_ms = sum(max(fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9)) * 1e3 for _, _, fl, by, _ in ops)
+    roofline["layerwise_roofline_ms"] = layerwise_ms
+    roofline["step_frac_of_layerwise"] = layerwise_ms / (ms / args.steps) if ms > 0 else None
+    roofline["accounted_gbytes_per_step"] = sum(by for _, _, _, by, _ in ops) / 1e9
+    roofline["whole_step_fraction_of_tensor_peak"] = (value / world * TRAIN_GFLOP_PER_FRAME / 1e3 / pk["tflops"]
+                                                      if args.size == 50 else None)
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -389,6 +415,8 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "launches_per_step": launches,
             "roofline": roofline, "last_metrics": metrics_box.get("m")}
     if rank == 0:
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(args, B, lang, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.size, lang)
         print(json.dumps(line), flush=True)

@@ -65,6 +65,18 @@ int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, 
  * stem conv consumes).  obs fp32 NCHW [N,3,224,224] in [0,255] -> xs bf16 [N,112,112,64]; channel
  * j = kw*16 + (dy*2+dx)*4 + c holds normalise(obs[n,c,2i+dy,2(q-2+kw)+dx]) (zero outside the image / for c == 3). */
 int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream);
+/* The same for frames that arrive as uint8 (format 1: uint8 NCHW [N,3,224,224] — what torchvision.io.read_image
+ * yields, r3m/utils/data_loaders.py:30-32; format 2: uint8 NHWC [N,224,224,3]; format 0: fp32 NCHW): the
+ * `obs.float()` of models_r3m.py:97 happens in registers, a quarter of the bytes cross PCIe and HBM. */
+int r3m_b200_preprocess_stem_format(const void* obs, int format, void* xs, int N, void* stream);
+
+/* torchvision.transforms.RandomResizedCrop(224, ...) arithmetic of the reference loader's augmentation
+ * (r3m/utils/data_loaders.py:47-50,81-102) on the GPU: for frame n, crop box boxes[n] = (top, left, h, w) of the uint8
+ * source frame ([N,3,H,W], or [N,H,W,3] when nhwc != 0) resized to 224x224 with antialiased bilinear interpolation
+ * (aten::_upsample_bilinear2d_aa; borders clamp to the crop).  out: fp32 NCHW [N,3,224,224] in [0,255], the loader's
+ * output contract.  boxes: DEVICE int32 [N][4], drawn by the host with the reference's sampling law. */
+int r3m_b200_random_resized_crop(const uint8_t* src, int nhwc, int N, int H, int W, const int* boxes, float* out,
+                                 void* stream);
 
 /* BatchNorm2d forward on a raw conv output (replaces aten::cudnn_batch_norm + relu_ [+ add_], tv resnet.py:89-105,
  * 143-163).  y, a, residual: bf16 [M][C].  train != 0: batch statistics from (sum, sq) = per-channel sum / sum of
@@ -165,7 +177,9 @@ int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_ca
 int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
 /* what: 0 embedding dim, 1 frames, 2 kernels launched by the last engine call */
 int r3m_b200_engine_get_int(void* handle, int what, int* value);
-/* what: 0 similarity of the TCN head: value != 0 negative L2 distance (default; R3M(l2dist=True)), 0 cosine */
+/* what: 0 similarity of the TCN head: value != 0 negative L2 distance (default; R3M(l2dist=True)), 0 cosine
+ *       1 format of the frames `obs` of forward / update_grads / profile_update: 0 fp32 NCHW (default), 1 uint8 NCHW,
+ *         2 uint8 NHWC (see r3m_b200_preprocess_stem_format); sticky */
 int r3m_b200_engine_set_int(void* handle, int what, int value);
 /* Byte offsets of {params, grads, Adam m, Adam v, BN buffers} inside the parameter block, and the element counts of
  * the flat parameter buffer / the BN-buffer region.  Valid before bind (pure layout query; no GPU needed). */
@@ -174,9 +188,9 @@ int r3m_b200_engine_param_block_layout(void* handle, size_t* offsets5, size_t* n
 /* After writing the parameter region: refresh the bf16 operand copies (forward filters, dgrad re-packs, stem). */
 int r3m_b200_engine_sync_weights(void* handle, void* stream);
 
-/* R3M.forward: obs fp32 NCHW [frames,3,224,224] in [0,255] -> out fp32 [frames][D] (out may be NULL: result stays in
+/* R3M.forward: obs [frames,3,224,224] in [0,255] (fp32 NCHW unless set_int(1) says otherwise) -> out fp32 [frames][D] (out may be NULL: result stays in
  * region 5).  train != 0 uses batch statistics and updates the running ones (nn.BatchNorm2d semantics). */
-int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* out, void* stream);
+int r3m_b200_engine_forward(void* handle, const void* obs, int train, float* out, void* stream);
 
 /* Trainer.update up to (and excluding) the optimiser step: forward, LP / TCN / language losses, backward.
  *   perms: int32 [15][clips] permutations in the reference's draw order (9 language, then 6 TCN; trainer.py:86-92,
@@ -184,7 +198,7 @@ int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* ou
  *   langweight == 0).  eval != 0: eval-mode BN, no gradients (trainer.py:28-29,155).  Metrics land in region 7.
  *   obs == NULL (training only): the forward pass was already enqueued with r3m_b200_engine_forward(obs, train = 1,
  *   out = NULL) on the same stream, so the host may prepare perms / lang inputs while it runs. */
-int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
+int r3m_b200_engine_update_grads(void* handle, const void* obs, const int* perms, const float* lang_emb,
                                  const float* lang_mask, float l2weight, float l1weight, float langweight,
                                  float tcnweight, int eval, void* stream);
 /* The backward pass alone (what `full_loss.backward()` of r3m/trainer.py:157 runs below the embeddings), for hosts
@@ -210,7 +224,7 @@ int r3m_b200_engine_adam_step(void* handle, float lr, float grad_scale, int step
  * in-stream around every kernel launch and returns, per kernel family f (0 conv_igemm [forward + dgrad], 1 wgrad,
  * 2 BatchNorm/normalise, 3 pooling, 4 loss heads, 5 optimiser + filter re-packs, 6 language head, 7 unused):
  * out32[4*f + {0,1,2,3}] = {device ms, algorithmic FLOPs, algorithmic HBM bytes, launches}.  out32 is HOST memory. */
-int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* perms, const float* lang_emb,
+int r3m_b200_engine_profile_update(void* handle, const void* obs, const int* perms, const float* lang_emb,
                                    const float* lang_mask, float l2weight, float l1weight, float langweight,
                                    float tcnweight, float lr, int step, double* out32, void* stream);
 

@@ -167,7 +167,63 @@ def pin_cosine_sim(out_dir):
         json.dump(pin, f, indent=1)
 
 
+def pin_loader_law(out_dir):
+    """The clip-index law of the reference loader (r3m/utils/data_loaders.py:64-79) and the crop boxes its
+    RandomResizedCrop draws (:47-50,81-102), recorded from the REAL R3MBuffer with the JPEG reader patched out:
+    tests/golden/loader_law.json (`python oracle/make_golden.py --loader-only`)."""
+    import random
+    import tempfile
+
+    import pandas as pd
+
+    import_reference()
+    import r3m.utils.data_loaders as dl
+    from torchvision import transforms
+
+    rec = {"cases": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        lens = [37, 120, 999, 12, 64]
+        pd.DataFrame({"path": [f"/vid{i}" for i in range(len(lens))], "len": lens,
+                      "txt": [f"C does thing {i}" for i in range(len(lens))]}).to_csv(f"{tmp}/manifest.csv")
+        for doaug, (H, W), seed in (("none", (224, 224), 1), ("rc", (240, 320), 2), ("rctraj", (480, 360), 3)):
+            seen, boxes = [], []
+            real_get, real_params = dl.get_ind, transforms.RandomResizedCrop.get_params
+
+            def fake_get(vid, index, ds, H=H, W=W, seen=seen):
+                seen.append([vid, int(index)])
+                return torch.zeros(3, H, W, dtype=torch.uint8)
+
+            def spy_params(img, scale, ratio, boxes=boxes):
+                out = real_params(img, scale, ratio)
+                boxes.append([int(v) for v in out])
+                return out
+
+            dl.get_ind = fake_get
+            transforms.RandomResizedCrop.get_params = staticmethod(spy_params)
+            try:
+                random.seed(seed)
+                np.random.seed(seed)
+                torch.manual_seed(seed)
+                buf = dl.R3MBuffer(f"{tmp}/", 1, "ego4d", "ego4d", 0.2, ["ego4d"], doaug=doaug)
+                labels = []
+                for _ in range(6):
+                    im, label = buf._sample()
+                    assert im.shape == (5, 3, 224, 224) or doaug == "none"
+                    labels.append(label)
+            finally:
+                dl.get_ind = real_get
+                transforms.RandomResizedCrop.get_params = staticmethod(real_params)
+            rec["cases"].append({"doaug": doaug, "H": H, "W": W, "seed": seed, "alpha": 0.2, "lens": lens,
+                                 "frames": seen, "boxes": boxes, "labels": labels})
+    with open(os.path.join(out_dir, "loader_law.json"), "w") as f:
+        json.dump(rec, f)
+    print("loader_law", [(c["doaug"], len(c["frames"]), len(c["boxes"])) for c in rec["cases"]])
+
+
 def main():
+    if "--loader-only" in sys.argv:
+        pin_loader_law(os.path.join(ROOT, "tests", "golden"))
+        return
     if "--cos-only" in sys.argv:
         pin_cosine_sim(os.path.join(ROOT, "tests", "golden"))
         return
@@ -265,6 +321,7 @@ def main():
         json.dump({"reference_commit": "b2334e726887fa0206962d7984c69c5fb09cceab", "torch": torch.__version__,
                    "oracle_vs_reference": pin}, f, indent=1)
     pin_cosine_sim(out_dir)
+    pin_loader_law(out_dir)
 
 
 if __name__ == "__main__":

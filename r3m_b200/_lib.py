@@ -53,6 +53,8 @@ _sig("r3m_b200_pack_dgrad_filter", [c_void_p, c_void_p] + [c_int] * 6 + [c_void_
 _sig("r3m_b200_conv_dgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p])
 _sig("r3m_b200_conv_wgrad", [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p])
 _sig("r3m_b200_preprocess_stem", [c_void_p, c_void_p, c_int, c_void_p])
+_sig("r3m_b200_preprocess_stem_format", [c_void_p, c_int, c_void_p, c_int, c_void_p])
+_sig("r3m_b200_random_resized_crop", [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p])
 _sig("r3m_b200_bn_apply", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 19)
 _sig("r3m_b200_bn_backward", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 17)
 _sig("r3m_b200_stem_bn_relu_maxpool", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 9)

@@ -195,7 +195,20 @@ int r3m_b200_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, 
 
 int r3m_b200_preprocess_stem(const float* obs, void* xs, int N, void* stream) {
   if (!obs || !xs || N < 1) return fail(R3M_B200_ERR_INVALID, "preprocess_stem: bad arguments");
-  CUDA_OR_FAIL(launch_preprocess_stem(obs, xs, N, (cudaStream_t)stream), "preprocess_stem");
+  CUDA_OR_FAIL(launch_preprocess_stem(obs, kObsF32NCHW, xs, N, (cudaStream_t)stream), "preprocess_stem");
+}
+
+int r3m_b200_preprocess_stem_format(const void* obs, int format, void* xs, int N, void* stream) {
+  if (!obs || !xs || N < 1) return fail(R3M_B200_ERR_INVALID, "preprocess_stem: null pointer or N < 1");
+  CUDA_OR_FAIL(launch_preprocess_stem(obs, format, xs, N, (cudaStream_t)stream), "preprocess_stem");
+  return R3M_B200_OK;
+}
+
+int r3m_b200_random_resized_crop(const uint8_t* src, int nhwc, int N, int H, int W, const int* boxes, float* out,
+                                 void* stream) {
+  if (!src || !boxes || !out) return fail(R3M_B200_ERR_INVALID, "random_resized_crop: null pointer");
+  CUDA_OR_FAIL(launch_crop_resize(src, nhwc, boxes, out, N, H, W, (cudaStream_t)stream), "crop_resize");
+  return R3M_B200_OK;
 }
 
 int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
@@ -435,6 +448,11 @@ int r3m_b200_engine_set_int(void* handle, int what, int value) {
   ENGINE_OR_FAIL(handle);
   switch (what) {
     case 0: eng->set_l2dist(value != 0); break;
+    case 1: {
+      std::string err = eng->set_obs_format(value);
+      if (!err.empty()) return fail(R3M_B200_ERR_INVALID, err);
+      break;
+    }
     default: return fail(R3M_B200_ERR_INVALID, "unknown setting");
   }
   return R3M_B200_OK;
@@ -450,12 +468,12 @@ int r3m_b200_engine_sync_weights(void* handle, void* stream) {
   ENGINE_OR_FAIL(handle);
   RETURN_STR(eng->sync_weights((cudaStream_t)stream));
 }
-int r3m_b200_engine_forward(void* handle, const float* obs, int train, float* out, void* stream) {
+int r3m_b200_engine_forward(void* handle, const void* obs, int train, float* out, void* stream) {
   ENGINE_OR_FAIL(handle);
   if (!obs) return fail(R3M_B200_ERR_INVALID, "null observation pointer");
   RETURN_STR(eng->forward(obs, train, out, (cudaStream_t)stream));
 }
-int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perms, const float* lang_emb,
+int r3m_b200_engine_update_grads(void* handle, const void* obs, const int* perms, const float* lang_emb,
                                  const float* lang_mask, float l2weight, float l1weight, float langweight,
                                  float tcnweight, int eval, void* stream) {
   ENGINE_OR_FAIL(handle);
@@ -467,7 +485,7 @@ int r3m_b200_engine_update_grads(void* handle, const float* obs, const int* perm
   h.tcnweight = tcnweight;
   RETURN_STR(eng->update_grads(obs, perms, lang_emb, lang_mask, h, eval, (cudaStream_t)stream));
 }
-int r3m_b200_engine_profile_update(void* handle, const float* obs, const int* perms, const float* lang_emb,
+int r3m_b200_engine_profile_update(void* handle, const void* obs, const int* perms, const float* lang_emb,
                                    const float* lang_mask, float l2weight, float l1weight, float langweight,
                                    float tcnweight, float lr, int step, double* out32, void* stream) {
   ENGINE_OR_FAIL(handle);

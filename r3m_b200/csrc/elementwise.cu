@@ -117,7 +117,30 @@ __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const
 }
 
 // ------------------------------------------------------------------------------------------------ preprocess
-__global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __restrict__ obs, bf16* __restrict__ xs,
+// Input formats (enum ObsFormat in elementwise.cuh): fp32 NCHW (the reference loader's contract), uint8 NCHW
+// (torchvision.io.read_image frames: 4x fewer PCIe / HBM bytes) and uint8 NHWC (decoder output order).  A thread
+// produces one 16-channel group of the stem operand from 2 rows x 2 columns x 3 colours of the frame.
+template <int FMT>
+__device__ __forceinline__ void load_px2(const void* __restrict__ obs, int n, int c, int row, int col, float& a, float& b) {
+  if (FMT == kObsF32NCHW) {
+    const float2 px = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(obs) +
+                                                       (((long long)n * 3 + c) * 224 + row) * 224 + col);
+    a = px.x;
+    b = px.y;
+  } else if (FMT == kObsU8NCHW) {
+    const uchar2 px = *reinterpret_cast<const uchar2*>(reinterpret_cast<const uint8_t*>(obs) +
+                                                       (((long long)n * 3 + c) * 224 + row) * 224 + col);
+    a = (float)px.x;
+    b = (float)px.y;
+  } else {  // uint8 NHWC: the two pixels are 3 bytes apart
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(obs) + (((long long)n * 224 + row) * 224 + col) * 3 + c;
+    a = (float)p[0];
+    b = (float)p[3];
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) preprocess_stem_kernel(const void* __restrict__ obs, bf16* __restrict__ xs,
                                                               int N) {
   pdl_sync();
   const long long total = (long long)N * 112 * 112 * 4;
@@ -131,22 +154,22 @@ __global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __res
     t /= 112;
     const int i = (int)(t % 112);
     const int n = (int)(t / 112);
-    const int col = 2 * (q - 2 + kw);  // even, so a float2 covers dx = 0, 1
+    const int col = 2 * (q - 2 + kw);  // even, so a pixel pair covers dx = 0, 1
     uint32_t w[8];
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
       float v[2][4];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float2 px = make_float2(0.f, 0.f);
+        float p0 = 0.f, p1 = 0.f;
         const bool inside = (col >= 0 && col < 224);
         if (inside) {
-          px = *reinterpret_cast<const float2*>(obs + (((long long)n * 3 + c) * 224 + (2 * i + dy)) * 224 + col);
-          px.x = (px.x * (1.f / 255.f) - mean[c]) * istd[c];
-          px.y = (px.y * (1.f / 255.f) - mean[c]) * istd[c];
+          load_px2<FMT>(obs, n, c, 2 * i + dy, col, p0, p1);
+          p0 = (p0 * (1.f / 255.f) - mean[c]) * istd[c];
+          p1 = (p1 * (1.f / 255.f) - mean[c]) * istd[c];
         }
-        v[0][c] = px.x;
-        v[1][c] = px.y;
+        v[0][c] = p0;
+        v[1][c] = p1;
       }
       v[0][3] = 0.f;
       v[1][3] = 0.f;
@@ -159,6 +182,68 @@ __global__ void __launch_bounds__(256) preprocess_stem_kernel(const float* __res
     uint4* dst = reinterpret_cast<uint4*>(xs + idx * 16);
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ crop + resize
+// torchvision.transforms.RandomResizedCrop's arithmetic on the GPU (r3m/utils/data_loaders.py:47-50,81-102): crop box
+// (top, left, h, w) of a uint8 frame -> 224 x 224 by bilinear interpolation WITH antialiasing, i.e. ATen's
+// upsample_bilinear2d_aa (separable triangle filter whose support grows with the down-scale factor; weights
+// normalised per output index; borders clamp to the CROP, as the reference crops first and resizes second).
+// out: fp32 NCHW [N,3,224,224] in [0,255] — the reference loader's contract.
+struct AaAxis {
+  int lo, n;      // first source index (inside the crop) and tap count
+  float center, inv, scale_w;
+};
+__device__ __forceinline__ AaAxis aa_axis(int o, int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = (scale >= 1.f) ? scale : 1.f;
+  AaAxis a;
+  a.center = scale * ((float)o + 0.5f);
+  a.inv = (scale >= 1.f) ? 1.f / scale : 1.f;
+  a.lo = max((int)(a.center - support + 0.5f), 0);
+  a.n = min((int)(a.center + support + 0.5f), in_size) - a.lo;
+  float total = 0.f;
+  for (int j = 0; j < a.n; ++j) total += fmaxf(0.f, 1.f - fabsf(((float)(j + a.lo) - a.center + 0.5f) * a.inv));
+  a.scale_w = total != 0.f ? 1.f / total : 0.f;
+  return a;
+}
+__device__ __forceinline__ float aa_weight(const AaAxis& a, int j) {
+  return fmaxf(0.f, 1.f - fabsf(((float)(j + a.lo) - a.center + 0.5f) * a.inv)) * a.scale_w;
+}
+
+template <bool NHWC>
+__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ src, const int* __restrict__ boxes,
+                                                          float* __restrict__ out, int N, int H, int W) {
+  pdl_sync();
+  const long long total = (long long)N * 224 * 224;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % 224);
+    const int y = (int)((idx / 224) % 224);
+    const int n = (int)(idx / (224 * 224));
+    const int top = boxes[4 * n], left = boxes[4 * n + 1], h = boxes[4 * n + 2], w = boxes[4 * n + 3];
+    const AaAxis ax = aa_axis(x, w, 224), ay = aa_axis(y, h, 224);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int jy = 0; jy < ay.n; ++jy) {
+      const float wy = aa_weight(ay, jy);
+      const int yy = top + ay.lo + jy;
+      float row[3] = {0.f, 0.f, 0.f};
+      for (int jx = 0; jx < ax.n; ++jx) {
+        const float wx = aa_weight(ax, jx);
+        const int xx = left + ax.lo + jx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint8_t v = NHWC ? src[(((long long)n * H + yy) * W + xx) * 3 + c]
+                                 : src[(((long long)n * 3 + c) * H + yy) * W + xx];
+          row[c] = fmaf(wx, (float)v, row[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, row[c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(((long long)n * 3 + c) * 224 + y) * 224 + x] = acc[c];
   }
 }
 
@@ -945,9 +1030,27 @@ int resident_blocks(int threads, size_t smem = 0) {
 
 }  // namespace
 
-cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream_t s) {
+cudaError_t launch_preprocess_stem(const void* obs, int format, void* xs, int N, cudaStream_t s) {
   const long long total = (long long)N * 112 * 112 * 4;
-  launch_kernel(preprocess_stem_kernel, grid_for(total, 256, 148 * 16), 256, 0, s, obs, reinterpret_cast<bf16*>(xs), N);
+  const int grid = grid_for(total, 256, 148 * 16);
+  bf16* dst = reinterpret_cast<bf16*>(xs);
+  switch (format) {
+    case kObsF32NCHW: launch_kernel(preprocess_stem_kernel<kObsF32NCHW>, grid, 256, 0, s, obs, dst, N); break;
+    case kObsU8NCHW: launch_kernel(preprocess_stem_kernel<kObsU8NCHW>, grid, 256, 0, s, obs, dst, N); break;
+    case kObsU8NHWC: launch_kernel(preprocess_stem_kernel<kObsU8NHWC>, grid, 256, 0, s, obs, dst, N); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crop_resize(const uint8_t* src, int nhwc, const int* boxes, float* out, int N, int H, int W,
+                               cudaStream_t s) {
+  if (N < 1 || H < 1 || W < 1) return cudaErrorInvalidValue;
+  const int grid = grid_for((long long)N * 224 * 224, 256, 148 * 16);
+  if (nhwc)
+    launch_kernel(crop_resize_kernel<true>, grid, 256, 0, s, src, boxes, out, N, H, W);
+  else
+    launch_kernel(crop_resize_kernel<false>, grid, 256, 0, s, src, boxes, out, N, H, W);
   return cudaGetLastError();
 }
 

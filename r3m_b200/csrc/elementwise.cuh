@@ -11,7 +11,15 @@ constexpr float kBnMomentum = 0.1f;
 // obs fp32 NCHW [N,3,224,224] in [0,255]  ->  stem operand bf16 [N,112,112,64]:
 //   channel j = kw*16 + (dy*2+dx)*4 + c  holds  normalise(obs[n, c, 2*i+dy, 2*(q-2+kw)+dx])   (0 outside / c == 3)
 // ref: r3m/models/models_r3m.py:97-98 (x/255, Normalize(mean,std)) fused with the space-to-depth re-layout.
-cudaError_t launch_preprocess_stem(const float* obs, void* xs, int N, cudaStream_t s);
+// The frames may arrive in three formats (obs is [N,3,224,224] or, for kObsU8NHWC, [N,224,224,3]).
+enum ObsFormat { kObsF32NCHW = 0, kObsU8NCHW = 1, kObsU8NHWC = 2 };
+cudaError_t launch_preprocess_stem(const void* obs, int format, void* xs, int N, cudaStream_t s);
+
+// RandomResizedCrop's arithmetic (r3m/utils/data_loaders.py:47-50): per-frame crop box (top, left, h, w) of a uint8
+// frame [N,3,H,W] (nhwc: [N,H,W,3]) -> fp32 NCHW [N,3,224,224] in [0,255] by antialiased bilinear interpolation
+// (ATen upsample_bilinear2d_aa semantics, borders clamped to the crop).  boxes: device int32 [N][4].
+cudaError_t launch_crop_resize(const uint8_t* src, int nhwc, const int* boxes, float* out, int N, int H, int W,
+                               cudaStream_t s);
 
 struct BnApplyArgs {
   const void* y = nullptr;      // bf16 [M][C] raw conv output

@@ -856,7 +856,7 @@ cudaError_t Engine::launch(const Op& op, cudaStream_t stream) {
   return e;
 }
 
-std::string Engine::profile_update(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+std::string Engine::profile_update(const void* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                                    const Hyper& h, float lr, int step, double* out, cudaStream_t stream) {
   profiling_ = true;
   prof_events_.clear();
@@ -902,7 +902,18 @@ std::string Engine::sync_weights(cudaStream_t stream) {
   return run(repack_, stream);
 }
 
-std::string Engine::forward(const float* obs, int train, float* out, cudaStream_t stream) {
+std::string Engine::set_obs_format(int format) {
+  if (format != kObsF32NCHW && format != kObsU8NCHW && format != kObsU8NHWC) return "unknown observation format";
+  if (format != obs_format_ && eval_graph_) {  // the captured eval graph holds the preprocess kernel of the old format
+    cudaGraphExecDestroy(eval_graph_);
+    eval_graph_ = nullptr;
+    eval_calls_ = 0;
+  }
+  obs_format_ = format;
+  return std::string();
+}
+
+std::string Engine::forward(const void* obs, int train, float* out, cudaStream_t stream) {
   if (!bound_) return "engine has no workspace bound";
   launches_ = 0;
   cudaError_t e;
@@ -914,8 +925,10 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
     // Launch-latency-bound regime (load_r3m users, r3m/example.py: batch 1-4): ~25 kernels of a few microseconds.
     // The frames are copied to a fixed staging buffer and the whole eval forward is replayed as one CUDA graph
     // (captured on the second call, once every kernel's attributes have been configured by a plain first call).
-    float* stage = reinterpret_cast<float*>(ws_ + off_obs_stage_);
-    e = cudaMemcpyAsync(stage, obs, (size_t)N_ * 3 * 224 * 224 * 4, cudaMemcpyDeviceToDevice, stream);
+    void* stage = ws_ + off_obs_stage_;
+    const int fmt = obs_format_;
+    e = cudaMemcpyAsync(stage, obs, (size_t)N_ * 3 * 224 * 224 * (fmt == kObsF32NCHW ? 4 : 1), cudaMemcpyDeviceToDevice,
+                        stream);
     if (e != cudaSuccess) return std::string("stage frames: ") + cudaGetErrorString(e);
     ++eval_calls_;
     if (eval_graph_ == nullptr && eval_calls_ >= 2) {
@@ -924,7 +937,7 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
       cudaStream_t cap = nullptr;
       if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
           cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-        cudaError_t ce = launch_preprocess_stem(stage, ws_ + off_xs_, N_, cap);
+        cudaError_t ce = launch_preprocess_stem(stage, fmt, ws_ + off_xs_, N_, cap);
         std::string cerr = run(fwd_eval_, cap);
         cudaError_t ee = cudaStreamEndCapture(cap, &graph);
         if (ce == cudaSuccess && cerr.empty() && ee == cudaSuccess && graph != nullptr) {
@@ -941,7 +954,7 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
       if (e != cudaSuccess) return std::string("graph launch: ") + cudaGetErrorString(e);
       launches_ = (int)fwd_eval_.size() + 1;
     } else {
-      e = launch_preprocess_stem(stage, ws_ + off_xs_, N_, stream);
+      e = launch_preprocess_stem(stage, fmt, ws_ + off_xs_, N_, stream);
       if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
       ++launches_;
       err = run(fwd_eval_, stream);
@@ -954,9 +967,9 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
     }
     {
       void* xs = ws_ + off_xs_;
-      const int N = N_;
-      e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
-                    (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+      const int N = N_, fmt = obs_format_;
+      e = launch(Op([obs, xs, N, fmt](cudaStream_t s) { return launch_preprocess_stem(obs, fmt, xs, N, s); }, kFamNorm,
+                    0.0, (double)N * (3.0 * 224 * 224 * (fmt == kObsF32NCHW ? 4 : 1) + 112.0 * 112 * 64 * 2)),
                  stream);
     }
     if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
@@ -976,7 +989,7 @@ std::string Engine::forward(const float* obs, int train, float* out, cudaStream_
   return std::string();
 }
 
-std::string Engine::update_grads(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+std::string Engine::update_grads(const void* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                                  const Hyper& h, int eval, cudaStream_t stream) {
   if (!bound_) return "engine has no workspace bound";
   if (B_ == 0) return "update needs frames == 5 * clips (r3m/trainer.py:39-40)";
@@ -990,9 +1003,9 @@ std::string Engine::update_grads(const float* obs, const int* perms, const float
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
     {
       void* xs = ws_ + off_xs_;
-      const int N = N_;
-      e = launch(Op([obs, xs, N](cudaStream_t s) { return launch_preprocess_stem(obs, xs, N, s); }, kFamNorm, 0.0,
-                    (double)N * (3.0 * 224 * 224 * 4 + 112.0 * 112 * 64 * 2)),
+      const int N = N_, fmt = obs_format_;
+      e = launch(Op([obs, xs, N, fmt](cudaStream_t s) { return launch_preprocess_stem(obs, fmt, xs, N, s); }, kFamNorm,
+                    0.0, (double)N * (3.0 * 224 * 224 * (fmt == kObsF32NCHW ? 4 : 1) + 112.0 * 112 * 64 * 2)),
                  stream);
     }
     if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);

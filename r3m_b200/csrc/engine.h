@@ -61,8 +61,11 @@ class Engine {
   int frames() const { return N_; }
 
   std::string sync_weights(cudaStream_t stream);  // params fp32 -> bf16 operands (+ dgrad / stem re-packs)
-  std::string forward(const float* obs, int train, float* out, cudaStream_t stream);
-  std::string update_grads(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+  // format of the frames passed to forward / update_grads (ObsFormat, elementwise.cuh): fp32 NCHW (default), uint8 NCHW,
+  // uint8 NHWC.  Sticky until changed.
+  std::string set_obs_format(int format);
+  std::string forward(const void* obs, int train, float* out, cudaStream_t stream);
+  std::string update_grads(const void* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                            const Hyper& h, int eval, cudaStream_t stream);
   // Backward pass alone, for callers that compute the loss themselves (the reference's own Trainer through
   // torch.autograd): dE = d(loss)/d(embeddings) fp32 [frames][D] of the preceding train-mode forward().  Filter
@@ -82,7 +85,7 @@ class Engine {
   const std::vector<std::string>& last_profile_labels() const { return prof_labels_; }
   // Runs ONE update_grads + adam_step with a CUDA-event pair around every launch (serialises nothing: events are
   // recorded in-stream) and accumulates per-family device time.  out: [kNumFamilies][4] = {ms, flops, bytes, launches}.
-  std::string profile_update(const float* obs, const int* perms, const float* lang_emb, const float* lang_mask,
+  std::string profile_update(const void* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                              const Hyper& h, float lr, int step, double* out, cudaStream_t stream);
   void param_block_layout(size_t* offsets5) const {
     offsets5[0] = off_P_; offsets5[1] = off_G_; offsets5[2] = off_M_; offsets5[3] = off_V_; offsets5[4] = off_buf_;
@@ -117,6 +120,7 @@ class Engine {
   int size_ = 0, N_ = 0, D_ = 0, B_ = 0, lang_ = 0, hidden_ = 0;
   bool bottleneck_ = false;
   bool l2dist_ = true;  // R3M.sim: negative L2 distance (default) or cosine similarity
+  int obs_format_ = 0;  // ObsFormat of the frames handed to forward / update_grads
   std::vector<Conv*> convs_;
   std::vector<Block*> blocks_;
   std::vector<TensorInfo> tensors_;

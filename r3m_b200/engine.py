@@ -108,24 +108,39 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_sync_weights(self._h, L.current_stream()))
 
-    def forward(self, obs, train):
-        """obs: float32 contiguous CUDA [frames,3,224,224] in [0,255] -> new float32 [frames, D]."""
-        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (self.frames, 3, 224, 224)
+    def _set_format(self, obs, nhwc=False):
+        """Frames are consumed as they are: float32 NCHW (the reference loader's contract), uint8 NCHW or uint8 NHWC
+        (``nhwc=True``: [frames,224,224,3]) — the ``obs.float()`` of models_r3m.py:97 happens inside the kernel."""
+        assert obs.is_cuda and obs.is_contiguous() and obs.numel() == self.frames * 3 * 224 * 224, tuple(obs.shape)
+        if obs.dtype == torch.float32 and not nhwc:
+            fmt = 0
+        elif obs.dtype == torch.uint8:
+            fmt = 2 if nhwc else 1
+        else:
+            raise L.R3MB200Error(f"frames must be float32 NCHW or uint8 (got {obs.dtype}, nhwc={nhwc})")
+        if fmt != getattr(self, "_obs_format", 0):
+            L.check(L.lib.r3m_b200_engine_set_int(self._h, 1, fmt))
+            self._obs_format = fmt
+
+    def forward(self, obs, train, nhwc=False):
+        """obs: contiguous CUDA [frames,3,224,224] float32 or uint8 ([frames,224,224,3] uint8 with nhwc) in [0,255]
+        -> new float32 [frames, D]."""
+        self._set_format(obs, nhwc)
         out = torch.empty(self.frames, self.embed_dim, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_forward(self._h, L.ptr(obs), int(train), L.ptr(out), L.current_stream()))
         return out
 
-    def forward_train_async(self, obs):
+    def forward_train_async(self, obs, nhwc=False):
         """Enqueue the train-mode forward only (embeddings stay in the engine); pair with update_grads(obs=None)."""
-        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.frames * 3 * 224 * 224
+        self._set_format(obs, nhwc)
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_forward(self._h, L.ptr(obs), 1, None, L.current_stream()))
 
-    def update_grads(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, eval_mode):
+    def update_grads(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, eval_mode, nhwc=False):
         """obs None: the forward pass was enqueued with forward_train_async(obs) (training only)."""
-        assert obs is None or (obs.dtype == torch.float32 and obs.is_contiguous()
-                               and obs.numel() == self.frames * 3 * 224 * 224)
+        if obs is not None:
+            self._set_format(obs, nhwc)
         assert perms.dtype == torch.int32 and perms.is_cuda and perms.is_contiguous()
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_update_grads(self._h, L.ptr(obs), L.ptr(perms), L.ptr(lang_emb),
@@ -167,6 +182,7 @@ class Engine:
     def profile_update(self, obs, perms, lang_emb, lang_mask, l2w, l1w, langw, tcnw, lr, step):
         """One instrumented step -> {family: {ms, flops, bytes, launches}} (see r3m_b200_engine_profile_update)."""
         out = (ctypes.c_double * 32)()
+        self._set_format(obs)
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_profile_update(self._h, L.ptr(obs), L.ptr(perms), L.ptr(lang_emb),
                                                          L.ptr(lang_mask), l2w, l1w, langw, tcnw, lr, step, out,

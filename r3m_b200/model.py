@@ -235,9 +235,11 @@ class R3M(nn.Module):
     # ------------------------------------------------------------------------------------------------ reference API
     def forward(self, obs, num_ims=1, obs_shape=[3, 224, 224]):  # noqa: B006 - reference signature
         """models_r3m.py:84-100.  obs in [0, 255], any dtype, [N, 3, H, W]."""
-        x = obs.float()
+        x = obs
         if list(obs_shape) != [3, 224, 224]:
-            x = _resize256_center_crop224(x)  # transforms.Resize(256) + CenterCrop(224), models_r3m.py:85-90
+            x = _resize256_center_crop224(x.float())  # transforms.Resize(256) + CenterCrop(224), models_r3m.py:85-90
+        elif x.dtype != torch.uint8:  # uint8 frames are consumed as they are (the engine converts in registers)
+            x = x.float()
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
             raise ValueError(f"expected [N, 3, 224, 224] frames, got {tuple(x.shape)}")
         if x.device != self._block.device:  # one GPU per process: inputs always follow the parameter block

@@ -110,7 +110,7 @@ class Trainer:
 
         bs = b_im.shape[0]
         frames = b_im.reshape(bs * 5, 3, 224, 224)  # trainer.py:39-40
-        if frames.dtype != torch.float32:
+        if frames.dtype not in (torch.float32, torch.uint8):  # uint8 frames go to the engine as they are
             frames = frames.float()
         if not frames.is_cuda:
             frames = frames.to(m._block.device, non_blocking=True)
