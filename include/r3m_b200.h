@@ -179,7 +179,10 @@ int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
 int r3m_b200_engine_get_int(void* handle, int what, int* value);
 /* what: 0 similarity of the TCN head: value != 0 negative L2 distance (default; R3M(l2dist=True)), 0 cosine
  *       1 format of the frames `obs` of forward / update_grads / profile_update: 0 fp32 NCHW (default), 1 uint8 NCHW,
- *         2 uint8 NHWC (see r3m_b200_preprocess_stem_format); sticky */
+ *         2 uint8 NHWC (see r3m_b200_preprocess_stem_format); sticky
+ *       2 precision tier of the EVAL-mode forward: 0 bf16 storage (default), 1 tf32 — fp32 storage rounded to tf32,
+ *         kind::tf32 tensor cores, fp32 accumulation: embeddings within 1e-3 (relative) of the fp32 reference
+ *         (r3m/models/models_r3m.py:97-99 computes in fp32); train-mode forwards and update() always run bf16 */
 int r3m_b200_engine_set_int(void* handle, int what, int value);
 /* Byte offsets of {params, grads, Adam m, Adam v, BN buffers} inside the parameter block, and the element counts of
  * the flat parameter buffer / the BN-buffer region.  Valid before bind (pure layout query; no GPU needed). */

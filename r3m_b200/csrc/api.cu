@@ -453,6 +453,11 @@ int r3m_b200_engine_set_int(void* handle, int what, int value) {
       if (!err.empty()) return fail(R3M_B200_ERR_INVALID, err);
       break;
     }
+    case 2: {
+      std::string err = eng->set_precision(value);
+      if (!err.empty()) return fail(R3M_B200_ERR_INVALID, err);
+      break;
+    }
     default: return fail(R3M_B200_ERR_INVALID, "unknown setting");
   }
   return R3M_B200_OK;

@@ -72,7 +72,11 @@ struct Cfg {
 //   kModeStats   dense output + BatchNorm statistics (training forward convs)
 //   kModeScatter strided scatter output with optional read-modify-write (stride-2 dgrad parity classes)
 enum { kModeDense = 0, kModeStats = 1, kModeScatter = 2 };
-template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE>
+// PREC: 0 = bf16 operands / bf16 output (training and the fast inference tier); 1 = fp32 storage with kind::tf32 tensor
+// core arithmetic and fp32 (tf32-rounded) output — the parity tier of the inference path (dense mode only).  The
+// 128-byte swizzle row then holds 32 channels instead of 64 and an MMA consumes K = 8 of them; tile BYTES, the operand
+// ring and the descriptor stepping are unchanged.
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE, int PREC = 0>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
@@ -92,6 +96,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   constexpr bool STATS = (MODE == kModeStats);
   constexpr bool do_stats = STATS;
+  static_assert(PREC == 0 || MODE == kModeDense, "the tf32 tier serves dense (inference) outputs only");
+  constexpr int kElemsK = PREC ? 32 : 64;  // operand elements per 128-byte K block
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -162,8 +168,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
               uint8_t* sa = st + j * C::kKbBytes;
-              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
-              tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, (kb0 + j) * kBlockK, n_tile * BN);
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kElemsK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
+              tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, (kb0 + j) * kElemsK, n_tile * BN);
               if (++cb == p.cblocks) {
                 cb = 0;
                 ++tap;
@@ -181,7 +187,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, kBlockM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc(PREC ? /*tf32*/ 2 : /*bf16*/ 1, kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -211,9 +217,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint64_t db = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
-                // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is >>4)
-                umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                          (kb0 | j | k) != 0 ? 1u : 0u);
+                // +32 bytes per MMA (K = 16 bf16 or 8 tf32) inside the 128-byte swizzle row (start-address field is >>4)
+                if constexpr (PREC == 0)
+                  umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                            (kb0 | j | k) != 0 ? 1u : 0u);
+                else
+                  umma_tf32(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                            (kb0 | j | k) != 0 ? 1u : 0u);
               }
             }
           }
@@ -299,7 +309,79 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      if (h >= kUnits) {
+      if constexpr (PREC == 1) {
+        // fp32 output: units of 32 rows x 32 columns (128-byte rows); folded BatchNorm (+ fp32 residual) (+ ReLU) on the
+        // accumulators, results rounded to tf32 (round-to-nearest: the next conv's tensor cores would truncate)
+        constexpr int kUnits32 = BN / 32;
+        const float* __restrict__ resp = reinterpret_cast<const float*>(p.ep_res);
+        uint32_t v[32];
+        if (h < kUnits32) tmem_ld_32x32(t_row + h * 32, v);
+#pragma unroll 1
+        for (int u = h; u < kUnits32; u += EPI / 4) {
+          tc_wait_ld();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (u + EPI / 4 < kUnits32) {
+            tmem_ld_32x32(t_row + (u + EPI / 4) * 32, v);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (do_affine) {
+            const float* sc = s_sum + n0 + u * 32;
+            const float* sh = s_sq + n0 + u * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+          }
+          if (resp != nullptr && m0 + lane < p.M_total) {
+            const float4* rrow = reinterpret_cast<const float4*>(resp + static_cast<long long>(m0 + lane) * p.ldo + n0 + u * 32);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 r = __ldg(rrow + c);
+              f[4 * c] += r.x;
+              f[4 * c + 1] += r.y;
+              f[4 * c + 2] += r.z;
+              f[4 * c + 3] += r.w;
+            }
+          }
+          if (p.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[j]) : "f"(f[j]));
+          const uint32_t stg_u32 = stg_base + buf * kUnitBytes;
+          if (++buf == BUFS) buf = 0;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BUFS - 1) : "memory");
+          __syncwarp();
+          const uint32_t rbase = stg_u32 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = rbase + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                         "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = n0 + u * 32;
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(stg_u32), "r"(c0), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (h >= kUnits32) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+      } else if (h >= kUnits) {
         // BN == 64: a single unit per quadrant; the second warp of the pair has nothing to drain
         tc_fence_before();
         __syncwarp();
@@ -492,25 +574,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE>
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE, int PREC = 0>
 cudaError_t launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE, PREC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE>, grid, C::kThreads, C::kSmemBytes, stream, tmA, tmB,
-                tmC, p);
+  launch_kernel(conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE, PREC>, grid, C::kThreads, C::kSmemBytes, stream, tmA,
+                tmB, tmC, p);
   return cudaGetLastError();
 }
 
 template <int BN, int STAGES, int BUFS, int EPI, int KPS>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  if (p.tf32) {
+    if (p.stat_sum != nullptr || p.out_mode != 0 || p.accumulate) return cudaErrorInvalidValue;
+    return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense, 1>(tmA, tmB, tmC, p, grid, stream);
+  }
   if (p.stat_sum != nullptr) {
     if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr) return cudaErrorInvalidValue;
     return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeStats>(tmA, tmB, tmC, p, grid, stream);

@@ -35,8 +35,9 @@ struct ConvKernelParams {
   // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.
   const float* ep_scale;
   const float* ep_shift;
-  const void* ep_res;  // bf16 [M][ldo] or null
+  const void* ep_res;  // bf16 [M][ldo] (fp32 in the tf32 tier) or null
   int ep_relu;
+  int tf32;  // 1: fp32 operands / output through kind::tf32 (cblocks counts 32-channel blocks); dense mode only
   int* error_flag;
 };
 

@@ -45,7 +45,11 @@ static int pick_bn(int Cout) {
 }
 
 std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
-  if (g.C % 64 != 0) return "gather conv: source channels must be a multiple of 64";
+  const int eb = g.tf32 ? 4 : 2;          // operand / output element bytes
+  const int kelems = g.tf32 ? 32 : 64;    // elements per 128-byte K block
+  if (g.C % kelems != 0) return "gather conv: source channels must be a multiple of one 128-byte K block";
+  if (g.tf32 && (g.stat_sum || g.out_mode != 0 || g.accumulate))
+    return "gather conv: the tf32 tier needs a dense, non-accumulating output without statistics";
   if (g.Cout % 64 != 0) return "gather conv: output channels must be a multiple of 64";
   if (g.ntaps < 1 || g.ntaps > kMaxTaps) return "gather conv: tap count out of range";
   if (g.stride < 1 || g.stride > 8) return "gather conv: stride out of range";
@@ -53,18 +57,18 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   *plan = {};
   const int upper_w = (g.Q - 1) * g.stride + 1 + g.base_w - g.W;
   const int upper_h = (g.P - 1) * g.stride + 1 + g.base_h - g.H;
-  std::string err = encode_im2col_map(&plan->tmA, g.src, g.C, g.W, g.H, g.N, g.base_w, g.base_h, upper_w, upper_h, 64,
-                                      128, g.stride);
+  std::string err = encode_im2col_map(&plan->tmA, g.src, g.C, g.W, g.H, g.N, g.base_w, g.base_h, upper_w, upper_h,
+                                      kelems, 128, g.stride, eb);
   if (!err.empty()) return err;
   const int bn = pick_bn(g.Cout);
   const uint64_t kdim = (uint64_t)g.ntaps * g.C;
-  err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * 2, 64, bn);
+  err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, bn, 128, eb);
   if (!err.empty()) return err;
   ConvKernelParams& p = plan->p;
   p.M_total = g.N * g.P * g.Q;
   if (g.out_mode == 0) {
-    err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * 2, 64, 32,
-                              /*swizzle_bytes=*/128);
+    err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * eb, kelems, 32,
+                              /*swizzle_bytes=*/128, eb);
     if (!err.empty()) return err;
   } else {
     plan->tmC = plan->tmB;
@@ -75,7 +79,8 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.base_w = g.base_w;
   p.base_h = g.base_h;
   p.num_taps = g.ntaps;
-  p.cblocks = g.C / 64;
+  p.cblocks = g.C / kelems;
+  p.tf32 = g.tf32;
   for (int t = 0; t < g.ntaps; ++t) {
     if (g.tap_w[t] < 0 || g.tap_h[t] < 0) return "gather conv: tap offsets must be non-negative";
     p.tap_w[t] = (uint16_t)g.tap_w[t];

@@ -30,6 +30,9 @@ struct GatherConv {
   const float* ep_shift = nullptr;
   const void* ep_res = nullptr;
   int ep_relu = 0;
+  // tf32 tier (inference parity): src / wpk / out / ep_res are fp32 (tf32-rounded values), C % 32 == 0; dense
+  // non-accumulating outputs without statistics only
+  int tf32 = 0;
 };
 
 struct ConvPlan {

@@ -247,6 +247,107 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tf32 tier
+// The inference parity tier keeps activations and filters in fp32 storage, rounded to tf32 (10-bit mantissa, round to
+// nearest: the tensor cores would otherwise TRUNCATE their fp32 operands, a biased error that does not average out).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  pdl_sync();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = round_tf32(src[i]);
+}
+
+// fp32 frames / stem operand variant of preprocess_stem_kernel: same gather, fp32 (tf32-rounded) output
+template <int FMT>
+__global__ void __launch_bounds__(256) preprocess_stem_f32_kernel(const void* __restrict__ obs, float* __restrict__ xs,
+                                                                  int N) {
+  pdl_sync();
+  const long long total = (long long)N * 112 * 112 * 4;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(idx & 3);
+    long long t = idx >> 2;
+    const int q = (int)(t % 112);
+    t /= 112;
+    const int i = (int)(t % 112);
+    const int n = (int)(t / 112);
+    const int col = 2 * (q - 2 + kw);
+    float o[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float p0 = 0.f, p1 = 0.f;
+        if (col >= 0 && col < 224) {
+          load_px2<FMT>(obs, n, c, 2 * i + dy, col, p0, p1);
+          // the reference's arithmetic order: (x / 255 - mean) / std  (models_r3m.py:97 + transforms.Normalize)
+          p0 = round_tf32((p0 / 255.f - mean[c]) / stdv[c]);
+          p1 = round_tf32((p1 / 255.f - mean[c]) / stdv[c]);
+        }
+        o[(dy * 2 + 0) * 4 + c] = p0;
+        o[(dy * 2 + 1) * 4 + c] = p1;
+      }
+      o[(dy * 2 + 0) * 4 + 3] = 0.f;
+      o[(dy * 2 + 1) * 4 + 3] = 0.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(xs + idx * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  }
+}
+
+// MaxPool2d(3, 2, 1) on the (already BatchNorm-ed and ReLU-ed) fp32 stem output: y [N,H,W,C] -> a [N,H/2,W/2,C]
+__global__ void __launch_bounds__(256) maxpool_f32_kernel(const float* __restrict__ y, float* __restrict__ a, int N, int H,
+                                                          int W, int C) {
+  pdl_sync();
+  const int C4 = C >> 2, P = H / 2, Q = W / 2;
+  const long long total = (long long)N * P * Q * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    long long t = idx / C4;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    const float ninf = __int_as_float(0xff800000);
+    float4 best = make_float4(ninf, ninf, ninf, ninf);
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int w = 2 * q - 1 + s2;
+        if (w < 0 || w >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + (((long long)n * H + h) * W + w) * C) + c4);
+        best.x = fmaxf(best.x, v.x);
+        best.y = fmaxf(best.y, v.y);
+        best.z = fmaxf(best.z, v.z);
+        best.w = fmaxf(best.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(a)[idx] = best;
+  }
+}
+
+__global__ void avgpool_fwd_f32_kernel(const float* __restrict__ a, float* __restrict__ out, int HW, int C) {
+  pdl_sync();
+  const int n = blockIdx.x;
+  const float inv = 1.0f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    const float* base = a + (long long)n * HW * C + c;
+    for (int i = 0; i < HW; ++i) s += base[(long long)i * C];
+    out[(long long)n * C + c] = s * inv;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ BN apply
 template <bool kDual, bool kRes>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
@@ -995,6 +1096,17 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__
   int o;
   wp[idx] = __float2bfloat16_rn(stem_map(k, rr, j, o) ? w[o] : 0.f);
 }
+__global__ void stem_pack_f32_kernel(const float* __restrict__ w, float* __restrict__ wp) {
+  pdl_sync();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 4 * 64) return;
+  const int j = idx & 63, rr = (idx >> 6) & 3, k = idx >> 8;
+  int o;
+  uint32_t r;
+  const float v = stem_map(k, rr, j, o) ? w[o] : 0.f;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  wp[idx] = __uint_as_float(r);
+}
 __global__ void stem_unpack_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
   pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1230,6 +1342,40 @@ cudaError_t launch_stem_pack(const float* w_oihw, void* wp_bf16, cudaStream_t s)
 
 cudaError_t launch_stem_unpack_grad(const float* dwp, float* dw_oihw, cudaStream_t s) {
   launch_kernel(stem_unpack_grad_kernel, 64, 256, 0, s, dwp, dw_oihw);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s) {
+  launch_kernel(round_tf32_kernel, grid_for((long long)n, 256, 148 * 16), 256, 0, s, src, dst, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess_stem_f32(const void* obs, int format, float* xs, int N, cudaStream_t s) {
+  const long long total = (long long)N * 112 * 112 * 4;
+  const int grid = grid_for(total, 256, 148 * 16);
+  switch (format) {
+    case kObsF32NCHW: launch_kernel(preprocess_stem_f32_kernel<kObsF32NCHW>, grid, 256, 0, s, obs, xs, N); break;
+    case kObsU8NCHW: launch_kernel(preprocess_stem_f32_kernel<kObsU8NCHW>, grid, 256, 0, s, obs, xs, N); break;
+    case kObsU8NHWC: launch_kernel(preprocess_stem_f32_kernel<kObsU8NHWC>, grid, 256, 0, s, obs, xs, N); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool_f32(const float* y, float* a, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 4 != 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  launch_kernel(maxpool_f32_kernel, grid_for((long long)N * (H / 2) * (W / 2) * (C / 4), 256, 148 * 16), 256, 0, s, y, a,
+                N, H, W, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_avgpool_fwd_f32(const float* a, float* out, int N, int HW, int C, cudaStream_t s) {
+  launch_kernel(avgpool_fwd_f32_kernel, N, std::min(1024, std::max(32, C)), 0, s, a, out, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_pack_f32(const float* w_oihw, float* wp, cudaStream_t s) {
+  launch_kernel(stem_pack_f32_kernel, 64, 256, 0, s, w_oihw, wp);
   return cudaGetLastError();
 }
 

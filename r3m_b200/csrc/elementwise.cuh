@@ -162,4 +162,11 @@ cudaError_t launch_pack_dgrad_multi(const PackDgradEntry* table_dev, int entries
 cudaError_t launch_stem_pack(const float* w_oihw, void* wp_bf16, cudaStream_t s);
 cudaError_t launch_stem_unpack_grad(const float* dwp, float* dw_oihw, cudaStream_t s);
 
+// ---- tf32 tier of the inference path: fp32 storage holding tf32-rounded values (see conv_igemm.cu PREC = 1)
+cudaError_t launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t s);
+cudaError_t launch_preprocess_stem_f32(const void* obs, int format, float* xs, int N, cudaStream_t s);
+cudaError_t launch_maxpool_f32(const float* y, float* a, int N, int H, int W, int C, cudaStream_t s);
+cudaError_t launch_avgpool_fwd_f32(const float* a, float* out, int N, int HW, int C, cudaStream_t s);
+cudaError_t launch_stem_pack_f32(const float* w_oihw, float* wp, cudaStream_t s);
+
 }  // namespace r3m

@@ -245,12 +245,31 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
       c->a_off = arena(c->out_elems(frames) * 2);
     if (!c->stem) c->mask_off = arena(c->out_elems(frames) / 8);
   }
+  {
+    // The tf32 inference tier (fwd_eval_tf32_) aliases the activation region [off_xs_, off_E_): an eval forward and a
+    // training step's saved activations are mutually exclusive anyway.  Pad the region to what that tier needs:
+    // the fp32 stem operand, five ping-pong activation buffers, the tf32-rounded copy of the parameters, the fp32 stem
+    // filter and its own embedding buffer.
+    size_t need = 0;
+    auto sub = [&](size_t bytes) {
+      const size_t o = align_up(need, kAlign);
+      need = o + bytes;
+      return o;
+    };
+    e->t32_xs_ = sub(N * 112 * 112 * 64 * 4);
+    for (int i = 0; i < 5; ++i) e->t32_buf_[i] = sub(N * kMaxActPerFrame * 4);
+    e->t32_params_ = sub(np * 4);
+    e->t32_stem_w_ = sub(64 * 4 * 64 * 4);
+    e->t32_E_ = sub(N * e->D_ * 4);
+    const size_t have = align_up(cur, kAlign) - e->off_xs_;
+    if (need > have) arena(need - have);
+  }
   e->off_E_ = arena(N * e->D_ * 4);
   e->off_dE_ = arena(N * e->D_ * 4);
   for (int i = 0; i < 7; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   // a model with a language head still embeds any number of frames (R3M.forward); only update() needs 5 * clips
   if (lang_head && e->B_ > 0) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
-  e->off_fold_ = arena(e->convs_.size() * sizeof(BnFoldEntry));
+  e->off_fold_ = arena(2 * e->convs_.size() * sizeof(BnFoldEntry));  // bf16 tier (stem excluded) | tf32 tier (all)
   e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
   if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
   e->ws_bytes_ = align_up(cur, kAlign);
@@ -502,6 +521,132 @@ std::string Engine::plan_all() {
                        kFamPool, 0.0, (double)N * C * (HW * 2 + 4)));
     }
     if (!err.empty()) return err;
+  }
+
+  // ------------------------------------------------------------------------------------------------ tf32 inference tier
+  {
+    std::vector<Op>& ops = fwd_eval_tf32_;
+    ops.clear();
+    uint8_t* base = ws_ + off_xs_;
+    float* xs32 = reinterpret_cast<float*>(base + t32_xs_);
+    float* pool[5];
+    for (int i = 0; i < 5; ++i) pool[i] = reinterpret_cast<float*>(base + t32_buf_[i]);
+    float* Pt = reinterpret_cast<float*>(base + t32_params_);
+    float* stem_w32 = reinterpret_cast<float*>(base + t32_stem_w_);
+    float* E32 = reinterpret_cast<float*>(base + t32_E_);
+    const size_t np = nparams_;
+    // per-call refresh of the derived operands (no dirty tracking: 0.2 GB of traffic, ~0.03 ms)
+    ops.push_back(Op([P, Pt, np](cudaStream_t s) { return launch_round_tf32(P, Pt, np, s); }, kFamOptim, 0.0, 8.0 * np));
+    ops.back().label = "round_tf32 (all parameters)";
+    {
+      const float* w = P + convs_[0]->w_off;
+      ops.push_back(Op([w, stem_w32](cudaStream_t s) { return launch_stem_pack_f32(w, stem_w32, s); }, kFamOptim));
+    }
+    {
+      std::vector<BnFoldEntry> table;
+      for (Conv* cp : convs_) {
+        const Conv& c = *cp;
+        BnFoldEntry fe;
+        fe.gamma = P + c.gamma_off;
+        fe.beta = P + c.beta_off;
+        fe.running_mean = buf + c.rm_off;
+        fe.running_var = buf + c.rv_off;
+        fe.scale = saved + c.save_off;
+        fe.shift = saved + c.save_off + c.Cout;
+        fe.C = c.Cout;
+        table.push_back(fe);
+      }
+      BnFoldEntry* table_dev = reinterpret_cast<BnFoldEntry*>(ws_ + off_fold_) + convs_.size();
+      cudaError_t ce = cudaMemcpy(table_dev, table.data(), table.size() * sizeof(BnFoldEntry), cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) return std::string("fold table upload: ") + cudaGetErrorString(ce);
+      const int entries = (int)table.size();
+      ops.push_back(Op([table_dev, entries](cudaStream_t s) { return launch_bn_fold(table_dev, entries, s); }, kFamNorm));
+      ops.back().label = "bn_fold (all layers, tf32 tier)";
+    }
+    auto conv32 = [&](const Conv& c, const float* src, float* dst, const float* residual, int relu,
+                      const std::string& label) {
+      GatherConv gc;
+      gc.N = N;
+      gc.out = dst;
+      gc.Cout = c.Cout;
+      gc.ldo = c.Cout;
+      gc.src = src;
+      if (c.stem) {
+        gc.H = 112;
+        gc.W = 112;
+        gc.C = 64;
+        gc.P = 112;
+        gc.Q = 112;
+        gc.stride = 1;
+        gc.base_h = -2;
+        gc.base_w = 0;
+        gc.ntaps = 4;
+        for (int t = 0; t < 4; ++t) {
+          gc.tap_h[t] = t;
+          gc.tap_w[t] = 0;
+        }
+        gc.wpk = stem_w32;
+      } else {
+        gc.H = c.H;
+        gc.W = c.W;
+        gc.C = c.Cin;
+        fill_fwd_geometry(&gc, c.R, c.R, c.stride, c.pad);
+        gc.wpk = Pt + c.w_off;
+      }
+      gc.ep_scale = saved + c.save_off;
+      gc.ep_shift = saved + c.save_off + c.Cout;
+      gc.ep_res = residual;
+      gc.ep_relu = relu;
+      gc.tf32 = 1;
+      ConvPlan plan;
+      std::string e2 = plan_conv(gc, &plan);
+      if (!e2.empty()) {
+        err = e2;
+        return;
+      }
+      const double kdim = c.stem ? 147.0 : (double)gc.ntaps * gc.C;
+      const double m = (double)gc.N * gc.P * gc.Q;
+      ops.push_back(Op([plan](cudaStream_t s) { return run_conv(plan, s); }, kFamConv, 2.0 * m * gc.Cout * kdim,
+                       4.0 * ((double)gc.N * gc.H * gc.W * gc.C + m * gc.Cout + gc.Cout * kdim)));
+      ops.back().label = label;
+    };
+    Conv& st = *convs_[0];
+    conv32(st, xs32, pool[0], nullptr, 1, "tf32 fwd+bn+relu conv1 (stem)");
+    {
+      const float* y = pool[0];
+      float* a = pool[1];
+      ops.push_back(Op([y, a, N](cudaStream_t s) { return launch_maxpool_f32(y, a, N, 112, 112, 64, s); }, kFamPool, 0.0,
+                       (double)N * 64 * 4 * (112.0 * 112 + 56.0 * 56)));
+    }
+    int cur = 1;
+    for (Block* blk : blocks_) {
+      int free_i[4], nf = 0;
+      for (int i = 0; i < 5; ++i)
+        if (i != cur) free_i[nf++] = i;
+      const float* x = pool[cur];
+      const float* in = x;
+      for (size_t i = 0; i + 1 < blk->main.size(); ++i) {
+        const Conv& c = *convs_[blk->main[i]];
+        conv32(c, in, pool[free_i[i]], nullptr, 1, "tf32 fwd+bn+relu " + c.name);
+        in = pool[free_i[i]];
+      }
+      const float* residual = x;
+      if (blk->ds >= 0) {
+        const Conv& d = *convs_[blk->ds];
+        conv32(d, x, pool[free_i[2]], nullptr, 0, "tf32 fwd+bn " + d.name);
+        residual = pool[free_i[2]];
+      }
+      const Conv& last = *convs_[blk->main.back()];
+      conv32(last, in, pool[free_i[3]], residual, 1, "tf32 fwd+bn+res+relu " + last.name);
+      cur = free_i[3];
+      if (!err.empty()) return err;
+    }
+    {
+      const float* a_last = pool[cur];
+      const int C = D_;
+      ops.push_back(Op([a_last, E32, N, C](cudaStream_t s) { return launch_avgpool_fwd_f32(a_last, E32, N, 49, C, s); },
+                       kFamPool, 0.0, (double)N * C * (49 * 4 + 4)));
+    }
   }
 
   // ------------------------------------------------------------------------------------------------ backward
@@ -921,6 +1066,26 @@ std::string Engine::forward(const void* obs, int train, float* out, cudaStream_t
   // an eval forward overwrites the activations and the saved-statistics slots (BN fold coefficients) that a pending
   // update_grads(obs = NULL) / backward() would read
   if (!train) fwd_train_valid_ = false;
+  if (!train && precision_ == 1) {
+    // parity tier: fp32 storage, kind::tf32 tensor cores, BatchNorm folded into the conv epilogues
+    float* xs32 = reinterpret_cast<float*>(ws_ + off_xs_ + t32_xs_);
+    const int N = N_, fmt = obs_format_;
+    e = launch(Op([obs, xs32, N, fmt](cudaStream_t s) { return launch_preprocess_stem_f32(obs, fmt, xs32, N, s); },
+                  kFamNorm),
+               stream);
+    if (e != cudaSuccess) return std::string("preprocess (tf32): ") + cudaGetErrorString(e);
+    err = run(fwd_eval_tf32_, stream);
+    if (!err.empty()) return err;
+    if (out) {
+      e = cudaMemcpyAsync(out, ws_ + off_xs_ + t32_E_, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return std::string("copy out: ") + cudaGetErrorString(e);
+      const int* flag = device_error_flag();
+      const size_t n = (size_t)N_ * D_;
+      e = launch(Op([flag, out, n](cudaStream_t s) { return launch_poison_on_flag(flag, out, n, s); }, kFamLoss), stream);
+      if (e != cudaSuccess) return std::string("poison_on_flag: ") + cudaGetErrorString(e);
+    }
+    return std::string();
+  }
   if (!train && N_ <= kGraphMaxFrames && !profiling_) {
     // Launch-latency-bound regime (load_r3m users, r3m/example.py: batch 1-4): ~25 kernels of a few microseconds.
     // The frames are copied to a fixed staging buffer and the whole eval forward is replayed as one CUDA graph

@@ -64,6 +64,13 @@ class Engine {
   // format of the frames passed to forward / update_grads (ObsFormat, elementwise.cuh): fp32 NCHW (default), uint8 NCHW,
   // uint8 NHWC.  Sticky until changed.
   std::string set_obs_format(int format);
+  // 0: bf16 storage (default; training and fast inference), 1: the tf32 parity tier — EVAL-mode forward only: fp32
+  // storage rounded to tf32, kind::tf32 tensor-core arithmetic, embeddings within 1e-3 of the fp32 reference
+  std::string set_precision(int precision) {
+    if (precision != 0 && precision != 1) return "precision must be 0 (bf16) or 1 (tf32)";
+    precision_ = precision;
+    return std::string();
+  }
   std::string forward(const void* obs, int train, float* out, cudaStream_t stream);
   std::string update_grads(const void* obs, const int* perms, const float* lang_emb, const float* lang_mask,
                            const Hyper& h, int eval, cudaStream_t stream);
@@ -121,6 +128,9 @@ class Engine {
   bool bottleneck_ = false;
   bool l2dist_ = true;  // R3M.sim: negative L2 distance (default) or cosine similarity
   int obs_format_ = 0;  // ObsFormat of the frames handed to forward / update_grads
+  int precision_ = 0;   // inference tier: 0 bf16, 1 tf32
+  // tf32 tier: byte offsets inside the aliased activation region (relative to off_xs_)
+  size_t t32_xs_ = 0, t32_buf_[5] = {0, 0, 0, 0, 0}, t32_params_ = 0, t32_stem_w_ = 0, t32_E_ = 0;
   std::vector<Conv*> convs_;
   std::vector<Block*> blocks_;
   std::vector<TensorInfo> tensors_;
@@ -155,7 +165,7 @@ class Engine {
   int eval_calls_ = 0;
   LangDims lang_dims_;
 
-  std::vector<Op> fwd_train_, fwd_eval_, bwd_, repack_;
+  std::vector<Op> fwd_train_, fwd_eval_, fwd_eval_tf32_, bwd_, repack_;
   // Filter gradients run on a second stream: nothing in the backward chain consumes them, and a wgrad CTA (tensor /
   // L2 bound, one per SM) co-resides with the HBM-bound BatchNorm-backward CTAs of the layer below.
   cudaStream_t side_ = nullptr;

@@ -10,18 +10,19 @@
 
 namespace r3m {
 
-// NHWC bf16 activation tensor viewed as rank-4 (C, W, H, N) for im2col-mode loads.
+// NHWC bf16 (elem_bytes 2) or fp32 (4) activation tensor viewed as rank-4 (C, W, H, N) for im2col-mode loads.
 //   lower_* / upper_* : bounding-box corners of the base pixel (CUDA driver API convention)
 //   channels          : channels per load (<= 64 -> one 128-byte swizzle row)
 //   pixels            : base pixels per load (GEMM rows of one stage)
 //   trav_stride       : traversal stride of the base pixel
 // Returns an empty string on success, else a diagnostic.
 std::string encode_im2col_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int lower_w, int lower_h,
-                              int upper_w, int upper_h, int channels, int pixels, int trav_stride);
+                              int upper_w, int upper_h, int channels, int pixels, int trav_stride, int elem_bytes = 2);
 
 // Row-major 2-D bf16 matrix [outer][inner] (inner contiguous), swizzled boxes of box_inner x box_outer.
 // swizzle_bytes: 128 (box_inner * 2 <= 128) or 64 (box_inner * 2 <= 64).
 std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                                uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes = 128);
+                                uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes = 128,
+                                int elem_bytes = 2);
 
 }  // namespace r3m

@@ -122,6 +122,10 @@ class Engine:
             L.check(L.lib.r3m_b200_engine_set_int(self._h, 1, fmt))
             self._obs_format = fmt
 
+    def set_precision(self, tier):
+        """Tier of the EVAL-mode forward: "bf16" (default) or "tf32" (fp32 storage, kind::tf32 tensor cores)."""
+        L.check(L.lib.r3m_b200_engine_set_int(self._h, 2, {"bf16": 0, "tf32": 1}[tier]))
+
     def forward(self, obs, train, nhwc=False):
         """obs: contiguous CUDA [frames,3,224,224] float32 or uint8 ([frames,224,224,3] uint8 with nhwc) in [0,255]
         -> new float32 [frames, D]."""

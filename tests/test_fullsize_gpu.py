@@ -185,3 +185,69 @@ def test_c2_forward_batch256_against_gpu_oracle(mode):
         assert rel(sd2["convnet.layer2.0.bn1.running_var"], post["convnet.layer2.0.bn1.running_var"]) < 2e-2
         assert int(sd2["convnet.bn1.num_batches_tracked"]) == 1
     _report("c2_forward_" + mode, {"ours_vs_fp32": d, "bf16_policy_vs_fp32": d_pol})
+
+
+@pytest.mark.parametrize("size", [18, 50])
+def test_tf32_tier_eval_embeddings_within_1e3_of_the_reference(size):
+    """North-star tolerance (embeddings <= 1e-3 relative) on the inference path: the tf32 tier (fp32 storage,
+    kind::tf32 tensor cores, round-to-nearest operands) against the goldens the REAL reference produced
+    (tests/golden/rn{18,50}_eval_b4.npz; reference semantics r3m/models/models_r3m.py:97-99: fp32 in, fp32 conv)."""
+    from r3m_b200 import R3M
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rn{size}_eval_b4.npz"))
+    params, buffers = O.eval_fixture_state(size)
+    frames = O.synthetic_frames(1, 7)[0, :4]
+    m = R3M("cuda", 1e-4, 1024, size=size, langweight=0.0)
+    sd = dict(params)
+    sd.update(buffers)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        bf16 = m(frames.cuda())
+        m.set_eval_precision("tf32")
+        tf32 = m(frames.cuda())
+        tf32_u8 = m(frames.to(torch.uint8).cuda())
+        again = m(frames.cuda())
+    d_bf16, d_tf32 = rel(bf16, z["embeddings"]), rel(tf32, z["embeddings"])
+    assert d_tf32 < 1e-3, (d_tf32, d_bf16)
+    assert d_bf16 < 5e-3
+    assert torch.equal(tf32, again) and torch.equal(tf32, tf32_u8)  # deterministic; uint8 frames identical
+    _report(f"tf32_eval_rn{size}_b4", {"tf32_vs_reference": d_tf32, "bf16_vs_reference": d_bf16})
+
+
+def test_tf32_tier_at_c2_size_and_back_to_bf16():
+    """BASELINE configs[1] size (ResNet-50, batch 256, eval BatchNorm) in the tf32 tier against the fp32 oracle on the
+    GPU; switching tiers back and forth leaves the bf16 results and a following training step intact."""
+    from r3m_b200 import R3M, Trainer
+
+    strict_fp32()
+    params, buffers = O.eval_fixture_state(50)
+    frames = O.varied_frames(52, 33).reshape(-1, 3, 224, 224)[:256].cuda()
+    m = R3M("cuda", 1e-4, 1024, size=50, langweight=0.0)
+    sd = dict(params)
+    sd.update(buffers)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        want = O.r3m_forward({k: v.to(dev) for k, v in params.items()}, {k: v.to(dev) for k, v in buffers.items()},
+                             frames, 50, False)
+        a = m(frames)
+        b = m.set_eval_precision("tf32")(frames)
+        c = m.set_eval_precision("bf16")(frames)
+    assert rel(b, want) < 1e-3, rel(b, want)
+    assert rel(a, want) < 5e-3 and torch.equal(a, c)
+    _report("tf32_c2_forward_eval", {"tf32_vs_fp32": rel(b, want), "bf16_vs_fp32": rel(a, want)})
+    # a training step on the same model afterwards (the tf32 tier aliases the activation arena)
+    m.set_eval_precision("tf32")
+    model = torch.nn.DataParallel(m, device_ids=[torch.cuda.current_device()])
+    clips = 4
+    batch = O.varied_frames(clips, 34).cuda()
+    perms = O.draw_permutations(clips, 35)
+    tr = Trainer(100)
+    m1, _ = tr.update(model, (batch, [""] * clips), 0, perms=perms)
+    with torch.no_grad():
+        m.eval()
+        m(frames[:20])
+    m2, _ = tr.update(model, (batch, [""] * clips), 1, perms=perms)
+    assert all(np.isfinite(list(x.values())).all() for x in (m1, m2))

@@ -188,3 +188,36 @@ def test_data_parallel_replication_is_refused():
     m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
     with pytest.raises(R3MB200Error):
         m._replicate_for_data_parallel()
+
+
+def test_snapshot_is_a_superset_of_the_reference_format(tmp_path):
+    """r3m/train_representation.py:123-138: {"r3m": DataParallel state_dict, "global_step"}; ours adds Adam + RNG."""
+    import random
+
+    import numpy as np
+
+    m = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
+    model = torch.nn.DataParallel(m)
+    m._flat(2).normal_()
+    m._flat(3).uniform_()
+    m.encoder_opt.steps = 11
+    torch.manual_seed(5)
+    random.seed(6)
+    np.random.seed(7)
+    path = tmp_path / "snapshot.pt"
+    assert r3m_b200.save_snapshot(str(path), model, 42, extra={"note": "x"})
+    want = (torch.rand(3), random.random(), np.random.rand())
+    payload = torch.load(path, weights_only=False)
+    assert set(payload) == {"r3m", "global_step", "r3m_b200"} and payload["global_step"] == 42
+    assert all(k.startswith("module.") for k in payload["r3m"])        # what the reference's load_snapshot feeds
+    m2 = R3M("cpu", 3e-4, 1024, size=18, langweight=0.0)
+    model2 = torch.nn.DataParallel(m2)
+    step, extra = r3m_b200.load_snapshot(str(path), model2)
+    assert step == 42 and extra == {"note": "x"} and m2.encoder_opt.steps == 11
+    assert torch.equal(m2._flat(0), m._flat(0)) and torch.equal(m2._flat(2), m._flat(2))
+    got = (torch.rand(3), random.random(), np.random.rand())
+    assert torch.equal(got[0], want[0]) and got[1:] == want[1:]       # the random streams continue where they were
+    # a snapshot written by the reference (no r3m_b200 entry) still loads: Adam restarts, as it does there
+    torch.save({"r3m": model.state_dict(), "global_step": 7}, path)
+    m3 = R3M("cpu", 1e-4, 1024, size=18, langweight=0.0)
+    assert r3m_b200.load_snapshot(str(path), torch.nn.DataParallel(m3)) == (7, None) and m3.encoder_opt.steps == 0
