@@ -26,10 +26,6 @@
 #include "launch.h"
 #include "ptx.cuh"
 
-#ifndef R3M_STATS_REGS
-#define R3M_STATS_REGS 1  // BatchNorm statistics of the conv epilogue accumulate in registers across tiles (0: per-unit shared atomics)
-#endif
-
 namespace r3m {
 
 namespace {
@@ -118,12 +114,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
   pdl_sync();  // everything above is CTA-local; global memory is first touched below
   const bool do_affine = !STATS && (p.ep_scale != nullptr);
-  if (do_stats) {
-    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-      s_sum[i] = 0.f;
-      s_sq[i] = 0.f;
-    }
-  } else if (do_affine) {
+  if (do_affine) {
     // the statistics arrays double as the per-channel scale / shift table of the fused inference epilogue
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
       s_sum[i] = p.ep_scale[i];
@@ -260,31 +251,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
     for (int i = 0; i < kUPW; ++i) racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
     int acc_ntile = -1;
-    auto flush_stats = [&](int nt) {
-#pragma unroll
-      for (int i = 0; i < kUPW; ++i) {
-        const int u = h + i * (EPI / 4);
-        if (u < kUnits) {
-          const int col = nt * BN + u * kUnitCols + 2 * lane;
-          atomicAdd(&s_sum[col], racc[i][0]);
-          atomicAdd(&s_sum[col + 1], racc[i][1]);
-          atomicAdd(&s_sq[col], racc[i][2]);
-          atomicAdd(&s_sq[col + 1], racc[i][3]);
-        }
-        racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
-      }
-    };
+    // Deterministic statistics: the host sizes the grid as a multiple of num_n_tiles, so a CTA keeps ONE column block
+    // (n_tile = blockIdx.x % num_n_tiles) for all its tiles and the per-lane partials never leave registers before the
+    // end.  Then: per-quadrant partials -> shared memory, summed over the four quadrants in fixed order -> this CTA's
+    // partial in global scratch -> the LAST CTA of the column block (ticket) adds the CTAs' partials in CTA order and
+    // writes the result.  No floating-point atomics anywhere: the sums are bit-identical from run to run.
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
-      if constexpr (STATS && R3M_STATS_REGS) {
-        if (n_tile != acc_ntile) {
-          if (acc_ntile >= 0) flush_stats(acc_ntile);
-          acc_ntile = n_tile;
-        }
-      }
+      if constexpr (STATS) acc_ntile = n_tile;
       long long row_off[dense ? 1 : 8];
       if constexpr (!dense) {
         // element offsets of the 8 rows this lane stores (row = 4*i + lane/8 of the warp's 32 rows)
@@ -491,7 +468,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               q0 = fmaf(a, a, q0);
               q1 = fmaf(b, b, q1);
             }
-#if R3M_STATS_REGS
 #pragma unroll
             for (int i = 0; i < kUPW; ++i)
               if (i == ui) {
@@ -500,13 +476,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 racc[i][2] += q0;
                 racc[i][3] += q1;
               }
-#else
-            const int col = n0 + u * kUnitCols + 2 * lane;
-            atomicAdd(&s_sum[col], s0);
-            atomicAdd(&s_sum[col + 1], s1);
-            atomicAdd(&s_sq[col], q0);
-            atomicAdd(&s_sq[col + 1], q1);
-#endif
           }
           if constexpr (!dense) {
             // strided scatter (stride-2 dgrad parity classes): 8 lanes x 16 B = one 128-byte row segment.  When
@@ -551,17 +520,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (dense && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
-#if R3M_STATS_REGS
-      if (acc_ntile >= 0) flush_stats(acc_ntile);
-#endif
-      // all epilogue warps are done with every tile of this CTA -> flush the CTA partials
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
-      for (int i = threadIdx.x - 128; i < p.Cout; i += EPI * 32) {
-        const float s = s_sum[i], qv = s_sq[i];
-        if (s != 0.f || qv != 0.f) {
-          atomicAdd(&p.stat_sum[i], s);
-          atomicAdd(&p.stat_sq[i], qv);
+      // s_sum doubles as the quadrant table [4][BN][2] (4 * 256 * 2 floats <= the 2 * StatC floats reserved)
+      float* s_part = s_sum;
+#pragma unroll
+      for (int i = 0; i < kUPW; ++i) {
+        const int u = h + i * (EPI / 4);
+        if (u < kUnits) {
+          float* dst = s_part + (q * BN + u * kUnitCols + 2 * lane) * 2;
+          dst[0] = racc[i][0];
+          dst[1] = racc[i][2];
+          dst[2] = racc[i][1];
+          dst[3] = racc[i][3];
         }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
+      const int et = threadIdx.x - 128;  // epilogue thread index
+      const int my_ntile = blockIdx.x % p.num_n_tiles;
+      const bool has_tiles = acc_ntile >= 0;  // false only when the grid exceeds the tile count (never: host clamps)
+      float* mine = p.stat_scratch + static_cast<size_t>(blockIdx.x) * (2 * BN);
+      for (int c = et; c < BN; c += EPI * 32) {
+        float sm = 0.f, sq = 0.f;
+        if (has_tiles) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            sm += s_part[(qq * BN + c) * 2];
+            sq += s_part[(qq * BN + c) * 2 + 1];
+          }
+        }
+        mine[2 * c] = sm;
+        mine[2 * c + 1] = sq;
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
+      int* s_flag = reinterpret_cast<int*>(tmem_slot) + 2;
+      if (et == 0) {
+        const int contributors = (gridDim.x - my_ntile + p.num_n_tiles - 1) / p.num_n_tiles;
+        const int t = atomicAdd(&p.stat_ticket[my_ntile], 1);
+        *s_flag = (t == contributors - 1) ? contributors : 0;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
+      const int contributors = *s_flag;
+      if (contributors > 0) {
+        __threadfence();
+        for (int c = et; c < BN; c += EPI * 32) {
+          float sm = 0.f, sq = 0.f;
+          for (int i = 0; i < contributors; ++i) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(
+                p.stat_scratch + static_cast<size_t>(my_ntile + i * p.num_n_tiles) * (2 * BN) + 2 * c));
+            sm += v.x;
+            sq += v.y;
+          }
+          p.stat_sum[my_ntile * BN + c] = sm;
+          p.stat_sq[my_ntile * BN + c] = sq;
+        }
+        if (et == 0) p.stat_ticket[my_ntile] = 0;  // ready for the next launch (stream order)
       }
     }
   }
@@ -598,7 +610,9 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense, 1>(tmA, tmB, tmC, p, grid, stream);
   }
   if (p.stat_sum != nullptr) {
-    if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr) return cudaErrorInvalidValue;
+    if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr || p.stat_scratch == nullptr ||
+        p.stat_ticket == nullptr || grid % p.num_n_tiles != 0)
+      return cudaErrorInvalidValue;
     return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeStats>(tmA, tmB, tmC, p, grid, stream);
   }
   if (p.out_mode != 0) {

@@ -28,9 +28,13 @@ struct ConvKernelParams {
   int ldo;
   int oH, oW, o_stride, o_h0, o_w0;
   int accumulate;  // out += result (bf16 read-modify-write)
-  // optional per-channel statistics of the (bf16-rounded) output
+  // optional per-channel statistics of the (bf16-rounded) output: WRITTEN (not accumulated), deterministically:
+  // per-CTA partials go to stat_scratch [grid][2 * BN], the last CTA of each column block (stat_ticket, one zeroed int
+  // per column block, self-resetting) adds them in CTA order.  The grid must be a multiple of num_n_tiles.
   float* stat_sum;
   float* stat_sq;
+  float* stat_scratch;
+  int* stat_ticket;
   // optional fused epilogue (inference: BatchNorm folded into a per-channel affine): out = [relu](acc * ep_scale[c] +
   // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.
   const float* ep_scale;
@@ -61,7 +65,11 @@ struct WgradKernelParams {
   int mblocks_total;      // ceil(M_total / pix_block)
   int mblocks_per_split;
   int num_stages;
-  float* dW;        // fp32, accumulated with red.add
+  float* dW;        // fp32, accumulated into
+  // split-K (splits > 1): fp32 scratch of splits * dw_elems floats; every split writes its partial dW there and a
+  // second kernel adds them to dW in split order (deterministic).  null: one split, added straight into dW.
+  float* scratch;
+  size_t dw_elems;  // Cout * ldw
   int* error_flag;
 };
 

@@ -38,6 +38,22 @@ int* device_error_flag() {
   return flag;
 }
 
+float* device_stat_scratch() {
+  static float* buf = nullptr;
+  if (!buf) {
+    const size_t bytes = kStatScratchFloats * sizeof(float) + kStatTickets * sizeof(int);
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(buf, 0, bytes);
+  }
+  return buf;
+}
+
+float* device_wgrad_scratch() {
+  static float* buf = nullptr;
+  if (!buf && cudaMalloc(&buf, kWgradScratchBytes) != cudaSuccess) return nullptr;
+  return buf;
+}
+
 static int pick_bn(int Cout) {
   if (Cout % 256 == 0) return 256;
   if (Cout % 128 == 0) return 128;
@@ -100,6 +116,14 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.accumulate = g.accumulate;
   p.stat_sum = g.stat_sum;
   p.stat_sq = g.stat_sq;
+  p.stat_scratch = g.stat_scratch;
+  p.stat_ticket = g.stat_ticket;
+  if (g.stat_sum && !g.stat_scratch) {
+    float* shared = device_stat_scratch();
+    if (!shared) return "could not allocate the statistics scratch";
+    p.stat_scratch = shared;
+    p.stat_ticket = reinterpret_cast<int*>(shared + kStatScratchFloats);
+  }
   if (g.ep_scale && (g.stat_sum || g.out_mode != 0 || g.accumulate))
     return "gather conv: the fused affine epilogue needs a dense, non-accumulating output without statistics";
   p.ep_scale = g.ep_scale;
@@ -110,6 +134,12 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   if (!p.error_flag) return "could not allocate the device error flag";
   plan->bn = bn;
   plan->grid = std::min(p.num_m_tiles * p.num_n_tiles, device_sm_count());
+  if (g.stat_sum) {
+    // deterministic statistics: every CTA keeps one column block (see conv_igemm.cu)
+    plan->grid -= plan->grid % p.num_n_tiles;
+    if ((size_t)plan->grid * 2 * bn > kStatScratchFloats || p.num_n_tiles > (int)kStatTickets)
+      return "gather conv: statistics scratch too small for this grid";
+  }
   return std::string();
 }
 
@@ -178,6 +208,20 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   splits = std::max(1, std::min(splits, p.mblocks_total));
   p.mblocks_per_split = (p.mblocks_total + splits - 1) / splits;
   plan->splits = (p.mblocks_total + p.mblocks_per_split - 1) / p.mblocks_per_split;
+  p.dw_elems = (size_t)d.Cout * p.ldw;
+  p.scratch = nullptr;
+  if (plan->splits > 1) {
+    // deterministic split-K: shrink the split count until the partial copies of dW fit the scratch
+    while (plan->splits > 1 && (size_t)plan->splits * p.dw_elems * 4 > kWgradScratchBytes) {
+      p.mblocks_per_split = (p.mblocks_total + plan->splits - 2) / (plan->splits - 1);
+      plan->splits = (p.mblocks_total + p.mblocks_per_split - 1) / p.mblocks_per_split;
+    }
+    if (plan->splits > 1) {
+      p.scratch = d.scratch ? d.scratch : device_wgrad_scratch();
+      if (!p.scratch) return "wgrad: could not allocate the split-K scratch";
+      if (p.dw_elems % 4 != 0) return "wgrad: |dW| must be a multiple of 4";
+    }
+  }
   return std::string();
 }
 

@@ -23,8 +23,12 @@ struct GatherConv {
   int ldo = 0;
   int oH = 0, oW = 0, o_stride = 1, o_h0 = 0, o_w0 = 0;
   int accumulate = 0;  // out += result (read-modify-write)
-  float* stat_sum = nullptr;  // optional per-channel sum / sum of squares of the stored (bf16) output
+  float* stat_sum = nullptr;  // optional per-channel sum / sum of squares of the stored (bf16) output (written)
   float* stat_sq = nullptr;
+  // deterministic two-level reduction of the statistics: [kStatScratchFloats] floats + [kStatTickets] zeroed ints; null:
+  // a process-wide buffer (launches that share it must be stream-ordered)
+  float* stat_scratch = nullptr;
+  int* stat_ticket = nullptr;
   // fused inference epilogue (see ConvKernelParams): per-channel affine (+ residual) (+ ReLU) on the accumulators
   const float* ep_scale = nullptr;
   const float* ep_shift = nullptr;
@@ -51,6 +55,8 @@ struct WgradDesc {
   int tap_h[kMaxTaps] = {0}, tap_w[kMaxTaps] = {0};
   int Cout = 0;
   float* dw = nullptr;  // fp32 [Cout][ntaps * C], accumulated into (caller zeroes)
+  // split-K scratch (kWgradScratchBytes); null: a process-wide buffer (launches that share it must be stream-ordered)
+  float* scratch = nullptr;
 };
 
 struct WgradPlan {
@@ -59,7 +65,12 @@ struct WgradPlan {
   int splits = 0, groups = 0, ktiles = 0;
 };
 
+constexpr size_t kStatScratchFloats = 160 * 512;  // grid (<= SM count) x 2 x BN (<= 256)
+constexpr size_t kStatTickets = 64;
+constexpr size_t kWgradScratchBytes = 40u << 20;  // >= splits * |dW| * 4 for every launch (one wave of <= 164 KB slabs)
+float* device_wgrad_scratch();
 int device_sm_count();
+float* device_stat_scratch();  // lazily allocated process-wide scratch: kStatScratchFloats floats + kStatTickets ints
 int* device_error_flag();  // lazily allocated device int, zero-initialised
 
 std::string plan_conv(const GatherConv& g, ConvPlan* plan);

@@ -116,6 +116,50 @@ __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ ordered reduce
+// Deterministic grid-wide sum of per-block partial vectors (V floats each): no floating-point atomics.  Blocks write
+// their partial to scratch; the last block of every group of kDetGroup consecutive blocks (ticket) adds the group's
+// partials in block order; the last group to finish adds the group sums in group order and hands every total to
+// emit(i, value).  The summation tree is fixed by the launch geometry, so the result is bit-identical from run to run.
+// scratch: (gridDim.x + groups) * V floats; tickets: 1 + groups ints, zero on entry, zero again on exit.
+constexpr int kDetGroup = 16;
+template <class Emit>
+__device__ __forceinline__ void det_grid_reduce(const float* partial, int V, const DetScratch d, Emit emit) {
+  __shared__ int s_last;
+  const int G = gridDim.x, tid = threadIdx.x;
+  float* mine = d.scratch + (size_t)blockIdx.x * V;
+  for (int i = tid; i < V; i += blockDim.x) mine[i] = partial[i];
+  __threadfence();
+  __syncthreads();
+  const int ngroups = (G + kDetGroup - 1) / kDetGroup, grp = blockIdx.x / kDetGroup;
+  const int gsize = min(kDetGroup, G - grp * kDetGroup);
+  if (tid == 0) s_last = (atomicAdd(&d.tickets[1 + grp], 1) == gsize - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* gsum = d.scratch + (size_t)(G + grp) * V;
+  for (int i = tid; i < V; i += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < gsize; ++b) a += __ldcg(d.scratch + (size_t)(grp * kDetGroup + b) * V + i);
+    gsum[i] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    d.tickets[1 + grp] = 0;
+    s_last = (atomicAdd(&d.tickets[0], 1) == ngroups - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < V; i += blockDim.x) {
+    float a = 0.f;
+    for (int g = 0; g < ngroups; ++g) a += __ldcg(d.scratch + (size_t)(G + g) * V + i);
+    emit(i, a);
+  }
+  if (tid == 0) d.tickets[0] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------ preprocess
 // Input formats (enum ObsFormat in elementwise.cuh): fp32 NCHW (the reference loader's contract), uint8 NCHW
 // (torchvision.io.read_image frames: 4x fewer PCIe / HBM bytes) and uint8 NHWC (decoder output order).  A thread
@@ -593,10 +637,33 @@ __global__ void __launch_bounds__(224) maxpool_bwd_kernel(const bf16* __restrict
 // compile-time constant (dh + 1 - 2i) * 3 + (dw + 1 - 2j): nine (window, pixel) pairs per channel instead of sixteen
 // per-pixel gathers, and the window loads are shared by the four pixels (the per-pixel gather was instruction bound:
 // 360 instructions per 8 channels, 1.5 TB/s).
+// Block-level sums of per-thread 8-channel partials (s1: sum dz, s2: sum dz * (y - mean), scaled by rstd here) without
+// shared-memory atomics: every thread parks its 16 values, thread c < 2C adds the copies of its channel in thread order.
+// out[0..C) = sum s1, out[C..2C) = sum s2 * rstd.  blockDim.x <= 256 and a multiple of C / 8.
+__device__ __forceinline__ void block_channel_sums(const float (&s1)[8], const float (&s2)[8], const float* __restrict__ rstd,
+                                                   int chunk, int C, float* tab /* [256][16] */, float* out /* [2C] */) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    tab[threadIdx.x * 16 + j] = s1[j];
+    tab[threadIdx.x * 16 + 8 + j] = s2[j] * rstd[chunk * 8 + j];
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    const int ch = c >> 3, j = c & 7;
+    float acc = 0.f;
+    for (int t = ch; t < (int)blockDim.x; t += C8) acc += tab[t * 16 + which * 8 + j];
+    out[i] = acc;
+  }
+  __syncthreads();
+}
+
 template <bool kApply>
 __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
   pdl_sync();
   __shared__ float s_red[2 * 256];  // C <= 256
+  __shared__ float s_tab[kApply ? 1 : 256 * 16];
   const int C8 = a.C >> 3;
   const int P = a.H / 2, Q = a.W / 2;
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
@@ -620,10 +687,6 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
       c1[j] = 0.f;
       c2[j] = 0.f;
     }
-  }
-  if (!kApply) {
-    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
-    __syncthreads();
   }
   for (int row = blockIdx.x; row < a.N * P; row += gridDim.x) {
     const int n = row / P, k = row - n * P;
@@ -699,13 +762,9 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
   }
   pdl_done();
   if (!kApply) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_red[chunk * 8 + j], c1[j]);
-      atomicAdd(&s_red[a.C + chunk * 8 + j], c2[j] * a.rstd[chunk * 8 + j]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
+    block_channel_sums(c1, c2, a.rstd, chunk, a.C, s_tab, s_red);
+    float* sums = a.sums;
+    det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
   } else if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = a.sums[c];
@@ -721,6 +780,7 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
 __global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemBwdArgs a) {
   pdl_sync();
   __shared__ float s_red[2 * 256];
+  __shared__ float s_tab[256 * 16];
   const int C8 = a.C >> 3;
   const int chunk = threadIdx.x % C8;  // the grid stride is a multiple of C8
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
@@ -733,8 +793,6 @@ __global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemB
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
-  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
-  __syncthreads();
 #pragma unroll 2
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const F8 g = ld8(dA + idx * 8);
@@ -749,13 +807,9 @@ __global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemB
     }
   }
   pdl_done();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&s_red[chunk * 8 + j], s1[j]);
-    atomicAdd(&s_red[a.C + chunk * 8 + j], s2[j] * a.rstd[chunk * 8 + j]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.sums[i], s_red[i]);
+  block_channel_sums(s1, s2, a.rstd, chunk, a.C, s_tab, s_red);
+  float* sums = a.sums;
+  det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
 }
 
 // ------------------------------------------------------------------------------------------------ avg pool
@@ -861,9 +915,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     }
   }
   pdl_done();
-  // Block reduction without shared-memory atomics (fp32 shared atomics are CAS loops; with up to 32 row-threads per
-  // channel they dominated the small layers): every thread parks its partials, then one thread per four outputs adds
-  // the rows_per_iter copies and issues ONE vector atomic to global memory.
+  // Block reduction without atomics: every thread parks its partials, one thread per four outputs adds the
+  // rows_per_iter copies in row order, and the grid-wide sum is the ordered two-level reduction above.
   const int q4 = kQ * a.C / 4;  // float4 slots per partial row
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -889,10 +942,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
       acc.z += v.z;
       acc.w += v.w;
     }
-    // slots [0, C/2) -> sums[0 .. 2C), slots [C/2, 3C/4) -> sums2[0 .. C)
-    float4* dst = (i < a.C / 2) ? reinterpret_cast<float4*>(a.sums) + i : reinterpret_cast<float4*>(a.sums2) + (i - a.C / 2);
-    atomicAdd(dst, acc);
+    s_part[i] = acc;  // row 0 of the table becomes the block's partial (slot i is touched by this thread only)
   }
+  __syncthreads();
+  // floats [0, 2C) -> sums, [2C, 3C) -> sums2; written, not accumulated
+  float* sums = a.sums;
+  float* sums2 = a.sums2;
+  const int twoC = 2 * a.C;
+  det_grid_reduce(reinterpret_cast<const float*>(s_part), kQ * a.C, a.det, [=](int i, float v) {
+    if (i < twoC)
+      sums[i] = v;
+    else
+      sums2[i - twoC] = v;
+  });
 }
 
 template <bool kDual, int kMask, bool kDz>
@@ -1206,16 +1268,35 @@ cudaError_t launch_maxpool_bwd(const void* dA, const uint8_t* argmax, void* dz, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s) {
+DetScratch device_det_scratch() {
+  static DetScratch d;
+  if (!d.scratch) {
+    float* buf = nullptr;
+    const size_t bytes = kDetScratchFloats * sizeof(float) + kDetTickets * sizeof(int);
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) return d;
+    cudaMemset(buf, 0, bytes);
+    d.scratch = buf;
+    d.tickets = reinterpret_cast<int*>(buf + kDetScratchFloats);
+  }
+  return d;
+}
+
+cudaError_t launch_stem_bwd(const StemBwdArgs& a_in, cudaStream_t s) {
+  StemBwdArgs a = a_in;
   if (a.C % 8 != 0 || a.C > 256 || kStemThreads % (a.C / 8) != 0 || (a.H & 1) || (a.W & 1))
     return cudaErrorInvalidValue;
+  if (!a.det.scratch) a.det = device_det_scratch();
+  if (!a.det.scratch) return cudaErrorMemoryAllocation;
   const int rows = a.N * (a.H / 2);  // one block iteration = one row of 2x2 quads
   if (a.ymax != nullptr && 256 % (a.C / 8) == 0) {
     const long long total = (long long)a.N * (a.H / 2) * (a.W / 2) * (a.C / 8);
     launch_kernel(stem_bwd_reduce_pooled_kernel,
-                  grid_for((total + 3) / 4, 256, resident_blocks<stem_bwd_reduce_pooled_kernel>(256)), 256, 0, s, a);
+                  std::min(kDetMaxBlocks, grid_for((total + 3) / 4, 256,
+                                                   resident_blocks<stem_bwd_reduce_pooled_kernel>(256))),
+                  256, 0, s, a);
   } else {
-    launch_kernel(stem_bwd_kernel<false>, std::min(rows, resident_blocks<stem_bwd_kernel<false>>(kStemThreads)),
+    launch_kernel(stem_bwd_kernel<false>,
+                  std::min(kDetMaxBlocks, std::min(rows, resident_blocks<stem_bwd_kernel<false>>(kStemThreads))),
                   kStemThreads, 0, s, a);
   }
   cudaError_t e = cudaGetLastError();
@@ -1241,8 +1322,11 @@ namespace {
 inline int mask_kind(const BnBwdArgs& a) { return a.a ? kMaskAct : (a.mask ? kMaskBits : kMaskNone); }
 }  // namespace
 
-cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
+  BnBwdArgs a = a_in;
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
+  if (!a.det.scratch) a.det = device_det_scratch();
+  if (!a.det.scratch) return cudaErrorMemoryAllocation;
   const int rows_per_iter = 256 / (a.C / 8);
   // several rows per thread so that the block reduction and the global atomics are amortised; at most one resident wave
   const bool dual = a.y2 != nullptr;
@@ -1251,7 +1335,8 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
     return cudaErrorInvalidValue;
 #define R3M_LAUNCH(D, K)                                                                      \
   launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                   \
-                grid_for((a.M + 15) / 16, rows_per_iter, resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem)), 256, \
+                std::min(kDetMaxBlocks, grid_for((a.M + 15) / 16, rows_per_iter,                     \
+                                                 resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem))), 256, \
                 smem, s, a)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;

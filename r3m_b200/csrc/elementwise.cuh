@@ -52,6 +52,18 @@ struct BnApplyArgs {
 };
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s);
 
+// Scratch of the deterministic grid-wide reductions (see det_grid_reduce in elementwise.cu): `scratch` holds
+// (blocks + blocks / 16 + 1) partial vectors, `tickets` 1 + blocks / 16 + 1 zero-initialised (self-resetting) ints.
+// Launches that share one DetScratch must be stream-ordered.
+struct DetScratch {
+  float* scratch = nullptr;
+  int* tickets = nullptr;
+};
+constexpr int kDetMaxBlocks = 592;                              // grid cap of the kernels that reduce through it
+constexpr size_t kDetScratchFloats = (size_t)(kDetMaxBlocks + kDetMaxBlocks / 16 + 2) * 3 * 2048;
+constexpr size_t kDetTickets = 64;
+DetScratch device_det_scratch();  // lazily allocated process-wide instance (kernel-level C-ABI entry points)
+
 // stem: y [N,112,112,64] -> BN -> ReLU -> maxpool 3x3 s2 p1 -> a [N,56,56,64], argmax code (0..8) per element
 struct StemPoolArgs {
   const void* y = nullptr;
@@ -88,10 +100,11 @@ struct StemBwdArgs {
   const float* mean = nullptr;
   const float* rstd = nullptr;
   const float* gamma = nullptr;
-  float* sums = nullptr;           // [2][C] zeroed scratch
+  float* sums = nullptr;           // [2][C] workspace: written by the reduce pass, read by the apply pass
   void* dy = nullptr;              // bf16 [N,H,W,C]
   float* dgamma = nullptr;
   float* dbeta = nullptr;
+  DetScratch det;                  // null members: the process-wide instance
 };
 cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s);
 
@@ -107,7 +120,8 @@ struct BnBwdArgs {
   const float* mean = nullptr;
   const float* rstd = nullptr;
   const float* gamma = nullptr;
-  float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); zeroed by the caller
+  float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); written by the reduce pass
+  DetScratch det;             // deterministic reduction scratch (null members: the process-wide instance)
   void* dy = nullptr;         // bf16 [M][C] gradient w.r.t. the raw conv output
   void* dz_out = nullptr;     // optional bf16 [M][C]: masked gradient (feeds the residual branch)
   float* dgamma = nullptr;    // [C]
@@ -117,7 +131,7 @@ struct BnBwdArgs {
   const float* mean2 = nullptr;
   const float* rstd2 = nullptr;
   const float* gamma2 = nullptr;
-  float* sums2 = nullptr;     // [C] workspace: sum(dz * xhat2); zeroed by the caller
+  float* sums2 = nullptr;     // [C] workspace: sum(dz * xhat2); written by the reduce pass
   void* dy2 = nullptr;
   float* dgamma2 = nullptr;
   float* dbeta2 = nullptr;

@@ -272,6 +272,15 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   e->off_fold_ = arena(2 * e->convs_.size() * sizeof(BnFoldEntry));  // bf16 tier (stem excluded) | tf32 tier (all)
   e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
   if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
+  // scratch of the deterministic reductions (zeroed once at bind: the tickets reset themselves):
+  //   conv statistics [kStatScratchFloats floats | kStatTickets ints], BatchNorm-backward / stem ordered reduce
+  //   [kDetScratchFloats floats | kDetTickets ints], loss-head partials, two wgrad split-K buffers (side / main stream)
+  e->off_det_ = arena(kStatScratchFloats * 4 + kStatTickets * 4);
+  e->off_det_bn_ = arena(kDetScratchFloats * 4 + kDetTickets * 4);
+  e->off_det_loss_ = arena(((size_t)N * 4 + (size_t)(e->B_ + 1) * 64) * 4);
+  e->det_small_bytes_ = align_up(cur, kAlign) - e->off_det_;
+  e->off_wgrad_scratch_[0] = arena(kWgradScratchBytes);
+  e->off_wgrad_scratch_[1] = arena(kWgradScratchBytes);
   e->ws_bytes_ = align_up(cur, kAlign);
   *out = e;
   return std::string();
@@ -286,6 +295,7 @@ std::string Engine::bind(void* params, size_t param_bytes, void* ws, size_t byte
   ws_ = reinterpret_cast<uint8_t*>(ws);
   cudaError_t e = cudaMemsetAsync(ws_ + off_saved_, 0, nsaved_ * 4 + 0, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws_ + off_det_, 0, det_small_bytes_, stream);
   if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   for (Conv* c : convs_) {
     c->y = reinterpret_cast<bf16*>(ws_ + c->y_off);
@@ -405,6 +415,8 @@ std::string Engine::plan_all() {
     if (train) {
       gc.stat_sum = zero + c.zero_off;
       gc.stat_sq = zero + c.zero_off + c.Cout;
+      gc.stat_scratch = reinterpret_cast<float*>(ws_ + off_det_);
+      gc.stat_ticket = reinterpret_cast<int*>(ws_ + off_det_ + kStatScratchFloats * 4);
     }
     return gc;
   };
@@ -699,6 +711,8 @@ std::string Engine::plan_all() {
     a.dz_out = dz_out;
     a.dgamma = G + c.gamma_off;
     a.dbeta = G + c.beta_off;
+    a.det.scratch = reinterpret_cast<float*>(ws_ + off_det_bn_);
+    a.det.tickets = reinterpret_cast<int*>(ws_ + off_det_bn_ + kDetScratchFloats * 4);
     if (second) {
       const Conv& d = *second;
       a.y2 = d.y;
@@ -736,6 +750,7 @@ std::string Engine::plan_all() {
     fill_fwd_geometry(&d, c.R, c.R, c.stride, c.pad);
     d.Cout = c.Cout;
     d.dw = G + c.w_off;
+    d.scratch = reinterpret_cast<float*>(ws_ + off_wgrad_scratch_[0]);  // side stream (all of them when single-stream)
     WgradPlan plan;
     std::string e2 = plan_wgrad(d, &plan);
     if (!e2.empty()) {
@@ -872,6 +887,8 @@ std::string Engine::plan_all() {
     sb.dy = s2;
     sb.dgamma = G + st.gamma_off;
     sb.dbeta = G + st.beta_off;
+    sb.det.scratch = reinterpret_cast<float*>(ws_ + off_det_bn_);
+    sb.det.tickets = reinterpret_cast<int*>(ws_ + off_det_bn_ + kDetScratchFloats * 4);
     // algorithmic bytes: reduce pass over the pooled elements (dA, ymax, codes); apply pass y + pooled gradient + codes
     // read, dy written
     bwd_.push_back(Op([sb](cudaStream_t s) { return launch_stem_bwd(sb, s); }, kFamNorm, 0.0,
@@ -897,6 +914,7 @@ std::string Engine::plan_all() {
     }
     d.Cout = 64;
     d.dw = stem_dwp;
+    d.scratch = reinterpret_cast<float*>(ws_ + off_wgrad_scratch_[1]);  // main stream: may overlap the side stream's
     WgradPlan plan;
     err = plan_wgrad(d, &plan);
     if (!err.empty()) return err;
@@ -1194,15 +1212,19 @@ std::string Engine::update_grads(const void* obs, const int* perms, const float*
   {
     const int N = N_, D = D_, B = B_;
     const float l2w = h.l2weight, l1w = h.l1weight, tcnw = h.tcnweight;
-    e = launch(Op([=](cudaStream_t s) { return launch_loss_lp(E, dE, N, D, l2w, l1w, metrics, s); }, kFamLoss, 0.0,
-                  (double)N * D * 8),
-               stream);
+    float* lp_scratch = reinterpret_cast<float*>(ws_ + off_det_loss_);
+    float* tcn_scratch = lp_scratch + (size_t)N * 4;
+    Op lp([=](cudaStream_t s) { return launch_loss_lp(E, dE, N, D, l2w, l1w, metrics, s, lp_scratch); }, kFamLoss, 0.0,
+          (double)N * D * 8);
+    lp.nlaunch = 2;
+    e = launch(lp, stream);
     if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
     if (tcnw > 0.f) {
       const int l2dist = l2dist_ ? 1 : 0;
-      e = launch(Op([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, l2dist, metrics, s); }, kFamLoss, 0.0,
-                    (double)B * 18 * D * 4 * 2),
-                 stream);
+      Op tcn([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, l2dist, metrics, s, tcn_scratch); },
+             kFamLoss, 0.0, (double)B * 18 * D * 4 * 2);
+      tcn.nlaunch = dE ? 3 : 2;
+      e = launch(tcn, stream);
       if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
     }
   }

@@ -154,6 +154,8 @@ class Engine {
          zero_bytes_ = 0, off_metrics_ = 0, off_stem_dwp_ = 0, off_wd_ = 0, off_stem_wp_ = 0, off_xs_ = 0, off_argmax_ = 0, off_ymax_ = 0,
          off_E_ = 0, off_dE_ = 0, off_g_[7] = {0, 0, 0, 0, 0, 0, 0};
   size_t nsaved_ = 0, nwd_ = 0;
+  // deterministic-reduction scratch (see Engine::create)
+  size_t off_det_ = 0, off_det_bn_ = 0, off_det_loss_ = 0, det_small_bytes_ = 0, off_wgrad_scratch_[2] = {0, 0};
   // language head (optional)
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
   size_t off_lang_ws_ = 0;

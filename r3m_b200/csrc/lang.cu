@@ -52,23 +52,49 @@ __global__ void __launch_bounds__(256) lang_layer1_kernel(const float* __restric
   }
 }
 
-// dU[clip of e0] += dpre1[row];  dV[e_t row] += dpre1[row];  dLc[b] += dpre1[row]   (targets zeroed by the caller)
+// Backward of the gather-add of layer 1, itself as a GATHER (no atomics: deterministic): one block per target row,
+//   block < B        : dU[c]      = sum of dpre1 rows whose e0 comes from clip c
+//   block < 6B       : dV[r]      = sum of dpre1 rows whose e_t is embedding row r = block - B
+//   else             : dLc[b]     = sum over the 15 evaluations of clip b
+// Evaluations 0..5 are in-clip (the source row is known); for the shuffled negatives 6..14 the block marks, in shared
+// memory, every clip b whose permutation points at the target clip (a scan, so any index map works, not only
+// bijections) and every thread then adds the marked rows in (evaluation, clip) order.
 __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __restrict__ dpre, const int* __restrict__ perms,
                                                               float* __restrict__ dU, float* __restrict__ dV,
                                                               float* __restrict__ dLc, LangDims d) {
   pdl_sync();
-  const int row = blockIdx.x;
-  const int j = row / d.B, b = row - j * d.B;
-  int r0, r1;
-  eval_rows(j, b, perms, d.B, r0, r1);
-  const float* g = dpre + (size_t)row * d.H;
+  extern __shared__ unsigned char s_hit[];  // [9][B]
+  const int B = d.B;
+  const int blk = blockIdx.x;
+  const int kind = blk < B ? 0 : (blk < 6 * B ? 1 : 2);
+  const int target = kind == 0 ? blk : (kind == 1 ? blk - B : blk - 6 * B);
+  const int c = kind == 1 ? target / 5 : target;  // clip of the target row
+  const int f = kind == 1 ? target - 5 * c : 0;   // frame of a dV row
+  float* out = (kind == 0 ? dU : (kind == 1 ? dV : dLc)) + (size_t)target * d.H;
+  for (int idx = threadIdx.x; idx < 9 * B; idx += blockDim.x) {
+    const int q = idx / B, t = q % 3;
+    const int ft = t == 0 ? 1 : (t == 1 ? 3 : 4);  // e_t frame of shuffled negative q
+    s_hit[idx] = (kind != 2 && perms[idx] == c && (kind == 0 || ft == f)) ? 1 : 0;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < d.H; i += blockDim.x) {
-    const float x = g[i];
-    if (x != 0.f) {
-      atomicAdd(&dU[(size_t)(r0 / 5) * d.H + i], x);
-      atomicAdd(&dV[(size_t)r1 * d.H + i], x);
-      atomicAdd(&dLc[(size_t)b * d.H + i], x);
+    float acc = 0.f;
+    for (int j = 0; j < 6; ++j) {
+      bool hit = true;
+      if (kind == 1) {
+        const int fj = j < 3 ? (j == 0 ? 1 : (j == 1 ? 3 : 4)) : (j == 3 ? 0 : (j == 4 ? 2 : 3));
+        hit = (fj == f);
+      }
+      if (hit) acc += dpre[(size_t)(j * B + c) * d.H + i];
     }
+    if (kind == 2) {
+      for (int j = 6; j < 15; ++j) acc += dpre[(size_t)(j * B + c) * d.H + i];
+    } else {
+      for (int q = 0; q < 9; ++q)
+        for (int b = 0; b < B; ++b)
+          if (s_hit[q * B + b]) acc += dpre[(size_t)((6 + q) * B + b) * d.H + i];
+    }
+    out[i] = acc;
   }
 }
 
@@ -93,10 +119,13 @@ struct GemmArgs {
   const float* mask;
   int ldm;
   int accumulate;  // C += result
-  int kchunk = 0;  // split-K (gridDim.z > 1): K range per z slice, a multiple of kTK; the slices add into C atomically
+  int kchunk = 0;  // split-K (gridDim.z > 1): K range per z slice, a multiple of kTK; slice z writes its partial product
+                   // to splitk[z][M][N] and splitk_reduce_kernel adds the slices in order (deterministic)
+  float* splitk = nullptr;
 };
 
 constexpr int kTM = 64, kTN = 128, kTK = 16;
+constexpr size_t kSplitKFloats = (size_t)4 << 20;  // split-K scratch of the head's few-tile GEMMs (16 MB)
 
 // one operand tile [kTK][ROWS] (k-major in shared memory) <- global, through registers
 template <int ROWS, bool kKContig>
@@ -219,9 +248,10 @@ __global__ void __launch_bounds__(128) sgemm_kernel(const GemmArgs g) {
       }
       float* dst = &g.C[(size_t)row * g.ldc + col];
       if (split) {
+        float* part = g.splitk + ((size_t)blockIdx.z * g.M + row) * g.N + col;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (col + j < g.N) atomicAdd(&dst[j], v[j]);
+          if (col + j < g.N) part[j] = v[j];
       } else if (col + 3 < g.N && (g.ldc & 3) == 0) {
         float4 o = make_float4(v[0], v[1], v[2], v[3]);
         if (g.accumulate) {
@@ -241,6 +271,19 @@ __global__ void __launch_bounds__(128) sgemm_kernel(const GemmArgs g) {
   }
 }
 
+// C[m][n] (+)= sum over slices (in slice order) of part[z][m][n]
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int M,
+                                                            int N, int ldc, int slices, int accumulate) {
+  pdl_sync();
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float a = accumulate ? C[(size_t)m * ldc + n] : 0.f;
+    for (int z = 0; z < slices; ++z) a += part[(size_t)z * total + i];
+    C[(size_t)m * ldc + n] = a;
+  }
+}
+
 template <bool kAK, bool kBK>
 cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
   // contiguous dimensions must be whole float4s, and every operand base 16-byte aligned
@@ -250,12 +293,13 @@ cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
   dim3 grid((g.N + kTN - 1) / kTN, (g.M + kTM - 1) / kTM);
   GemmArgs a = g;
   // Few-tile GEMMs with a long K (the M = clips rows of the factorised first layer) are split along K so that they
-  // fill the machine; their slices add into C atomically, so C must be pre-zeroed or `accumulate`, without epilogue.
+  // fill the machine; the slices land in a.splitk and are added in slice order by a second kernel (no epilogue).
   const int tiles = grid.x * grid.y;
   if (a.kchunk < 0) {
     a.kchunk = 0;
-    if (tiles < 100 && !a.bias && !a.relu && !a.mask) {
+    if (tiles < 100 && !a.bias && !a.relu && !a.mask && a.splitk != nullptr) {
       int splits = std::min((148 + tiles - 1) / tiles, a.K / 64);
+      while (splits > 1 && (size_t)splits * a.M * a.N > kSplitKFloats) --splits;
       if (splits > 1) {
         a.kchunk = ((a.K + splits - 1) / splits + kTK - 1) / kTK * kTK;
         grid.z = (a.K + a.kchunk - 1) / a.kchunk;
@@ -263,6 +307,10 @@ cudaError_t run_gemm(const GemmArgs& g, cudaStream_t s) {
     }
   }
   launch_kernel(sgemm_kernel<kAK, kBK>, grid, 128, 0, s, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || grid.z <= 1) return e;
+  launch_kernel(splitk_reduce_kernel, 148 * 4, 256, 0, s, (const float*)a.splitk, a.C, a.M, a.N, a.ldc, (int)grid.z,
+                a.accumulate);
   return cudaGetLastError();
 }
 
@@ -284,42 +332,58 @@ __global__ void __launch_bounds__(256) lang_score_kernel(const float* __restrict
   }
 }
 
-// InfoNCE over 1 positive + 4 negatives, 3 targets per clip (trainer.py:93-117); one thread per clip.
-__global__ void lang_loss_kernel(const float* __restrict__ S, const float* __restrict__ mask, float* __restrict__ dS,
-                                 int B, float langw, float* __restrict__ metrics) {
+// InfoNCE over 1 positive + 4 negatives, 3 targets per clip (trainer.py:93-117).  ONE block: a thread handles clips
+// tid, tid + blockDim, ...; the four metric sums go through a fixed shuffle / shared-memory tree (deterministic).
+__global__ void __launch_bounds__(256) lang_loss_kernel(const float* __restrict__ S, const float* __restrict__ mask,
+                                                        float* __restrict__ dS, int B, float langw,
+                                                        float* __restrict__ metrics) {
   pdl_sync();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  __shared__ float red[4 * 32];
   const float invB = 1.0f / (float)B;
-  const float mk = mask[b];
-  float loss = 0.f;
-  for (int t = 0; t < 3; ++t) {
-    const float pos = S[t * B + b];
-    float neg[4];
-    neg[0] = S[(3 + t) * B + b];
-    for (int i = 0; i < 3; ++i) neg[1 + i] = S[(6 + 3 * i + t) * B + b];
-    const float ep = expf(pos);
-    float en[4], sum = 0.f, mx = neg[0];
-    for (int k = 0; k < 4; ++k) {
-      en[k] = expf(neg[k]);
-      sum += en[k];
-      mx = fmaxf(mx, neg[k]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // rewloss, rewacc1..3
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float mk = mask[b];
+    float loss = 0.f;
+    for (int t = 0; t < 3; ++t) {
+      const float pos = S[t * B + b];
+      float neg[4];
+      neg[0] = S[(3 + t) * B + b];
+      for (int i = 0; i < 3; ++i) neg[1 + i] = S[(6 + 3 * i + t) * B + b];
+      const float ep = expf(pos);
+      float en[4], sum = 0.f, mx = neg[0];
+      for (int k = 0; k < 4; ++k) {
+        en[k] = expf(neg[k]);
+        sum += en[k];
+        mx = fmaxf(mx, neg[k]);
+      }
+      const float Dn = kLossEps + ep + sum;
+      const float r = ep / Dn;
+      loss += -logf(kLossEps + r);
+      acc[1 + t] += (mx < pos) ? 1.f : 0.f;
+      if (dS) {
+        const float f = langw * mk * invB * (1.0f / 3.0f);
+        const float gr = -f / (kLossEps + r);
+        dS[t * B + b] = gr * (r - r * r);
+        dS[(3 + t) * B + b] = gr * (-r * en[0] / Dn);
+        for (int i = 0; i < 3; ++i) dS[(6 + 3 * i + t) * B + b] = gr * (-r * en[1 + i] / Dn);
+      }
     }
-    const float Dn = kLossEps + ep + sum;
-    const float r = ep / Dn;
-    loss += -logf(kLossEps + r);
-    atomicAdd(&metrics[kRewAcc1 + t], (mx < pos) ? invB : 0.f);
-    if (dS) {
-      const float f = langw * mk * invB * (1.0f / 3.0f);
-      const float gr = -f / (kLossEps + r);
-      dS[t * B + b] = gr * (r - r * r);
-      dS[(3 + t) * B + b] = gr * (-r * en[0] / Dn);
-      for (int i = 0; i < 3; ++i) dS[(6 + 3 * i + t) * B + b] = gr * (-r * en[1 + i] / Dn);
-    }
+    acc[0] += mk * loss * (1.0f / 3.0f);
   }
-  const float lb = mk * loss * (1.0f / 3.0f) * invB;
-  atomicAdd(&metrics[kRewLoss], lb);
-  atomicAdd(&metrics[kFullLoss], langw * lb);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0)
+    for (int i = 0; i < 4; ++i) red[i * 32 + warp] = acc[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < nwarp; ++w)
+      for (int i = 0; i < 4; ++i) tot[i] += red[i * 32 + w];
+    metrics[kRewLoss] += tot[0] * invB;
+    metrics[kFullLoss] += langw * tot[0] * invB;
+    for (int t = 0; t < 3; ++t) metrics[kRewAcc1 + t] += tot[1 + t] * invB;
+  }
 }
 
 // dH4[row, j] = dS[row] * w5[j] * (H4[row, j] > 0)
@@ -334,29 +398,24 @@ __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restric
   }
 }
 
-// out[j] += sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 8 row-slices, gridDim.y
-// row groups combined with atomics: `out` lives in the gradient buffer, which is zero at this point of the step
-// (a one-thread-per-column loop over ~1000 rows took 70 us per call).
-__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
-                                                      float* __restrict__ out, int rows, int cols) {
+// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 32 row-slices; the slices are
+// added in slice order (no atomics: deterministic).
+__global__ void __launch_bounds__(1024) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
+                                                       float* __restrict__ out, int rows, int cols) {
   pdl_sync();
-  __shared__ float part[8][33];
+  __shared__ float part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
   float acc = 0.f;
   if (j < cols)
-    for (int r = blockIdx.y * 8 + ty; r < rows; r += 8 * gridDim.y)
-      acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
+    for (int r = ty; r < rows; r += 32) acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
   part[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && j < cols) {
     float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v += part[i][tx];
-    if (gridDim.y == 1)
-      out[j] = v;
-    else
-      atomicAdd(&out[j], v);
+    for (int i = 0; i < 32; ++i) v += part[i][tx];
+    out[j] = v;
   }
 }
 
@@ -380,7 +439,7 @@ __global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ 
 size_t lang_workspace_floats(const LangDims& d) {
   const size_t r = (size_t)d.rows();
   auto up = [](size_t v) { return (v + 63) / 64 * 64; };
-  return 2 * (2 * up((size_t)d.B * d.H) + up((size_t)5 * d.B * d.H)) + 6 * up(r * d.H) + 2 * up(r);
+  return 2 * (2 * up((size_t)d.B * d.H) + up((size_t)5 * d.B * d.H)) + 6 * up(r * d.H) + 2 * up(r) + kSplitKFloats;
 }
 
 void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws) {
@@ -411,6 +470,8 @@ void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws) {
   ws->S = p;
   p += up(r);
   ws->dS = p;
+  p += up(r);
+  ws->splitk = p;
 }
 
 cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWorkspace& ws, const float* E, float* dE,
@@ -432,14 +493,12 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   const int B = d.B, D = d.D;
   // ---- forward layer 1 (factorised): U = E0 . W1a^T, V = E . W1b^T, Lc = L . W1c^T, then gather-add + bias + ReLU
   {
-    // U, V, Lc are contiguous and zeroed by one memset: their GEMMs are split along K (kchunk = -1: automatic)
-    e = cudaMemsetAsync(ws.U, 0, (size_t)(ws.Hact[0] - ws.U) * sizeof(float), s);
-    if (e != cudaSuccess) return e;
-    GemmArgs gu{E, p.w[0], ws.U, B, H, D, 5 * D, K1, H, nullptr, 0, nullptr, 0, 0, -1};
+    // few-tile products: split along K (kchunk = -1: automatic), slices reduced in order through ws.splitk
+    GemmArgs gu{E, p.w[0], ws.U, B, H, D, 5 * D, K1, H, nullptr, 0, nullptr, 0, 0, -1, ws.splitk};
     R3M_TRY((run_gemm<true, true>(gu, s)));
-    GemmArgs gv{E, p.w[0] + D, ws.V, 5 * B, H, D, D, K1, H, nullptr, 0, nullptr, 0, 0, -1};
+    GemmArgs gv{E, p.w[0] + D, ws.V, 5 * B, H, D, D, K1, H, nullptr, 0, nullptr, 0, 0, -1, ws.splitk};
     R3M_TRY((run_gemm<true, true>(gv, s)));
-    GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0, -1};
+    GemmArgs gl{lang_emb, p.w[0] + 2 * D, ws.Lc, B, H, d.L, d.L, K1, H, nullptr, 0, nullptr, 0, 0, -1, ws.splitk};
     R3M_TRY((run_gemm<true, true>(gl, s)));
     launch_kernel(lang_layer1_kernel, rows, 256, 0, s, ws.U, ws.V, ws.Lc, p.b[0], perms, ws.Hact[0], d);
     R3M_TRY(cudaGetLastError());
@@ -451,11 +510,11 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   }
   launch_kernel(lang_score_kernel, rows, 256, 0, s, ws.Hact[3], p.w[4], p.b[4], ws.S, H);
   R3M_TRY(cudaGetLastError());
-  launch_kernel(lang_loss_kernel, (d.B + 127) / 128, 128, 0, s, ws.S, lang_mask, dE ? ws.dS : nullptr, d.B, langw, metrics);
+  launch_kernel(lang_loss_kernel, 1, 256, 0, s, ws.S, lang_mask, dE ? ws.dS : nullptr, d.B, langw, metrics);
   R3M_TRY(cudaGetLastError());
   if (dE) {
     // ---- backward
-    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
     R3M_TRY(cudaGetLastError());
     launch_kernel(vec_sum_kernel, 1, 256, 0, s, ws.dS, p.db[4], rows);
     R3M_TRY(cudaGetLastError());
@@ -465,7 +524,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
-      launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, dHl, nullptr, p.db[l], rows, H);
+      launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
       GemmArgs gw{dHl, ws.Hact[l - 1], p.dw[l], H, H, rows, H, H, H, nullptr, 0, nullptr, 0, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
@@ -476,14 +535,9 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     }
     // ---- layer 1 backward (factorised)
     const float* dpre = ws.dH[cur];
-    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 16), 256, 0, s, dpre, nullptr, p.db[0], rows, H);
+    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, dpre, nullptr, p.db[0], rows, H);
     R3M_TRY(cudaGetLastError());
-    e = cudaMemsetAsync(ws.dU, 0, (size_t)((ws.U - ws.dU)) * sizeof(float), s);
-    if (e != cudaSuccess) {
-      if (launches) *launches = n;
-      return e;
-    }
-    launch_kernel(lang_layer1_bwd_kernel, rows, 256, 0, s, dpre, perms, ws.dU, ws.dV, ws.dLc, d);
+    launch_kernel(lang_layer1_bwd_kernel, 7 * B, 256, (size_t)9 * B, s, dpre, perms, ws.dU, ws.dV, ws.dLc, d);
     R3M_TRY(cudaGetLastError());
     // dW1 = [dU^T E0 | dV^T E | dLc^T L]   (column blocks of the [H][2D+768] gradient)
     GemmArgs wa{ws.dU, E, p.dw[0], H, D, B, H, 5 * D, K1, nullptr, 0, nullptr, 0, 0};
@@ -493,9 +547,9 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     GemmArgs wc{ws.dLc, lang_emb, p.dw[0] + 2 * D, H, d.L, B, H, d.L, K1, nullptr, 0, nullptr, 0, 0};
     R3M_TRY((run_gemm<false, false>(wc, s)));
     // dE0 += dU . W1a,  dE += dV . W1b   (the sentence embedding is frozen: no gradient through W1c's input)
-    GemmArgs ea{ws.dU, p.w[0], dE, B, D, H, H, K1, 5 * D, nullptr, 0, nullptr, 0, 1, -1};
+    GemmArgs ea{ws.dU, p.w[0], dE, B, D, H, H, K1, 5 * D, nullptr, 0, nullptr, 0, 1, -1, ws.splitk};
     R3M_TRY((run_gemm<true, false>(ea, s)));
-    GemmArgs eb{ws.dV, p.w[0] + D, dE, 5 * B, D, H, H, K1, D, nullptr, 0, nullptr, 0, 1, -1};
+    GemmArgs eb{ws.dV, p.w[0] + D, dE, 5 * B, D, H, H, K1, D, nullptr, 0, nullptr, 0, 1, -1, ws.splitk};
     R3M_TRY((run_gemm<true, false>(eb, s)));
   }
 #undef R3M_TRY

@@ -30,19 +30,20 @@ struct LangWorkspace {  // device scratch, sized by lang_workspace_floats()
   float* U;        // [B][H]   e0 . W1a^T
   float* V;        // [5B][H]  e  . W1b^T
   float* Lc;       // [B][H]   l  . W1c^T
-  float* dU;       // gradients of the three products (scatter-added from the 15B rows)
+  float* dU;       // gradients of the three products (gathered from the 15B rows)
   float* dV;
   float* dLc;
   float* Hact[4];  // post-ReLU hidden activations [rows][H]
   float* S;        // [rows] scores
   float* dS;       // [rows]
   float* dH[2];    // ping-pong [rows][H]
+  float* splitk;   // slices of the split-K GEMMs (summed in slice order: deterministic)
 };
 size_t lang_workspace_floats(const LangDims& d);
 void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws);
 
 // Forward + InfoNCE loss (+ metrics).  When dE != null also the full backward: parameter gradients are WRITTEN to
-// p.dw / p.db and d(langw * rewloss)/dE is atomically accumulated into dE.  Returns the number of kernels launched
+// p.dw / p.db and d(langw * rewloss)/dE is accumulated into dE (ordered reductions only: no atomics).  Returns the number of kernels launched
 // through *launches.
 cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWorkspace& ws, const float* E, float* dE,
                           const int* perms, const float* lang_emb, const float* lang_mask, float langw,

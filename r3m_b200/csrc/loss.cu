@@ -10,6 +10,8 @@ namespace r3m {
 
 namespace {
 
+constexpr int kTcnPart = 40;  // per-clip record of the TCN head: alpha[9], beta_u[9], beta_v[9], pad[9], loss, aligned
+
 template <int kN>
 __device__ __forceinline__ void block_sum(float (&v)[kN], float* smem /* [kN][32] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -29,7 +31,7 @@ __device__ __forceinline__ void block_sum(float (&v)[kN], float* smem /* [kN][32
 }
 
 __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ E, float* __restrict__ dE, int rows,
-                                                      int D, float l2w, float l1w, float* __restrict__ metrics) {
+                                                      int D, float l2w, float l1w, float* __restrict__ part) {
   pdl_sync();
   __shared__ float red[3 * 32];
   const int row = blockIdx.x;
@@ -44,11 +46,10 @@ __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ 
   block_sum<3>(acc, red);
   const float norm = sqrtf(acc[0]);
   const float inv_rows = 1.0f / (float)rows;
-  if (threadIdx.x == 0) {
-    atomicAdd(&metrics[kL2], norm * inv_rows);
-    atomicAdd(&metrics[kL1], acc[1] * inv_rows);
-    atomicAdd(&metrics[kL0], acc[2] * inv_rows);
-    atomicAdd(&metrics[kFullLoss], (l2w * norm + l1w * acc[1]) * inv_rows);
+  if (threadIdx.x == 0) {  // per-row values; lp_finalize_kernel adds them in row order (no atomics: deterministic)
+    part[row * 4 + 0] = norm;
+    part[row * 4 + 1] = acc[1];
+    part[row * 4 + 2] = acc[2];
   }
   if (dE) {
     const float c2 = norm > 0.f ? l2w * inv_rows / norm : 0.f;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256) loss_lp_kernel(const float* __restrict__ 
 template <bool kCos>
 __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__ E, float* __restrict__ dE,
                                                        const int* __restrict__ perms, int B, int D, float tcnw,
-                                                       float* __restrict__ metrics) {
+                                                       float* __restrict__ part /* [B][kTcnPart] */) {
   pdl_sync();
   constexpr int kAcc = kCos ? 27 : 9;
   __shared__ float red[kAcc * 32];
@@ -134,9 +135,8 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
     const float r1 = e12 / D1, r2 = e01 / D2;
     const float L1 = -logf(kLossEps + r1), L2 = -logf(kLossEps + r2);
     const float invB = 1.0f / (float)B;
-    atomicAdd(&metrics[kTcnLoss], 0.5f * (L1 + L2) * invB);
-    atomicAdd(&metrics[kFullLoss], tcnw * 0.5f * (L1 + L2) * invB);
-    atomicAdd(&metrics[kAligned], ((s02 < s12) && (s01 > s02)) ? invB : 0.f);
+    part[b * kTcnPart + 36] = 0.5f * (L1 + L2);
+    part[b * kTcnPart + 37] = ((s02 < s12) && (s01 > s02)) ? 1.f : 0.f;
     const float f = tcnw * 0.5f * invB;
     const float g1 = -f / (kLossEps + r1), g2 = -f / (kLossEps + r2);  // dLoss/dr1, dLoss/dr2
     coef[1] = g1 * (r1 - r1 * r1);
@@ -148,24 +148,125 @@ __global__ void __launch_bounds__(256) loss_tcn_kernel(const float* __restrict__
     }
   }
   __syncthreads();
-  if (!dE) return;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float w = coef[k];
-      if (w == 0.f || (!kCos && ca[k] == 0.f)) continue;
-      const float u = E[(size_t)urow[k] * D + d], v = E[(size_t)vrow[k] * D + d];
-      float gu, gv;
-      if (kCos) {
-        gu = w * (ca[k] * v - cb[k] * u);
-        gv = w * (ca[k] * u - cc[k] * v);
-      } else {
-        gu = -w * ca[k] * (u - v);
-        gv = -gu;
-      }
-      atomicAdd(&dE[(size_t)urow[k] * D + d], gu);
-      atomicAdd(&dE[(size_t)vrow[k] * D + d], gv);
+  // pair k of this clip: alpha = w * ca multiplies the partner row, beta the own row (u side: cb, v side: cc; for the
+  // L2 similarity both sides see -alpha * (own - partner)); consumed by loss_tcn_gather_kernel
+  if (threadIdx.x < 9) {
+    const int k = threadIdx.x;
+    const float w = coef[k];
+    const bool live = !(w == 0.f || (!kCos && ca[k] == 0.f));
+    part[b * kTcnPart + k] = live ? w * ca[k] : 0.f;
+    part[b * kTcnPart + 9 + k] = live ? w * cb[k] : 0.f;
+    part[b * kTcnPart + 18 + k] = live ? w * cc[k] : 0.f;
+  }
+  (void)dE;
+}
+
+// d(tcnw * tcnloss)/dE by GATHER (one block per embedding row, no atomics: deterministic): row (c, f) collects every
+// pair of loss_tcn_kernel it takes part in — its own clip's pairs in pair order, then, as the v side, the shuffled
+// negatives of the clips whose permutation points at clip c (marked in shared memory by a parallel scan, so any index
+// map works, not only bijections; added in (negative, clip) order).
+template <bool kCos>
+__global__ void __launch_bounds__(256) loss_tcn_gather_kernel(const float* __restrict__ E, float* __restrict__ dE,
+                                                              const int* __restrict__ perms, int B, int D,
+                                                              const float* __restrict__ part) {
+  pdl_sync();
+  extern __shared__ unsigned char s_hit[];  // [3][B]
+  __shared__ int own_partner[5];
+  __shared__ float own_alpha[5], own_beta[5];
+  __shared__ int s_own;
+  const int r = blockIdx.x, c = r / 5, f = r - 5 * c;
+  if (f < 2) return;  // e0 and eg take no part in the TCN head
+  const float* er = E + (size_t)r * D;
+  const float* pc = part + (size_t)c * kTcnPart;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    auto push = [&](int partner, float alpha, float beta) {
+      own_partner[n] = partner;
+      own_alpha[n] = alpha;
+      own_beta[n] = beta;
+      ++n;
+    };
+    // own clip: k = 0 (u = es2, v = es0), 1 (u = es2, v = es1), 2 (u = es1, v = es0), 3..5 (u = es0), 6..8 (u = es2)
+    if (f == 2) {
+      push(5 * c + 4, pc[0], pc[18 + 0]);
+      push(5 * c + 3, pc[2], pc[18 + 2]);
+      for (int j = 0; j < 3; ++j) push(5 * perms[(9 + 2 * j) * B + c] + 2, pc[3 + j], pc[9 + 3 + j]);
+    } else if (f == 3) {
+      push(5 * c + 4, pc[1], pc[18 + 1]);
+      push(5 * c + 2, pc[2], pc[9 + 2]);
+    } else {
+      push(5 * c + 2, pc[0], pc[9 + 0]);
+      push(5 * c + 3, pc[1], pc[9 + 1]);
+      for (int j = 0; j < 3; ++j) push(5 * perms[(10 + 2 * j) * B + c] + 4, pc[6 + j], pc[9 + 6 + j]);
     }
+    s_own = n;
+  }
+  // incoming: clip b's shuffled negative j points at clip c -> this row is the v side of pair (b, 3 + j | 6 + j)
+  for (int idx = threadIdx.x; idx < 3 * B; idx += blockDim.x) {
+    const int j = idx / B, b = idx - j * B;
+    const int q = (f == 2) ? 9 + 2 * j : 10 + 2 * j;
+    s_hit[idx] = (f != 3 && perms[q * B + b] == c) ? 1 : 0;
+  }
+  __syncthreads();
+  const int n_own = s_own;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float own = er[d];
+    float acc = 0.f;
+    auto add = [&](int partner, float alpha, float beta) {
+      if (alpha == 0.f && beta == 0.f) return;
+      const float other = E[(size_t)partner * D + d];
+      if (kCos)
+        acc += alpha * other - beta * own;
+      else
+        acc -= alpha * (own - other);
+    };
+    for (int i = 0; i < n_own; ++i) add(own_partner[i], own_alpha[i], own_beta[i]);
+    if (f != 3) {
+      for (int j = 0; j < 3; ++j) {
+        const int k = (f == 2) ? 3 + j : 6 + j;
+        for (int b = 0; b < B; ++b)
+          if (s_hit[j * B + b]) add(5 * b + f, part[(size_t)b * kTcnPart + k], part[(size_t)b * kTcnPart + 18 + k]);
+      }
+    }
+    dE[(size_t)r * D + d] += acc;
+  }
+}
+
+// metrics += means of the per-row / per-clip partials, added in index order by ONE block (deterministic)
+__global__ void __launch_bounds__(256) lp_finalize_kernel(const float* __restrict__ part, int rows, float l2w, float l1w,
+                                                          float* __restrict__ metrics) {
+  pdl_sync();
+  __shared__ float red[3 * 32];
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    acc[0] += part[i * 4 + 0];
+    acc[1] += part[i * 4 + 1];
+    acc[2] += part[i * 4 + 2];
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    const float inv = 1.0f / (float)rows;
+    metrics[kL2] += acc[0] * inv;
+    metrics[kL1] += acc[1] * inv;
+    metrics[kL0] += acc[2] * inv;
+    metrics[kFullLoss] += (l2w * acc[0] + l1w * acc[1]) * inv;
+  }
+}
+__global__ void __launch_bounds__(256) tcn_finalize_kernel(const float* __restrict__ part, int B, float tcnw,
+                                                           float* __restrict__ metrics) {
+  pdl_sync();
+  __shared__ float red[2 * 32];
+  float acc[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    acc[0] += part[i * kTcnPart + 36];
+    acc[1] += part[i * kTcnPart + 37];
+  }
+  block_sum<2>(acc, red);
+  if (threadIdx.x == 0) {
+    const float inv = 1.0f / (float)B;
+    metrics[kTcnLoss] += acc[0] * inv;
+    metrics[kFullLoss] += tcnw * acc[0] * inv;
+    metrics[kAligned] += acc[1] * inv;
   }
 }
 
@@ -193,18 +294,49 @@ cudaError_t launch_publish_flag(const int* flag, float* metrics, cudaStream_t s)
   return cudaGetLastError();
 }
 
+namespace {
+float* loss_scratch(size_t floats) {  // process-wide fallback (kernel-level C-ABI calls; stream-ordered use)
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    cap = 0;
+    if (cudaMalloc(&buf, floats * sizeof(float)) != cudaSuccess) return nullptr;
+    cap = floats;
+  }
+  return buf;
+}
+}  // namespace
+
 cudaError_t launch_loss_lp(const float* E, float* dE, int rows, int D, float l2w, float l1w, float* metrics,
-                           cudaStream_t s) {
-  launch_kernel(loss_lp_kernel, rows, 256, 0, s, E, dE, rows, D, l2w, l1w, metrics);
+                           cudaStream_t s, float* scratch) {
+  if (!scratch) scratch = loss_scratch((size_t)rows * 4);
+  if (!scratch) return cudaErrorMemoryAllocation;
+  launch_kernel(loss_lp_kernel, rows, 256, 0, s, E, dE, rows, D, l2w, l1w, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  launch_kernel(lp_finalize_kernel, 1, 256, 0, s, (const float*)scratch, rows, l2w, l1w, metrics);
   return cudaGetLastError();
 }
 
 cudaError_t launch_loss_tcn(const float* E, float* dE, const int* perms, int B, int D, float tcnw, int l2dist,
-                            float* metrics, cudaStream_t s) {
+                            float* metrics, cudaStream_t s, float* scratch) {
+  if (!scratch) scratch = loss_scratch((size_t)B * kTcnPart);
+  if (!scratch) return cudaErrorMemoryAllocation;
   if (l2dist)
-    launch_kernel(loss_tcn_kernel<false>, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
+    launch_kernel(loss_tcn_kernel<false>, B, 256, 0, s, E, dE, perms, B, D, tcnw, scratch);
   else
-    launch_kernel(loss_tcn_kernel<true>, B, 256, 0, s, E, dE, perms, B, D, tcnw, metrics);
+    launch_kernel(loss_tcn_kernel<true>, B, 256, 0, s, E, dE, perms, B, D, tcnw, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  launch_kernel(tcn_finalize_kernel, 1, 256, 0, s, (const float*)scratch, B, tcnw, metrics);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || dE == nullptr) return e;
+  if (l2dist)
+    launch_kernel(loss_tcn_gather_kernel<false>, 5 * B, 256, (size_t)3 * B, s, E, dE, perms, B, D, (const float*)scratch);
+  else
+    launch_kernel(loss_tcn_gather_kernel<true>, 5 * B, 256, (size_t)3 * B, s, E, dE, perms, B, D, (const float*)scratch);
   return cudaGetLastError();
 }
 

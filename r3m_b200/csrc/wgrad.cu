@@ -10,6 +10,8 @@
 // sits in TMEM for the whole CTA lifetime (up to all 512 columns) and is added to global memory once, with
 // vectorised red.global.add.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue.
+#include <algorithm>
+
 #include "conv_igemm.cuh"
 #include "launch.h"
 #include "ptx.cuh"
@@ -152,20 +154,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
         int tap = item0 / p.cblocks;
         int cb = item0 - tap * p.cblocks;
         for (int g = 0; g < g_count; ++g) {
-          float* dst_row = p.dW + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
+          // split-K partials go to this split's private copy of dW (summed in split order by wgrad_reduce_kernel: no
+          // floating-point atomics, bit-identical from run to run); a single split adds straight into dW
+          float* base = p.scratch ? p.scratch + static_cast<size_t>(blockIdx.x) * p.dw_elems : p.dW;
+          float* dst_row = base + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + g * 64 + half * 32, v);
             tc_wait_ld();
             if (row_ok) {
+              if (p.scratch) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float* d = dst_row + half * 32 + j * 4;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(v[4 * j])),
-                             "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
-                             "f"(__uint_as_float(v[4 * j + 3]))
-                             : "memory");
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(dst_row + half * 32 + j * 4) =
+                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float* d = dst_row + half * 32 + j * 4;
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(v[4 * j])),
+                               "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                               "f"(__uint_as_float(v[4 * j + 3]))
+                               : "memory");
+                }
               }
             }
           }
@@ -186,6 +199,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   }
 }
 
+// dW[i] += sum over splits (in split order) of scratch[s][i]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ scratch, float4* __restrict__ dW,
+                                                           size_t n4, int splits) {
+  pdl_sync();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = dW[i];
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = __ldcg(scratch + (size_t)s * n4 + i);
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+      a.w += v.w;
+    }
+    dW[i] = a;
+  }
+}
+
 }  // namespace
 
 int wgrad_smem_bytes(int group, int num_stages, int pix_block) {
@@ -202,6 +232,12 @@ cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const 
     configured_bytes = bytes;
   }
   launch_kernel(wgrad_kernel, dim3(splits, groups, ktiles), 256, bytes, stream, tmDy, tmX, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || p.scratch == nullptr) return e;
+  const size_t n4 = p.dw_elems / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  launch_kernel(wgrad_reduce_kernel, blocks, 256, 0, stream, reinterpret_cast<const float4*>(p.scratch),
+                reinterpret_cast<float4*>(p.dW), n4, splits);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,81 @@
+"""Run-to-run determinism and exact resume.  Every reduction of the step is ordered
+— BatchNorm statistics (per-CTA partials + last-CTA finalize), BatchNorm-backward sums (two-level ordered tree), wgrad
+split-K (per-split partial copies summed in split order), loss heads (gathers instead of scatter-adds) — so two runs
+from the same state give bit-identical gradients, and a run resumed from a snapshot continues bit for bit."""
+import pytest
+import torch
+
+from gpu_common import build_model, well_conditioned_state
+from oracle import r3m_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _one_step(size, clips, lang, steps=1, seed=0):
+    from r3m_b200 import Trainer
+
+    params, buffers = O.init_state(size, 80 + seed, lang=bool(lang))
+    lang_emb = O.stub_lang_embedding(clips, 81) if lang else None
+    m, model = build_model(size, params, buffers, float(lang), lang_emb)
+    tr = Trainer(100)
+    sentences = ["" if i % 4 == 3 else "s%d" % i for i in range(clips)]
+    out = []
+    for i in range(steps):
+        frames = O.structured_frames(clips, 82 + i).cuda()
+        perms = O.draw_permutations(clips, 90 + i)
+        metrics, _ = tr.update(model, (frames, sentences), i, perms=perms, lang_emb=lang_emb)
+        out.append((metrics, m._flat(1).clone(), m._any_engine().embeddings().clone()))
+    return m, out
+
+
+@pytest.mark.parametrize("size,clips,lang", [(18, 6, 1), (50, 12, 1), (34, 8, 0), (50, 64, 1)])
+def test_two_runs_are_bit_identical(size, clips, lang):
+    """Default (ill-conditioned) init on purpose: any reordered fp32 sum would be amplified to per-cent differences."""
+    ma, a = _one_step(size, clips, lang, steps=2)
+    mb, b = _one_step(size, clips, lang, steps=2)
+    for (m1, g1, e1), (m2, g2, e2) in zip(a, b):
+        assert torch.equal(e1, e2), "embeddings differ between two identical runs"
+        assert torch.equal(g1, g2), "gradients differ between two identical runs"
+        assert m1 == m2, (m1, m2)
+    assert torch.equal(ma._flat(0), mb._flat(0)) and torch.equal(ma._flat(4), mb._flat(4))
+
+
+def test_resume_from_snapshot_is_bit_exact(tmp_path):
+    """train 3 steps == train 2, save_snapshot, build a fresh model, load_snapshot, train 1 — weights, Adam moments,
+    BatchNorm running statistics, step counters and the permutation stream (torch's CPU generator) all continue."""
+    import r3m_b200
+    from r3m_b200 import Trainer
+
+    size, clips = 18, 6
+    params, buffers = well_conditioned_state(size, 100, True)
+    lang_emb = O.stub_lang_embedding(clips, 101)
+    sentences = ["s%d" % i for i in range(clips)]
+    batches = [O.varied_frames(clips, 102 + i).cuda() for i in range(3)]
+
+    def fresh():
+        return build_model(size, params, buffers, 1.0, lang_emb)
+
+    m_ref, model_ref = fresh()
+    torch.manual_seed(7)
+    tr = Trainer(100)
+    for i in range(3):
+        metrics_ref, _ = tr.update(model_ref, (batches[i], sentences), i)  # permutations from the global generator
+
+    m_a, model_a = fresh()
+    torch.manual_seed(7)
+    tr = Trainer(100)
+    for i in range(2):
+        tr.update(model_a, (batches[i], sentences), i)
+    path = str(tmp_path / "snapshot.pt")
+    assert r3m_b200.save_snapshot(path, model_a, 2)
+    torch.manual_seed(12345)  # the resumed process starts with an unrelated generator state
+    m_b, model_b = fresh()
+    step, _ = r3m_b200.load_snapshot(path, model_b)
+    assert step == 2 and m_b.encoder_opt.steps == 2
+    metrics_b, _ = Trainer(100).update(model_b, (batches[2], sentences), step)
+    assert metrics_b == metrics_ref
+    for which in (0, 2, 3, 4):  # parameters, Adam m, Adam v, BatchNorm running statistics
+        assert torch.equal(m_b._flat(which), m_ref._flat(which)), which
+    sd_b, sd_ref = model_b.state_dict(), model_ref.state_dict()
+    assert all(torch.equal(sd_b[k], sd_ref[k]) for k in sd_ref)
+    assert int(sd_b["module.convnet.bn1.num_batches_tracked"]) == 3
