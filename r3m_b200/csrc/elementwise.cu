@@ -126,7 +126,7 @@ constexpr int kDetGroup = 16;
 template <class Emit>
 __device__ __forceinline__ void det_grid_reduce(const float* partial, int V, const DetScratch d, Emit emit) {
   __shared__ int s_last;
-  const int G = gridDim.x, tid = threadIdx.x;
+  const int G = gridDim.x, tid = threadIdx.x;  // blocks along x reduce together; d is per blockIdx.y slice
   float* mine = d.scratch + (size_t)blockIdx.x * V;
   for (int i = tid; i < V; i += blockDim.x) mine[i] = partial[i];
   __threadfence();
@@ -874,9 +874,13 @@ __device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bit
 template <bool kDual, int kMask>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   pdl_sync();
-  extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * C / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
+  extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * Cs / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
   constexpr int kQ = kDual ? 3 : 2;
-  const int C8 = a.C >> 3;
+  // Wide layers are cut into channel slices of Cs = 256 (blockIdx.y): a block then covers 8 rows per iteration instead
+  // of 1 and its partial vector is kQ * 256 floats instead of kQ * C, which keeps the ordered reduction's scratch
+  // traffic far below the tensor's own (C = 2048: 1.8 MB instead of 14.5 MB).
+  const int Cs = min(a.C, 256), c_base = blockIdx.y * Cs;
+  const int C8 = Cs >> 3, ld8c = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
@@ -884,8 +888,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   float mean[8], mean2[8], s1[8], s2[8], s3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    mean[j] = a.mean[chunk * 8 + j];
-    mean2[j] = kDual ? a.mean2[chunk * 8 + j] : 0.f;
+    mean[j] = a.mean[c_base + chunk * 8 + j];
+    mean2[j] = kDual ? a.mean2[c_base + chunk * 8 + j] : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
     s3[j] = 0.f;
@@ -897,14 +901,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const uint8_t* __restrict__ mask = a.mask;
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + chunk * 8;
+    const long long off = row * a.C + c_base + chunk * 8;
     // all loads of the row first
     F8 g = ld8(dA + off);
     const F8 yy = ld8(y + off);
     F8 m, t;
     unsigned bits = 0;
     if (kMask == kMaskAct) m = ld8(act + off);
-    if (kMask == kMaskBits) bits = __ldg(mask + row * C8 + chunk);
+    if (kMask == kMaskBits) bits = __ldg(mask + row * ld8c + (c_base >> 3) + chunk);
     if (kDual) t = ld8(y2 + off);
     mask_gradient<kMask>(g, m, bits);
 #pragma unroll
@@ -917,20 +921,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   pdl_done();
   // Block reduction without atomics: every thread parks its partials, one thread per four outputs adds the
   // rows_per_iter copies in row order, and the grid-wide sum is the ordered two-level reduction above.
-  const int q4 = kQ * a.C / 4;  // float4 slots per partial row
+  const int q4 = kQ * Cs / 4;  // float4 slots per partial row
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    s2[j] *= a.rstd[chunk * 8 + j];
-    if (kDual) s3[j] *= a.rstd2[chunk * 8 + j];
+    s2[j] *= a.rstd[c_base + chunk * 8 + j];
+    if (kDual) s3[j] *= a.rstd2[c_base + chunk * 8 + j];
   }
   float4* mine = s_part + (size_t)r0 * q4 + chunk * 2;
   mine[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
   mine[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
-  mine[a.C / 4] = make_float4(s2[0], s2[1], s2[2], s2[3]);
-  mine[a.C / 4 + 1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+  mine[Cs / 4] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  mine[Cs / 4 + 1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
   if (kDual) {
-    mine[a.C / 2] = make_float4(s3[0], s3[1], s3[2], s3[3]);
-    mine[a.C / 2 + 1] = make_float4(s3[4], s3[5], s3[6], s3[7]);
+    mine[Cs / 2] = make_float4(s3[0], s3[1], s3[2], s3[3]);
+    mine[Cs / 2 + 1] = make_float4(s3[4], s3[5], s3[6], s3[7]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < q4; i += blockDim.x) {
@@ -945,15 +949,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     s_part[i] = acc;  // row 0 of the table becomes the block's partial (slot i is touched by this thread only)
   }
   __syncthreads();
-  // floats [0, 2C) -> sums, [2C, 3C) -> sums2; written, not accumulated
+  // slice-local floats [0, Cs) -> sums[c], [Cs, 2Cs) -> sums[C + c], [2Cs, 3Cs) -> sums2[c]; written, not accumulated
   float* sums = a.sums;
   float* sums2 = a.sums2;
-  const int twoC = 2 * a.C;
-  det_grid_reduce(reinterpret_cast<const float*>(s_part), kQ * a.C, a.det, [=](int i, float v) {
-    if (i < twoC)
-      sums[i] = v;
+  const int C = a.C, V = kQ * Cs;
+  const int groups = (gridDim.x + kDetGroup - 1) / kDetGroup;
+  DetScratch d;
+  d.scratch = a.det.scratch + (size_t)blockIdx.y * (gridDim.x + groups) * V;
+  d.tickets = a.det.tickets + blockIdx.y * (1 + groups);
+  det_grid_reduce(reinterpret_cast<const float*>(s_part), V, d, [=](int i, float v) {
+    const int which = i / Cs, c = c_base + i - which * Cs;
+    if (which == 0)
+      sums[c] = v;
+    else if (which == 1)
+      sums[C + c] = v;
     else
-      sums2[i - twoC] = v;
+      sums2[c] = v;
   });
 }
 
@@ -1327,17 +1338,19 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   if (!a.det.scratch) a.det = device_det_scratch();
   if (!a.det.scratch) return cudaErrorMemoryAllocation;
-  const int rows_per_iter = 256 / (a.C / 8);
-  // several rows per thread so that the block reduction and the global atomics are amortised; at most one resident wave
+  const int Cs = std::min(a.C, 256), slices = a.C / Cs;
+  const int rows_per_iter = 256 / (Cs / 8);
+  // several rows per thread so that the block reduction and the ordered grid reduction are amortised; at most one
+  // resident wave, at most kDetMaxBlocks blocks in all
   const bool dual = a.y2 != nullptr;
-  const size_t smem = (size_t)rows_per_iter * (dual ? 3 : 2) * a.C * sizeof(float);  // = 16 / 24 KB for every C
+  const size_t smem = (size_t)rows_per_iter * (dual ? 3 : 2) * Cs * sizeof(float);  // = 16 / 24 KB for every C
   if ((reinterpret_cast<uintptr_t>(a.sums) & 15) != 0 || (dual && (reinterpret_cast<uintptr_t>(a.sums2) & 15) != 0))
     return cudaErrorInvalidValue;
 #define R3M_LAUNCH(D, K)                                                                      \
   launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                   \
-                std::min(kDetMaxBlocks, grid_for((a.M + 15) / 16, rows_per_iter,                     \
-                                                 resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem))), 256, \
-                smem, s, a)
+                dim3(std::max(1, std::min(kDetMaxBlocks, std::min(grid_for((a.M + 15) / 16, rows_per_iter, 1 << 20), \
+                                          resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem))) / slices), slices), \
+                256, smem, s, a)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;
     case kMaskBits: if (dual) R3M_LAUNCH(true, kMaskBits); else R3M_LAUNCH(false, kMaskBits); break;

@@ -61,7 +61,7 @@ struct DetScratch {
 };
 constexpr int kDetMaxBlocks = 592;                              // grid cap of the kernels that reduce through it
 constexpr size_t kDetScratchFloats = (size_t)(kDetMaxBlocks + kDetMaxBlocks / 16 + 2) * 3 * 2048;
-constexpr size_t kDetTickets = 64;
+constexpr size_t kDetTickets = 128;
 DetScratch device_det_scratch();  // lazily allocated process-wide instance (kernel-level C-ABI entry points)
 
 // stem: y [N,112,112,64] -> BN -> ReLU -> maxpool 3x3 s2 p1 -> a [N,56,56,64], argmax code (0..8) per element

@@ -59,7 +59,8 @@ def _update_case(size, clips, lang, params, buffers, frames, perms, lang_emb, se
     o_metrics, o_grads, o_emb, o_post, o_buf = oracle_update_on_gpu(size, params, buffers, frames, perms, hyper,
                                                                     lang_emb, mask)
     # loss heads on IDENTICAL embeddings: north-star 1e-4
-    _check_loss_heads(eng, named, params, emb.cpu(), perms, hyper, lang_emb, mask, metrics, clips)
+    _check_loss_heads(eng, named, params, emb.cpu(), perms, hyper, lang_emb, mask, metrics, clips,
+                      enumerate_kinks=clips <= 16)
     return m, metrics, emb, ours, o_metrics, o_grads, o_emb, o_buf
 
 
