@@ -253,9 +253,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc_ntile = -1;
     // Deterministic statistics: the host sizes the grid as a multiple of num_n_tiles, so a CTA keeps ONE column block
     // (n_tile = blockIdx.x % num_n_tiles) for all its tiles and the per-lane partials never leave registers before the
-    // end.  Then: per-quadrant partials -> shared memory, summed over the four quadrants in fixed order -> this CTA's
-    // partial in global scratch -> the LAST CTA of the column block (ticket) adds the CTAs' partials in CTA order and
-    // writes the result.  No floating-point atomics anywhere: the sums are bit-identical from run to run.
+    // end.  Then: per-quadrant partials -> shared memory, summed over the four quadrants in fixed order -> added to the
+    // column block's fixed-point accumulators (fx_add: exact, order independent) -> the LAST CTA of the column block
+    // (ticket) converts the totals to fp32.  No floating-point atomics: the sums are bit-identical from run to run.
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -536,19 +536,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
       const int et = threadIdx.x - 128;  // epilogue thread index
       const int my_ntile = blockIdx.x % p.num_n_tiles;
-      const bool has_tiles = acc_ntile >= 0;  // false only when the grid exceeds the tile count (never: host clamps)
-      float* mine = p.stat_scratch + static_cast<size_t>(blockIdx.x) * (2 * BN);
-      for (int c = et; c < BN; c += EPI * 32) {
-        float sm = 0.f, sq = 0.f;
-        if (has_tiles) {
+      // this CTA's column sums -> fixed-point accumulators (exact integer adds: independent of the CTAs' arrival order)
+      unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.stat_scratch) + static_cast<size_t>(my_ntile) * BN * 4;
+      if (acc_ntile >= 0) {
+        for (int c = et; c < BN; c += EPI * 32) {
+          float sm = 0.f, sq = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             sm += s_part[(qq * BN + c) * 2];
             sq += s_part[(qq * BN + c) * 2 + 1];
           }
+          fx_add(acc + 4 * c, sm);
+          fx_add(acc + 4 * c + 2, sq);
         }
-        mine[2 * c] = sm;
-        mine[2 * c + 1] = sq;
       }
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
@@ -556,24 +556,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (et == 0) {
         const int contributors = (gridDim.x - my_ntile + p.num_n_tiles - 1) / p.num_n_tiles;
         const int t = atomicAdd(&p.stat_ticket[my_ntile], 1);
-        *s_flag = (t == contributors - 1) ? contributors : 0;
+        *s_flag = (t == contributors - 1) ? 1 : 0;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
-      const int contributors = *s_flag;
-      if (contributors > 0) {
+      if (*s_flag) {
+        // last CTA of the column block: totals -> fp32, accumulators and ticket back to zero for the next launch
         __threadfence();
         for (int c = et; c < BN; c += EPI * 32) {
-          float sm = 0.f, sq = 0.f;
-          for (int i = 0; i < contributors; ++i) {
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(
-                p.stat_scratch + static_cast<size_t>(my_ntile + i * p.num_n_tiles) * (2 * BN) + 2 * c));
-            sm += v.x;
-            sq += v.y;
-          }
-          p.stat_sum[my_ntile * BN + c] = sm;
-          p.stat_sq[my_ntile * BN + c] = sq;
+          const unsigned long long l0 = __ldcg(acc + 4 * c), h0 = __ldcg(acc + 4 * c + 1);
+          const unsigned long long l1 = __ldcg(acc + 4 * c + 2), h1 = __ldcg(acc + 4 * c + 3);
+          p.stat_sum[my_ntile * BN + c] = fx_to_float(l0, h0);
+          p.stat_sq[my_ntile * BN + c] = fx_to_float(l1, h1);
+          acc[4 * c] = 0ull;
+          acc[4 * c + 1] = 0ull;
+          acc[4 * c + 2] = 0ull;
+          acc[4 * c + 3] = 0ull;
         }
-        if (et == 0) p.stat_ticket[my_ntile] = 0;  // ready for the next launch (stream order)
+        if (et == 0) p.stat_ticket[my_ntile] = 0;
       }
     }
   }

@@ -28,9 +28,10 @@ struct ConvKernelParams {
   int ldo;
   int oH, oW, o_stride, o_h0, o_w0;
   int accumulate;  // out += result (bf16 read-modify-write)
-  // optional per-channel statistics of the (bf16-rounded) output: WRITTEN (not accumulated), deterministically:
-  // per-CTA partials go to stat_scratch [grid][2 * BN], the last CTA of each column block (stat_ticket, one zeroed int
-  // per column block, self-resetting) adds them in CTA order.  The grid must be a multiple of num_n_tiles.
+  // optional per-channel statistics of the (bf16-rounded) output: WRITTEN (not accumulated), deterministically: every
+  // CTA adds its column sums to fixed-point accumulators in stat_scratch (Cout * 2 values * 16 bytes, zero on entry and
+  // exit), the last CTA of each column block (stat_ticket, one zeroed int per column block, self-resetting) converts
+  // them to fp32.  The grid must be a multiple of num_n_tiles.
   float* stat_sum;
   float* stat_sq;
   float* stat_scratch;

@@ -117,45 +117,29 @@ __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const
 }
 
 // ------------------------------------------------------------------------------------------------ ordered reduce
-// Deterministic grid-wide sum of per-block partial vectors (V floats each): no floating-point atomics.  Blocks write
-// their partial to scratch; the last block of every group of kDetGroup consecutive blocks (ticket) adds the group's
-// partials in block order; the last group to finish adds the group sums in group order and hands every total to
-// emit(i, value).  The summation tree is fixed by the launch geometry, so the result is bit-identical from run to run.
-// scratch: (gridDim.x + groups) * V floats; tickets: 1 + groups ints, zero on entry, zero again on exit.
-constexpr int kDetGroup = 16;
+// Deterministic grid-wide sum of per-block partial vectors (V floats each).  Every block adds its partial into V
+// fixed-point accumulators (fx_add, ptx.cuh: exact integer arithmetic, so the arrival order does not matter — fp32
+// atomics would make the result depend on it); the last block to arrive (ticket) converts the totals to fp32, hands them
+// to emit(i, value) and clears the accumulators for the next launch.  One short tail instead of a multi-level tree.
+// d.scratch: V * 2 64-bit words, zero on entry and on exit; d.tickets: one int, likewise.  Blocks along x reduce
+// together (a caller with several blockIdx.y slices passes each slice its own DetScratch).
 template <class Emit>
 __device__ __forceinline__ void det_grid_reduce(const float* partial, int V, const DetScratch d, Emit emit) {
   __shared__ int s_last;
-  const int G = gridDim.x, tid = threadIdx.x;  // blocks along x reduce together; d is per blockIdx.y slice
-  float* mine = d.scratch + (size_t)blockIdx.x * V;
-  for (int i = tid; i < V; i += blockDim.x) mine[i] = partial[i];
+  const int tid = threadIdx.x;
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(d.scratch);
+  for (int i = tid; i < V; i += blockDim.x) fx_add(acc + 2 * i, partial[i]);
   __threadfence();
   __syncthreads();
-  const int ngroups = (G + kDetGroup - 1) / kDetGroup, grp = blockIdx.x / kDetGroup;
-  const int gsize = min(kDetGroup, G - grp * kDetGroup);
-  if (tid == 0) s_last = (atomicAdd(&d.tickets[1 + grp], 1) == gsize - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  float* gsum = d.scratch + (size_t)(G + grp) * V;
-  for (int i = tid; i < V; i += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < gsize; ++b) a += __ldcg(d.scratch + (size_t)(grp * kDetGroup + b) * V + i);
-    gsum[i] = a;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    d.tickets[1 + grp] = 0;
-    s_last = (atomicAdd(&d.tickets[0], 1) == ngroups - 1) ? 1 : 0;
-  }
+  if (tid == 0) s_last = (atomicAdd(&d.tickets[0], 1) == (int)gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   for (int i = tid; i < V; i += blockDim.x) {
-    float a = 0.f;
-    for (int g = 0; g < ngroups; ++g) a += __ldcg(d.scratch + (size_t)(G + g) * V + i);
-    emit(i, a);
+    const unsigned long long lo = __ldcg(acc + 2 * i), hi = __ldcg(acc + 2 * i + 1);
+    emit(i, fx_to_float(lo, hi));
+    acc[2 * i] = 0ull;
+    acc[2 * i + 1] = 0ull;
   }
   if (tid == 0) d.tickets[0] = 0;
 }
@@ -877,8 +861,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * Cs / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
   constexpr int kQ = kDual ? 3 : 2;
   // Wide layers are cut into channel slices of Cs = 256 (blockIdx.y): a block then covers 8 rows per iteration instead
-  // of 1 and its partial vector is kQ * 256 floats instead of kQ * C, which keeps the ordered reduction's scratch
-  // traffic far below the tensor's own (C = 2048: 1.8 MB instead of 14.5 MB).
+  // of 1 and its partial vector (one fixed-point atomic or two per entry) is kQ * 256 floats instead of kQ * C.
   const int Cs = min(a.C, 256), c_base = blockIdx.y * Cs;
   const int C8 = Cs >> 3, ld8c = a.C >> 3;
   const int chunk = threadIdx.x % C8;
@@ -953,10 +936,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   float* sums = a.sums;
   float* sums2 = a.sums2;
   const int C = a.C, V = kQ * Cs;
-  const int groups = (gridDim.x + kDetGroup - 1) / kDetGroup;
   DetScratch d;
-  d.scratch = a.det.scratch + (size_t)blockIdx.y * (gridDim.x + groups) * V;
-  d.tickets = a.det.tickets + blockIdx.y * (1 + groups);
+  d.scratch = a.det.scratch + (size_t)blockIdx.y * V * 4;  // V accumulators of two 64-bit words
+  d.tickets = a.det.tickets + blockIdx.y;
   det_grid_reduce(reinterpret_cast<const float*>(s_part), V, d, [=](int i, float v) {
     const int which = i / Cs, c = c_base + i - which * Cs;
     if (which == 0)
@@ -1348,8 +1330,10 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
     return cudaErrorInvalidValue;
 #define R3M_LAUNCH(D, K)                                                                      \
   launch_kernel(bn_bwd_reduce_kernel<D, K>,                                                   \
-                dim3(std::max(1, std::min(kDetMaxBlocks, std::min(grid_for((a.M + 15) / 16, rows_per_iter, 1 << 20), \
-                                          resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem))) / slices), slices), \
+                dim3(std::max(1, std::min(std::min(kDetMaxBlocks, resident_blocks<bn_bwd_reduce_kernel<D, K>>(256, smem)) / \
+                                              slices,                                                       \
+                                          grid_for((a.M + 15) / 16, rows_per_iter, 1 << 20))),                \
+                     slices),                                                                               \
                 256, smem, s, a)
   switch (mask_kind(a)) {
     case kMaskAct: if (dual) R3M_LAUNCH(true, kMaskAct); else R3M_LAUNCH(false, kMaskAct); break;

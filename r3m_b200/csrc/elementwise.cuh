@@ -52,15 +52,15 @@ struct BnApplyArgs {
 };
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s);
 
-// Scratch of the deterministic grid-wide reductions (see det_grid_reduce in elementwise.cu): `scratch` holds
-// (blocks + blocks / 16 + 1) partial vectors, `tickets` 1 + blocks / 16 + 1 zero-initialised (self-resetting) ints.
-// Launches that share one DetScratch must be stream-ordered.
+// Scratch of the deterministic grid-wide reductions (see det_grid_reduce in elementwise.cu): `scratch` holds the
+// fixed-point accumulators (two 64-bit words per reduced value), `tickets` one int per channel slice; both zero on
+// entry and left zero on exit.  Launches that share one DetScratch must be stream-ordered.
 struct DetScratch {
   float* scratch = nullptr;
   int* tickets = nullptr;
 };
-constexpr int kDetMaxBlocks = 592;                              // grid cap of the kernels that reduce through it
-constexpr size_t kDetScratchFloats = (size_t)(kDetMaxBlocks + kDetMaxBlocks / 16 + 2) * 3 * 2048;
+constexpr int kDetMaxBlocks = 1184;                             // grid cap of the kernels that reduce through it
+constexpr size_t kDetScratchFloats = (size_t)3 * 2048 * 4;      // 3 * C accumulators of 16 bytes, C <= 2048
 constexpr size_t kDetTickets = 128;
 DetScratch device_det_scratch();  // lazily allocated process-wide instance (kernel-level C-ABI entry points)
 

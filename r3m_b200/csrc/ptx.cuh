@@ -219,6 +219,50 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// ---------------------------------------------------------------------------------------------
+// order-independent (hence run-to-run deterministic) accumulation of floats
+// ---------------------------------------------------------------------------------------------
+// A 128-bit two's-complement fixed-point accumulator (Q64.64: resolution 2^-64 ~ 5e-20, range +-9e18) held in two
+// 64-bit words {lo, hi}.  A float converts to it exactly (24-bit mantissa, any exponent in range; bits below 2^-64 are
+// truncated) and integer addition is associative, so the sum does not depend on the order in which blocks arrive —
+// unlike fp32 atomics.  Cost: one or two 64-bit atomics per value.
+__device__ __forceinline__ void fx_add(unsigned long long* acc, float v) {
+  if (v == 0.f || !(fabsf(v) < 9.0e18f)) return;  // zeros, and inf / nan / out of range (never produced by sane inputs)
+  int e;
+  const float m = frexpf(fabsf(v), &e);                  // |v| = m * 2^e, m in [0.5, 1)
+  const unsigned long long mant = (unsigned long long)(m * 16777216.f);  // 24-bit integer, exact
+  const int shift = e - 24 + 64;                         // |v| * 2^64 = mant << shift
+  unsigned long long lo, hi;
+  if (shift >= 64) {
+    hi = mant << (shift - 64);
+    lo = 0ull;
+  } else if (shift >= 0) {
+    lo = mant << shift;
+    hi = shift > 40 ? (mant >> (64 - shift)) : 0ull;
+  } else {
+    lo = shift > -24 ? (mant >> (-shift)) : 0ull;
+    hi = 0ull;
+  }
+  if (v < 0.f) {
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  if (lo != 0ull) {
+    const unsigned long long old = atomicAdd(acc, lo);
+    if (old + lo < old) hi += 1ull;  // carry out of the low word
+  }
+  if (hi != 0ull) atomicAdd(acc + 1, hi);
+}
+__device__ __forceinline__ float fx_to_float(unsigned long long lo, unsigned long long hi) {
+  const bool neg = (hi >> 63) != 0ull;
+  if (neg) {
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  const double v = (double)hi + (double)lo * 5.42101086242752217e-20;  // 2^-64
+  return (float)(neg ? -v : v);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
