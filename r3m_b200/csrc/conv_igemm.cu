@@ -537,7 +537,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int et = threadIdx.x - 128;  // epilogue thread index
       const int my_ntile = blockIdx.x % p.num_n_tiles;
       // this CTA's column sums -> fixed-point accumulators (exact integer adds: independent of the CTAs' arrival order)
-      unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.stat_scratch) + static_cast<size_t>(my_ntile) * BN * 4;
+      // raw mode (engine): the layer's own accumulators, converted by the consuming BatchNorm kernel — no tail at all
+      unsigned long long* acc = (p.stat_raw ? reinterpret_cast<unsigned long long*>(p.stat_sum)
+                                            : reinterpret_cast<unsigned long long*>(p.stat_scratch)) +
+                                static_cast<size_t>(my_ntile) * BN * 4;
       if (acc_ntile >= 0) {
         for (int c = et; c < BN; c += EPI * 32) {
           float sm = 0.f, sq = 0.f;
@@ -550,6 +553,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           fx_add(acc + 4 * c + 2, sq);
         }
       }
+      if (!p.stat_raw) {
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
       int* s_flag = reinterpret_cast<int*>(tmem_slot) + 2;
@@ -573,6 +577,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           acc[4 * c + 3] = 0ull;
         }
         if (et == 0) p.stat_ticket[my_ntile] = 0;
+      }
       }
     }
   }
@@ -609,8 +614,8 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense, 1>(tmA, tmB, tmC, p, grid, stream);
   }
   if (p.stat_sum != nullptr) {
-    if (p.out_mode != 0 || p.ep_scale != nullptr || p.stat_sq == nullptr || p.stat_scratch == nullptr ||
-        p.stat_ticket == nullptr || grid % p.num_n_tiles != 0)
+    if (p.out_mode != 0 || p.ep_scale != nullptr || grid % p.num_n_tiles != 0 ||
+        (!p.stat_raw && (p.stat_sq == nullptr || p.stat_scratch == nullptr || p.stat_ticket == nullptr)))
       return cudaErrorInvalidValue;
     return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeStats>(tmA, tmB, tmC, p, grid, stream);
   }

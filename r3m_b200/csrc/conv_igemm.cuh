@@ -36,6 +36,8 @@ struct ConvKernelParams {
   float* stat_sq;
   float* stat_scratch;
   int* stat_ticket;
+  int stat_raw;  // 1: stat_sum points at the layer's own accumulators (Cout * 4 64-bit words, zero on entry); the kernel
+                 // only adds into them and the consumer converts (no scratch, no ticket, no finalize tail)
   // optional fused epilogue (inference: BatchNorm folded into a per-channel affine): out = [relu](acc * ep_scale[c] +
   // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.
   const float* ep_scale;

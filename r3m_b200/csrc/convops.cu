@@ -118,7 +118,8 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.stat_sq = g.stat_sq;
   p.stat_scratch = g.stat_scratch;
   p.stat_ticket = g.stat_ticket;
-  if (g.stat_sum && !g.stat_scratch) {
+  p.stat_raw = g.stat_raw;
+  if (g.stat_sum && !g.stat_scratch && !g.stat_raw) {
     float* shared = device_stat_scratch();
     if (!shared) return "could not allocate the statistics scratch";
     p.stat_scratch = shared;

@@ -29,6 +29,7 @@ struct GatherConv {
   // a process-wide buffer (launches that share it must be stream-ordered)
   float* stat_scratch = nullptr;
   int* stat_ticket = nullptr;
+  int stat_raw = 0;  // 1: stat_sum is the layer's raw fixed-point accumulator block (see ConvKernelParams)
   // fused inference epilogue (see ConvKernelParams): per-channel affine (+ residual) (+ ReLU) on the accumulators
   const float* ep_scale = nullptr;
   const float* ep_shift = nullptr;

@@ -84,12 +84,27 @@ __device__ __forceinline__ void st8(bf16* p, const F8& f) {
 #endif
 }
 
-__device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, float inv_m, const float* gamma,
-                                          const float* beta, const float* rm, const float* rv, int c, float& scale,
-                                          float& shift, float& mean, float& var) {
+// Per-channel statistics arrive either as fp32 arrays or "raw": the fixed-point accumulators the producing kernel added
+// into (fx_add, ptx.cuh) — the engine's path: no finalize pass in the producer, the consumer converts on read.
+//   conv statistics  raw layout: channel c -> words [4c, 4c+1] = sum, [4c+2, 4c+3] = sum of squares (sum == sq == base)
+//   backward sums    raw layout: entry i   -> words [2i, 2i+1]
+__device__ __forceinline__ float stat_at(const float* p, int raw, int c, int which) {
+  if (!raw) return p[c];
+  const unsigned long long* acc = reinterpret_cast<const unsigned long long*>(p) + 4 * c + 2 * which;
+  return fx_to_float(__ldg(acc), __ldg(acc + 1));
+}
+__device__ __forceinline__ float bsum_at(const float* p, int raw, int i) {
+  if (!raw) return p[i];
+  const unsigned long long* acc = reinterpret_cast<const unsigned long long*>(p) + 2 * i;
+  return fx_to_float(__ldg(acc), __ldg(acc + 1));
+}
+
+__device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, int raw, float inv_m,
+                                          const float* gamma, const float* beta, const float* rm, const float* rv, int c,
+                                          float& scale, float& shift, float& mean, float& var) {
   if (train) {
-    mean = sum[c] * inv_m;
-    var = fmaxf(sq[c] * inv_m - mean * mean, 0.f);
+    mean = stat_at(sum, raw, c, 0) * inv_m;
+    var = fmaxf(stat_at(sq, raw, c, 1) * inv_m - mean * mean, 0.f);
   } else {
     mean = rm[c];
     var = rv[c];
@@ -100,12 +115,12 @@ __device__ __forceinline__ void bn_coeffs(int train, const float* sum, const flo
 }
 
 // block 0 publishes the batch statistics for backward and folds them into the running estimates
-__device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const float* sq, float* save_mean,
+__device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const float* sq, int raw, float* save_mean,
                                            float* save_rstd, float* rm, float* rv, int update_running) {
   const float inv_m = 1.0f / (float)M;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = sum[c] * inv_m;
-    const float var = fmaxf(sq[c] * inv_m - mean * mean, 0.f);
+    const float mean = stat_at(sum, raw, c, 0) * inv_m;
+    const float var = fmaxf(stat_at(sq, raw, c, 1) * inv_m - mean * mean, 0.f);
     if (save_mean) save_mean[c] = mean;
     if (save_rstd) save_rstd[c] = 1.0f / sqrtf(var + kBnEps);
     if (update_running && rm && rv) {
@@ -390,12 +405,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float mean, var;
-    bn_coeffs(a.train, a.sum, a.sq, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
               mean, var);
     sc2[j] = 0.f;
     if (dual) {
       float shift2;
-      bn_coeffs(a.train, a.sum2, a.sq2, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, chunk * 8 + j,
+      bn_coeffs(a.train, a.sum2, a.sq2, a.stat_raw, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, chunk * 8 + j,
                 sc2[j], shift2, mean, var);
       sh[j] += shift2;
     }
@@ -436,9 +451,9 @@ R3M_UNROLL(R3M_BN_APPLY_UNROLL)
   if (a.train && blockIdx.x == 0) {
     // every block has already read sum/sq into registers for its own coefficients; running stats are separate
     // buffers, so the in-place update below cannot race with other blocks
-    bn_publish(a.C, a.M, a.sum, a.sq, a.save_mean, a.save_rstd, a.running_mean, a.running_var, a.update_running);
+    bn_publish(a.C, a.M, a.sum, a.sq, a.stat_raw, a.save_mean, a.save_rstd, a.running_mean, a.running_var, a.update_running);
     if (dual)
-      bn_publish(a.C, a.M, a.sum2, a.sq2, a.save_mean2, a.save_rstd2, a.running_mean2, a.running_var2,
+      bn_publish(a.C, a.M, a.sum2, a.sq2, a.stat_raw, a.save_mean2, a.save_rstd2, a.running_mean2, a.running_var2,
                  a.update_running);
   }
 }
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float mean, var;
-    bn_coeffs(a.train, a.sum, a.sq, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
               mean, var);
   }
 #pragma unroll
@@ -549,7 +564,7 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
   }
   pdl_done();
   if (a.train && blockIdx.x == 0) {
-    bn_publish(a.C, a.N * a.H * a.W, a.sum, a.sq, a.save_mean, a.save_rstd, a.running_mean, a.running_var,
+    bn_publish(a.C, a.N * a.H * a.W, a.sum, a.sq, a.stat_raw, a.save_mean, a.save_rstd, a.running_mean, a.running_var,
                a.update_running);
   }
 }
@@ -662,7 +677,7 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
     const int c = chunk * 8 + j;
     if (kApply) {
       const float mean = a.mean[c], rstd = a.rstd[c];
-      const float mdz = a.sums[c] * inv_m, mdzx = a.sums[a.C + c] * inv_m;
+      const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
       c0[j] = a.gamma[c] * rstd;
       c1[j] = -c0[j] * rstd * mdzx;
       c2[j] = -c0[j] * mdz - c1[j] * mean;
@@ -748,11 +763,16 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
   if (!kApply) {
     block_channel_sums(c1, c2, a.rstd, chunk, a.C, s_tab, s_red);
     float* sums = a.sums;
-    det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
+    if (a.sums_raw) {
+      unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
+      for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + 2 * i, s_red[i]);
+    } else {
+      det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
+    }
   } else if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      if (a.dbeta) a.dbeta[c] = a.sums[c];
-      if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+      if (a.dbeta) a.dbeta[c] = bsum_at(a.sums, a.sums_raw, c);
+      if (a.dgamma) a.dgamma[c] = bsum_at(a.sums, a.sums_raw, a.C + c);
     }
   }
 }
@@ -793,7 +813,12 @@ __global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemB
   pdl_done();
   block_channel_sums(s1, s2, a.rstd, chunk, a.C, s_tab, s_red);
   float* sums = a.sums;
-  det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
+  if (a.sums_raw) {
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + 2 * i, s_red[i]);
+  } else {
+    det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ avg pool
@@ -936,6 +961,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   float* sums = a.sums;
   float* sums2 = a.sums2;
   const int C = a.C, V = kQ * Cs;
+  if (a.sums_raw) {
+    // engine path: straight into the layer's own fixed-point accumulators (zeroed per step); bn_bwd_apply converts
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
+    unsigned long long* acc2 = reinterpret_cast<unsigned long long*>(sums2);
+    const float* part = reinterpret_cast<const float*>(s_part);
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      const int which = i / Cs, c = c_base + i - which * Cs;
+      fx_add(which == 2 ? acc2 + 2 * c : acc + 2 * (which * C + c), part[i]);
+    }
+    return;
+  }
   DetScratch d;
   d.scratch = a.det.scratch + (size_t)blockIdx.y * V * 4;  // V accumulators of two 64-bit words
   d.tickets = a.det.tickets + blockIdx.y;
@@ -965,13 +1001,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
     const float mean = a.mean[c], rstd = a.rstd[c];
-    const float mdz = a.sums[c] * inv_m, mdzx = a.sums[a.C + c] * inv_m;
+    const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
     cA[j] = a.gamma[c] * rstd;
     cB[j] = -cA[j] * rstd * mdzx;
     cC[j] = -cA[j] * mdz - cB[j] * mean;
     if (kDual) {
       const float mean2 = a.mean2[c], rstd2 = a.rstd2[c];
-      const float mdzx2 = a.sums2[c] * inv_m;
+      const float mdzx2 = bsum_at(a.sums2, a.sums_raw, c) * inv_m;
       cA2[j] = a.gamma2[c] * rstd2;
       cB2[j] = -cA2[j] * rstd2 * mdzx2;
       cC2[j] = -cA2[j] * mdz - cB2[j] * mean2;
@@ -1013,11 +1049,11 @@ R3M_UNROLL(R3M_BN_BWD_UNROLL)
   pdl_done();
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      if (a.dbeta) a.dbeta[c] = a.sums[c];
-      if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+      if (a.dbeta) a.dbeta[c] = bsum_at(a.sums, a.sums_raw, c);
+      if (a.dgamma) a.dgamma[c] = bsum_at(a.sums, a.sums_raw, a.C + c);
       if (kDual) {
-        if (a.dbeta2) a.dbeta2[c] = a.sums[c];
-        if (a.dgamma2) a.dgamma2[c] = a.sums2[c];
+        if (a.dbeta2) a.dbeta2[c] = bsum_at(a.sums, a.sums_raw, c);
+        if (a.dgamma2) a.dgamma2[c] = bsum_at(a.sums2, a.sums_raw, c);
       }
     }
   }

@@ -37,6 +37,9 @@ struct BnApplyArgs {
   float* save_mean = nullptr;   // [C] written in train mode (for backward)
   float* save_rstd = nullptr;
   int update_running = 1;
+  // 1: sum (== sq) and sum2 (== sq2) point at the producing conv's raw fixed-point accumulators (4 64-bit words per
+  // channel: sum lo/hi, sum-of-squares lo/hi; see fx_add) instead of fp32 arrays — the engine's path
+  int stat_raw = 0;
   uint8_t* mask_out = nullptr;  // optional [M][C/8]: bit j of byte (row, chunk) = (a[row][8*chunk+j] > 0)
   // optional second BatchNorm whose (un-activated) output is added before the ReLU: the downsample branch of a
   // residual block, a = relu(bn(y) + bn2(y2))  (tv resnet.py:100-103, 155-161) without materialising bn2(y2)
@@ -81,6 +84,7 @@ struct StemPoolArgs {
   float* save_mean = nullptr;
   float* save_rstd = nullptr;
   int update_running = 1;
+  int stat_raw = 0;  // see BnApplyArgs
 };
 cudaError_t launch_stem_bn_relu_maxpool(const StemPoolArgs& a, cudaStream_t s);
 // dz[n,h,w,c] = sum over pooling windows whose argmax is (h,w) of dA[window]   (dead maxima carry code 15: no match)
@@ -105,6 +109,9 @@ struct StemBwdArgs {
   float* dgamma = nullptr;
   float* dbeta = nullptr;
   DetScratch det;                  // null members: the process-wide instance
+  // 1: `sums` is 2C raw fixed-point accumulators (two 64-bit words each, zero on entry): the reduce pass adds into them
+  // and the apply pass converts on read — no finalize tail (the engine's path)
+  int sums_raw = 0;
 };
 cudaError_t launch_stem_bwd(const StemBwdArgs& a, cudaStream_t s);
 
@@ -122,6 +129,8 @@ struct BnBwdArgs {
   const float* gamma = nullptr;
   float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); written by the reduce pass
   DetScratch det;             // deterministic reduction scratch (null members: the process-wide instance)
+  int sums_raw = 0;           // 1: sums / sums2 are raw fixed-point accumulators (2C / C entries of two 64-bit words,
+                              // zero on entry); the apply pass converts on read (the engine's path)
   void* dy = nullptr;         // bf16 [M][C] gradient w.r.t. the raw conv output
   void* dz_out = nullptr;     // optional bf16 [M][C]: masked gradient (feeds the residual branch)
   float* dgamma = nullptr;    // [C]

@@ -20,7 +20,10 @@ struct Engine::Conv {
   bool stem = false;
   size_t w_off = 0, gamma_off = 0, beta_off = 0;  // flat parameter buffer (elements)
   size_t rm_off = 0, rv_off = 0;                  // BN buffers region (floats)
-  size_t zero_off = 0;                            // per-step zeroed region (floats): sum[C] sq[C] bwd_sums[2C]
+  // per-step zeroed region (floats): fixed-point accumulators (fx_add, ptx.cuh) of the layer's BatchNorm reductions —
+  // [0, 8C) forward statistics (sum, sum of squares: 4 64-bit words per channel), [8C, 16C) backward sums (2C entries of
+  // 2 words), [16C, 20C) the downsample branch's extra backward sum (C entries)
+  size_t zero_off = 0;
   size_t save_off = 0;                            // saved batch statistics (floats): mean[C] rstd[C]
   size_t wd_off = 0;                              // dgrad-packed filters (bf16 elements)
   size_t y_off = 0, a_off = 0;                    // arena byte offsets of the raw / activated outputs
@@ -153,7 +156,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
     c->beta_off = take(np, c->Cout, 128);
     c->rm_off = take(nb, c->Cout, 32);
     c->rv_off = take(nb, c->Cout, 32);
-    c->zero_off = take(nz, 5 * (size_t)c->Cout, 32);  // sum, sq, bwd sums (2C), downsample-branch bwd sum
+    c->zero_off = take(nz, 20 * (size_t)c->Cout, 32);
     c->save_off = take(ns, 2 * (size_t)c->Cout, 32);
     if (!c->stem) c->wd_off = take(nwd, wn, 128);
     TensorInfo t;
@@ -321,7 +324,8 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.relu = relu;
   a.train = train;
   a.sum = zero + c.zero_off;
-  a.sq = zero + c.zero_off + c.Cout;
+  a.sq = a.sum;
+  a.stat_raw = 1;
   a.gamma = P + c.gamma_off;
   a.beta = P + c.beta_off;
   a.running_mean = buf + c.rm_off;
@@ -334,7 +338,7 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
     const Conv& d = *second;
     a.y2 = d.y;
     a.sum2 = zero + d.zero_off;
-    a.sq2 = zero + d.zero_off + d.Cout;
+    a.sq2 = a.sum2;
     a.gamma2 = P + d.gamma_off;
     a.beta2 = P + d.beta_off;
     a.running_mean2 = buf + d.rm_off;
@@ -413,10 +417,9 @@ std::string Engine::plan_all() {
       gc.wpk = Pb + c.w_off;
     }
     if (train) {
-      gc.stat_sum = zero + c.zero_off;
-      gc.stat_sq = zero + c.zero_off + c.Cout;
-      gc.stat_scratch = reinterpret_cast<float*>(ws_ + off_det_);
-      gc.stat_ticket = reinterpret_cast<int*>(ws_ + off_det_ + kStatScratchFloats * 4);
+      gc.stat_sum = zero + c.zero_off;  // the layer's raw accumulators: the BatchNorm kernels convert on read
+      gc.stat_sq = gc.stat_sum;
+      gc.stat_raw = 1;
     }
     return gc;
   };
@@ -436,7 +439,8 @@ std::string Engine::plan_all() {
       a.N = N;
       a.train = train;
       a.sum = zero + st.zero_off;
-      a.sq = zero + st.zero_off + 64;
+      a.sq = a.sum;
+      a.stat_raw = 1;
       a.gamma = P + st.gamma_off;
       a.beta = P + st.beta_off;
       a.running_mean = buf + st.rm_off;
@@ -706,7 +710,8 @@ std::string Engine::plan_all() {
     a.mean = saved + c.save_off;
     a.rstd = saved + c.save_off + c.Cout;
     a.gamma = P + c.gamma_off;
-    a.sums = zero + c.zero_off + 2 * c.Cout;
+    a.sums = zero + c.zero_off + 8 * c.Cout;
+    a.sums_raw = 1;
     a.dy = dy;
     a.dz_out = dz_out;
     a.dgamma = G + c.gamma_off;
@@ -719,7 +724,7 @@ std::string Engine::plan_all() {
       a.mean2 = saved + d.save_off;
       a.rstd2 = saved + d.save_off + d.Cout;
       a.gamma2 = P + d.gamma_off;
-      a.sums2 = zero + c.zero_off + 4 * c.Cout;
+      a.sums2 = zero + c.zero_off + 16 * c.Cout;
       a.dy2 = dy2;
       a.dgamma2 = G + d.gamma_off;
       a.dbeta2 = G + d.beta_off;
@@ -883,7 +888,8 @@ std::string Engine::plan_all() {
     sb.mean = saved + st.save_off;
     sb.rstd = saved + st.save_off + 64;
     sb.gamma = P + st.gamma_off;
-    sb.sums = zero + st.zero_off + 2 * 64;
+    sb.sums = zero + st.zero_off + 8 * 64;
+    sb.sums_raw = 1;
     sb.dy = s2;
     sb.dgamma = G + st.gamma_off;
     sb.dbeta = G + st.beta_off;
@@ -1316,8 +1322,8 @@ std::string Engine::debug_run_block_backward(int block, cudaStream_t stream) {
   if (b.ds >= 0) cs.push_back(b.ds);
   for (int ci : cs) {
     const Conv& c = *convs_[ci];
-    cudaError_t e = cudaMemsetAsync(reinterpret_cast<float*>(ws_ + off_zero_) + c.zero_off + 2 * c.Cout, 0,
-                                    3 * (size_t)c.Cout * 4, stream);
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<float*>(ws_ + off_zero_) + c.zero_off + 8 * c.Cout, 0,
+                                    12 * (size_t)c.Cout * 4, stream);
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   }
   const bool saved = profiling_;
