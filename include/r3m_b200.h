@@ -120,6 +120,12 @@ int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* ym
                            const float* mean, const float* rstd, const float* gamma, float* sums, void* dy,
                            float* dgamma, float* dbeta, void* stream);
 
+/* Test hook of the deterministic reductions: out[0] = the exact sum of x[0..n) rounded once to fp32, accumulated by
+ * `blocks` thread blocks through the 128-bit fixed-point accumulators that replace fp32 atomics in the step's
+ * BatchNorm statistics / BatchNorm-backward sums (aten's cudnn_batch_norm reductions are order dependent; these are
+ * not).  The result is independent of `blocks`. */
+int r3m_b200_ordered_sum(const float* x, size_t n, float* out, int blocks, void* stream);
+
 /* Side-band upload of the step's small host inputs (replaces the `.cuda()` calls of r3m/trainer.py:108 and the index
  * tensors of :86-92,135-137): dst (device) <- host_pinned (page-locked host memory, device-accessible under unified
  * addressing), copied by a kernel on `stream` instead of the H2D copy engine, so it never queues behind a bulk frame

@@ -1497,4 +1497,33 @@ cudaError_t launch_stem_pack_f32(const float* w_oihw, float* wp, cudaStream_t s)
   return cudaGetLastError();
 }
 
+namespace {
+__global__ void __launch_bounds__(256) ordered_sum_kernel(const float* __restrict__ x, size_t n, unsigned long long* acc,
+                                                          int* ticket, float* __restrict__ out) {
+  pdl_sync();
+  __shared__ int s_last;
+  // one fx_add per element on purpose: the test wants to see that ANY grouping / order gives the same bits
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) fx_add(acc, x[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    out[0] = fx_to_float(__ldcg(acc), __ldcg(acc + 1));
+    acc[0] = 0ull;
+    acc[1] = 0ull;
+    *ticket = 0;
+  }
+}
+}  // namespace
+
+cudaError_t launch_ordered_sum(const float* x, size_t n, float* out, int blocks, cudaStream_t s) {
+  DetScratch d = device_det_scratch();
+  if (!d.scratch) return cudaErrorMemoryAllocation;
+  launch_kernel(ordered_sum_kernel, std::max(1, std::min(blocks, 1024)), 256, 0, s, x, n,
+                reinterpret_cast<unsigned long long*>(d.scratch), d.tickets, out);
+  return cudaGetLastError();
+}
+
 }  // namespace r3m

@@ -192,4 +192,8 @@ cudaError_t launch_maxpool_f32(const float* y, float* a, int N, int H, int W, in
 cudaError_t launch_avgpool_fwd_f32(const float* a, float* out, int N, int HW, int C, cudaStream_t s);
 cudaError_t launch_stem_pack_f32(const float* w_oihw, float* wp, cudaStream_t s);
 
+// out[0] = the EXACT sum of x[0..n) rounded once to fp32, through the fixed-point accumulators every deterministic
+// reduction of the step uses (test hook: the result must not depend on `blocks`, i.e. on grouping and arrival order)
+cudaError_t launch_ordered_sum(const float* x, size_t n, float* out, int blocks, cudaStream_t s);
+
 }  // namespace r3m

@@ -253,14 +253,33 @@ __device__ __forceinline__ void fx_add(unsigned long long* acc, float v) {
   }
   if (hi != 0ull) atomicAdd(acc + 1, hi);
 }
+// exact value of the accumulator rounded to nearest-even fp32; integer arithmetic only (fp64 is slow on this part)
 __device__ __forceinline__ float fx_to_float(unsigned long long lo, unsigned long long hi) {
   const bool neg = (hi >> 63) != 0ull;
   if (neg) {
     lo = ~lo + 1ull;
     hi = ~hi + (lo == 0ull ? 1ull : 0ull);
   }
-  const double v = (double)hi + (double)lo * 5.42101086242752217e-20;  // 2^-64
-  return (float)(neg ? -v : v);
+  if ((hi | lo) == 0ull) return 0.f;
+  const int lz = hi ? __clzll((long long)hi) : 64 + __clzll((long long)lo);  // leading zeros of the 128-bit magnitude
+  unsigned long long top, rest;  // magnitude << lz: top = bits 127..64, rest = bits 63..0
+  if (lz == 0) {
+    top = hi;
+    rest = lo;
+  } else if (lz < 64) {
+    top = (hi << lz) | (lo >> (64 - lz));
+    rest = lo << lz;
+  } else {
+    top = lz == 64 ? lo : lo << (lz - 64);
+    rest = 0ull;
+  }
+  unsigned int mant = (unsigned int)(top >> 40);  // 24 significant bits
+  const bool round_bit = ((top >> 39) & 1ull) != 0ull;
+  const bool sticky = ((top & ((1ull << 39) - 1ull)) | rest) != 0ull;
+  if (round_bit && (sticky || (mant & 1u))) ++mant;  // may reach 2^24: still exact in fp32
+  // bit 127 of the shifted magnitude weighs 2^(63 - lz); it is bit 23 of mant
+  const float v = (float)mant * __int_as_float((40 - lz + 127) << 23);
+  return neg ? -v : v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -79,3 +79,31 @@ def test_resume_from_snapshot_is_bit_exact(tmp_path):
     sd_b, sd_ref = model_b.state_dict(), model_ref.state_dict()
     assert all(torch.equal(sd_b[k], sd_ref[k]) for k in sd_ref)
     assert int(sd_b["module.convnet.bn1.num_batches_tracked"]) == 3
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-6, 1e5])
+def test_fixed_point_accumulator_is_exact_and_order_independent(lib, scale):
+    """fx_add / fx_to_float (csrc/ptx.cuh): the sum of fp32 values through the Q64.64 accumulator equals the exactly
+    rounded sum (math.fsum), whatever the number of blocks (grouping, arrival order) — including heavy cancellation."""
+    import math
+
+    g = torch.Generator().manual_seed(int(scale * 7) % 1000)
+    x = torch.randn(200_000, generator=g) * scale
+    x[::7] *= -1e3
+    x[5] = 0.0
+    x = torch.cat([x, -x[:100_000] * (1 + 2 ** -12)])  # near-cancelling pairs
+    want = torch.tensor(math.fsum(x.double().tolist()), dtype=torch.float64).float()
+    xd = x.cuda()
+    outs = []
+    for blocks in (1, 7, 148, 1024):
+        out = torch.zeros(1, device="cuda")
+        lib.check(lib.lib.r3m_b200_ordered_sum(lib.ptr(xd), xd.numel(), lib.ptr(out), blocks, lib.current_stream()))
+        outs.append(out.cpu())
+    assert all(torch.equal(o, outs[0]) for o in outs)
+    assert torch.equal(outs[0], want.reshape(1)), (float(outs[0]), float(want))
+    # a permutation of the inputs does not change a single bit either
+    perm = torch.randperm(xd.numel(), generator=g).cuda()
+    out = torch.zeros(1, device="cuda")
+    xp = xd[perm].contiguous()
+    lib.check(lib.lib.r3m_b200_ordered_sum(lib.ptr(xp), xp.numel(), lib.ptr(out), 148, lib.current_stream()))
+    assert torch.equal(out.cpu(), outs[0])
