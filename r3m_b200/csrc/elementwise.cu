@@ -401,19 +401,31 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
   constexpr bool dual = kDual;
+  // The per-channel coefficients are computed ONCE per block into shared memory (statistics -> scale / shift: a sqrt, a
+  // division and, on the engine's path, the conversion of the producers' fixed-point accumulators) instead of once per
+  // thread for its 8 channels: with narrow layers 32 threads of a block share a channel chunk.
+  extern __shared__ float s_coef[];  // [3][C]: scale, shift (+ shift2), scale2
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float mean, var, scale, shift, scale2 = 0.f;
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, c, scale, shift,
+              mean, var);
+    if (dual) {
+      float shift2;
+      bn_coeffs(a.train, a.sum2, a.sq2, a.stat_raw, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, c, scale2,
+                shift2, mean, var);
+      shift += shift2;
+    }
+    s_coef[c] = scale;
+    s_coef[a.C + c] = shift;
+    s_coef[2 * a.C + c] = scale2;
+  }
+  __syncthreads();
   float sc[8], sh[8], sc2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float mean, var;
-    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
-              mean, var);
-    sc2[j] = 0.f;
-    if (dual) {
-      float shift2;
-      bn_coeffs(a.train, a.sum2, a.sq2, a.stat_raw, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, chunk * 8 + j,
-                sc2[j], shift2, mean, var);
-      sh[j] += shift2;
-    }
+    sc[j] = s_coef[chunk * 8 + j];
+    sh[j] = s_coef[a.C + chunk * 8 + j];
+    sc2[j] = s_coef[2 * a.C + chunk * 8 + j];
   }
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
@@ -495,13 +507,19 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
   // One block iteration = one pooled row (n, p); threads stride over (q, chunk) with 32-bit arithmetic only.  blockDim
   // is a multiple of C8, so a thread keeps its 8-channel chunk and the coefficients are hoisted.
   const int chunk = threadIdx.x % C8;
+  __shared__ float s_sc[256], s_sh[256];  // C <= 256: coefficients once per block (see bn_apply_kernel)
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float mean, var;
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, c, s_sc[c], s_sh[c],
+              mean, var);
+  }
+  __syncthreads();
   float sc[8], sh[8];
   uint32_t flip[4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float mean, var;
-    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, chunk * 8 + j, sc[j], sh[j],
-              mean, var);
+    sc[j] = s_sc[chunk * 8 + j];
+    sh[j] = s_sh[chunk * 8 + j];
   }
 #pragma unroll
   for (int w = 0; w < 4; ++w) flip[w] = (sc[2 * w] < 0.f ? 0x8000u : 0u) | (sc[2 * w + 1] < 0.f ? 0x80000000u : 0u);
@@ -662,7 +680,7 @@ template <bool kApply>
 __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
   pdl_sync();
   __shared__ float s_red[2 * 256];  // C <= 256
-  __shared__ float s_tab[kApply ? 1 : 256 * 16];
+  __shared__ float s_tab[kApply ? 256 : 256 * 16];
   const int C8 = a.C >> 3;
   const int P = a.H / 2, Q = a.W / 2;
   const bf16* __restrict__ dA = reinterpret_cast<const bf16*>(a.dA);
@@ -672,15 +690,24 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
   const int chunk = threadIdx.x % C8;  // blockDim is a multiple of C8
   const float inv_m = 1.0f / ((float)a.N * a.H * a.W);
   float c0[8], c1[8], c2[8];  // reduce: mean, s1, s2;  apply: cA, cB, cC
+  if (kApply) {  // constants once per block (the sums may be fixed-point accumulators: see bn_bwd_apply_kernel)
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const float mean = a.mean[c], rstd = a.rstd[c];
+      const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
+      const float A = a.gamma[c] * rstd, B = -A * rstd * mdzx;
+      s_red[c] = A;
+      s_red[a.C + c] = B;
+      s_tab[c] = -A * mdz - B * mean;
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
     if (kApply) {
-      const float mean = a.mean[c], rstd = a.rstd[c];
-      const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
-      c0[j] = a.gamma[c] * rstd;
-      c1[j] = -c0[j] * rstd * mdzx;
-      c2[j] = -c0[j] * mdz - c1[j] * mean;
+      c0[j] = s_red[c];
+      c1[j] = s_red[a.C + c];
+      c2[j] = s_tab[c];
     } else {
       c0[j] = a.mean[c];
       c1[j] = 0.f;
@@ -995,22 +1022,39 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   const int r0 = threadIdx.x / C8;
   const float inv_m = 1.0f / (float)a.M;
   // dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat)),  xhat = (y - mean) * rstd
-  //    = cA * dz + cB * y + cC   with per-channel constants (three registers per channel instead of five)
+  //    = cA * dz + cB * y + cC   with per-channel constants (three registers per channel instead of five), computed once
+  // per block into shared memory (on the engine's path this includes converting the reduce pass' fixed-point sums)
+  extern __shared__ float s_coef[];  // [kDual ? 6 : 3][C]
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float mean = a.mean[c], rstd = a.rstd[c];
+    const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
+    const float A = a.gamma[c] * rstd;
+    const float B = -A * rstd * mdzx;
+    s_coef[c] = A;
+    s_coef[a.C + c] = B;
+    s_coef[2 * a.C + c] = -A * mdz - B * mean;
+    if (kDual) {
+      const float mean2 = a.mean2[c], rstd2 = a.rstd2[c];
+      const float mdzx2 = bsum_at(a.sums2, a.sums_raw, c) * inv_m;
+      const float A2 = a.gamma2[c] * rstd2;
+      const float B2 = -A2 * rstd2 * mdzx2;
+      s_coef[3 * a.C + c] = A2;
+      s_coef[4 * a.C + c] = B2;
+      s_coef[5 * a.C + c] = -A2 * mdz - B2 * mean2;
+    }
+  }
+  __syncthreads();
   float cA[8], cB[8], cC[8], cA2[8], cB2[8], cC2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    const float mean = a.mean[c], rstd = a.rstd[c];
-    const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
-    cA[j] = a.gamma[c] * rstd;
-    cB[j] = -cA[j] * rstd * mdzx;
-    cC[j] = -cA[j] * mdz - cB[j] * mean;
+    cA[j] = s_coef[c];
+    cB[j] = s_coef[a.C + c];
+    cC[j] = s_coef[2 * a.C + c];
     if (kDual) {
-      const float mean2 = a.mean2[c], rstd2 = a.rstd2[c];
-      const float mdzx2 = bsum_at(a.sums2, a.sums_raw, c) * inv_m;
-      cA2[j] = a.gamma2[c] * rstd2;
-      cB2[j] = -cA2[j] * rstd2 * mdzx2;
-      cC2[j] = -cA2[j] * mdz - cB2[j] * mean2;
+      cA2[j] = s_coef[3 * a.C + c];
+      cB2[j] = s_coef[4 * a.C + c];
+      cC2[j] = s_coef[5 * a.C + c];
     } else {
       cA2[j] = cB2[j] = cC2[j] = 0.f;
     }
@@ -1218,7 +1262,8 @@ inline int grid_for(long long work_items, int threads, int max_blocks) {
 // R3M_GRID_WAVES (experiments) scales the wave count.
 template <auto Kernel>
 int resident_blocks(int threads, size_t smem = 0) {
-  static int blocks = 0;
+  static int cache[64] = {0};  // per 1 KB bucket of dynamic shared memory (the occupancy depends on it)
+  int& blocks = cache[std::min<size_t>(63, (smem + 1023) >> 10)];
   if (blocks == 0) {
     int occ = 0, dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1266,9 +1311,10 @@ cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
   if (a.y2 && a.residual) return cudaErrorInvalidValue;  // a block tail has either an identity or a downsample branch
+  const size_t coef_smem = 3 * (size_t)a.C * sizeof(float);
 #define R3M_LAUNCH(D, R)                                                                              \
-  launch_kernel(bn_apply_kernel<D, R>, grid_for(a.M, rows_per_iter, resident_blocks<bn_apply_kernel<D, R>>(256)), \
-                256, 0, s, a)
+  launch_kernel(bn_apply_kernel<D, R>,                                                                         \
+                grid_for(a.M, rows_per_iter, resident_blocks<bn_apply_kernel<D, R>>(256, coef_smem)), 256, coef_smem, s, a)
   if (a.y2)
     R3M_LAUNCH(true, false);
   else if (a.residual)
@@ -1384,9 +1430,11 @@ cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   const int rows_per_iter = 256 / (a.C / 8);
   const bool dual = a.y2 != nullptr, dz = a.dz_out != nullptr;
+  const size_t coef_smem = (dual ? 6 : 3) * (size_t)a.C * sizeof(float);
 #define R3M_LAUNCH1(D, K, Z)                                                                                      \
   launch_kernel(bn_bwd_apply_kernel<D, K, Z>,                                                                     \
-                grid_for(a.M, rows_per_iter, resident_blocks<bn_bwd_apply_kernel<D, K, Z>>(256)), 256, 0, s, a)
+                grid_for(a.M, rows_per_iter, resident_blocks<bn_bwd_apply_kernel<D, K, Z>>(256, coef_smem)), 256, \
+                coef_smem, s, a)
 #define R3M_LAUNCH(D, K)            \
   do {                              \
     if (dz) R3M_LAUNCH1(D, K, true); \
