@@ -540,7 +540,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // raw mode (engine): the layer's own accumulators, converted by the consuming BatchNorm kernel — no tail at all
       unsigned long long* acc = (p.stat_raw ? reinterpret_cast<unsigned long long*>(p.stat_sum)
                                             : reinterpret_cast<unsigned long long*>(p.stat_scratch)) +
-                                static_cast<size_t>(my_ntile) * BN * 4;
+                                static_cast<size_t>(my_ntile) * BN * 2 * kFxWords;
       if (acc_ntile >= 0) {
         for (int c = et; c < BN; c += EPI * 32) {
           float sm = 0.f, sq = 0.f;
@@ -549,8 +549,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             sm += s_part[(qq * BN + c) * 2];
             sq += s_part[(qq * BN + c) * 2 + 1];
           }
-          fx_add(acc + 4 * c, sm);
-          fx_add(acc + 4 * c + 2, sq);
+          fx_add(acc + 2 * kFxWords * c, sm);
+          fx_add(acc + 2 * kFxWords * c + kFxWords, sq);
         }
       }
       if (!p.stat_raw) {
@@ -567,14 +567,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // last CTA of the column block: totals -> fp32, accumulators and ticket back to zero for the next launch
         __threadfence();
         for (int c = et; c < BN; c += EPI * 32) {
-          const unsigned long long l0 = __ldcg(acc + 4 * c), h0 = __ldcg(acc + 4 * c + 1);
-          const unsigned long long l1 = __ldcg(acc + 4 * c + 2), h1 = __ldcg(acc + 4 * c + 3);
-          p.stat_sum[my_ntile * BN + c] = fx_to_float(l0, h0);
-          p.stat_sq[my_ntile * BN + c] = fx_to_float(l1, h1);
-          acc[4 * c] = 0ull;
-          acc[4 * c + 1] = 0ull;
-          acc[4 * c + 2] = 0ull;
-          acc[4 * c + 3] = 0ull;
+          p.stat_sum[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c);
+          p.stat_sq[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c + kFxWords);
+          fx_clear(acc + 2 * kFxWords * c);
+          fx_clear(acc + 2 * kFxWords * c + kFxWords);
         }
         if (et == 0) p.stat_ticket[my_ntile] = 0;
       }

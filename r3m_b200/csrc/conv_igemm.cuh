@@ -29,14 +29,14 @@ struct ConvKernelParams {
   int oH, oW, o_stride, o_h0, o_w0;
   int accumulate;  // out += result (bf16 read-modify-write)
   // optional per-channel statistics of the (bf16-rounded) output: WRITTEN (not accumulated), deterministically: every
-  // CTA adds its column sums to fixed-point accumulators in stat_scratch (Cout * 2 values * 16 bytes, zero on entry and
+  // CTA adds its column sums to fixed-point accumulators in stat_scratch (Cout * 2 values * 32 bytes, zero on entry and
   // exit), the last CTA of each column block (stat_ticket, one zeroed int per column block, self-resetting) converts
   // them to fp32.  The grid must be a multiple of num_n_tiles.
   float* stat_sum;
   float* stat_sq;
   float* stat_scratch;
   int* stat_ticket;
-  int stat_raw;  // 1: stat_sum points at the layer's own accumulators (Cout * 4 64-bit words, zero on entry); the kernel
+  int stat_raw;  // 1: stat_sum points at the layer's own accumulators (Cout * 8 64-bit words, zero on entry); the kernel
                  // only adds into them and the consumer converts (no scratch, no ticket, no finalize tail)
   // optional fused epilogue (inference: BatchNorm folded into a per-channel affine): out = [relu](acc * ep_scale[c] +
   // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.

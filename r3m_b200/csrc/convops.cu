@@ -138,7 +138,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   if (g.stat_sum) {
     // deterministic statistics: every CTA keeps one column block (see conv_igemm.cu)
     plan->grid -= plan->grid % p.num_n_tiles;
-    if ((size_t)g.Cout * 8 > kStatScratchFloats || p.num_n_tiles > (int)kStatTickets)
+    if ((size_t)g.Cout * 16 > kStatScratchFloats || p.num_n_tiles > (int)kStatTickets)
       return "gather conv: statistics scratch too small for this grid";
   }
   return std::string();

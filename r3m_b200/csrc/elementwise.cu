@@ -86,17 +86,16 @@ __device__ __forceinline__ void st8(bf16* p, const F8& f) {
 
 // Per-channel statistics arrive either as fp32 arrays or "raw": the fixed-point accumulators the producing kernel added
 // into (fx_add, ptx.cuh) — the engine's path: no finalize pass in the producer, the consumer converts on read.
-//   conv statistics  raw layout: channel c -> words [4c, 4c+1] = sum, [4c+2, 4c+3] = sum of squares (sum == sq == base)
-//   backward sums    raw layout: entry i   -> words [2i, 2i+1]
+//   conv statistics  raw layout: channel c -> kFxWords words of the sum, then kFxWords of the sum of squares
+//                    (sum == sq == base)
+//   backward sums    raw layout: entry i   -> kFxWords words
 __device__ __forceinline__ float stat_at(const float* p, int raw, int c, int which) {
   if (!raw) return p[c];
-  const unsigned long long* acc = reinterpret_cast<const unsigned long long*>(p) + 4 * c + 2 * which;
-  return fx_to_float(__ldg(acc), __ldg(acc + 1));
+  return fx_to_float(reinterpret_cast<const unsigned long long*>(p) + (2 * c + which) * kFxWords);
 }
 __device__ __forceinline__ float bsum_at(const float* p, int raw, int i) {
   if (!raw) return p[i];
-  const unsigned long long* acc = reinterpret_cast<const unsigned long long*>(p) + 2 * i;
-  return fx_to_float(__ldg(acc), __ldg(acc + 1));
+  return fx_to_float(reinterpret_cast<const unsigned long long*>(p) + i * kFxWords);
 }
 
 __device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, int raw, float inv_m,
@@ -136,14 +135,14 @@ __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const
 // fixed-point accumulators (fx_add, ptx.cuh: exact integer arithmetic, so the arrival order does not matter — fp32
 // atomics would make the result depend on it); the last block to arrive (ticket) converts the totals to fp32, hands them
 // to emit(i, value) and clears the accumulators for the next launch.  One short tail instead of a multi-level tree.
-// d.scratch: V * 2 64-bit words, zero on entry and on exit; d.tickets: one int, likewise.  Blocks along x reduce
+// d.scratch: V * kFxWords 64-bit words, zero on entry and on exit; d.tickets: one int, likewise.  Blocks along x reduce
 // together (a caller with several blockIdx.y slices passes each slice its own DetScratch).
 template <class Emit>
 __device__ __forceinline__ void det_grid_reduce(const float* partial, int V, const DetScratch d, Emit emit) {
   __shared__ int s_last;
   const int tid = threadIdx.x;
   unsigned long long* acc = reinterpret_cast<unsigned long long*>(d.scratch);
-  for (int i = tid; i < V; i += blockDim.x) fx_add(acc + 2 * i, partial[i]);
+  for (int i = tid; i < V; i += blockDim.x) fx_add(acc + kFxWords * i, partial[i]);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&d.tickets[0], 1) == (int)gridDim.x - 1) ? 1 : 0;
@@ -151,10 +150,8 @@ __device__ __forceinline__ void det_grid_reduce(const float* partial, int V, con
   if (!s_last) return;
   __threadfence();
   for (int i = tid; i < V; i += blockDim.x) {
-    const unsigned long long lo = __ldcg(acc + 2 * i), hi = __ldcg(acc + 2 * i + 1);
-    emit(i, fx_to_float(lo, hi));
-    acc[2 * i] = 0ull;
-    acc[2 * i + 1] = 0ull;
+    emit(i, fx_to_float(acc + kFxWords * i));
+    fx_clear(acc + kFxWords * i);
   }
   if (tid == 0) d.tickets[0] = 0;
 }
@@ -395,7 +392,10 @@ __global__ void avgpool_fwd_f32_kernel(const float* __restrict__ a, float* __res
 template <bool kDual, bool kRes>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   pdl_sync();
-  const int C8 = a.C >> 3;
+  // wide layers (C >= 1024) are cut into channel slices of 256 (blockIdx.y): a block then builds the coefficient table
+  // of its slice only and covers 8 rows per iteration
+  const int Cs = gridDim.y > 1 ? 256 : a.C, c_base = blockIdx.y * Cs;
+  const int C8 = Cs >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
@@ -404,8 +404,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   // The per-channel coefficients are computed ONCE per block into shared memory (statistics -> scale / shift: a sqrt, a
   // division and, on the engine's path, the conversion of the producers' fixed-point accumulators) instead of once per
   // thread for its 8 channels: with narrow layers 32 threads of a block share a channel chunk.
-  extern __shared__ float s_coef[];  // [3][C]: scale, shift (+ shift2), scale2
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+  extern __shared__ float s_coef[];  // [3][Cs]: scale, shift (+ shift2), scale2
+  for (int cl = threadIdx.x; cl < Cs; cl += blockDim.x) {
+    const int c = c_base + cl;
     float mean, var, scale, shift, scale2 = 0.f;
     bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, c, scale, shift,
               mean, var);
@@ -415,17 +416,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
                 shift2, mean, var);
       shift += shift2;
     }
-    s_coef[c] = scale;
-    s_coef[a.C + c] = shift;
-    s_coef[2 * a.C + c] = scale2;
+    s_coef[cl] = scale;
+    s_coef[Cs + cl] = shift;
+    s_coef[2 * Cs + cl] = scale2;
   }
   __syncthreads();
   float sc[8], sh[8], sc2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = s_coef[chunk * 8 + j];
-    sh[j] = s_coef[a.C + chunk * 8 + j];
-    sc2[j] = s_coef[2 * a.C + chunk * 8 + j];
+    sh[j] = s_coef[Cs + chunk * 8 + j];
+    sc2[j] = s_coef[2 * Cs + chunk * 8 + j];
   }
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 R3M_UNROLL(R3M_BN_APPLY_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + chunk * 8;
+    const long long off = row * a.C + c_base + chunk * 8;
     // all loads of the row first (no control flow between them)
     F8 f = ld8_last(y + off);
     F8 t, r;
@@ -456,11 +457,11 @@ R3M_UNROLL(R3M_BN_APPLY_UNROLL)
       unsigned bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) bits |= (__bfloat162float(__float2bfloat16_rn(f.v[j])) > 0.f ? 1u : 0u) << j;
-      a.mask_out[row * C8 + chunk] = (uint8_t)bits;
+      a.mask_out[row * (a.C >> 3) + (c_base >> 3) + chunk] = (uint8_t)bits;
     }
   }
   pdl_done();
-  if (a.train && blockIdx.x == 0) {
+  if (a.train && blockIdx.x == 0 && blockIdx.y == 0) {
     // every block has already read sum/sq into registers for its own coefficients; running stats are separate
     // buffers, so the in-place update below cannot race with other blocks
     bn_publish(a.C, a.M, a.sum, a.sq, a.stat_raw, a.save_mean, a.save_rstd, a.running_mean, a.running_var, a.update_running);
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(224) stem_bwd_kernel(const StemBwdArgs a) {
     float* sums = a.sums;
     if (a.sums_raw) {
       unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
-      for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + 2 * i, s_red[i]);
+      for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + kFxWords * i, s_red[i]);
     } else {
       det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
     }
@@ -842,7 +843,7 @@ __global__ void __launch_bounds__(256) stem_bwd_reduce_pooled_kernel(const StemB
   float* sums = a.sums;
   if (a.sums_raw) {
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
-    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + 2 * i, s_red[i]);
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) fx_add(acc + kFxWords * i, s_red[i]);
   } else {
     det_grid_reduce(s_red, 2 * a.C, a.det, [=](int i, float v) { sums[i] = v; });
   }
@@ -995,12 +996,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     const float* part = reinterpret_cast<const float*>(s_part);
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
       const int which = i / Cs, c = c_base + i - which * Cs;
-      fx_add(which == 2 ? acc2 + 2 * c : acc + 2 * (which * C + c), part[i]);
+      fx_add(which == 2 ? acc2 + kFxWords * c : acc + kFxWords * (which * C + c), part[i]);
     }
     return;
   }
   DetScratch d;
-  d.scratch = a.det.scratch + (size_t)blockIdx.y * V * 4;  // V accumulators of two 64-bit words
+  d.scratch = a.det.scratch + (size_t)blockIdx.y * V * 2 * kFxWords;  // V accumulators of kFxWords 64-bit words
   d.tickets = a.det.tickets + blockIdx.y;
   det_grid_reduce(reinterpret_cast<const float*>(s_part), V, d, [=](int i, float v) {
     const int which = i / Cs, c = c_base + i - which * Cs;
@@ -1016,7 +1017,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
 template <bool kDual, int kMask, bool kDz>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   pdl_sync();
-  const int C8 = a.C >> 3;
+  const int Cs = gridDim.y > 1 ? 256 : a.C, c_base = blockIdx.y * Cs;  // channel slices for wide layers (see bn_apply)
+  const int C8 = Cs >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
@@ -1024,23 +1026,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   // dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat)),  xhat = (y - mean) * rstd
   //    = cA * dz + cB * y + cC   with per-channel constants (three registers per channel instead of five), computed once
   // per block into shared memory (on the engine's path this includes converting the reduce pass' fixed-point sums)
-  extern __shared__ float s_coef[];  // [kDual ? 6 : 3][C]
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+  extern __shared__ float s_coef[];  // [kDual ? 6 : 3][Cs]
+  for (int cl = threadIdx.x; cl < Cs; cl += blockDim.x) {
+    const int c = c_base + cl;
     const float mean = a.mean[c], rstd = a.rstd[c];
     const float mdz = bsum_at(a.sums, a.sums_raw, c) * inv_m, mdzx = bsum_at(a.sums, a.sums_raw, a.C + c) * inv_m;
     const float A = a.gamma[c] * rstd;
     const float B = -A * rstd * mdzx;
-    s_coef[c] = A;
-    s_coef[a.C + c] = B;
-    s_coef[2 * a.C + c] = -A * mdz - B * mean;
+    s_coef[cl] = A;
+    s_coef[Cs + cl] = B;
+    s_coef[2 * Cs + cl] = -A * mdz - B * mean;
     if (kDual) {
       const float mean2 = a.mean2[c], rstd2 = a.rstd2[c];
       const float mdzx2 = bsum_at(a.sums2, a.sums_raw, c) * inv_m;
       const float A2 = a.gamma2[c] * rstd2;
       const float B2 = -A2 * rstd2 * mdzx2;
-      s_coef[3 * a.C + c] = A2;
-      s_coef[4 * a.C + c] = B2;
-      s_coef[5 * a.C + c] = -A2 * mdz - B2 * mean2;
+      s_coef[3 * Cs + cl] = A2;
+      s_coef[4 * Cs + cl] = B2;
+      s_coef[5 * Cs + cl] = -A2 * mdz - B2 * mean2;
     }
   }
   __syncthreads();
@@ -1049,12 +1052,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
     cA[j] = s_coef[c];
-    cB[j] = s_coef[a.C + c];
-    cC[j] = s_coef[2 * a.C + c];
+    cB[j] = s_coef[Cs + c];
+    cC[j] = s_coef[2 * Cs + c];
     if (kDual) {
-      cA2[j] = s_coef[3 * a.C + c];
-      cB2[j] = s_coef[4 * a.C + c];
-      cC2[j] = s_coef[5 * a.C + c];
+      cA2[j] = s_coef[3 * Cs + c];
+      cB2[j] = s_coef[4 * Cs + c];
+      cC2[j] = s_coef[5 * Cs + c];
     } else {
       cA2[j] = cB2[j] = cC2[j] = 0.f;
     }
@@ -1070,13 +1073,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
 R3M_UNROLL(R3M_BN_BWD_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + chunk * 8;
+    const long long off = row * a.C + c_base + chunk * 8;
     F8 g = ld8_last(dA + off);
     const F8 yy = ld8_last(y + off);
     F8 m, t;
     unsigned bits = 0;
     if (kMask == kMaskAct) m = ld8(act + off);
-    if (kMask == kMaskBits) bits = __ldg(mask + row * C8 + chunk);
+    if (kMask == kMaskBits) bits = __ldg(mask + row * (a.C >> 3) + (c_base >> 3) + chunk);
     if (kDual) t = ld8_last(y2 + off);
     mask_gradient<kMask>(g, m, bits);
     if (kDz) st8(dzo + off, g);
@@ -1091,7 +1094,7 @@ R3M_UNROLL(R3M_BN_BWD_UNROLL)
     }
   }
   pdl_done();
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = bsum_at(a.sums, a.sums_raw, c);
       if (a.dgamma) a.dgamma[c] = bsum_at(a.sums, a.sums_raw, a.C + c);
@@ -1309,12 +1312,16 @@ cudaError_t launch_bn_fold(const BnFoldEntry* table_dev, int entries, cudaStream
 
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
-  const int rows_per_iter = 256 / (a.C / 8);
   if (a.y2 && a.residual) return cudaErrorInvalidValue;  // a block tail has either an identity or a downsample branch
-  const size_t coef_smem = 3 * (size_t)a.C * sizeof(float);
-#define R3M_LAUNCH(D, R)                                                                              \
-  launch_kernel(bn_apply_kernel<D, R>,                                                                         \
-                grid_for(a.M, rows_per_iter, resident_blocks<bn_apply_kernel<D, R>>(256, coef_smem)), 256, coef_smem, s, a)
+  const int slices = a.C >= 1024 ? a.C / 256 : 1, Cs = a.C / slices;
+  const int rows_per_iter = 256 / (Cs / 8);
+  const size_t coef_smem = 3 * (size_t)Cs * sizeof(float);
+#define R3M_LAUNCH(D, R)                                                                                               \
+  launch_kernel(bn_apply_kernel<D, R>,                                                                                 \
+                dim3(std::max(1, grid_for(a.M, rows_per_iter, resident_blocks<bn_apply_kernel<D, R>>(256, coef_smem) / \
+                                                                  slices)),                                          \
+                     slices),                                                                                        \
+                256, coef_smem, s, a)
   if (a.y2)
     R3M_LAUNCH(true, false);
   else if (a.residual)
@@ -1428,13 +1435,16 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
 
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
-  const int rows_per_iter = 256 / (a.C / 8);
+  const int slices = a.C >= 1024 ? a.C / 256 : 1, Cs = a.C / slices;
+  const int rows_per_iter = 256 / (Cs / 8);
   const bool dual = a.y2 != nullptr, dz = a.dz_out != nullptr;
-  const size_t coef_smem = (dual ? 6 : 3) * (size_t)a.C * sizeof(float);
-#define R3M_LAUNCH1(D, K, Z)                                                                                      \
-  launch_kernel(bn_bwd_apply_kernel<D, K, Z>,                                                                     \
-                grid_for(a.M, rows_per_iter, resident_blocks<bn_bwd_apply_kernel<D, K, Z>>(256, coef_smem)), 256, \
-                coef_smem, s, a)
+  const size_t coef_smem = (dual ? 6 : 3) * (size_t)Cs * sizeof(float);
+#define R3M_LAUNCH1(D, K, Z)                                                                                          \
+  launch_kernel(bn_bwd_apply_kernel<D, K, Z>,                                                                         \
+                dim3(std::max(1, grid_for(a.M, rows_per_iter,                                                         \
+                                          resident_blocks<bn_bwd_apply_kernel<D, K, Z>>(256, coef_smem) / slices)),   \
+                     slices),                                                                                       \
+                256, coef_smem, s, a)
 #define R3M_LAUNCH(D, K)            \
   do {                              \
     if (dz) R3M_LAUNCH1(D, K, true); \
@@ -1558,9 +1568,8 @@ __global__ void __launch_bounds__(256) ordered_sum_kernel(const float* __restric
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    out[0] = fx_to_float(__ldcg(acc), __ldcg(acc + 1));
-    acc[0] = 0ull;
-    acc[1] = 0ull;
+    out[0] = fx_to_float(acc);
+    fx_clear(acc);
     *ticket = 0;
   }
 }

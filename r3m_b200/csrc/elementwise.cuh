@@ -37,8 +37,8 @@ struct BnApplyArgs {
   float* save_mean = nullptr;   // [C] written in train mode (for backward)
   float* save_rstd = nullptr;
   int update_running = 1;
-  // 1: sum (== sq) and sum2 (== sq2) point at the producing conv's raw fixed-point accumulators (4 64-bit words per
-  // channel: sum lo/hi, sum-of-squares lo/hi; see fx_add) instead of fp32 arrays — the engine's path
+  // 1: sum (== sq) and sum2 (== sq2) point at the producing conv's raw fixed-point accumulators (8 64-bit words per
+  // channel: 4 limbs of the sum, 4 of the sum of squares; see fx_add) instead of fp32 arrays — the engine's path
   int stat_raw = 0;
   uint8_t* mask_out = nullptr;  // optional [M][C/8]: bit j of byte (row, chunk) = (a[row][8*chunk+j] > 0)
   // optional second BatchNorm whose (un-activated) output is added before the ReLU: the downsample branch of a
@@ -56,14 +56,14 @@ struct BnApplyArgs {
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s);
 
 // Scratch of the deterministic grid-wide reductions (see det_grid_reduce in elementwise.cu): `scratch` holds the
-// fixed-point accumulators (two 64-bit words per reduced value), `tickets` one int per channel slice; both zero on
+// fixed-point accumulators (four 64-bit words per reduced value), `tickets` one int per channel slice; both zero on
 // entry and left zero on exit.  Launches that share one DetScratch must be stream-ordered.
 struct DetScratch {
   float* scratch = nullptr;
   int* tickets = nullptr;
 };
 constexpr int kDetMaxBlocks = 1184;                             // grid cap of the kernels that reduce through it
-constexpr size_t kDetScratchFloats = (size_t)3 * 2048 * 4;      // 3 * C accumulators of 16 bytes, C <= 2048
+constexpr size_t kDetScratchFloats = (size_t)3 * 2048 * 8;      // 3 * C accumulators of 32 bytes, C <= 2048
 constexpr size_t kDetTickets = 128;
 DetScratch device_det_scratch();  // lazily allocated process-wide instance (kernel-level C-ABI entry points)
 
@@ -109,7 +109,7 @@ struct StemBwdArgs {
   float* dgamma = nullptr;
   float* dbeta = nullptr;
   DetScratch det;                  // null members: the process-wide instance
-  // 1: `sums` is 2C raw fixed-point accumulators (two 64-bit words each, zero on entry): the reduce pass adds into them
+  // 1: `sums` is 2C raw fixed-point accumulators (four 64-bit words each, zero on entry): the reduce pass adds into them
   // and the apply pass converts on read — no finalize tail (the engine's path)
   int sums_raw = 0;
 };
@@ -129,7 +129,7 @@ struct BnBwdArgs {
   const float* gamma = nullptr;
   float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); written by the reduce pass
   DetScratch det;             // deterministic reduction scratch (null members: the process-wide instance)
-  int sums_raw = 0;           // 1: sums / sums2 are raw fixed-point accumulators (2C / C entries of two 64-bit words,
+  int sums_raw = 0;           // 1: sums / sums2 are raw fixed-point accumulators (2C / C entries of four 64-bit words,
                               // zero on entry); the apply pass converts on read (the engine's path)
   void* dy = nullptr;         // bf16 [M][C] gradient w.r.t. the raw conv output
   void* dz_out = nullptr;     // optional bf16 [M][C]: masked gradient (feeds the residual branch)

@@ -21,8 +21,8 @@ struct Engine::Conv {
   size_t w_off = 0, gamma_off = 0, beta_off = 0;  // flat parameter buffer (elements)
   size_t rm_off = 0, rv_off = 0;                  // BN buffers region (floats)
   // per-step zeroed region (floats): fixed-point accumulators (fx_add, ptx.cuh) of the layer's BatchNorm reductions —
-  // [0, 8C) forward statistics (sum, sum of squares: 4 64-bit words per channel), [8C, 16C) backward sums (2C entries of
-  // 2 words), [16C, 20C) the downsample branch's extra backward sum (C entries)
+  // [0, 16C) forward statistics (sum, sum of squares: 4 64-bit words each per channel), [16C, 32C) backward sums (2C
+  // entries of 4 words), [32C, 40C) the downsample branch's extra backward sum (C entries)
   size_t zero_off = 0;
   size_t save_off = 0;                            // saved batch statistics (floats): mean[C] rstd[C]
   size_t wd_off = 0;                              // dgrad-packed filters (bf16 elements)
@@ -156,7 +156,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
     c->beta_off = take(np, c->Cout, 128);
     c->rm_off = take(nb, c->Cout, 32);
     c->rv_off = take(nb, c->Cout, 32);
-    c->zero_off = take(nz, 20 * (size_t)c->Cout, 32);
+    c->zero_off = take(nz, 40 * (size_t)c->Cout, 32);
     c->save_off = take(ns, 2 * (size_t)c->Cout, 32);
     if (!c->stem) c->wd_off = take(nwd, wn, 128);
     TensorInfo t;
@@ -710,7 +710,7 @@ std::string Engine::plan_all() {
     a.mean = saved + c.save_off;
     a.rstd = saved + c.save_off + c.Cout;
     a.gamma = P + c.gamma_off;
-    a.sums = zero + c.zero_off + 8 * c.Cout;
+    a.sums = zero + c.zero_off + 16 * c.Cout;
     a.sums_raw = 1;
     a.dy = dy;
     a.dz_out = dz_out;
@@ -724,7 +724,7 @@ std::string Engine::plan_all() {
       a.mean2 = saved + d.save_off;
       a.rstd2 = saved + d.save_off + d.Cout;
       a.gamma2 = P + d.gamma_off;
-      a.sums2 = zero + c.zero_off + 16 * c.Cout;
+      a.sums2 = zero + c.zero_off + 32 * c.Cout;
       a.dy2 = dy2;
       a.dgamma2 = G + d.gamma_off;
       a.dbeta2 = G + d.beta_off;
@@ -888,7 +888,7 @@ std::string Engine::plan_all() {
     sb.mean = saved + st.save_off;
     sb.rstd = saved + st.save_off + 64;
     sb.gamma = P + st.gamma_off;
-    sb.sums = zero + st.zero_off + 8 * 64;
+    sb.sums = zero + st.zero_off + 16 * 64;
     sb.sums_raw = 1;
     sb.dy = s2;
     sb.dgamma = G + st.gamma_off;
@@ -1322,8 +1322,8 @@ std::string Engine::debug_run_block_backward(int block, cudaStream_t stream) {
   if (b.ds >= 0) cs.push_back(b.ds);
   for (int ci : cs) {
     const Conv& c = *convs_[ci];
-    cudaError_t e = cudaMemsetAsync(reinterpret_cast<float*>(ws_ + off_zero_) + c.zero_off + 8 * c.Cout, 0,
-                                    12 * (size_t)c.Cout * 4, stream);
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<float*>(ws_ + off_zero_) + c.zero_off + 16 * c.Cout, 0,
+                                    24 * (size_t)c.Cout * 4, stream);
     if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
   }
   const bool saved = profiling_;

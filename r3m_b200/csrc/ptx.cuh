@@ -222,44 +222,42 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 // ---------------------------------------------------------------------------------------------
 // order-independent (hence run-to-run deterministic) accumulation of floats
 // ---------------------------------------------------------------------------------------------
-// A 128-bit two's-complement fixed-point accumulator (Q64.64: resolution 2^-64 ~ 5e-20, range +-9e18) held in two
-// 64-bit words {lo, hi}.  A float converts to it exactly (24-bit mantissa, any exponent in range; bits below 2^-64 are
-// truncated) and integer addition is associative, so the sum does not depend on the order in which blocks arrive —
-// unlike fp32 atomics.  Cost: one or two 64-bit atomics per value.
+// A 128-bit fixed-point accumulator (Q64.64: resolution 2^-64 ~ 5e-20, range +-9e18) kept as FOUR signed 32-bit limbs,
+// each in its own 64-bit word (kFxWords = 4 words per value): value = sum_k limb[k] * 2^(32 k - 64).  A float converts
+// to it exactly (24-bit mantissa: it touches at most two neighbouring limbs; bits below 2^-64 are truncated), limbs are
+// added with fire-and-forget 64-bit reductions — no carries at add time (a limb word absorbs 2^31 contributions before
+// it could overflow) and no returned values to wait for — and integer addition is associative, so the total does not
+// depend on the order in which blocks arrive, unlike fp32 atomics.  The reader folds the limbs (fx_to_float).
+constexpr int kFxWords = 4;
+__device__ __forceinline__ void fx_red(unsigned long long* p, long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void fx_add(unsigned long long* acc, float v) {
   if (v == 0.f || !(fabsf(v) < 9.0e18f)) return;  // zeros, and inf / nan / out of range (never produced by sane inputs)
   int e;
   const float m = frexpf(fabsf(v), &e);                  // |v| = m * 2^e, m in [0.5, 1)
-  const unsigned long long mant = (unsigned long long)(m * 16777216.f);  // 24-bit integer, exact
-  const int shift = e - 24 + 64;                         // |v| * 2^64 = mant << shift
-  unsigned long long lo, hi;
-  if (shift >= 64) {
-    hi = mant << (shift - 64);
-    lo = 0ull;
-  } else if (shift >= 0) {
-    lo = mant << shift;
-    hi = shift > 40 ? (mant >> (64 - shift)) : 0ull;
-  } else {
-    lo = shift > -24 ? (mant >> (-shift)) : 0ull;
-    hi = 0ull;
+  const long long mant = (long long)(m * 16777216.f);    // 24-bit integer, exact
+  const int shift = e - 24 + 64;                         // |v| * 2^64 = mant << shift, shift in (-inf, 103]
+  if (shift <= -24) return;                              // below the accumulator's resolution
+  const long long sgn = v < 0.f ? -1ll : 1ll;
+  if (shift < 0) {
+    fx_red(acc, sgn * (mant >> (-shift)));
+    return;
   }
-  if (v < 0.f) {
-    lo = ~lo + 1ull;
-    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
-  }
-  if (lo != 0ull) {
-    const unsigned long long old = atomicAdd(acc, lo);
-    if (old + lo < old) hi += 1ull;  // carry out of the low word
-  }
-  if (hi != 0ull) atomicAdd(acc + 1, hi);
+  const int k = shift >> 5, r = shift & 31;              // mant << shift = (mant << r) << (32 k): limbs k and k + 1
+  const long long wide = mant << r;                      // < 2^55
+  const long long low = wide & 0xFFFFFFFFll, high = wide >> 32;
+  if (low) fx_red(acc + k, sgn * low);
+  if (high) fx_red(acc + k + 1, sgn * high);             // k + 1 <= 3 because |v| < 2^63
 }
 // exact value of the accumulator rounded to nearest-even fp32; integer arithmetic only (fp64 is slow on this part)
-__device__ __forceinline__ float fx_to_float(unsigned long long lo, unsigned long long hi) {
-  const bool neg = (hi >> 63) != 0ull;
-  if (neg) {
-    lo = ~lo + 1ull;
-    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
-  }
+__device__ __forceinline__ float fx_to_float(const unsigned long long* acc) {
+  __int128 t = 0;
+#pragma unroll
+  for (int k = kFxWords - 1; k >= 0; --k) t = (t << 32) + (__int128)(long long)__ldcg(acc + k);
+  const bool neg = t < 0;
+  const unsigned __int128 mag = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;
+  const unsigned long long hi = (unsigned long long)(mag >> 64), lo = (unsigned long long)mag;
   if ((hi | lo) == 0ull) return 0.f;
   const int lz = hi ? __clzll((long long)hi) : 64 + __clzll((long long)lo);  // leading zeros of the 128-bit magnitude
   unsigned long long top, rest;  // magnitude << lz: top = bits 127..64, rest = bits 63..0
@@ -280,6 +278,10 @@ __device__ __forceinline__ float fx_to_float(unsigned long long lo, unsigned lon
   // bit 127 of the shifted magnitude weighs 2^(63 - lz); it is bit 23 of mant
   const float v = (float)mant * __int_as_float((40 - lz + 127) << 23);
   return neg ? -v : v;
+}
+__device__ __forceinline__ void fx_clear(unsigned long long* acc) {
+#pragma unroll
+  for (int k = 0; k < kFxWords; ++k) acc[k] = 0ull;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
