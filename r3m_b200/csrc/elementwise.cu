@@ -896,6 +896,7 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 // ReLU-mask source of the backward kernels (compile-time, so that the row loop has no control flow between its loads:
 // a branch between the loads serialises them and the kernels become latency bound — measured 3.8 vs 6.2 TB/s)
 enum { kMaskNone = 0, kMaskAct = 1, kMaskBits = 2 };
+constexpr int kBwdSlice = 64;  // channels per block of bn_bwd_reduce_kernel
 
 template <int kMask>
 __device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bits) {
@@ -913,9 +914,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   pdl_sync();
   extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * Cs / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
   constexpr int kQ = kDual ? 3 : 2;
-  // Wide layers are cut into channel slices of Cs = 256 (blockIdx.y): a block then covers 8 rows per iteration instead
-  // of 1 and its partial vector (one fixed-point atomic or two per entry) is kQ * 256 floats instead of kQ * C.
-  const int Cs = min(a.C, 256), c_base = blockIdx.y * Cs;
+  // The tensor is cut into channel slices of kBwdSlice = 64 channels (blockIdx.y): a block covers 32 rows per iteration
+  // (one fully used 128-byte line per row) and its partial vector is kQ * 64 floats instead of kQ * C, so the number of
+  // fixed-point reductions the grid issues (blocks x partial length: the kernel's tail) is C / 64 times smaller.
+  const int Cs = kBwdSlice, c_base = blockIdx.y * Cs;
   const int C8 = Cs >> 3, ld8c = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
@@ -1409,7 +1411,8 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   if (!a.det.scratch) a.det = device_det_scratch();
   if (!a.det.scratch) return cudaErrorMemoryAllocation;
-  const int Cs = std::min(a.C, 256), slices = a.C / Cs;
+  if (a.C % kBwdSlice != 0) return cudaErrorInvalidValue;
+  const int Cs = kBwdSlice, slices = a.C / Cs;
   const int rows_per_iter = 256 / (Cs / 8);
   // several rows per thread so that the block reduction and the ordered grid reduction are amortised; at most one
   // resident wave, at most kDetMaxBlocks blocks in all
