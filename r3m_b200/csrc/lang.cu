@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __res
                                                               float* __restrict__ dLc, LangDims d) {
   pdl_sync();
   extern __shared__ unsigned char s_hit[];  // [9][B]
+  __shared__ int s_src[64];                  // compacted source rows of the shuffled negatives (in (q, b) order)
+  __shared__ int s_n;
   const int B = d.B;
   const int blk = blockIdx.x;
   const int kind = blk < B ? 0 : (blk < 6 * B ? 1 : 2);
@@ -77,6 +79,28 @@ __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __res
     s_hit[idx] = (kind != 2 && perms[idx] == c && (kind == 0 || ft == f)) ? 1 : 0;
   }
   __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp 0 compacts the marks in (q, b) order (ballot + prefix popcount: deterministic); a permutation marks exactly
+    // one clip per negative, so the list has <= 9 entries — the rare overflow of a non-bijective map stays in s_hit
+    int n = 0;
+    for (int base = 0; base < 9 * B; base += 32) {
+      const int idx = base + threadIdx.x;
+      const bool hit = idx < 9 * B && s_hit[idx];
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = n + __popc(m & ((1u << threadIdx.x) - 1u));
+        if (pos < 64) {
+          s_src[pos] = (6 * B) + idx;  // row (6 + q) * B + b of dpre
+          s_hit[idx] = 0;
+        }
+      }
+      n += __popc(m);
+    }
+    if (threadIdx.x == 0) s_n = n;
+  }
+  __syncthreads();
+  const int n_list = min(s_n, 64);
+  const bool overflow = s_n > 64;
   for (int i = threadIdx.x; i < d.H; i += blockDim.x) {
     float acc = 0.f;
     for (int j = 0; j < 6; ++j) {
@@ -90,9 +114,10 @@ __global__ void __launch_bounds__(256) lang_layer1_bwd_kernel(const float* __res
     if (kind == 2) {
       for (int j = 6; j < 15; ++j) acc += dpre[(size_t)(j * B + c) * d.H + i];
     } else {
-      for (int q = 0; q < 9; ++q)
-        for (int b = 0; b < B; ++b)
-          if (s_hit[q * B + b]) acc += dpre[(size_t)((6 + q) * B + b) * d.H + i];
+      for (int k = 0; k < n_list; ++k) acc += dpre[(size_t)s_src[k] * d.H + i];
+      if (overflow)
+        for (int idx = 0; idx < 9 * B; ++idx)
+          if (s_hit[idx]) acc += dpre[(size_t)(6 * B + idx) * d.H + i];
     }
     out[i] = acc;
   }
@@ -398,23 +423,23 @@ __global__ void __launch_bounds__(256) lang_dscore_kernel(const float* __restric
   }
 }
 
-// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 32 columns x 32 row-slices; the slices are
+// out[j] = sum_row scale[row] * Mtx[row, j]   (scale == null -> 1).  Block = 16 columns x 64 row-slices; the slices are
 // added in slice order (no atomics: deterministic).
 __global__ void __launch_bounds__(1024) col_sum_kernel(const float* __restrict__ Mtx, const float* __restrict__ scale,
                                                        float* __restrict__ out, int rows, int cols) {
   pdl_sync();
-  __shared__ float part[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + tx;
+  __shared__ float part[64][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j = blockIdx.x * 16 + tx;
   float acc = 0.f;
   if (j < cols)
-    for (int r = ty; r < rows; r += 32) acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
+    for (int r = ty; r < rows; r += 64) acc = fmaf(scale ? scale[r] : 1.f, Mtx[(size_t)r * cols + j], acc);
   part[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && j < cols) {
     float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v += part[i][tx];
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) v += part[i][tx];
     out[j] = v;
   }
 }
@@ -514,7 +539,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
   R3M_TRY(cudaGetLastError());
   if (dE) {
     // ---- backward
-    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
+    launch_kernel(col_sum_kernel, dim3((H + 15) / 16, 1), 1024, 0, s, ws.Hact[3], ws.dS, p.dw[4], rows, H);  // dw5 = dS^T H4
     R3M_TRY(cudaGetLastError());
     launch_kernel(vec_sum_kernel, 1, 256, 0, s, ws.dS, p.db[4], rows);
     R3M_TRY(cudaGetLastError());
@@ -524,7 +549,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
-      launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, dHl, nullptr, p.db[l], rows, H);
+      launch_kernel(col_sum_kernel, dim3((H + 15) / 16, 1), 1024, 0, s, dHl, nullptr, p.db[l], rows, H);
       R3M_TRY(cudaGetLastError());
       GemmArgs gw{dHl, ws.Hact[l - 1], p.dw[l], H, H, rows, H, H, H, nullptr, 0, nullptr, 0, 0};
       R3M_TRY((run_gemm<false, false>(gw, s)));
@@ -535,7 +560,7 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     }
     // ---- layer 1 backward (factorised)
     const float* dpre = ws.dH[cur];
-    launch_kernel(col_sum_kernel, dim3((H + 31) / 32, 1), 1024, 0, s, dpre, nullptr, p.db[0], rows, H);
+    launch_kernel(col_sum_kernel, dim3((H + 15) / 16, 1), 1024, 0, s, dpre, nullptr, p.db[0], rows, H);
     R3M_TRY(cudaGetLastError());
     launch_kernel(lang_layer1_bwd_kernel, 7 * B, 256, (size_t)9 * B, s, dpre, perms, ws.dU, ws.dV, ws.dLc, d);
     R3M_TRY(cudaGetLastError());

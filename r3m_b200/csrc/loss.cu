@@ -208,7 +208,28 @@ __global__ void __launch_bounds__(256) loss_tcn_gather_kernel(const float* __res
     s_hit[idx] = (f != 3 && perms[q * B + b] == c) ? 1 : 0;
   }
   __syncthreads();
-  const int n_own = s_own;
+  __shared__ int in_idx[32];
+  __shared__ int s_nin;
+  if (threadIdx.x < 32) {  // compact the marks in (negative, clip) order; a permutation yields exactly three
+    int n = 0;
+    for (int base = 0; base < 3 * B; base += 32) {
+      const int idx = base + threadIdx.x;
+      const bool hit = idx < 3 * B && s_hit[idx];
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = n + __popc(m & ((1u << threadIdx.x) - 1u));
+        if (pos < 32) {
+          in_idx[pos] = idx;
+          s_hit[idx] = 0;
+        }
+      }
+      n += __popc(m);
+    }
+    if (threadIdx.x == 0) s_nin = n;
+  }
+  __syncthreads();
+  const int n_own = s_own, n_in = min(s_nin, 32);
+  const bool overflow = s_nin > 32;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float own = er[d];
     float acc = 0.f;
@@ -221,12 +242,16 @@ __global__ void __launch_bounds__(256) loss_tcn_gather_kernel(const float* __res
         acc -= alpha * (own - other);
     };
     for (int i = 0; i < n_own; ++i) add(own_partner[i], own_alpha[i], own_beta[i]);
-    if (f != 3) {
-      for (int j = 0; j < 3; ++j) {
-        const int k = (f == 2) ? 3 + j : 6 + j;
-        for (int b = 0; b < B; ++b)
-          if (s_hit[j * B + b]) add(5 * b + f, part[(size_t)b * kTcnPart + k], part[(size_t)b * kTcnPart + 18 + k]);
-      }
+    for (int i = 0; i < n_in; ++i) {
+      const int idx = in_idx[i], j = idx / B, b = idx - j * B, k = (f == 2) ? 3 + j : 6 + j;
+      add(5 * b + f, part[(size_t)b * kTcnPart + k], part[(size_t)b * kTcnPart + 18 + k]);
+    }
+    if (overflow) {
+      for (int idx = 0; idx < 3 * B; ++idx)
+        if (s_hit[idx]) {
+          const int j = idx / B, b = idx - j * B, k = (f == 2) ? 3 + j : 6 + j;
+          add(5 * b + f, part[(size_t)b * kTcnPart + k], part[(size_t)b * kTcnPart + 18 + k]);
+        }
     }
     dE[(size_t)r * D + d] += acc;
   }
