@@ -216,6 +216,16 @@ int r3m_b200_engine_update_grads(void* handle, const void* obs, const int* perms
  * Filter gradients are ACCUMULATED into region 1 (zero it for a fresh gradient), BatchNorm gradients are written. */
 int r3m_b200_engine_backward(void* handle, const float* dE, void* stream);
 
+/* Overlapping the step's one collective with the backward pass (replaces the gradient reduction of nn.DataParallel,
+ * r3m/train_representation.py:30).  The flat gradient buffer (region 1) is cut into r3m_b200_engine_num_grad_chunks()
+ * chunks [begin, end) (elements) in the order the backward pass completes them: the language head + layer 4 first, the
+ * stem + layer 1 last.  After r3m_b200_engine_update_grads / _backward has RETURNED, r3m_b200_engine_wait_grad_chunk
+ * makes `stream` wait (cudaStreamWaitEvent) for chunk k of that call, so the host can enqueue one all-reduce per chunk
+ * on a communication stream while the rest of the backward pass is still running. */
+int r3m_b200_engine_num_grad_chunks(void* handle, int* count);
+int r3m_b200_engine_grad_chunk(void* handle, int k, size_t* begin, size_t* end);
+int r3m_b200_engine_wait_grad_chunk(void* handle, int k, void* stream);
+
 /* Test hooks for the block-level backward parity test: the bf16 NHWC buffers of residual block `block`
  * (0 .. r3m_b200_engine_num_blocks()-1, forward order) — what: 0 input activation, 1 output activation, 2 incoming
  * gradient (read by the block's backward), 3 outgoing gradient (written) — and a run of ONLY that block's backward

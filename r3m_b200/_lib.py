@@ -91,6 +91,9 @@ _sig("r3m_b200_engine_update_grads", [c_void_p, c_void_p, c_void_p, c_void_p, c_
 _sig("r3m_b200_engine_adam_step", [c_void_p, c_float, c_float, c_int, c_void_p])
 _sig("r3m_b200_engine_backward", [c_void_p, c_void_p, c_void_p])
 _sig("r3m_b200_engine_num_blocks", [c_void_p, c_int_p])
+_sig("r3m_b200_engine_num_grad_chunks", [c_void_p, c_int_p])
+_sig("r3m_b200_engine_grad_chunk", [c_void_p, c_int, c_size_p, c_size_p])
+_sig("r3m_b200_engine_wait_grad_chunk", [c_void_p, c_int, c_void_p])
 _sig("r3m_b200_engine_debug_block", [c_void_p, c_int, c_int, c_void_pp, c_size_p])
 _sig("r3m_b200_engine_debug_run_block_backward", [c_void_p, c_int, c_void_p])
 _sig("r3m_b200_engine_profile_ops", [c_void_p, ctypes.POINTER(ctypes.c_double), c_int, c_int_p])

@@ -529,6 +529,20 @@ int r3m_b200_engine_backward(void* handle, const float* dE, void* stream) {
   if (!dE) return fail(R3M_B200_ERR_INVALID, "null gradient pointer");
   RETURN_STR(eng->backward(dE, (cudaStream_t)stream));
 }
+int r3m_b200_engine_num_grad_chunks(void* handle, int* count) {
+  ENGINE_OR_FAIL(handle);
+  *count = eng->num_grad_chunks();
+  return R3M_B200_OK;
+}
+int r3m_b200_engine_grad_chunk(void* handle, int k, size_t* begin, size_t* end) {
+  ENGINE_OR_FAIL(handle);
+  if (!begin || !end) return fail(R3M_B200_ERR_INVALID, "null pointer");
+  RETURN_STR(eng->grad_chunk(k, begin, end));
+}
+int r3m_b200_engine_wait_grad_chunk(void* handle, int k, void* stream) {
+  ENGINE_OR_FAIL(handle);
+  RETURN_STR(eng->wait_grad_chunk(k, (cudaStream_t)stream));
+}
 int r3m_b200_engine_num_blocks(void* handle, int* count) {
   ENGINE_OR_FAIL(handle);
   *count = eng->num_blocks();

@@ -667,6 +667,7 @@ std::string Engine::plan_all() {
 
   // ------------------------------------------------------------------------------------------------ backward
   bwd_.clear();
+  chunks_.clear();
   // Cross-stream schedule.  Every wgrad goes to the side stream and is released by the NEXT BatchNorm-backward reduce
   // pass of the main chain:   dgrad(c) | bn_bwd_reduce(below) | wgrad(c) on the side stream || bn_bwd_apply(below) | ...
   // A wgrad CTA takes a whole SM's shared memory, so it can only share the SM with kernels that use none: the apply
@@ -873,6 +874,17 @@ std::string Engine::plan_all() {
     }
     std::swap(d_out, d_in);
     if (!err.empty()) return err;
+    // Gradient chunks for the overlapped all-reduce: when the FIRST block of layer 2 / 3 / 4 has been scheduled, every
+    // gradient from that layer's first parameter to the end of the flat buffer is final once (a) the main stream has
+    // passed this point (BatchNorm gradients) and (b) the side stream has finished this block's filter gradients.
+    if (bi > 0 && blk->ds >= 0) {  // the first blocks of layers 2-4 are the ones with a downsample branch (bi > 0)
+      GradChunk gc;
+      gc.begin = convs_[blk->main[0]]->w_off;
+      if (bwd_.back().record < 0) bwd_.back().record = n_events++;
+      gc.main_event = bwd_.back().record;
+      gc.side_event = held_wgrads.empty() ? -1 : held_wgrads.back().record;
+      chunks_.push_back(gc);
+    }
   }
   {
     // stem: maxpool backward + ReLU mask + BN backward fused in two passes -> filter gradient (no data gradient)
@@ -931,6 +943,12 @@ std::string Engine::plan_all() {
     // join: the step's last backward op waits for every filter gradient still running on the side stream
     for (auto& kv : pending_reader) bwd_.back().wait.push_back(kv.second);
     pending_reader.clear();
+    GradChunk tail;  // the stem and layer 1: final when the whole backward pass is
+    tail.begin = 0;
+    bwd_.back().record = n_events++;
+    tail.main_event = bwd_.back().record;
+    tail.side_event = -1;
+    chunks_.push_back(tail);
   }
 
   while ((int)evs_.size() < n_events) {
@@ -999,7 +1017,7 @@ std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
       }
     cudaError_t e = launch(op, s);
     if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
-    if (two_streams && op.record >= 0) {
+    if (op.record >= 0) {  // also in single-stream runs: the gradient-chunk markers are read by wait_grad_chunk
       cudaError_t re = cudaEventRecord(evs_[op.record], s);
       if (re != cudaSuccess) return std::string("event record failed: ") + cudaGetErrorString(re);
     }
@@ -1290,6 +1308,24 @@ std::string Engine::backward(const float* dE, cudaStream_t stream) {
   float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
   e = launch(Op([flag, metrics](cudaStream_t s) { return launch_publish_flag(flag, metrics, s); }, kFamLoss), stream);
   if (e != cudaSuccess) return std::string("publish_flag: ") + cudaGetErrorString(e);
+  return std::string();
+}
+
+int Engine::num_grad_chunks() const { return (int)chunks_.size(); }
+
+std::string Engine::grad_chunk(int k, size_t* begin, size_t* end) const {
+  if (k < 0 || k >= (int)chunks_.size()) return "gradient chunk index out of range";
+  *begin = chunks_[k].begin;
+  *end = (k == 0) ? nparams_ : chunks_[k - 1].begin;
+  return std::string();
+}
+
+std::string Engine::wait_grad_chunk(int k, cudaStream_t stream) {
+  if (k < 0 || k >= (int)chunks_.size()) return "gradient chunk index out of range";
+  const GradChunk& c = chunks_[k];
+  cudaError_t e = cudaStreamWaitEvent(stream, evs_[c.main_event], 0);
+  if (e == cudaSuccess && c.side_event >= 0) e = cudaStreamWaitEvent(stream, evs_[c.side_event], 0);
+  if (e != cudaSuccess) return std::string("stream wait failed: ") + cudaGetErrorString(e);
   return std::string();
 }
 

@@ -78,6 +78,13 @@ class Engine {
   // torch.autograd): dE = d(loss)/d(embeddings) fp32 [frames][D] of the preceding train-mode forward().  Filter
   // gradients are ACCUMULATED into the gradient region, BatchNorm gradients written.
   std::string backward(const float* dE, cudaStream_t stream);
+  // Gradient chunks for an all-reduce that overlaps the backward pass: chunk k covers the flat gradient elements
+  // [begin, end) — chunk 0 the language head and layer 4, then layer 3, layer 2, and last the stem with layer 1 — in the
+  // order in which the backward pass completes them.  wait_grad_chunk makes `stream` wait (cudaStreamWaitEvent) until
+  // the LAST update_grads / backward enqueued on this engine has produced chunk k; call it after that call returned.
+  int num_grad_chunks() const;
+  std::string grad_chunk(int k, size_t* begin, size_t* end) const;
+  std::string wait_grad_chunk(int k, cudaStream_t stream);
   // Test hooks (tests/test_block_backward_gpu.py): the buffers of residual block `block` (what: 0 input activation,
   // 1 output activation, 2 incoming gradient, 3 outgoing gradient; all bf16 NHWC) and a run of ONLY that block's
   // backward ops on one stream, after a train-mode forward.
@@ -168,6 +175,12 @@ class Engine {
   LangDims lang_dims_;
 
   std::vector<Op> fwd_train_, fwd_eval_, fwd_eval_tf32_, bwd_, repack_;
+  struct GradChunk {
+    size_t begin = 0;     // first flat gradient element of the chunk (it ends where the previous chunk begins)
+    int main_event = -1;  // recorded on the main stream / the side stream when the chunk's last producers are enqueued
+    int side_event = -1;
+  };
+  std::vector<GradChunk> chunks_;
   // Filter gradients run on a second stream: nothing in the backward chain consumes them, and a wgrad CTA (tensor /
   // L2 bound, one per SM) co-resides with the HBM-bound BatchNorm-backward CTAs of the layer below.
   cudaStream_t side_ = nullptr;

@@ -163,6 +163,21 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_backward(self._h, L.ptr(dE), L.current_stream()))
 
+    def grad_chunks(self):
+        """[(begin, end)] element ranges of the flat gradient buffer in the order the backward pass completes them."""
+        n = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_num_grad_chunks(self._h, ctypes.byref(n)))
+        out = []
+        for k in range(n.value):
+            b, e = ctypes.c_size_t(), ctypes.c_size_t()
+            L.check(L.lib.r3m_b200_engine_grad_chunk(self._h, k, ctypes.byref(b), ctypes.byref(e)))
+            out.append((int(b.value), int(e.value)))
+        return out
+
+    def wait_grad_chunk(self, k, stream):
+        """Make `stream` (torch.cuda.Stream) wait until chunk k of the last enqueued update_grads / backward is final."""
+        L.check(L.lib.r3m_b200_engine_wait_grad_chunk(self._h, k, ctypes.c_void_p(stream.cuda_stream)))
+
     # ---- test hooks (tests/test_block_backward_gpu.py)
     def num_blocks(self):
         v = ctypes.c_int()

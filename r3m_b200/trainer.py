@@ -24,14 +24,37 @@ def _world():
     return 1
 
 
-def allreduce_gradients(module):
+_COMM_STREAMS = {}
+
+
+def allreduce_gradients(module, engine=None):
     """The step's ONLY collective: sum the flat fp32 gradient buffer over all ranks (NCCL over NVLink on GPUs; any
-    torch.distributed backend works).  Returns the factor Adam must apply to turn the sum into the mean."""
+    torch.distributed backend works).  Returns the factor Adam must apply to turn the sum into the mean.
+
+    With ``engine`` (the engine whose ``update_grads`` has just been enqueued) on a CUDA device the buffer is reduced
+    in the engine's gradient chunks — language head + layer 4 first, stem + layer 1 last, the order in which the backward
+    pass completes them — each on a communication stream that waits only for ITS chunk
+    (``r3m_b200_engine_wait_grad_chunk``), so all but the last chunk travel while the backward pass is still running.
+    Same result as one all-reduce of the whole buffer (the chunks partition it)."""
     world = _world()
     if world > 1:
         import torch.distributed as dist
 
-        dist.all_reduce(module._flat(1), op=dist.ReduceOp.SUM)
+        G = module._flat(1)
+        if engine is None or not G.is_cuda:
+            dist.all_reduce(G, op=dist.ReduceOp.SUM)
+        else:
+            dev = G.device
+            comm = _COMM_STREAMS.get(dev)
+            if comm is None:
+                comm = _COMM_STREAMS[dev] = torch.cuda.Stream(device=dev)
+            works = []
+            for k, (b, e) in enumerate(engine.grad_chunks()):
+                engine.wait_grad_chunk(k, comm)
+                with torch.cuda.stream(comm):
+                    works.append(dist.all_reduce(G[b:e], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()  # the current stream waits for the collective; the host does not block
     return 1.0 / world
 
 
@@ -138,7 +161,7 @@ class Trainer:
         t6 = time.time()
         if not eval:
             m._nbt += 1
-            m.encoder_opt.step(grad_scale=allreduce_gradients(m))
+            m.encoder_opt.step(grad_scale=allreduce_gradients(m, eng))
             self.last_launches += eng.launches()
         vals = eng.read_metrics()
         for i, k in enumerate(METRIC_KEYS):

@@ -124,3 +124,39 @@ def test_language_model_embeds_any_number_of_frames():
     with pytest.raises(R3MB200Error):
         m._engine(3).update_grads(x[:3].contiguous(), torch.zeros(15, 1, dtype=torch.int32, device="cuda"), None, None,
                                   1e-5, 1e-5, 0.0, 1.0, True)
+
+
+@pytest.mark.parametrize("size", [18, 50])
+def test_gradient_chunks_partition_the_flat_buffer_in_completion_order(size):
+    """The overlapped all-reduce reduces the gradient buffer chunk by chunk (r3m_b200/trainer.py:allreduce_gradients):
+    the chunks must tile [0, num_params) exactly, last layers first, and waiting for a chunk on another stream must see
+    the finished gradients of that chunk (compared with a fully synchronised read)."""
+    from r3m_b200 import Trainer
+
+    params, buffers = well_conditioned_state(size, 60, True)
+    lang_emb = O.stub_lang_embedding(4, 61)
+    m, model = build_model(size, params, buffers, 1.0, lang_emb)
+    frames = O.varied_frames(4, 62).cuda()
+    perms = O.draw_permutations(4, 63)
+    eng = m._engine(20)
+    chunks = eng.grad_chunks()
+    assert len(chunks) == 4
+    assert chunks[0][1] == m._layout.num_params and chunks[-1][0] == 0
+    assert all(chunks[k][0] == chunks[k + 1][1] for k in range(3)) and all(b < e for b, e in chunks)
+    names = {t.offset: t.name for t in m._layout.tensors if t.kind in (0, 1)}
+    assert [names[b] for b, _ in chunks] == ["convnet.layer4.0.conv1.weight", "convnet.layer3.0.conv1.weight",
+                                             "convnet.layer2.0.conv1.weight", "convnet.conv1.weight"]
+    G = m._flat(1)
+    side = torch.cuda.Stream()
+    copies = []
+    # enqueue forward + losses + backward, then read every chunk on the side stream as soon as IT is final
+    eng.forward_train_async(frames.reshape(-1, 3, 224, 224).contiguous())
+    eng.update_grads(None, perms.to(torch.int32).cuda(), lang_emb.cuda(), torch.ones(4, device="cuda"), 1e-5, 1e-5, 1.0,
+                     1.0, False)
+    for k, (b, e) in enumerate(chunks):
+        eng.wait_grad_chunk(k, side)
+        with torch.cuda.stream(side):
+            copies.append(G[b:e].clone())
+    torch.cuda.synchronize()
+    for (b, e), c in zip(chunks, copies):
+        assert torch.equal(c, G[b:e]) and float(c.abs().max()) > 0
