@@ -253,6 +253,38 @@ int r3m_b200_engine_profile_ops(void* handle, double* out, int capacity_ops, int
 /* Human-readable label (layer / role) of launch `index` of the last profile. */
 int r3m_b200_engine_profile_label(void* handle, int index, char* out, int capacity);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Sentence encoder: the frozen DistilBERT of the language branch (r3m/models/models_language.py:13-35:
+ * AutoModel("distilbert-base-uncased")(input_ids, attention_mask).last_hidden_state.mean(1) under no_grad).
+ * Tokenisation stays on the host (the reference's AutoTokenizer); everything from the token ids on runs here:
+ * embeddings + LayerNorm, `layers` x [q/k/v Linear, softmax attention, out Linear + residual + LayerNorm, Linear +
+ * exact GELU, Linear + residual + LayerNorm], mean over positions.  The Linears run on the tcgen05 kernel in its tf32
+ * tier (fp32 storage, fp32 accumulation); everything else is fp32.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* distilbert-base-uncased: vocab 30522, max_pos 512, dim 768, heads 12, layers 6, ffn 3072 (head size must be 64). */
+int r3m_b200_distilbert_create(int vocab, int max_pos, int dim, int heads, int layers, int ffn, void** handle);
+int r3m_b200_distilbert_destroy(void* handle);
+/* Flat fp32 parameter buffer: element count, and the table of named tensors in transformers' state_dict naming
+ * ("embeddings.word_embeddings.weight", "transformer.layer.0.attention.q_lin.weight", ...; Linear weights [out][in]). */
+int r3m_b200_distilbert_num_params(void* handle, size_t* count);
+int r3m_b200_distilbert_num_tensors(void* handle, int* count);
+int r3m_b200_distilbert_tensor_info(void* handle, int index, char* name, int name_capacity, long long* offset, int* ndim,
+                                    int* dims2);
+/* The caller owns both device allocations: params (num_params floats, 16-byte aligned, filled from the checkpoint)
+ * and a workspace (1024-byte aligned) sized for at most max_tokens = sentences x padded length per call. */
+int r3m_b200_distilbert_workspace_bytes(void* handle, int max_tokens, size_t* bytes);
+int r3m_b200_distilbert_bind(void* handle, float* params, void* workspace, size_t bytes, int max_tokens);
+/* After (re)writing params: refresh the tf32-rounded operand copies. */
+int r3m_b200_distilbert_sync_weights(void* handle, void* stream);
+/* ids int32 [B][T], mask fp32 [B][T] (1 token, 0 padding; every sentence needs at least one token) ->
+ * out fp32 [B][dim] = last_hidden_state.mean(1) (padding positions included, as the reference does);
+ * hidden (optional) fp32 [B][T][dim] = last_hidden_state. */
+int r3m_b200_distilbert_forward(void* handle, const int* ids, const float* mask, int B, int T, float* out, float* hidden,
+                                void* stream);
+/* Kernels launched by the last r3m_b200_distilbert_forward. */
+int r3m_b200_distilbert_launches(void* handle, int* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,19 @@ _sig("r3m_b200_engine_profile_label", [c_void_p, c_int, ctypes.c_char_p, c_int])
 _sig("r3m_b200_engine_profile_update", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                         c_float, c_float, c_int, ctypes.POINTER(ctypes.c_double), c_void_p])
 
+c_float_p = ctypes.POINTER(c_float)
+_sig("r3m_b200_distilbert_create", [c_int] * 6 + [c_void_pp])
+_sig("r3m_b200_distilbert_destroy", [c_void_p])
+_sig("r3m_b200_distilbert_num_params", [c_void_p, c_size_p])
+_sig("r3m_b200_distilbert_num_tensors", [c_void_p, c_int_p])
+_sig("r3m_b200_distilbert_tensor_info", [c_void_p, c_int, ctypes.c_char_p, c_int, ctypes.POINTER(ctypes.c_longlong),
+                                         c_int_p, c_int_p])
+_sig("r3m_b200_distilbert_workspace_bytes", [c_void_p, c_int, c_size_p])
+_sig("r3m_b200_distilbert_bind", [c_void_p, c_void_p, c_void_p, c_size_t, c_int])
+_sig("r3m_b200_distilbert_sync_weights", [c_void_p, c_void_p])
+_sig("r3m_b200_distilbert_forward", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p])
+_sig("r3m_b200_distilbert_launches", [c_void_p, c_int_p])
+
 
 def ptr(t):
     """Device (or host) address of a torch tensor, or None."""

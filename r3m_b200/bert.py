@@ -1,0 +1,117 @@
+"""The frozen DistilBERT sentence encoder of the language branch on the library's own kernels (C ABI: include/r3m_b200.h
+"Sentence encoder"; reference: r3m/models/models_language.py:13-35).  torch holds the device memory; tokenisation is the
+caller's (the reference's AutoTokenizer).  There is no CPU path."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+DISTILBERT_BASE = dict(vocab=30522, max_pos=512, dim=768, heads=12, layers=6, ffn=3072)
+
+
+def _aligned_empty(nbytes, device):
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    shift = (-raw.data_ptr()) % 1024
+    return raw[shift:shift + nbytes]
+
+
+class DistilBertLayout:
+    """Named tensors of the flat fp32 parameter buffer (transformers' DistilBertModel.state_dict() naming); no GPU."""
+
+    def __init__(self, **dims):
+        d = dict(DISTILBERT_BASE)
+        d.update(dims)
+        self.dims = d
+        h = ctypes.c_void_p()
+        L.check(L.lib.r3m_b200_distilbert_create(d["vocab"], d["max_pos"], d["dim"], d["heads"], d["layers"], d["ffn"],
+                                                 ctypes.byref(h)))
+        try:
+            self.tensors = _tensor_table(h)
+            n = ctypes.c_size_t()
+            L.check(L.lib.r3m_b200_distilbert_num_params(h, ctypes.byref(n)))
+            self.num_params = int(n.value)
+        finally:
+            L.lib.r3m_b200_distilbert_destroy(h)
+
+
+def _tensor_table(h):
+    n = ctypes.c_int()
+    L.check(L.lib.r3m_b200_distilbert_num_tensors(h, ctypes.byref(n)))
+    out = {}
+    buf = ctypes.create_string_buffer(256)
+    for i in range(n.value):
+        off = ctypes.c_longlong()
+        ndim = ctypes.c_int()
+        dims = (ctypes.c_int * 2)()
+        L.check(L.lib.r3m_b200_distilbert_tensor_info(h, i, buf, 256, ctypes.byref(off), ctypes.byref(ndim), dims))
+        out[buf.value.decode()] = (int(off.value), tuple(dims[j] for j in range(ndim.value)))
+    return out
+
+
+class DistilBertEncoder:
+    """`state_dict`: a transformers DistilBertModel state_dict (keys with or without a "distilbert." prefix).
+    `encode(input_ids, attention_mask)` -> fp32 [B, dim] = last_hidden_state.mean(1), like LangEncoder.forward."""
+
+    def __init__(self, state_dict, device, max_tokens=8192, **dims):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.R3MB200Error(f"r3m_b200 computes on an sm_100 GPU only (sentence encoder asked for {device})")
+        d = dict(DISTILBERT_BASE)
+        d.update(dims)
+        self.dims, self.device, self.max_tokens = d, device, int(max_tokens)
+        self._h = ctypes.c_void_p()
+        L.check(L.lib.r3m_b200_distilbert_create(d["vocab"], d["max_pos"], d["dim"], d["heads"], d["layers"], d["ffn"],
+                                                 ctypes.byref(self._h)))
+        self.tensors = _tensor_table(self._h)
+        n = ctypes.c_size_t()
+        L.check(L.lib.r3m_b200_distilbert_num_params(self._h, ctypes.byref(n)))
+        self.params = torch.zeros(int(n.value), dtype=torch.float32, device=device)
+        nbytes = ctypes.c_size_t()
+        L.check(L.lib.r3m_b200_distilbert_workspace_bytes(self._h, self.max_tokens, ctypes.byref(nbytes)))
+        self._ws = _aligned_empty(int(nbytes.value), device)
+        with torch.cuda.device(device):
+            L.check(L.lib.r3m_b200_distilbert_bind(self._h, L.ptr(self.params), L.ptr(self._ws), self._ws.numel(),
+                                                   self.max_tokens))
+        self.load_state_dict(state_dict)
+
+    def load_state_dict(self, state_dict):
+        sd = {(k[len("distilbert."):] if k.startswith("distilbert.") else k): v for k, v in state_dict.items()}
+        missing = [k for k in self.tensors if k not in sd]
+        if missing:
+            raise KeyError(f"sentence-encoder state_dict lacks {missing[:4]}{'...' if len(missing) > 4 else ''}")
+        for name, (off, shape) in self.tensors.items():
+            t = sd[name]
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+            n = t.numel()
+            self.params[off:off + n].copy_(t.detach().reshape(-1).to(torch.float32))
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_distilbert_sync_weights(self._h, L.current_stream()))
+
+    def encode(self, input_ids, attention_mask=None, return_hidden=False):
+        ids = input_ids.to(self.device, torch.int32).contiguous()
+        if ids.dim() != 2:
+            raise ValueError("input_ids must be [sentences, positions]")
+        B, T = ids.shape
+        if attention_mask is None:
+            mask = torch.ones(B, T, dtype=torch.float32, device=self.device)
+        else:
+            mask = attention_mask.to(self.device, torch.float32).contiguous()
+        out = torch.empty(B, self.dims["dim"], dtype=torch.float32, device=self.device)
+        hidden = torch.empty(B, T, self.dims["dim"], dtype=torch.float32, device=self.device) if return_hidden else None
+        with torch.cuda.device(self.device):
+            L.check(L.lib.r3m_b200_distilbert_forward(self._h, L.ptr(ids), L.ptr(mask), B, T, L.ptr(out), L.ptr(hidden),
+                                                      L.current_stream()))
+        return (out, hidden) if return_hidden else out
+
+    @property
+    def launches_last_call(self):
+        n = ctypes.c_int()
+        L.check(L.lib.r3m_b200_distilbert_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib.r3m_b200_distilbert_destroy(h)

@@ -323,13 +323,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[4 * c + 3] += r.w;
             }
           }
-          if (p.ep_relu) {
+          if (p.ep_relu == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.ep_relu == 2) {  // exact (erf) GELU: the sentence encoder's feed-forward activation
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
           }
           uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[j]) : "f"(f[j]));
+          for (int j = 0; j < 32; ++j) {
+            if (p.ep_exact)
+              pk[j] = __float_as_uint(f[j]);
+            else
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[j]) : "f"(f[j]));
+          }
           const uint32_t stg_u32 = stg_base + buf * kUnitBytes;
           if (++buf == BUFS) buf = 0;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BUFS - 1) : "memory");

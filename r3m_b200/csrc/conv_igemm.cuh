@@ -43,7 +43,8 @@ struct ConvKernelParams {
   const float* ep_scale;
   const float* ep_shift;
   const void* ep_res;  // bf16 [M][ldo] (fp32 in the tf32 tier) or null
-  int ep_relu;
+  int ep_relu;  // 0 none, 1 ReLU, 2 exact GELU (tf32 tier only)
+  int ep_exact;  // tf32 tier: 1 = store the fp32 result as is (consumer is not a tensor-core operand), 0 = round to tf32
   int tf32;  // 1: fp32 operands / output through kind::tf32 (cblocks counts 32-channel blocks); dense mode only
   int* error_flag;
 };

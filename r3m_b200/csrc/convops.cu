@@ -131,6 +131,8 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.ep_shift = g.ep_shift;
   p.ep_res = g.ep_res;
   p.ep_relu = g.ep_relu;
+  p.ep_exact = g.ep_exact;
+  if ((g.ep_relu == 2 || g.ep_exact) && !g.tf32) return "gather conv: GELU / exact outputs exist in the tf32 tier only";
   p.error_flag = device_error_flag();
   if (!p.error_flag) return "could not allocate the device error flag";
   plan->bn = bn;

@@ -34,7 +34,8 @@ struct GatherConv {
   const float* ep_scale = nullptr;
   const float* ep_shift = nullptr;
   const void* ep_res = nullptr;
-  int ep_relu = 0;
+  int ep_relu = 0;   // 0 none, 1 ReLU, 2 exact GELU (tf32 tier only)
+  int ep_exact = 0;  // tf32 tier: keep the fp32 result unrounded (see ConvKernelParams)
   // tf32 tier (inference parity): src / wpk / out / ep_res are fp32 (tf32-rounded values), C % 32 == 0; dense
   // non-accumulating outputs without statistics only
   int tf32 = 0;

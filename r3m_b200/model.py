@@ -320,17 +320,43 @@ def _resize256_center_crop224(x):
 
 
 class LangEncoder(nn.Module):
-    """models_language.py:13-35: frozen distilbert-base-uncased, mean-pooled last hidden state (padding included)."""
+    """models_language.py:13-35: frozen distilbert-base-uncased, mean-pooled last hidden state (padding included).
+    The tokenizer is the reference's (transformers AutoTokenizer, host side); the encoder arithmetic runs on this
+    library's kernels (r3m_b200.bert.DistilBertEncoder: tcgen05 tf32 Linears, fp32 attention / LayerNorm), loaded from
+    the same checkpoint.  `tokenizer` / `hf_model` can be injected (offline use, tests); by default both come from
+    `from_pretrained("distilbert-base-uncased")` like the reference's."""
 
-    def __init__(self, device, finetune=False, scratch=False):
+    def __init__(self, device, finetune=False, scratch=False, tokenizer=None, hf_model=None):
         super().__init__()
-        from transformers import AutoModel, AutoTokenizer
-
         self.device = device
         self.modelname = "distilbert-base-uncased"
-        self.tokenizer = AutoTokenizer.from_pretrained(self.modelname)
-        self.model = AutoModel.from_pretrained(self.modelname).to(self.device)
-        self.lang_size = LANG_DIM
+        if tokenizer is None or hf_model is None:
+            from transformers import AutoModel, AutoTokenizer
+
+            tokenizer = tokenizer or AutoTokenizer.from_pretrained(self.modelname)
+            hf_model = hf_model or AutoModel.from_pretrained(self.modelname)
+        self.tokenizer = tokenizer
+        cfg = hf_model.config
+        self._dims = dict(vocab=cfg.vocab_size, max_pos=cfg.max_position_embeddings, dim=cfg.dim, heads=cfg.n_heads,
+                          layers=cfg.n_layers, ffn=cfg.hidden_dim)
+        if getattr(cfg, "activation", "gelu") != "gelu" or getattr(cfg, "sinusoidal_pos_embds", False):
+            raise ValueError("r3m_b200.LangEncoder implements DistilBERT with GELU and learned position embeddings")
+        # the checkpointed module (state_dict keys `lang_enc.model.*`, like the reference's); its weights are copied into
+        # the native encoder at first use and again after every load_state_dict
+        self.model = hf_model
+        self.lang_size = cfg.dim
+        self._enc = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_enc", None))
+
+    def _encoder(self):
+        if self._enc is None:
+            from .bert import DistilBertEncoder
+
+            dev = torch.device(self.device)
+            if dev.type == "cuda" and dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            self._enc = DistilBertEncoder(self.model.state_dict(), dev, **self._dims)
+        return self._enc
 
     def forward(self, langs):
         try:
@@ -339,9 +365,7 @@ class LangEncoder(nn.Module):
             pass
         with torch.no_grad():
             enc = self.tokenizer(list(langs), return_tensors="pt", padding=True)
-            dev = next(self.model.parameters()).device
-            out = self.model(enc["input_ids"].to(dev), attention_mask=enc["attention_mask"].to(dev)).last_hidden_state
-            return out.mean(1)
+            return self._encoder().encode(enc["input_ids"], enc["attention_mask"])
 
 
 _LANG_ENCODER_FACTORY = None
