@@ -446,6 +446,7 @@ int r3m_b200_engine_get_int(void* handle, int what, int* value) {
     case 0: *value = eng->embed_dim(); break;
     case 1: *value = eng->frames(); break;
     case 2: *value = eng->launches_last_call(); break;
+    case 3: *value = eng->graph_replays(); break;
     default: return fail(R3M_B200_ERR_INVALID, "unknown query");
   }
   return R3M_B200_OK;

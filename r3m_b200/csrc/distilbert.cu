@@ -3,6 +3,7 @@
 // TransformerBlock), which is what r3m/models/models_language.py:23-35 runs under torch.no_grad().
 #include "distilbert.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -22,6 +23,21 @@ __device__ __forceinline__ float round_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
+}
+
+// fp32 on tf32 tensor cores without losing fp32: x = hi + lo with both parts tf32 (round-to-nearest), and
+//   a . w  ~=  a_hi . w_hi + a_lo . w_hi + a_hi . w_lo      (the dropped lo . lo term is ~2^-22 relative),
+// evaluated as ONE GEMM over a three-times-longer reduction axis: activations stored [hi | lo | hi], weights
+// [hi | hi | lo] (fp32 accumulation in the tensor core).
+__device__ __forceinline__ void split_tf32(float v, float* hi, float* lo) {
+  *hi = round_tf32(v);
+  *lo = round_tf32(v - *hi);
+}
+__device__ __forceinline__ void split4(const float4& v, float4* hi, float4* lo) {
+  split_tf32(v.x, &hi->x, &lo->x);
+  split_tf32(v.y, &hi->y, &lo->y);
+  split_tf32(v.z, &hi->z, &lo->z);
+  split_tf32(v.w, &hi->w, &lo->w);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
     }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + kLnEps);
   float4* xo = reinterpret_cast<float4*>(x + static_cast<size_t>(m) * dim);
-  float4* xro = reinterpret_cast<float4*>(xr + static_cast<size_t>(m) * dim);
+  float4* xro = reinterpret_cast<float4*>(xr + static_cast<size_t>(m) * 3 * dim);  // [hi | lo | hi]
   const float4* wv = reinterpret_cast<const float4*>(w);
   const float4* bv = reinterpret_cast<const float4*>(b);
 #pragma unroll
@@ -97,7 +113,11 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
       y.z = (v[i].z - mean) * rstd * g.z + o.z;
       y.w = (v[i].w - mean) * rstd * g.w + o.w;
       xo[lane + 32 * i] = y;
-      xro[lane + 32 * i] = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
+      float4 hi, lo;
+      split4(y, &hi, &lo);
+      xro[lane + 32 * i] = hi;
+      xro[nv * 32 + lane + 32 * i] = lo;
+      xro[2 * nv * 32 + lane + 32 * i] = hi;
     }
 }
 
@@ -190,9 +210,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     }
     if (active) {
       const float inv = (l > 0.f) ? 1.f / l : 0.f;
-      float* o = ctx + static_cast<size_t>(b * T + qi) * dim + hd * kHeadDim;
-      o[lane] = round_tf32(acc0 * inv);
-      o[lane + 32] = round_tf32(acc1 * inv);
+      float* o = ctx + static_cast<size_t>(b * T + qi) * 3 * dim + hd * kHeadDim;  // [hi | lo | hi]
+      float h0, l0, h1, l1;
+      split_tf32(acc0 * inv, &h0, &l0);
+      split_tf32(acc1 * inv, &h1, &l1);
+      o[lane] = h0;
+      o[lane + 32] = h1;
+      o[dim + lane] = l0;
+      o[dim + lane + 32] = l1;
+      o[2 * dim + lane] = h0;
+      o[2 * dim + lane + 32] = h1;
     }
     __syncwarp();
   }
@@ -211,6 +238,25 @@ __global__ void __launch_bounds__(256) mean_pool_kernel(const float* __restrict_
       s += v;
     }
     out[static_cast<size_t>(b) * dim + d] = s / static_cast<float>(T);
+  }
+}
+
+// rows [R][K] fp32 -> [R][3K]: activations (weights == 0) as [hi | lo | hi], weights (weights == 1) as [hi | hi | lo]
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                     long long rows, int K, int weights) {
+  pdl_sync();
+  const long long total = rows * (K / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / (K / 4);
+    const int c = static_cast<int>(i % (K / 4));
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    float4 hi, lo;
+    split4(v, &hi, &lo);
+    float4* o = reinterpret_cast<float4*>(dst + r * 3 * K);
+    o[c] = hi;
+    o[K / 4 + c] = weights ? hi : lo;
+    o[2 * (K / 4) + c] = weights ? lo : hi;
   }
 }
 
@@ -268,6 +314,10 @@ std::string DistilBert::create(const BertDims& d, DistilBert** out) {
     L.b[5] = add(pre + "ffn.lin2.bias", kLinearB, d.dim, 0);
     L.ln2_w = add(pre + "output_layer_norm.weight", kVector, d.dim, 0);
     L.ln2_b = add(pre + "output_layer_norm.bias", kVector, d.dim, 0);
+    for (int i = 0; i < 6; ++i) {
+      L.wt[i] = 3 * m->lin_weight_floats_;
+      m->lin_weight_floats_ += static_cast<size_t>(i == 4 ? d.ffn : d.dim) * (i == 5 ? d.ffn : d.dim);
+    }
     m->layers_.push_back(L);
   }
   m->lin_end_ = off;
@@ -278,12 +328,14 @@ std::string DistilBert::create(const BertDims& d, DistilBert** out) {
 
 size_t DistilBert::workspace_bytes(int max_tokens) const {
   const size_t M = static_cast<size_t>(max_tokens > 0 ? max_tokens : 0);
-  size_t b = align_up((lin_end_ - lin_begin_) * 4, 1024);
-  b += 3 * align_up(M * d_.dim * 4, 1024);      // x, xr, ctx
-  b += align_up(M * 3 * d_.dim * 4, 1024);      // qkv
-  b += align_up(M * d_.dim * 4, 1024);          // h
-  b += align_up(M * d_.ffn * 4, 1024);          // ff
-  b += align_up(static_cast<size_t>(d_.ffn > 3 * d_.dim ? d_.ffn : 3 * d_.dim) * 4, 1024);  // ones
+  size_t b = align_up(3 * lin_weight_floats_ * 4, 1024);  // split weights [hi | hi | lo]
+  b += align_up(M * d_.dim * 4, 1024);                    // x
+  b += 2 * align_up(M * 3 * d_.dim * 4, 1024);            // xr, ctx (split)
+  b += align_up(M * 3 * d_.dim * 4, 1024);                // qkv
+  b += align_up(M * d_.dim * 4, 1024);                    // h
+  b += align_up(M * d_.ffn * 4, 1024);                    // ff
+  b += align_up(M * 3 * d_.ffn * 4, 1024);                // ffs (split)
+  b += align_up(static_cast<size_t>(d_.ffn) * 4, 1024);   // ones
   return b;
 }
 
@@ -303,25 +355,33 @@ std::string DistilBert::bind(float* params, void* ws, size_t ws_bytes, int max_t
     p += align_up(bytes, 1024);
     return r;
   };
-  Pt_ = take((lin_end_ - lin_begin_) * 4);
+  Pt_ = take(3 * lin_weight_floats_ * 4);
   x_ = take(M * d_.dim * 4);
-  xr_ = take(M * d_.dim * 4);
-  ctx_ = take(M * d_.dim * 4);
+  xr_ = take(M * 3 * d_.dim * 4);
+  ctx_ = take(M * 3 * d_.dim * 4);
   qkv_ = take(M * 3 * d_.dim * 4);
   h_ = take(M * d_.dim * 4);
   ff_ = take(M * d_.ffn * 4);
-  ones_ = take(static_cast<size_t>(d_.ffn > 3 * d_.dim ? d_.ffn : 3 * d_.dim) * 4);
+  ffs_ = take(M * 3 * d_.ffn * 4);
+  ones_ = take(static_cast<size_t>(d_.ffn) * 4);
   return std::string();
 }
 
 std::string DistilBert::sync_weights(cudaStream_t stream) {
   if (!P_) return "distilbert: not bound";
-  cudaError_t e = launch_round_tf32(P_ + lin_begin_, Pt_, lin_end_ - lin_begin_, stream);
-  if (e != cudaSuccess) return std::string("distilbert round_tf32: ") + cudaGetErrorString(e);
-  const int n = d_.ffn > 3 * d_.dim ? d_.ffn : 3 * d_.dim;
+  for (const Layer& L : layers_)
+    for (int i = 0; i < 6; ++i) {
+      const long long rows = (i == 4) ? d_.ffn : d_.dim;
+      const int K = (i == 5) ? d_.ffn : d_.dim;
+      const long long work = rows * (K / 4);
+      const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 148 * 8));
+      launch_kernel(split3_kernel, dim3(grid), dim3(256), 0, stream, static_cast<const float*>(P_ + L.w[i]),
+                    Pt_ + L.wt[i], rows, K, 1);
+    }
+  const int n = d_.ffn;
   launch_kernel(fill_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, ones_, n, 1.0f);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return std::string("distilbert fill: ") + cudaGetErrorString(e);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return std::string("distilbert sync_weights: ") + cudaGetErrorString(e);
   return std::string();
 }
 
@@ -335,8 +395,8 @@ std::string DistilBert::plan_for(int M, Plans** out) {
   std::string err;
   // y[M][Cout] (row pitch ldo, column offset col0) = act(src[M][K] . W[Cout][K]^T + bias [+ res]); the per-channel
   // affine table of the epilogue holds at most 2048 channels per launch, wider outputs go out as column slices
-  auto gemm = [&](const float* src, int K, size_t w_off, size_t b_off, int Cout, float* dst, int ldo, const float* res,
-                  int act, int exact) {
+  auto gemm = [&](const float* src, int K3, size_t wt_off, size_t b_off, int Cout, float* dst, int ldo, const float* res,
+                  int act) {
     const int slices = (Cout + 2047) / 2048;
     const int per = Cout / slices;
     if (per * slices != Cout || per % 64 != 0) {
@@ -348,10 +408,10 @@ std::string DistilBert::plan_for(int M, Plans** out) {
       g.src = src;
       g.N = M;
       g.H = g.W = g.P = g.Q = 1;
-      g.C = K;
+      g.C = K3;
       g.stride = 1;
       g.ntaps = 1;
-      g.wpk = Pt_ + (w_off - lin_begin_) + static_cast<size_t>(s) * per * K;
+      g.wpk = Pt_ + wt_off + static_cast<size_t>(s) * per * K3;
       g.Cout = per;
       g.out = dst + s * per;
       g.ldo = ldo;
@@ -359,7 +419,7 @@ std::string DistilBert::plan_for(int M, Plans** out) {
       g.ep_shift = P_ + b_off + s * per;
       g.ep_res = res ? res + s * per : nullptr;
       g.ep_relu = act;
-      g.ep_exact = exact;
+      g.ep_exact = 1;  // every consumer re-splits (or is fp32 SIMT): keep the fp32 result
       g.tf32 = 1;
       ConvPlan cp;
       const std::string e2 = plan_conv(g, &cp);
@@ -370,12 +430,13 @@ std::string DistilBert::plan_for(int M, Plans** out) {
       pl.gemm.push_back(cp);
     }
   };
+  const int D3 = 3 * d_.dim, F3 = 3 * d_.ffn;
   for (const Layer& L : layers_) {
     const size_t before = pl.gemm.size();
-    for (int i = 0; i < 3; ++i) gemm(xr_, d_.dim, L.w[i], L.b[i], d_.dim, qkv_ + i * d_.dim, 3 * d_.dim, nullptr, 0, 1);
-    gemm(ctx_, d_.dim, L.w[3], L.b[3], d_.dim, h_, d_.dim, x_, 0, 1);        // out_lin + residual -> sa_layer_norm
-    gemm(xr_, d_.dim, L.w[4], L.b[4], d_.ffn, ff_, d_.ffn, nullptr, 2, 0);   // lin1 + GELU (operand of lin2: rounded)
-    gemm(ff_, d_.ffn, L.w[5], L.b[5], d_.dim, h_, d_.dim, x_, 0, 1);         // lin2 + residual -> output_layer_norm
+    for (int i = 0; i < 3; ++i) gemm(xr_, D3, L.wt[i], L.b[i], d_.dim, qkv_ + i * d_.dim, D3, nullptr, 0);
+    gemm(ctx_, D3, L.wt[3], L.b[3], d_.dim, h_, d_.dim, x_, 0);    // out_lin + residual -> sa_layer_norm
+    gemm(xr_, D3, L.wt[4], L.b[4], d_.ffn, ff_, d_.ffn, nullptr, 2);  // lin1 + GELU
+    gemm(ffs_, F3, L.wt[5], L.b[5], d_.dim, h_, d_.dim, x_, 0);   // lin2 + residual -> output_layer_norm
     if (!err.empty()) return err;
     pl.per_layer = static_cast<int>(pl.gemm.size() - before);
   }
@@ -421,8 +482,18 @@ std::string DistilBert::forward(const int* ids, const float* mask, int B, int T,
                   static_cast<const float*>(nullptr), static_cast<const float*>(P_ + L.ln1_w),
                   static_cast<const float*>(P_ + L.ln1_b), x_, xr_, M, T, d_.dim, d_.vocab, flag);
     ++launches_;
-    for (int i = 0; i < ff1_slices + 1 && e == cudaSuccess; ++i, ++launches_) e = run_conv(pl->gemm[gi++], stream);
-    if (e != cudaSuccess) return std::string("distilbert ffn: ") + cudaGetErrorString(e);
+    for (int i = 0; i < ff1_slices && e == cudaSuccess; ++i, ++launches_) e = run_conv(pl->gemm[gi++], stream);
+    if (e != cudaSuccess) return std::string("distilbert ffn.lin1: ") + cudaGetErrorString(e);
+    {
+      const long long work = static_cast<long long>(M) * (d_.ffn / 4);
+      const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 148 * 8));
+      launch_kernel(split3_kernel, dim3(grid), dim3(256), 0, stream, static_cast<const float*>(ff_), ffs_,
+                    static_cast<long long>(M), d_.ffn, 0);
+      ++launches_;
+    }
+    e = run_conv(pl->gemm[gi++], stream);
+    ++launches_;
+    if (e != cudaSuccess) return std::string("distilbert ffn.lin2: ") + cudaGetErrorString(e);
     launch_kernel(layernorm_kernel<false>, ln_grid, ln_block, 0, stream, static_cast<const float*>(h_),
                   static_cast<const int*>(nullptr), static_cast<const float*>(nullptr),
                   static_cast<const float*>(nullptr), static_cast<const float*>(P_ + L.ln2_w),

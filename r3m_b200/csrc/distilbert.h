@@ -3,7 +3,8 @@
 // The arithmetic of transformers' DistilBertModel (embeddings + LayerNorm, 6 x [multi-head attention, residual + LayerNorm,
 // GELU feed-forward, residual + LayerNorm]) on the sm_100a kernels of this library: every Linear is the tcgen05
 // implicit-GEMM kernel in its tf32 tier (a 1x1 "convolution" over the token axis; bias, residual and GELU fused into the
-// epilogue), attention / LayerNorm / pooling are small fused fp32 kernels.  Inference only (the reference freezes it).
+// epilogue) with fp32 operands split into two tf32 terms (three products: fp32-grade results, see distilbert.cu);
+// attention / LayerNorm / pooling are small fused fp32 kernels.  Inference only (the reference freezes it).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -40,7 +41,8 @@ class DistilBert {
 
  private:
   struct Layer {
-    size_t w[6], b[6];  // q, k, v, out, ff1, ff2
+    size_t w[6], b[6];  // q, k, v, out, ff1, ff2 (offsets in the parameter buffer)
+    size_t wt[6];       // offsets of the split operand copies [Cout][hi | hi | lo]
     size_t ln1_w, ln1_b, ln2_w, ln2_b;
   };
   struct Plans {
@@ -53,13 +55,15 @@ class DistilBert {
   std::vector<TensorInfo> tensors_;
   std::vector<Layer> layers_;
   size_t word_off_ = 0, pos_off_ = 0, eln_w_ = 0, eln_b_ = 0, nparams_ = 0;
-  size_t lin_begin_ = 0, lin_end_ = 0;  // the transformer layers' parameters (the span that gets a tf32-rounded copy)
+  size_t lin_begin_ = 0, lin_end_ = 0;  // the transformer layers' parameters
+  size_t lin_weight_floats_ = 0;        // Linear weights of all layers (their split copies take three times this)
   float* P_ = nullptr;   // fp32 master parameters
-  float* Pt_ = nullptr;  // tf32-rounded copy of [lin_begin_, lin_end_)
+  float* Pt_ = nullptr;  // split operand copies of the Linear weights: [Cout][hi | hi | lo] (distilbert.cu: split_tf32)
   int max_tokens_ = 0;
-  // activations (fp32): x residual stream (exact), xr its tf32-rounded copy (GEMM operand), qkv [M][3*dim], ctx
-  // attention output (tf32-rounded), h pre-LayerNorm sums, ff GELU(lin1) (tf32-rounded)
-  float *x_ = nullptr, *xr_ = nullptr, *qkv_ = nullptr, *ctx_ = nullptr, *h_ = nullptr, *ff_ = nullptr, *ones_ = nullptr;
+  // activations (fp32): x residual stream, xr / ctx / ffs the split [hi | lo | hi] GEMM operands (LayerNorm output,
+  // attention output, GELU output), qkv [M][3*dim], h pre-LayerNorm sums, ff GELU(lin1) before the split
+  float *x_ = nullptr, *xr_ = nullptr, *qkv_ = nullptr, *ctx_ = nullptr, *h_ = nullptr, *ff_ = nullptr, *ffs_ = nullptr,
+        *ones_ = nullptr;
   std::map<int, Plans> plans_;
   int launches_ = 0;
 };

@@ -55,6 +55,11 @@ constexpr int kGraphMaxFrames = 16;  // eval forwards up to this many frames are
 
 Engine::~Engine() {
   if (eval_graph_) cudaGraphExecDestroy(eval_graph_);
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (cudaEvent_t ev : ext_evs_)
+    if (ev) cudaEventDestroy(ev);
+  if (cap_) cudaStreamDestroy(cap_);
   for (cudaEvent_t ev : evs_) cudaEventDestroy(ev);
   if (side_) cudaStreamDestroy(side_);
   for (Conv* c : convs_) delete c;
@@ -957,6 +962,18 @@ std::string Engine::plan_all() {
     evs_.push_back(ev);
   }
   if (!side_ && cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking) != cudaSuccess) return "side stream creation failed";
+  for (auto& kv : graphs_)  // a re-plan (re-bind) invalidates every captured pointer
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+  ext_evs_.resize(evs_.size(), nullptr);
+  for (const GradChunk& c : chunks_)
+    for (int id : {c.main_event, c.side_event})
+      if (id >= 0 && !ext_evs_[id] && cudaEventCreateWithFlags(&ext_evs_[id], cudaEventDisableTiming) != cudaSuccess)
+        return "cudaEventCreate failed";
+  {
+    const char* env = std::getenv("R3M_STEP_GRAPH");
+    use_graph_ = !(env && env[0] == '0');
+  }
   {
     const char* env = std::getenv("R3M_WGRAD_STREAM");
     use_side_ = !(env && env[0] == '0');
@@ -1019,9 +1036,57 @@ std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
     if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
     if (op.record >= 0) {  // also in single-stream runs: the gradient-chunk markers are read by wait_grad_chunk
       cudaError_t re = cudaEventRecord(evs_[op.record], s);
+      if (re == cudaSuccess && capturing_ && ext_evs_[op.record] != nullptr)
+        re = cudaEventRecordWithFlags(ext_evs_[op.record], s, cudaEventRecordExternal);
       if (re != cudaSuccess) return std::string("event record failed: ") + cudaGetErrorString(re);
     }
   }
+  return std::string();
+}
+
+std::string Engine::run_cached(const std::vector<uint64_t>& key, cudaStream_t stream,
+                               const std::function<std::string(cudaStream_t)>& body, bool* graphed) {
+  *graphed = false;
+  constexpr size_t kMaxGraphs = 8;  // distinct input-pointer sets worth keeping (double-buffered feeders need two)
+  if (!use_graph_ || profiling_ || capturing_) return body(stream);
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    if (graphs_.size() >= kMaxGraphs) return body(stream);
+    it = graphs_.emplace(key, GraphEntry()).first;
+  }
+  GraphEntry& ge = it->second;
+  if (ge.exec == nullptr && !ge.failed && ge.seen >= 1) {
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+    if (!cap_ && cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking) != cudaSuccess) cap_ = nullptr;
+    cudaGraph_t graph = nullptr;
+    const int before = launches_;
+    if (cap_ && cudaStreamBeginCapture(cap_, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      capturing_ = true;
+      const std::string cerr = body(cap_);
+      capturing_ = false;
+      const cudaError_t ee = cudaStreamEndCapture(cap_, &graph);
+      if (cerr.empty() && ee == cudaSuccess && graph != nullptr &&
+          cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess) {
+        ge.launches = launches_ - before;
+      } else {
+        ge.exec = nullptr;
+        ge.failed = true;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+    } else {
+      ge.failed = true;
+      (void)cudaGetLastError();
+    }
+    launches_ = before;
+  }
+  ++ge.seen;
+  if (ge.exec == nullptr) return body(stream);
+  const cudaError_t e = cudaGraphLaunch(ge.exec, stream);
+  if (e != cudaSuccess) return std::string("graph launch: ") + cudaGetErrorString(e);
+  launches_ += ge.launches;
+  ++graph_replays_;
+  *graphed = true;
   return std::string();
 }
 
@@ -1168,19 +1233,25 @@ std::string Engine::forward(const void* obs, int train, float* out, cudaStream_t
       if (!err.empty()) return err;
     }
   } else {
-    if (train) {
-      e = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, stream);
-      if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
-    }
-    {
+    auto body = [this, obs, train](cudaStream_t st) -> std::string {
+      if (train) {
+        cudaError_t me = cudaMemsetAsync(ws_ + off_zero_, 0, zero_bytes_, st);
+        if (me != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(me);
+      }
       void* xs = ws_ + off_xs_;
       const int N = N_, fmt = obs_format_;
-      e = launch(Op([obs, xs, N, fmt](cudaStream_t s) { return launch_preprocess_stem(obs, fmt, xs, N, s); }, kFamNorm,
+      cudaError_t pe =
+          launch(Op([obs, xs, N, fmt](cudaStream_t s) { return launch_preprocess_stem(obs, fmt, xs, N, s); }, kFamNorm,
                     0.0, (double)N * (3.0 * 224 * 224 * (fmt == kObsF32NCHW ? 4 : 1) + 112.0 * 112 * 64 * 2)),
-                 stream);
-    }
-    if (e != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(e);
-    err = run(train ? fwd_train_ : fwd_eval_, stream);
+                 st);
+      if (pe != cudaSuccess) return std::string("preprocess: ") + cudaGetErrorString(pe);
+      return run(train ? fwd_train_ : fwd_eval_, st);
+    };
+    bool graphed = false;
+    if (train)
+      err = run_cached({1u, (uint64_t)reinterpret_cast<uintptr_t>(obs), (uint64_t)obs_format_}, stream, body, &graphed);
+    else
+      err = body(stream);
     if (!err.empty()) return err;
     fwd_train_valid_ = train != 0;
     fwd_launches_ = launches_;
@@ -1226,73 +1297,91 @@ std::string Engine::update_grads(const void* obs, const int* perms, const float*
     launches_ = fwd_launches_;
   }
   fwd_train_valid_ = false;
-  if (!eval) {
-    e = cudaMemsetAsync(pws_ + off_G_, 0, nparams_ * 4, stream);
-    if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
-  }
-  const float* E = reinterpret_cast<const float*>(ws_ + off_E_);
-  float* dE = eval ? nullptr : reinterpret_cast<float*>(ws_ + off_dE_);
-  float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
-  {
-    const int N = N_, D = D_, B = B_;
-    const float l2w = h.l2weight, l1w = h.l1weight, tcnw = h.tcnweight;
-    float* lp_scratch = reinterpret_cast<float*>(ws_ + off_det_loss_);
-    float* tcn_scratch = lp_scratch + (size_t)N * 4;
-    Op lp([=](cudaStream_t s) { return launch_loss_lp(E, dE, N, D, l2w, l1w, metrics, s, lp_scratch); }, kFamLoss, 0.0,
-          (double)N * D * 8);
-    lp.nlaunch = 2;
-    e = launch(lp, stream);
-    if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
-    if (tcnw > 0.f) {
-      const int l2dist = l2dist_ ? 1 : 0;
-      Op tcn([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, l2dist, metrics, s, tcn_scratch); },
-             kFamLoss, 0.0, (double)B * 18 * D * 4 * 2);
-      tcn.nlaunch = dE ? 3 : 2;
-      e = launch(tcn, stream);
-      if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
+  // everything behind the forward pass: gradient clear, loss heads, language head, backward, watchdog flag
+  auto tail = [this, perms, lang_emb, lang_mask, h, eval](cudaStream_t st) -> std::string {
+    cudaError_t e;
+    if (!eval) {
+      e = cudaMemsetAsync(pws_ + off_G_, 0, nparams_ * 4, st);
+      if (e != cudaSuccess) return std::string("memset: ") + cudaGetErrorString(e);
     }
-  }
-  if (h.langweight > 0.f) {
-    float* P = reinterpret_cast<float*>(pws_ + off_P_);
-    float* G = reinterpret_cast<float*>(pws_ + off_G_);
-    LangParams lp;
-    for (int l = 0; l < 5; ++l) {
-      lp.w[l] = P + lang_w_off_[l];
-      lp.b[l] = P + lang_b_off_[l];
-      lp.dw[l] = G + lang_w_off_[l];
-      lp.db[l] = G + lang_b_off_[l];
+    const float* E = reinterpret_cast<const float*>(ws_ + off_E_);
+    float* dE = eval ? nullptr : reinterpret_cast<float*>(ws_ + off_dE_);
+    float* metrics = reinterpret_cast<float*>(ws_ + off_metrics_);
+    {
+      const int N = N_, D = D_, B = B_;
+      const float l2w = h.l2weight, l1w = h.l1weight, tcnw = h.tcnweight;
+      float* lp_scratch = reinterpret_cast<float*>(ws_ + off_det_loss_);
+      float* tcn_scratch = lp_scratch + (size_t)N * 4;
+      Op lp([=](cudaStream_t s) { return launch_loss_lp(E, dE, N, D, l2w, l1w, metrics, s, lp_scratch); }, kFamLoss, 0.0,
+            (double)N * D * 8);
+      lp.nlaunch = 2;
+      e = launch(lp, st);
+      if (e != cudaSuccess) return std::string("loss_lp: ") + cudaGetErrorString(e);
+      if (tcnw > 0.f) {
+        const int l2dist = l2dist_ ? 1 : 0;
+        Op tcn([=](cudaStream_t s) { return launch_loss_tcn(E, dE, perms, B, D, tcnw, l2dist, metrics, s, tcn_scratch); },
+               kFamLoss, 0.0, (double)B * 18 * D * 4 * 2);
+        tcn.nlaunch = dE ? 3 : 2;
+        e = launch(tcn, st);
+        if (e != cudaSuccess) return std::string("loss_tcn: ") + cudaGetErrorString(e);
+      }
     }
-    LangWorkspace lw;
-    lang_carve_workspace(reinterpret_cast<float*>(ws_ + off_lang_ws_), lang_dims_, &lw);
-    const LangDims ld = lang_dims_;
-    const float langw = h.langweight;
-    int n_lang = 0;
-    int* n_ptr = &n_lang;
-    // the head is ~25 launches; it is charged to the "lang" family as one profiled unit
-    // algorithmic MACs of the factorised head: layer 1 once per distinct row (B e0 rows, 5B e_t rows, B sentences),
-    // layers 2-4 over the 15B evaluations
-    const double rows = ld.rows(), H = ld.H, Bc = ld.B, Dd = ld.D, Ll = ld.L;
-    const double l1_mac = (6.0 * Bc * Dd + Bc * Ll) * H;
-    const double fwd_mac = l1_mac + rows * (3 * H * H + H);
-    const double bwd_mac = 2.0 * rows * 3 * H * H + (l1_mac + 6.0 * Bc * Dd * H);
-    e = launch(Op([=](cudaStream_t s) {
-                 return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s);
-               },
-               kFamLang, 2.0 * (fwd_mac + (eval ? 0.0 : bwd_mac)), 0.0),
-               stream);
-    if (e != cudaSuccess) return std::string("lang head: ") + cudaGetErrorString(e);
-    launches_ += n_lang - 1;
-  }
-  if (!eval) {
-    err = run(bwd_, stream);
-    if (!err.empty()) return err;
-  }
-  {
+    if (h.langweight > 0.f) {
+      float* P = reinterpret_cast<float*>(pws_ + off_P_);
+      float* G = reinterpret_cast<float*>(pws_ + off_G_);
+      LangParams lp;
+      for (int l = 0; l < 5; ++l) {
+        lp.w[l] = P + lang_w_off_[l];
+        lp.b[l] = P + lang_b_off_[l];
+        lp.dw[l] = G + lang_w_off_[l];
+        lp.db[l] = G + lang_b_off_[l];
+      }
+      LangWorkspace lw;
+      lang_carve_workspace(reinterpret_cast<float*>(ws_ + off_lang_ws_), lang_dims_, &lw);
+      const LangDims ld = lang_dims_;
+      const float langw = h.langweight;
+      int n_lang = 0;
+      int* n_ptr = &n_lang;
+      // the head is ~25 launches; it is charged to the "lang" family as one profiled unit
+      // algorithmic MACs of the factorised head: layer 1 once per distinct row (B e0 rows, 5B e_t rows, B sentences),
+      // layers 2-4 over the 15B evaluations
+      const double rows = ld.rows(), H = ld.H, Bc = ld.B, Dd = ld.D, Ll = ld.L;
+      const double l1_mac = (6.0 * Bc * Dd + Bc * Ll) * H;
+      const double fwd_mac = l1_mac + rows * (3 * H * H + H);
+      const double bwd_mac = 2.0 * rows * 3 * H * H + (l1_mac + 6.0 * Bc * Dd * H);
+      e = launch(Op([=](cudaStream_t s) {
+                   return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s);
+                 },
+                 kFamLang, 2.0 * (fwd_mac + (eval ? 0.0 : bwd_mac)), 0.0),
+                 st);
+      if (e != cudaSuccess) return std::string("lang head: ") + cudaGetErrorString(e);
+      launches_ += n_lang - 1;
+    }
+    if (!eval) {
+      const std::string berr = run(bwd_, st);
+      if (!berr.empty()) return berr;
+    }
     const int* flag = device_error_flag();
-    e = launch(Op([flag, metrics](cudaStream_t s) { return launch_publish_flag(flag, metrics, s); }, kFamLoss), stream);
+    e = launch(Op([flag, metrics](cudaStream_t s) { return launch_publish_flag(flag, metrics, s); }, kFamLoss), st);
     if (e != cudaSuccess) return std::string("publish_flag: ") + cudaGetErrorString(e);
+    return std::string();
+  };
+  bool graphed = false;
+  if (!eval) {
+    auto bits = [](float v) {
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      return (uint64_t)u;
+    };
+    err = run_cached({2u, (uint64_t)reinterpret_cast<uintptr_t>(perms), (uint64_t)reinterpret_cast<uintptr_t>(lang_emb),
+                      (uint64_t)reinterpret_cast<uintptr_t>(lang_mask), bits(h.l2weight), bits(h.l1weight),
+                      bits(h.langweight), bits(h.tcnweight), (uint64_t)(l2dist_ ? 1 : 0), (uint64_t)(use_side_ ? 1 : 0)},
+                     stream, tail, &graphed);
+    last_bwd_graphed_ = graphed;
+  } else {
+    err = tail(stream);
   }
-  return std::string();
+  return err;
 }
 
 std::string Engine::backward(const float* dE, cudaStream_t stream) {
@@ -1300,6 +1389,7 @@ std::string Engine::backward(const float* dE, cudaStream_t stream) {
   if (!fwd_train_valid_) return "backward() needs a preceding train-mode forward() on this engine (its activations are gone)";
   launches_ = 0;
   fwd_train_valid_ = false;
+  last_bwd_graphed_ = false;
   cudaError_t e = cudaMemcpyAsync(ws_ + off_dE_, dE, (size_t)N_ * D_ * 4, cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) return std::string("copy dE: ") + cudaGetErrorString(e);
   std::string err = run(bwd_, stream);
@@ -1323,8 +1413,10 @@ std::string Engine::grad_chunk(int k, size_t* begin, size_t* end) const {
 std::string Engine::wait_grad_chunk(int k, cudaStream_t stream) {
   if (k < 0 || k >= (int)chunks_.size()) return "gradient chunk index out of range";
   const GradChunk& c = chunks_[k];
-  cudaError_t e = cudaStreamWaitEvent(stream, evs_[c.main_event], 0);
-  if (e == cudaSuccess && c.side_event >= 0) e = cudaStreamWaitEvent(stream, evs_[c.side_event], 0);
+  // a replayed graph records the chunk markers through their external twins (see run())
+  const std::vector<cudaEvent_t>& evs = last_bwd_graphed_ ? ext_evs_ : evs_;
+  cudaError_t e = cudaStreamWaitEvent(stream, evs[c.main_event], 0);
+  if (e == cudaSuccess && c.side_event >= 0) e = cudaStreamWaitEvent(stream, evs[c.side_event], 0);
   if (e != cudaSuccess) return std::string("stream wait failed: ") + cudaGetErrorString(e);
   return std::string();
 }

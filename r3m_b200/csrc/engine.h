@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -94,6 +95,7 @@ class Engine {
   // step: 1-based Adam step count (bias correction); the caller owns it because engines share a parameter block
   std::string adam_step(float lr, float grad_scale, int step, cudaStream_t stream);
   int launches_last_call() const { return launches_; }
+  int graph_replays() const { return graph_replays_; }  // cudaGraphLaunch calls of the training step so far
   // per-launch records of the last profile_update: {family, ms, flops, bytes} each
   const std::vector<double>& last_profile_ops() const { return prof_last_; }
   const std::vector<std::string>& last_profile_labels() const { return prof_labels_; }
@@ -155,6 +157,29 @@ class Engine {
   std::vector<double> prof_flops_, prof_bytes_, prof_last_;
   std::vector<std::string> prof_labels_, prof_labels_run_;
   cudaError_t launch(const Op& op, cudaStream_t stream);
+
+  // Whole-step CUDA graphs.  The training step is two fixed launch sequences — the train-mode forward (memset,
+  // preprocess, ~105 launches) and everything behind it (loss heads, language head, the two-stream backward pass: ~250
+  // launches) — whose only variable inputs are pointers and a few scalars.  The first call with a given set of them runs
+  // plainly (it also configures every kernel's attributes), the second is captured (relaxed stream capture, the side
+  // stream joins through the schedule's own events) and instantiated, every later one is ONE cudaGraphLaunch.
+  // R3M_STEP_GRAPH=0 disables it.  The gradient-chunk markers are additionally recorded as EXTERNAL events so that
+  // wait_grad_chunk works on a replayed graph.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    int launches = 0;
+    bool failed = false;
+  };
+  std::string run_cached(const std::vector<uint64_t>& key, cudaStream_t stream,
+                         const std::function<std::string(cudaStream_t)>& body, bool* graphed);
+  std::map<std::vector<uint64_t>, GraphEntry> graphs_;
+  bool use_graph_ = true;
+  bool capturing_ = false;
+  bool last_bwd_graphed_ = false;
+  int graph_replays_ = 0;
+  cudaStream_t cap_ = nullptr;
+  std::vector<cudaEvent_t> ext_evs_;   // external twins of the gradient-chunk events (null elsewhere)
 
   // arena offsets (bytes)
   size_t off_P_ = 0, off_G_ = 0, off_M_ = 0, off_V_ = 0, off_Pb_ = 0, off_buf_ = 0, off_saved_ = 0, off_zero_ = 0,

@@ -104,6 +104,12 @@ class Engine:
         L.check(L.lib.r3m_b200_engine_get_int(self._h, 2, ctypes.byref(v)))
         return v.value
 
+    def graph_replays(self):
+        """cudaGraphLaunch calls so far (the training step replays two captured graphs; R3M_STEP_GRAPH=0 disables)."""
+        v = ctypes.c_int()
+        L.check(L.lib.r3m_b200_engine_get_int(self._h, 3, ctypes.byref(v)))
+        return v.value
+
     def sync_weights(self):
         with torch.cuda.device(self.device):
             L.check(L.lib.r3m_b200_engine_sync_weights(self._h, L.current_stream()))

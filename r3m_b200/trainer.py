@@ -99,11 +99,9 @@ class Trainer:
             self._side_dev = torch.empty(total, dtype=torch.uint8, device=dev)
             self._side_key = key
         host, devb = self._side_host, self._side_dev
-        if perms.is_cuda:  # already resident (benchmarks / tests may inject device tensors)
-            perms_dev = perms.to(device=dev, dtype=torch.int32).contiguous()
-        else:
+        perms_dev = devb[:perms.numel() * 4].view(torch.int32).view(perms.shape)
+        if not perms.is_cuda:
             host[:perms.numel() * 4].view(torch.int32).copy_(perms.reshape(-1).to(torch.int32))
-            perms_dev = devb[:perms.numel() * 4].view(torch.int32).view(perms.shape)
         mask_dev = emb_dev = None
         if mask is not None:
             host[n_perm:n_perm + mask.numel() * 4].view(torch.float32).copy_(mask)
@@ -113,8 +111,17 @@ class Trainer:
             host[o:o + lang_emb.numel() * 4].view(torch.float32).copy_(lang_emb.reshape(-1).to(torch.float32))
             emb_dev = devb[o:o + lang_emb.numel() * 4].view(torch.float32).view(lang_emb.shape)
         elif lang_emb is not None:
-            emb_dev = lang_emb.to(device=dev, dtype=torch.float32).contiguous()
+            # a device-resident embedding (the native sentence encoder's output) is copied into a buffer that keeps its
+            # address from step to step: the captured step graph (engine: run_cached) is keyed on its input pointers
+            key_e = (str(dev), tuple(lang_emb.shape))
+            if getattr(self, "_emb_key", None) != key_e:
+                self._emb_buf = torch.empty(lang_emb.shape, dtype=torch.float32, device=dev)
+                self._emb_key = key_e
+            self._emb_buf.copy_(lang_emb)
+            emb_dev = self._emb_buf
         L.check(L.lib.r3m_b200_pull_host(host.data_ptr(), devb.data_ptr(), total, L.current_stream()))
+        if perms.is_cuda:  # already resident (benchmarks / tests may inject device tensors): after the pull, same stream
+            perms_dev.copy_(perms)
         return perms_dev, mask_dev, emb_dev
 
     def update(self, model, batch, step, eval=False, perms=None, lang_emb=None):

@@ -1,8 +1,9 @@
 """SURVEY.md §8 f2 — the frozen DistilBERT sentence encoder (r3m/models/models_language.py:13-35) on the library's own
 kernels, against transformers' DistilBertModel (the module the reference instantiates) in strict fp32 on the same GPU.
 distilbert-base-uncased's weights are unreachable offline, so both sides load the same seeded random-init checkpoint of
-the real architecture (full size) — the arithmetic under test does not depend on the values.  Tolerance: the north
-star's embedding bound, 1e-3 relative (the Linears run on tf32 tensor cores: 10-bit mantissa operands, fp32 accumulate)."""
+the real architecture (full size) — the arithmetic under test does not depend on the values.  Tolerance 1e-4 relative,
+ten times tighter than the north star's embedding bound: the Linears run on tf32 tensor cores with every fp32 operand
+split into two tf32 terms (three products, fp32 accumulation), which measured 1.3e-3 with plain tf32 rounding."""
 import pytest
 import torch
 
@@ -10,7 +11,7 @@ from gpu_common import rel, strict_fp32
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-3
+TOL = 1e-4
 
 
 def _hf_model(seed, **cfg):
@@ -64,8 +65,8 @@ def test_full_size_encoder_matches_transformers(B, T):
     torch.cuda.synchronize()
     assert rel(got_h, want_h) < TOL, rel(got_h, want_h)
     assert rel(got, want) < TOL, rel(got, want)
-    assert float((got_h - want_h).abs().max()) < 2e-2  # no single token is off (LayerNorm output is O(1))
-    assert enc.launches_last_call == 1 + 6 * 10 + 1
+    assert float((got_h - want_h).abs().max()) < 2e-3  # no single token is off (LayerNorm output is O(1))
+    assert enc.launches_last_call == 1 + 6 * 11 + 1
 
 
 def test_long_sentences_take_the_tiled_attention_path():

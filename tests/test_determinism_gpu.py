@@ -107,3 +107,36 @@ def test_fixed_point_accumulator_is_exact_and_order_independent(lib, scale):
     xp = xd[perm].contiguous()
     lib.check(lib.lib.r3m_b200_ordered_sum(lib.ptr(xp), xp.numel(), lib.ptr(out), 148, lib.current_stream()))
     assert torch.equal(out.cpu(), outs[0])
+
+
+@pytest.mark.parametrize("size,clips,lang", [(18, 6, 1), (50, 10, 1)])
+def test_step_graph_replay_equals_plain_launches(monkeypatch, size, clips, lang):
+    """Whole-step CUDA graphs (engine.cu: run_cached): from the third step with the same input buffers on, the train-mode
+    forward and everything behind it (loss heads, language head, two-stream backward) are ONE cudaGraphLaunch each.  Same
+    kernels in the same dependency order: weights, Adam moments and metrics must equal the plainly launched run bit for
+    bit, and the replay must actually have happened."""
+    from r3m_b200 import Trainer
+
+    def run(graph):
+        monkeypatch.setenv("R3M_STEP_GRAPH", "1" if graph else "0")
+        params, buffers = well_conditioned_state(size, 120, bool(lang))
+        lang_emb = O.stub_lang_embedding(clips, 121).cuda() if lang else None
+        m, model = build_model(size, params, buffers, float(lang), lang_emb)
+        tr = Trainer(100)
+        sentences = ["s%d" % i for i in range(clips)]
+        frames = torch.empty(clips, 5, 3, 224, 224, device="cuda")  # one buffer, refilled: the feeder's contract
+        metrics = []
+        for i in range(5):
+            frames.copy_(O.varied_frames(clips, 122 + i).reshape(frames.shape))
+            mt, _ = tr.update(model, (frames, sentences), i, perms=O.draw_permutations(clips, 130 + i), lang_emb=lang_emb)
+            metrics.append(mt)
+        eng = m._any_engine()
+        return m, metrics, eng.graph_replays(), tr.last_launches
+
+    m0, met0, rep0, n0 = run(False)
+    m1, met1, rep1, n1 = run(True)
+    assert rep0 == 0 and rep1 == 2 * 3, (rep0, rep1)  # steps 3-5: forward graph + backward graph
+    assert n0 == n1, (n0, n1)  # the launch count reported for a replayed step is the captured one
+    assert met0 == met1
+    for which in (0, 2, 3, 4):
+        assert torch.equal(m0._flat(which), m1._flat(which)), which
