@@ -183,7 +183,7 @@ int r3m_b200_engine_tensor_info(void* handle, int index, char* name, int name_ca
 int r3m_b200_engine_region(void* handle, int which, void** ptr, size_t* count);
 /* what: 0 embedding dim, 1 frames, 2 kernels launched by the last engine call (replayed graphs count their kernels),
  *       3 cudaGraphLaunch calls so far: the training step is replayed as two captured CUDA graphs (train-mode forward;
- *         loss heads + language head + two-stream backward) from the third call with the same input pointers on;
+ *         loss heads + language head + two-stream backward) from the second call with the same input pointers on;
  *         environment R3M_STEP_GRAPH=0 keeps plain launches */
 int r3m_b200_engine_get_int(void* handle, int what, int* value);
 /* what: 0 similarity of the TCN head: value != 0 negative L2 distance (default; R3M(l2dist=True)), 0 cosine

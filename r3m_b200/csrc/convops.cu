@@ -9,6 +9,8 @@
 
 namespace r3m {
 
+thread_local int g_pdl_suppress = 0;
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

@@ -3,11 +3,13 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 
 #include "elementwise.cuh"
+#include "launch.h"
 #include "loss.cuh"
 
 namespace r3m {
@@ -738,7 +740,7 @@ std::string Engine::plan_all() {
     const double mc = (double)a.M * a.C * 2;
     const double rd = 2 + (mask ? 1.0 / 16 : 0.0) + (second ? 1 : 0);
     guard_write(dy);
-    if (dy2) guard_write(dy2);
+    if (second && dy2) guard_write(dy2);  // identity blocks pass the buffer but do not write it
     const size_t first = bwd_.size();
     bwd_.push_back(Op([a](cudaStream_t s) { return launch_bn_bwd_reduce(a, s); }, kFamNorm, 0.0, mc * rd));
     bwd_.back().label = "bn_bwd_reduce " + c.bn;
@@ -956,6 +958,14 @@ std::string Engine::plan_all() {
     chunks_.push_back(tail);
   }
 
+  {
+    std::vector<char> recorded(n_events, 0);
+    for (const Op& op : bwd_) {
+      for (int ev : op.wait)
+        if (!recorded[ev]) return "backward schedule: op '" + op.label + "' waits on an event recorded later";
+      if (op.record >= 0) recorded[op.record] = 1;
+    }
+  }
   while ((int)evs_.size() < n_events) {
     cudaEvent_t ev;
     if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return "cudaEventCreate failed";
@@ -1032,7 +1042,12 @@ std::string Engine::run(const std::vector<Op>& ops, cudaStream_t stream) {
         cudaError_t we = cudaStreamWaitEvent(s, evs_[ev], 0);
         if (we != cudaSuccess) return std::string("stream wait failed: ") + cudaGetErrorString(we);
       }
+    // a kernel node with several incoming edges (a cross-stream join) cannot carry a programmatic dependency
+    static const bool join_pdl = std::getenv("R3M_GRAPH_JOIN_PDL") != nullptr;
+    const bool suppress = capturing_ && two_streams && !op.wait.empty() && !join_pdl;
+    if (suppress) ++g_pdl_suppress;
     cudaError_t e = launch(op, s);
+    if (suppress) --g_pdl_suppress;
     if (e != cudaSuccess) return std::string("kernel launch failed: ") + cudaGetErrorString(e);
     if (op.record >= 0) {  // also in single-stream runs: the gradient-chunk markers are read by wait_grad_chunk
       cudaError_t re = cudaEventRecord(evs_[op.record], s);
@@ -1071,6 +1086,9 @@ std::string Engine::run_cached(const std::vector<uint64_t>& key, cudaStream_t st
       } else {
         ge.exec = nullptr;
         ge.failed = true;
+        if (std::getenv("R3M_GRAPH_DEBUG"))
+          fprintf(stderr, "r3m_b200: step-graph capture failed (kind %llu): body '%s', end-capture %s, last error %s\n",
+                  (unsigned long long)key[0], cerr.c_str(), cudaGetErrorString(ee), cudaGetErrorString(cudaPeekAtLastError()));
       }
       if (graph) cudaGraphDestroy(graph);
       (void)cudaGetLastError();

@@ -11,6 +11,8 @@
 namespace r3m {
 
 bool pdl_enabled();
+// > 0: launch without the PDL attribute (Engine::run sets it around the cross-stream join points of a stream capture)
+extern thread_local int g_pdl_suppress;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -24,7 +26,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && g_pdl_suppress == 0) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -111,7 +111,7 @@ def test_fixed_point_accumulator_is_exact_and_order_independent(lib, scale):
 
 @pytest.mark.parametrize("size,clips,lang", [(18, 6, 1), (50, 10, 1)])
 def test_step_graph_replay_equals_plain_launches(monkeypatch, size, clips, lang):
-    """Whole-step CUDA graphs (engine.cu: run_cached): from the third step with the same input buffers on, the train-mode
+    """Whole-step CUDA graphs (engine.cu: run_cached): from the second step with the same input buffers on, the train-mode
     forward and everything behind it (loss heads, language head, two-stream backward) are ONE cudaGraphLaunch each.  Same
     kernels in the same dependency order: weights, Adam moments and metrics must equal the plainly launched run bit for
     bit, and the replay must actually have happened."""
@@ -135,7 +135,7 @@ def test_step_graph_replay_equals_plain_launches(monkeypatch, size, clips, lang)
 
     m0, met0, rep0, n0 = run(False)
     m1, met1, rep1, n1 = run(True)
-    assert rep0 == 0 and rep1 == 2 * 3, (rep0, rep1)  # steps 3-5: forward graph + backward graph
+    assert rep0 == 0 and rep1 == 2 * 4, (rep0, rep1)  # steps 2-5 (captured on the second call): forward + backward graph
     assert n0 == n1, (n0, n1)  # the launch count reported for a replayed step is the captured one
     assert met0 == met1
     for which in (0, 2, 3, 4):
