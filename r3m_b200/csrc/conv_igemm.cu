@@ -136,8 +136,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m_idx = tile / p.num_n_tiles;
+        const int n_tile = tile - m_idx * p.num_n_tiles;
+        const int m_tile = p.rev_m ? p.num_m_tiles - 1 - m_idx : m_idx;
         const int m0 = m_tile * kBlockM;
         const int n_img = m0 / p.PQ;
         const int rem = m0 - n_img * p.PQ;
@@ -257,8 +258,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // column block's fixed-point accumulators (fx_add: exact, order independent) -> the LAST CTA of the column block
     // (ticket) converts the totals to fp32.  No floating-point atomics: the sums are bit-identical from run to run.
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m_idx = tile / p.num_n_tiles;
+      const int n_tile = tile - m_idx * p.num_n_tiles;
+      const int m_tile = p.rev_m ? p.num_m_tiles - 1 - m_idx : m_idx;
       const int m0 = m_tile * kBlockM + q * 32;
       const int n0 = n_tile * BN;
       if constexpr (STATS) acc_ntile = n_tile;

@@ -22,6 +22,7 @@ struct ConvKernelParams {
   // GEMM N
   int Cout;
   int num_m_tiles, num_n_tiles;
+  int rev_m;  // 1: M tiles are walked last-to-first (L2 reuse of the rows the producing kernel wrote last)
   // output
   void* out;     // bf16
   int out_mode;  // 0: row m at m*ldo;  1: row m=(n,p,q) scattered to ((n*oH + p*o_stride+o_h0)*oW + q*o_stride+o_w0)*ldo

@@ -116,6 +116,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.o_h0 = g.o_h0;
   p.o_w0 = g.o_w0;
   p.accumulate = g.accumulate;
+  p.rev_m = g.rev_m;
   p.stat_sum = g.stat_sum;
   p.stat_sq = g.stat_sq;
   p.stat_scratch = g.stat_scratch;

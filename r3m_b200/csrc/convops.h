@@ -23,6 +23,7 @@ struct GatherConv {
   int ldo = 0;
   int oH = 0, oW = 0, o_stride = 1, o_h0 = 0, o_w0 = 0;
   int accumulate = 0;  // out += result (read-modify-write)
+  int rev_m = 0;       // walk the M tiles last-to-first (see ConvKernelParams)
   float* stat_sum = nullptr;  // optional per-channel sum / sum of squares of the stored (bf16) output (written)
   float* stat_sq = nullptr;
   // deterministic two-level reduction of the statistics: [kStatScratchFloats] floats + [kStatTickets] zeroed ints; null:

@@ -34,12 +34,27 @@ typedef __nv_bfloat16 bf16;
 struct F8 {
   float v[8];
 };
-__device__ __forceinline__ F8 ld8(const bf16* p) {
+__device__ __forceinline__ uint4 ld8_raw(const bf16* p) {
 #if R3M_STREAM_HINTS & 1
-  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));  // streaming (evict-first) read
+  return __ldcs(reinterpret_cast<const uint4*>(p));  // streaming (evict-first) read
 #else
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));  // every ld8 source is read-only within its kernel
+  return __ldg(reinterpret_cast<const uint4*>(p));  // every ld8 source is read-only within its kernel
 #endif
+}
+__device__ __forceinline__ F8 cvt8(const uint4& u) {
+  F8 f;
+  f.v[0] = bf16lo(u.x);
+  f.v[1] = bf16hi(u.x);
+  f.v[2] = bf16lo(u.y);
+  f.v[3] = bf16hi(u.y);
+  f.v[4] = bf16lo(u.z);
+  f.v[5] = bf16hi(u.z);
+  f.v[6] = bf16lo(u.w);
+  f.v[7] = bf16hi(u.w);
+  return f;
+}
+__device__ __forceinline__ F8 ld8(const bf16* p) {
+  const uint4 u = ld8_raw(p);
   F8 f;
   f.v[0] = bf16lo(u.x);
   f.v[1] = bf16hi(u.x);
@@ -435,7 +450,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 R3M_UNROLL(R3M_BN_APPLY_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + c_base + chunk * 8;
+    const long long rr = a.reverse ? (long long)a.M - 1 - row : row;
+    const long long off = rr * a.C + c_base + chunk * 8;
     // all loads of the row first (no control flow between them)
     F8 f = ld8_last(y + off);
     F8 t, r;
@@ -457,7 +473,7 @@ R3M_UNROLL(R3M_BN_APPLY_UNROLL)
       unsigned bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) bits |= (__bfloat162float(__float2bfloat16_rn(f.v[j])) > 0.f ? 1u : 0u) << j;
-      a.mask_out[row * (a.C >> 3) + (c_base >> 3) + chunk] = (uint8_t)bits;
+      a.mask_out[rr * (a.C >> 3) + (c_base >> 3) + chunk] = (uint8_t)bits;
     }
   }
   pdl_done();
@@ -937,17 +953,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   const bf16* __restrict__ y2 = reinterpret_cast<const bf16*>(a.y2);
   const uint8_t* __restrict__ mask = a.mask;
-  for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
-       row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + c_base + chunk * 8;
-    // all loads of the row first
-    F8 g = ld8(dA + off);
-    const F8 yy = ld8(y + off);
+  // Four rows per trip with every load issued before the first use: the small layers give a thread 16-60 rows, and one
+  // dependent DRAM round trip per row made them latency bound (33 MB in 16 us, ncu).  Rows are still accumulated in
+  // row order (the sums do not depend on the unroll factor).
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  long long row = (long long)blockIdx.x * rows_per_iter + r0;
+  auto accumulate = [&](const uint4& ug, const uint4& uy, const uint4& um, const uint4& ut, unsigned bits) {
+    F8 g = cvt8(ug);
+    const F8 yy = cvt8(uy);
     F8 m, t;
-    unsigned bits = 0;
-    if (kMask == kMaskAct) m = ld8(act + off);
-    if (kMask == kMaskBits) bits = __ldg(mask + row * ld8c + (c_base >> 3) + chunk);
-    if (kDual) t = ld8(y2 + off);
+    if (kMask == kMaskAct) m = cvt8(um);
+    if (kDual) t = cvt8(ut);
     mask_gradient<kMask>(g, m, bits);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -955,6 +971,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
       s2[j] = fmaf(g.v[j], yy.v[j] - mean[j], s2[j]);
       if (kDual) s3[j] = fmaf(g.v[j], t.v[j] - mean2[j], s3[j]);
     }
+  };
+  constexpr int kU = 4;
+  for (; !a.single_rows && row + (kU - 1) * stride < a.M; row += kU * stride) {
+    uint4 ug[kU], uy[kU], um[kU], ut[kU];
+    unsigned bits[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long r = a.rev_reduce ? (long long)a.M - 1 - (row + u * stride) : row + u * stride;
+      const long long off = r * a.C + c_base + chunk * 8;
+      ug[u] = ld8_raw(dA + off);
+      uy[u] = ld8_raw(y + off);
+      um[u] = make_uint4(0, 0, 0, 0);
+      ut[u] = make_uint4(0, 0, 0, 0);
+      bits[u] = 0;
+      if (kMask == kMaskAct) um[u] = ld8_raw(act + off);
+      if (kMask == kMaskBits) bits[u] = __ldg(mask + r * ld8c + (c_base >> 3) + chunk);
+      if (kDual) ut[u] = ld8_raw(y2 + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) accumulate(ug[u], uy[u], um[u], ut[u], bits[u]);
+  }
+  for (; row < a.M; row += stride) {
+    const long long r = a.rev_reduce ? (long long)a.M - 1 - row : row;
+    const long long off = r * a.C + c_base + chunk * 8;
+    const uint4 ug = ld8_raw(dA + off), uy = ld8_raw(y + off);
+    uint4 um = make_uint4(0, 0, 0, 0), ut = um;
+    unsigned bits = 0;
+    if (kMask == kMaskAct) um = ld8_raw(act + off);
+    if (kMask == kMaskBits) bits = __ldg(mask + r * ld8c + (c_base >> 3) + chunk);
+    if (kDual) ut = ld8_raw(y2 + off);
+    accumulate(ug, uy, um, ut, bits);
   }
   pdl_done();
   // Block reduction without atomics: every thread parks its partials, one thread per four outputs adds the
@@ -1075,13 +1122,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
 R3M_UNROLL(R3M_BN_BWD_UNROLL)
   for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
        row += (long long)gridDim.x * rows_per_iter) {
-    const long long off = row * a.C + c_base + chunk * 8;
+    const long long rr = a.rev_apply ? (long long)a.M - 1 - row : row;
+    const long long off = rr * a.C + c_base + chunk * 8;
     F8 g = ld8_last(dA + off);
     const F8 yy = ld8_last(y + off);
     F8 m, t;
     unsigned bits = 0;
     if (kMask == kMaskAct) m = ld8(act + off);
-    if (kMask == kMaskBits) bits = __ldg(mask + row * (a.C >> 3) + (c_base >> 3) + chunk);
+    if (kMask == kMaskBits) bits = __ldg(mask + rr * (a.C >> 3) + (c_base >> 3) + chunk);
     if (kDual) t = ld8_last(y2 + off);
     mask_gradient<kMask>(g, m, bits);
     if (kDz) st8(dzo + off, g);
@@ -1408,6 +1456,8 @@ inline int mask_kind(const BnBwdArgs& a) { return a.a ? kMaskAct : (a.mask ? kMa
 
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
   BnBwdArgs a = a_in;
+  static const int ab = std::getenv("R3M_AB") ? atoi(std::getenv("R3M_AB")) : 0;  // A/B aid: bit 1 = one row per trip
+  a.single_rows = (ab & 2) ? 1 : 0;
   if (a.C % 8 != 0 || a.C > 2048 || 256 % (a.C / 8) != 0) return cudaErrorInvalidValue;
   if (!a.det.scratch) a.det = device_det_scratch();
   if (!a.det.scratch) return cudaErrorMemoryAllocation;

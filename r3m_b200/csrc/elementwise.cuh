@@ -40,6 +40,9 @@ struct BnApplyArgs {
   // 1: sum (== sq) and sum2 (== sq2) point at the producing conv's raw fixed-point accumulators (8 64-bit words per
   // channel: 4 limbs of the sum, 4 of the sum of squares; see fx_add) instead of fp32 arrays — the engine's path
   int stat_raw = 0;
+  // 1: walk the rows last-to-first.  The engine alternates the traversal direction of consecutive passes over a tensor:
+  // the rows a producer wrote LAST are still in the 126 MB L2 when its consumer starts from that end
+  int reverse = 0;
   uint8_t* mask_out = nullptr;  // optional [M][C/8]: bit j of byte (row, chunk) = (a[row][8*chunk+j] > 0)
   // optional second BatchNorm whose (un-activated) output is added before the ReLU: the downsample branch of a
   // residual block, a = relu(bn(y) + bn2(y2))  (tv resnet.py:100-103, 155-161) without materialising bn2(y2)
@@ -129,6 +132,8 @@ struct BnBwdArgs {
   const float* gamma = nullptr;
   float* sums = nullptr;      // [2][C] workspace: sum(dz), sum(dz * xhat); written by the reduce pass
   DetScratch det;             // deterministic reduction scratch (null members: the process-wide instance)
+  int single_rows = 0;  // A/B aid (R3M_AB bit 1): reduce pass without the four-row software pipeline
+  int rev_reduce = 0, rev_apply = 0;  // traversal direction of the two passes (see BnApplyArgs::reverse)
   int sums_raw = 0;           // 1: sums / sums2 are raw fixed-point accumulators (2C / C entries of four 64-bit words,
                               // zero on entry); the apply pass converts on read (the engine's path)
   void* dy = nullptr;         // bf16 [M][C] gradient w.r.t. the raw conv output

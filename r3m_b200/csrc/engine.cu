@@ -340,6 +340,8 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.save_mean = saved + c.save_off;
   a.save_rstd = saved + c.save_off + c.Cout;
   if (train && relu) a.mask_out = c.mask;
+  // the conv that has just written y walked the rows first-to-last, and the conv that reads `dst` next does too
+  a.reverse = (train && l2_order_) ? 1 : 0;
   if (second) {
     // downsample branch folded in: a = relu(bn(y) + bn_ds(y_ds)), bn_ds(y_ds) is never materialised
     const Conv& d = *second;
@@ -360,6 +362,10 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
 }
 
 std::string Engine::plan_all() {
+  {
+    const char* env = std::getenv("R3M_L2_ORDER");
+    l2_order_ = !(env && env[0] == '0');
+  }
   float* P = reinterpret_cast<float*>(pws_ + off_P_);
   float* G = reinterpret_cast<float*>(pws_ + off_G_);
   bf16* Pb = reinterpret_cast<bf16*>(pws_ + off_Pb_);
@@ -707,9 +713,18 @@ std::string Engine::plan_all() {
     }
     held_wgrads.clear();
   };
+  // Traversal directions (L2 reuse between consecutive passes over a tensor): `cur` is the direction (0 first-to-last,
+  // 1 last-to-first) in which the gradient the next BatchNorm backward consumes was written.  The reduce pass walks it
+  // the opposite way, the apply pass opposite to the reduce pass (it re-reads the same two tensors), and the data
+  // gradient that consumes the apply pass' output opposite to that — so the direction flips once per layer.
+  int cur = 0;
   auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const uint8_t* mask, bf16* dy, bf16* dz_out,
                          const Conv* second, bf16* dy2) {
     BnBwdArgs a;
+    if (l2_order_) {
+      a.rev_reduce = !cur;
+      a.rev_apply = cur;  // writes dy in direction `cur`
+    }
     a.dA = dA;
     a.mask = mask;
     a.y = c.y;
@@ -782,6 +797,9 @@ std::string Engine::plan_all() {
     held_wgrads.push_back(w);
   };
   auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
+    // reads dy (written in direction `cur` by the apply pass) the other way round and leaves dx in that direction
+    const int dgrad_rev = l2_order_ ? !cur : 0;
+    cur = dgrad_rev;
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
     size_t off = 0;
     for (const DgradClass& k : cls) {
@@ -818,6 +836,7 @@ std::string Engine::plan_all() {
         gc.o_w0 = k.pw;
       }
       gc.accumulate = accumulate;
+      gc.rev_m = dgrad_rev;
       push_conv(bwd_, gc, "dgrad " + c.name + (accumulate ? " (+=)" : "") + (c.stride > 1 ? " class " + std::to_string(k.ph) + std::to_string(k.pw) : ""));
       if (err.empty()) bwd_.back().block = cur_block;
       off += (size_t)c.Cin * k.ntaps * c.Cout;

@@ -23,8 +23,15 @@ def step_ops(size=50, clips=64, lang=1):
     if lang:
         emb = m.lang_enc([""] * clips).cuda().float().contiguous()
         mask = torch.ones(clips, device="cuda")
+    ncu = os.environ.get("R3M_NCU") == "1"  # under `ncu --profile-from-start off`: capture exactly the third step
     for i in range(3):
+        if ncu and i == 2:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
         fam = eng.profile_update(frames, perms, emb, mask, 1e-5, 1e-5, float(lang), 1.0, 1e-4, i + 1)
+        if ncu and i == 2:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
     ops = eng.profile_ops()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"step_ops_rn{size}.csv"), "w") as f:
