@@ -13,11 +13,12 @@ import torch
 from . import _lib  # noqa: F401  (fails loudly when libr3m_b200.so is missing)
 from .model import R3M, set_lang_encoder_factory  # noqa: F401
 from .trainer import Trainer  # noqa: F401
-from .data import FrameFeeder, GpuAugment, R3MBufferU8  # noqa: F401
+from .data import FrameFeeder, GpuAugment, R3MBufferU8, nvjpeg_batch_decoder  # noqa: F401
+from .bert import DistilBertEncoder  # noqa: F401
 from .checkpoint import load_snapshot, save_snapshot  # noqa: F401
 
 __all__ = ["R3M", "Trainer", "load_r3m", "load_r3m_reproduce", "set_lang_encoder_factory", "FrameFeeder", "GpuAugment",
-           "R3MBufferU8", "save_snapshot", "load_snapshot"]
+           "R3MBufferU8", "nvjpeg_batch_decoder", "DistilBertEncoder", "save_snapshot", "load_snapshot"]
 
 VALID_ARGS = ["_target_", "device", "lr", "hidden_dim", "size", "l2weight", "l1weight", "langweight", "tcnweight",
               "l2dist", "bs"]  # r3m/__init__.py:15

@@ -195,15 +195,39 @@ class FrameFeeder:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# JPEG decode on the GPU (nvJPEG through torchvision.io.decode_jpeg: a library call, like the reference's
+# torchvision.io.read_image on the CPU, data_loaders.py:30-32) — the frames are born in device memory as uint8 and go
+# to GpuAugment / the stem kernel without crossing PCIe decoded
+# ---------------------------------------------------------------------------------------------------------------
+def nvjpeg_batch_decoder(device="cuda"):
+    """``batch_decoder`` for R3MBufferU8: the clip's JPEG files are read on the host (compressed bytes only) and decoded
+    together by nvJPEG on ``device`` -> uint8 [n,3,H,W] there.  Use in the training process (CUDA in DataLoader workers
+    needs the spawn start method)."""
+    import torchvision
+    from torchvision.io import ImageReadMode
+
+    dev = torch.device(device)
+
+    def decode(paths):
+        data = [torchvision.io.read_file(p) for p in paths]
+        frames = torchvision.io.decode_jpeg(data, mode=ImageReadMode.RGB, device=dev)
+        return torch.stack(frames)
+
+    return decode
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # dataset (host)
 # ---------------------------------------------------------------------------------------------------------------
 class R3MBufferU8(torch.utils.data.IterableDataset):
     """``R3MBuffer`` (data_loaders.py:38-105) that keeps what it decodes as uint8 and leaves the augmentation to the GPU:
     yields ``(uint8 [5,3,H,W], label)`` with the reference's manifest columns (path, len, txt), index law and label
-    rule (``txt[2:]``).  ``decoder(path) -> uint8 [3,H,W]`` defaults to ``torchvision.io.read_image``."""
+    rule (``txt[2:]``).  ``decoder(path) -> uint8 [3,H,W]`` defaults to ``torchvision.io.read_image``; ``batch_decoder``
+    (``nvjpeg_batch_decoder``) decodes the clip's five files in one nvJPEG call on the GPU instead."""
 
-    def __init__(self, ego4dpath, alpha, datasources=("ego4d",), manifest=None, decoder=None):
+    def __init__(self, ego4dpath, alpha, datasources=("ego4d",), manifest=None, decoder=None, batch_decoder=None):
         super().__init__()
+        self._decode_batch = batch_decoder  # optional: list of paths -> uint8 [n,3,H,W] (e.g. nvjpeg_batch_decoder)
         if "ego4d" not in datasources:
             raise NameError("Invalid Dataset")  # data_loaders.py:61
         self.alpha, self.data_sources = alpha, list(datasources)
@@ -226,7 +250,11 @@ class R3MBufferU8(torch.utils.data.IterableDataset):
         vidlen, txt, vid = m["len"], m["txt"], m["path"]
         label = txt[2:]
         inds = sample_clip_indices(vidlen, self.alpha)
-        im = torch.stack([self._decode(f"{vid}/{i:06}.jpg") for i in inds])
+        paths = [f"{vid}/{i:06}.jpg" for i in inds]
+        if self._decode_batch is not None:
+            im = self._decode_batch(paths)
+        else:
+            im = torch.stack([self._decode(p) for p in paths])
         return im, label
 
     def __iter__(self):

@@ -100,3 +100,36 @@ def test_trainer_update_accepts_uint8_frames_from_the_feeder():
         out.append((metrics, m._any_engine().embeddings().clone()))
     assert rel(out[1][1], out[0][1]) < 2e-2  # same operands; the BatchNorm-statistics atomics reorder run to run
     assert abs(out[0][0]["l2loss"] - out[1][0]["l2loss"]) < 1e-2 * out[0][0]["l2loss"]
+
+
+def test_nvjpeg_batch_decoder_feeds_the_uint8_path(tmp_path):
+    """JPEG decode on the GPU (nvJPEG via torchvision) behind R3MBufferU8 — same clip-index law and
+    labels as the CPU decoder, pixels within the decoders' IDCT round-off, frames born on the device as uint8."""
+    import numpy as np
+    import pandas as pd
+    import random
+    import torchvision
+
+    from r3m_b200.data import R3MBufferU8, nvjpeg_batch_decoder
+
+    g = torch.Generator().manual_seed(3)
+    vid = tmp_path / "vid0"
+    vid.mkdir()
+    yy, xx = torch.meshgrid(torch.arange(120.0), torch.arange(160.0), indexing="ij")
+    for i in range(12):
+        img = torch.stack([(yy * (1 + c) + xx * 0.7 + 9 * i) % 256 for c in range(3)]).to(torch.uint8)
+        img = (img.float() * 0.8 + 20 * torch.rand(3, 120, 160, generator=g)).clamp(0, 255).to(torch.uint8)
+        torchvision.io.write_jpeg(img, str(vid / f"{i:06}.jpg"), quality=92)
+    manifest = pd.DataFrame({"path": [str(vid)], "len": [12], "txt": ["C opens the drawer"]})
+
+    def sample(**kw):
+        random.seed(5)
+        np.random.seed(5)
+        return R3MBufferU8("", 0.2, manifest=manifest, **kw)._sample()
+
+    cpu_im, cpu_label = sample()
+    gpu_im, gpu_label = sample(batch_decoder=nvjpeg_batch_decoder("cuda"))
+    assert gpu_label == cpu_label == "opens the drawer"
+    assert gpu_im.is_cuda and gpu_im.dtype == torch.uint8 and tuple(gpu_im.shape) == (5, 3, 120, 160)
+    diff = (gpu_im.cpu().int() - cpu_im.int()).abs()
+    assert diff.float().mean() < 1.0 and int(diff.max()) <= 8, (float(diff.float().mean()), int(diff.max()))
