@@ -925,15 +925,17 @@ __device__ __forceinline__ void mask_gradient(F8& g, const F8& act, unsigned bit
   }
 }
 
+// Reduce pass of one block: (bx, by) of a (gx, C / 64) grid.  Leaves the block's partial sums — V = kQ * 64 floats, slice-local
+// [0, 64) sum(dz), [64, 128) sum(dz * xhat), [128, 192) sum(dz * xhat2) — in s_part[0 .. V / 4).
 template <bool kDual, int kMask>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
-  pdl_sync();
-  extern __shared__ float4 s_part[];  // [rows_per_iter][kQ * Cs / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
+__device__ __forceinline__ void bn_bwd_reduce_body(const BnBwdArgs& a, float4* s_part, int bx, int by, int gx,
+                                                   bool signal_dependents) {
+  // s_part: [rows_per_iter][kQ * Cs / 4]: per-thread partials of sum(dz), sum(dz*xhat)[, 2]
   constexpr int kQ = kDual ? 3 : 2;
   // The tensor is cut into channel slices of kBwdSlice = 64 channels (blockIdx.y): a block covers 32 rows per iteration
   // (one fully used 128-byte line per row) and its partial vector is kQ * 64 floats instead of kQ * C, so the number of
   // fixed-point reductions the grid issues (blocks x partial length: the kernel's tail) is C / 64 times smaller.
-  const int Cs = kBwdSlice, c_base = blockIdx.y * Cs;
+  const int Cs = kBwdSlice, c_base = by * Cs;
   const int C8 = Cs >> 3, ld8c = a.C >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
@@ -956,8 +958,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   // Four rows per trip with every load issued before the first use: the small layers give a thread 16-60 rows, and one
   // dependent DRAM round trip per row made them latency bound (33 MB in 16 us, ncu).  Rows are still accumulated in
   // row order (the sums do not depend on the unroll factor).
-  const long long stride = (long long)gridDim.x * rows_per_iter;
-  long long row = (long long)blockIdx.x * rows_per_iter + r0;
+  const long long stride = (long long)gx * rows_per_iter;
+  long long row = (long long)bx * rows_per_iter + r0;
   auto accumulate = [&](const uint4& ug, const uint4& uy, const uint4& um, const uint4& ut, unsigned bits) {
     F8 g = cvt8(ug);
     const F8 yy = cvt8(uy);
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     if (kDual) ut = ld8_raw(y2 + off);
     accumulate(ug, uy, um, ut, bits);
   }
-  pdl_done();
+  if (signal_dependents) pdl_done();
   // Block reduction without atomics: every thread parks its partials, one thread per four outputs adds the
   // rows_per_iter copies in row order, and the grid-wide sum is the ordered two-level reduction above.
   const int q4 = kQ * Cs / 4;  // float4 slots per partial row
@@ -1034,19 +1036,36 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     s_part[i] = acc;  // row 0 of the table becomes the block's partial (slot i is touched by this thread only)
   }
   __syncthreads();
+}
+
+// slice-local partial i of channel slice `by` -> the layer's fixed-point accumulators (engine path: added, zero per step)
+template <bool kDual>
+__device__ __forceinline__ void bn_bwd_emit_raw(const BnBwdArgs& a, const float4* s_part, int by) {
+  constexpr int kQ = kDual ? 3 : 2;
+  const int Cs = kBwdSlice, c_base = by * Cs, C = a.C, V = kQ * Cs;
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(a.sums);
+  unsigned long long* acc2 = reinterpret_cast<unsigned long long*>(a.sums2);
+  const float* part = reinterpret_cast<const float*>(s_part);
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const int which = i / Cs, c = c_base + i - which * Cs;
+    fx_add(which == 2 ? acc2 + kFxWords * c : acc + kFxWords * (which * C + c), part[i]);
+  }
+}
+
+template <bool kDual, int kMask>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  pdl_sync();
+  extern __shared__ float4 s_part[];
+  constexpr int kQ = kDual ? 3 : 2;
+  bn_bwd_reduce_body<kDual, kMask>(a, s_part, blockIdx.x, blockIdx.y, gridDim.x, true);
+  const int Cs = kBwdSlice, c_base = blockIdx.y * Cs;
   // slice-local floats [0, Cs) -> sums[c], [Cs, 2Cs) -> sums[C + c], [2Cs, 3Cs) -> sums2[c]; written, not accumulated
   float* sums = a.sums;
   float* sums2 = a.sums2;
   const int C = a.C, V = kQ * Cs;
   if (a.sums_raw) {
     // engine path: straight into the layer's own fixed-point accumulators (zeroed per step); bn_bwd_apply converts
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(sums);
-    unsigned long long* acc2 = reinterpret_cast<unsigned long long*>(sums2);
-    const float* part = reinterpret_cast<const float*>(s_part);
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-      const int which = i / Cs, c = c_base + i - which * Cs;
-      fx_add(which == 2 ? acc2 + kFxWords * c : acc + kFxWords * (which * C + c), part[i]);
-    }
+    bn_bwd_emit_raw<kDual>(a, s_part, blockIdx.y);
     return;
   }
   DetScratch d;
@@ -1063,10 +1082,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   });
 }
 
+// Apply pass of one block: (bx, by) of a (gx, ny) grid.
 template <bool kDual, int kMask, bool kDz>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
-  pdl_sync();
-  const int Cs = gridDim.y > 1 ? 256 : a.C, c_base = blockIdx.y * Cs;  // channel slices for wide layers (see bn_apply)
+__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdArgs& a, float* s_coef, int bx, int by, int gx, int ny,
+                                                  bool signal_dependents) {
+  const int Cs = ny > 1 ? 256 : a.C, c_base = by * Cs;  // channel slices for wide layers (see bn_apply)
   const int C8 = Cs >> 3;
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
@@ -1075,7 +1095,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   // dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat)),  xhat = (y - mean) * rstd
   //    = cA * dz + cB * y + cC   with per-channel constants (three registers per channel instead of five), computed once
   // per block into shared memory (on the engine's path this includes converting the reduce pass' fixed-point sums)
-  extern __shared__ float s_coef[];  // [kDual ? 6 : 3][Cs]
+  // s_coef: [kDual ? 6 : 3][Cs]
   for (int cl = threadIdx.x; cl < Cs; cl += blockDim.x) {
     const int c = c_base + cl;
     const float mean = a.mean[c], rstd = a.rstd[c];
@@ -1120,8 +1140,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   bf16* __restrict__ dy2 = reinterpret_cast<bf16*>(a.dy2);
   bf16* __restrict__ dzo = reinterpret_cast<bf16*>(a.dz_out);
 R3M_UNROLL(R3M_BN_BWD_UNROLL)
-  for (long long row = (long long)blockIdx.x * rows_per_iter + r0; row < a.M;
-       row += (long long)gridDim.x * rows_per_iter) {
+  for (long long row = (long long)bx * rows_per_iter + r0; row < a.M; row += (long long)gx * rows_per_iter) {
     const long long rr = a.rev_apply ? (long long)a.M - 1 - row : row;
     const long long off = rr * a.C + c_base + chunk * 8;
     F8 g = ld8_last(dA + off);
@@ -1143,8 +1162,8 @@ R3M_UNROLL(R3M_BN_BWD_UNROLL)
       st8(dy2 + off, o);
     }
   }
-  pdl_done();
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
+  if (signal_dependents) pdl_done();
+  if (bx == 0 && by == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (a.dbeta) a.dbeta[c] = bsum_at(a.sums, a.sums_raw, c);
       if (a.dgamma) a.dgamma[c] = bsum_at(a.sums, a.sums_raw, a.C + c);
@@ -1154,6 +1173,46 @@ R3M_UNROLL(R3M_BN_BWD_UNROLL)
       }
     }
   }
+}
+
+template <bool kDual, int kMask, bool kDz>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  pdl_sync();
+  extern __shared__ float s_coef[];
+  bn_bwd_apply_body<kDual, kMask, kDz>(a, s_coef, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y, true);
+}
+
+// Reduce + grid barrier + apply in ONE launch, for layers whose gradient and raw output (2 x M x C bf16) stay in the
+// 126 MB L2 between the two passes: the second pass never goes to DRAM, and the launch, the drain of the reduce grid and
+// the refill of the apply grid (about 10 us for a 16-33 MB layer) disappear.  Every block of the grid is resident by
+// construction (the host sizes the grid to one wave of THIS kernel and launches it cooperatively, so work on other
+// streams cannot keep part of the grid unscheduled while the rest spins); the barrier is a counter in the step's zeroed
+// region.  A watchdog turns a lost block into an error flag instead of a hang.
+template <int kMask>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnBwdArgs a, int slices_r, int slices_a, int* counter,
+                                                           int* error_flag) {
+  pdl_sync();
+  extern __shared__ float4 s_dyn[];
+  const int b = blockIdx.x, G = gridDim.x;
+  bn_bwd_reduce_body<false, kMask>(a, s_dyn, b / slices_r, b % slices_r, G / slices_r, false);
+  bn_bwd_emit_raw<false>(a, s_dyn, b % slices_r);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1);
+    const uint64_t t0 = globaltimer_ns();
+    while (*reinterpret_cast<volatile int*>(counter) < G) {
+      if (globaltimer_ns() - t0 > R3M_WAIT_TIMEOUT_NS) {
+        atomicExch(error_flag, 31);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  pdl_done();
+  bn_bwd_apply_body<false, kMask, false>(a, reinterpret_cast<float*>(s_dyn), b / slices_a, b % slices_a, G / slices_a,
+                                         slices_a, false);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam / casts
@@ -1482,6 +1541,33 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
     case kMaskBits: if (dual) R3M_LAUNCH(true, kMaskBits); else R3M_LAUNCH(false, kMaskBits); break;
     default: if (dual) R3M_LAUNCH(true, kMaskNone); else R3M_LAUNCH(false, kMaskNone); break;
   }
+#undef R3M_LAUNCH
+  return cudaGetLastError();
+}
+
+bool bn_bwd_can_fuse(const BnBwdArgs& a) {
+  // one BatchNorm, no residual share, raw accumulators (the engine's path), channel slicing of both passes compatible
+  return a.y2 == nullptr && a.dz_out == nullptr && a.sums_raw && a.a == nullptr && a.C % kBwdSlice == 0 && a.C <= 2048 &&
+         256 % (std::min(a.C, 256) / 8) == 0;
+}
+
+cudaError_t launch_bn_bwd_fused(const BnBwdArgs& a, int* counter, int* flag, cudaStream_t s) {
+  if (!bn_bwd_can_fuse(a) || counter == nullptr || flag == nullptr) return cudaErrorInvalidValue;
+  const int slices_r = a.C / kBwdSlice, slices_a = a.C >= 1024 ? a.C / 256 : 1;  // slices_a divides slices_r
+  const int rows_r = 256 / (kBwdSlice / 8);
+  const size_t smem = std::max((size_t)rows_r * 2 * kBwdSlice * sizeof(float), 3 * (size_t)(a.C / slices_a) * sizeof(float));
+  int grid = 0;
+#define R3M_LAUNCH(K)                                                                                   \
+  do {                                                                                                  \
+    grid = resident_blocks<bn_bwd_fused_kernel<K>>(256, smem);                                          \
+    grid -= grid % slices_r;                                                                            \
+    if (grid < slices_r) return cudaErrorInvalidValue;                                                  \
+    launch_kernel_cooperative(bn_bwd_fused_kernel<K>, dim3(grid), 256, smem, s, a, slices_r, slices_a, counter, flag); \
+  } while (0)
+  if (a.mask)
+    R3M_LAUNCH(kMaskBits);
+  else
+    R3M_LAUNCH(kMaskNone);
 #undef R3M_LAUNCH
   return cudaGetLastError();
 }

@@ -152,6 +152,11 @@ struct BnBwdArgs {
 };
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
+// Both passes in one launch with a grid barrier between them (layers that stay L2 resident; see bn_bwd_fused_kernel).
+// counter: one int, zero on entry (the engine keeps it in the step's zeroed region); error_flag: the device watchdog
+// flag (a lost block sets it instead of hanging the grid).
+bool bn_bwd_can_fuse(const BnBwdArgs& a);
+cudaError_t launch_bn_bwd_fused(const BnBwdArgs& a, int* counter, int* error_flag, cudaStream_t s);
 
 // Inference: fold BatchNorm (running statistics) into a per-channel affine, for all layers in one launch.
 struct BnFoldEntry {

@@ -211,6 +211,7 @@ class Engine {
   cudaStream_t side_ = nullptr;
   std::vector<cudaEvent_t> evs_;
   bool use_side_ = true;
+  bool fuse_bn_bwd_ = false;  // small layers: BatchNorm backward as one launch with a grid barrier (R3M_FUSE_BN_BWD=1)
   bool l2_order_ = true;  // alternate the traversal direction of consecutive passes over a tensor (R3M_L2_ORDER=0: off)
 };
 

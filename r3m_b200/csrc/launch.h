@@ -30,4 +30,22 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Cooperative launch (all blocks of the grid are resident together: required by kernels with a software grid barrier,
+// so that concurrent work on other streams can never leave part of the grid unscheduled while the rest spins).  No PDL.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                             cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative;
+  attr.val.cooperative = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 }  // namespace r3m

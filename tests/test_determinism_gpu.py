@@ -140,3 +140,37 @@ def test_step_graph_replay_equals_plain_launches(monkeypatch, size, clips, lang)
     assert met0 == met1
     for which in (0, 2, 3, 4):
         assert torch.equal(m0._flat(which), m1._flat(which)), which
+
+
+def test_schedule_variants_are_bit_identical(monkeypatch):
+    """The engine's schedule knobs change WHEN and in WHAT ORDER data is touched, never the arithmetic: the fused
+    BatchNorm backward (one cooperative launch with a grid barrier, R3M_FUSE_BN_BWD=1; its sums go through the same
+    order-independent fixed-point accumulators) and the L2-aware traversal order (R3M_L2_ORDER=0 switches it off) must
+    leave every weight bit-identical to the default schedule."""
+    from r3m_b200 import Trainer
+
+    size, clips = 50, 10
+
+    def run(env):
+        for k in ("R3M_FUSE_BN_BWD", "R3M_L2_ORDER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        params, buffers = well_conditioned_state(size, 140, True)
+        lang_emb = O.stub_lang_embedding(clips, 141)
+        m, model = build_model(size, params, buffers, 1.0, lang_emb)
+        tr = Trainer(100)
+        sentences = ["s%d" % i for i in range(clips)]
+        for i in range(2):
+            tr.update(model, (O.varied_frames(clips, 142 + i).cuda(), sentences), i,
+                      perms=O.draw_permutations(clips, 150 + i), lang_emb=lang_emb)
+        return m
+
+    base = run({})
+    fused = run({"R3M_FUSE_BN_BWD": "1"})
+    for which in (0, 2, 3, 4):
+        assert torch.equal(base._flat(which), fused._flat(which)), which
+    # the traversal order changes the order of the fp32 partial sums inside a CTA: not bit-identical, but the same step
+    plain = run({"R3M_L2_ORDER": "0"})
+    a, b = base._flat(0).double(), plain._flat(0).double()
+    assert float((a - b).norm() / b.norm()) < 1e-4
