@@ -117,8 +117,10 @@ def test_nvjpeg_batch_decoder_feeds_the_uint8_path(tmp_path):
     vid.mkdir()
     yy, xx = torch.meshgrid(torch.arange(120.0), torch.arange(160.0), indexing="ij")
     for i in range(12):
-        img = torch.stack([(yy * (1 + c) + xx * 0.7 + 9 * i) % 256 for c in range(3)]).to(torch.uint8)
-        img = (img.float() * 0.8 + 20 * torch.rand(3, 120, 160, generator=g)).clamp(0, 255).to(torch.uint8)
+        # smooth content (no hard chroma edges: the two decoders upsample 4:2:0 chroma differently) plus mild noise
+        img = torch.stack([128 + 90 * torch.sin(yy / (17.0 + 5 * c) + 0.3 * i) * torch.cos(xx / (23.0 - 4 * c))
+                           for c in range(3)])
+        img = (img + 4 * torch.rand(3, 120, 160, generator=g)).clamp(0, 255).to(torch.uint8)
         torchvision.io.write_jpeg(img, str(vid / f"{i:06}.jpg"), quality=92)
     manifest = pd.DataFrame({"path": [str(vid)], "len": [12], "txt": ["C opens the drawer"]})
 
@@ -131,5 +133,9 @@ def test_nvjpeg_batch_decoder_feeds_the_uint8_path(tmp_path):
     gpu_im, gpu_label = sample(batch_decoder=nvjpeg_batch_decoder("cuda"))
     assert gpu_label == cpu_label == "opens the drawer"
     assert gpu_im.is_cuda and gpu_im.dtype == torch.uint8 and tuple(gpu_im.shape) == (5, 3, 120, 160)
-    diff = (gpu_im.cpu().int() - cpu_im.int()).abs()
-    assert diff.float().mean() < 1.0 and int(diff.max()) <= 8, (float(diff.float().mean()), int(diff.max()))
+    diff = (gpu_im.cpu().int() - cpu_im.int()).abs().float()
+    # nvJPEG and libjpeg-turbo differ in IDCT rounding and chroma upsampling: a couple of grey levels, never a wrong frame
+    assert diff.mean() < 1.5 and float(diff.flatten().kthvalue(int(0.999 * diff.numel())).values) <= 12, \
+        (float(diff.mean()), float(diff.max()))
+    other = torch.roll(cpu_im, 1, 0).int()  # a DIFFERENT frame of the clip is far away: the check can fail
+    assert (other - cpu_im.int()).abs().float().mean() > 5 * max(float(diff.mean()), 0.2)
