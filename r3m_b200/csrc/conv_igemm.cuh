@@ -60,7 +60,8 @@ struct WgradKernelParams {
   int base_w, base_h;
   int cblocks;      // 64-channel blocks of the activation per tap
   int num_items;    // taps * cblocks   (one item = one 64-wide slice of the filter's K axis)
-  int group;        // items per CTA (<= 8)
+  int group;        // items per CTA (<= 8); pair mode: items per CTA PAIR (even, <= 8)
+  int pair;         // 1: wgrad_pair_kernel (cta_group::2, clusters of two CTAs along the k-tile axis; Cout % 256 == 0)
   uint16_t tap_w[kMaxTaps];
   uint16_t tap_h[kMaxTaps];
   int Cout;         // rows of dW

@@ -188,6 +188,15 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   } else {
     p.group = std::min(group_pref, p.num_items);
   }
+  // CTA pairs (cta_group::2) wherever two adjacent 128-row k-slabs exist and the items split evenly: each CTA then
+  // stages half of the group's activation items (R3M_WGRAD_PAIR=0: single-CTA kernel everywhere)
+  static const bool pair_env = !(getenv("R3M_WGRAD_PAIR") && getenv("R3M_WGRAD_PAIR")[0] == '0');
+  p.pair = (pair_env && d.Cout % 256 == 0 && p.num_items % 2 == 0 && pix == 128) ? 1 : 0;
+  if (p.pair) {
+    const int groups = (p.num_items + 7) / 8;
+    p.group = (p.num_items + groups - 1) / groups;
+    p.group += p.group & 1;  // even: the pair splits every group in two
+  }
   for (int t = 0; t < d.ntaps; ++t) {
     p.tap_w[t] = (uint16_t)d.tap_w[t];
     p.tap_h[t] = (uint16_t)d.tap_h[t];
@@ -197,7 +206,7 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   p.ldw = d.ntaps * d.C;
   p.pix_block = pix;
   p.mblocks_total = (M + pix - 1) / pix;
-  p.num_stages = std::min(6, (227 * 1024 - 2048) / ((2 + p.group) * pix * 128));
+  p.num_stages = std::min(6, (227 * 1024 - 2048) / ((2 + (p.pair ? p.group / 2 : p.group)) * pix * 128));
   if (p.num_stages < 2) return "wgrad: group too large for the shared-memory budget";
   if (const char* e = getenv("R3M_WGRAD_STAGES")) p.num_stages = std::min(p.num_stages, atoi(e));
   p.dW = d.dw;

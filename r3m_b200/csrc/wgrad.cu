@@ -25,6 +25,48 @@ constexpr int kTmemCols = 512;
 // One "atom" = [pix_block pixels][64 channels] bf16, one TMA op.  The TMA unit retires roughly one op per ~300 cycles
 // per SM regardless of its size (measured), so the reduction block per stage is as tall as shared memory allows.
 
+// Epilogue of one epilogue warp: its 32 rows of the CTA's 128 x (64 * g_count) slab, TMEM -> global.  Item t of the
+// group sits in TMEM columns [64 t, 64 t + 64).
+__device__ __forceinline__ void wgrad_store_slab(const WgradKernelParams& p, uint32_t tmem_base, int item0, int g_count,
+                                                 int k0, int ew, int row, bool row_ok) {
+  int tap = item0 / p.cblocks;
+  int cb = item0 - tap * p.cblocks;
+  for (int g = 0; g < g_count; ++g) {
+    // split-K partials go to this split's private copy of dW (summed in split order by wgrad_reduce_kernel: no
+    // floating-point atomics, bit-identical from run to run); a single split adds straight into dW
+    float* base = p.scratch ? p.scratch + static_cast<size_t>(blockIdx.x) * p.dw_elems : p.dW;
+    float* dst_row = base + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + g * 64 + half * 32, v);
+      tc_wait_ld();
+      if (row_ok) {
+        if (p.scratch) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst_row + half * 32 + j * 4) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* d = dst_row + half * 32 + j * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(v[4 * j])),
+                         "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                         "f"(__uint_as_float(v[4 * j + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+    if (++cb == p.cblocks) {
+      cb = 0;
+      ++tap;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
              const WgradKernelParams p) {
@@ -152,42 +194,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
         if (lane == 0) atomicExch(p.error_flag, 13);
       } else {
         tc_fence_after();
-        int tap = item0 / p.cblocks;
-        int cb = item0 - tap * p.cblocks;
-        for (int g = 0; g < g_count; ++g) {
-          // split-K partials go to this split's private copy of dW (summed in split order by wgrad_reduce_kernel: no
-          // floating-point atomics, bit-identical from run to run); a single split adds straight into dW
-          float* base = p.scratch ? p.scratch + static_cast<size_t>(blockIdx.x) * p.dw_elems : p.dW;
-          float* dst_row = base + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + g * 64 + half * 32, v);
-            tc_wait_ld();
-            if (row_ok) {
-              if (p.scratch) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  *reinterpret_cast<float4*>(dst_row + half * 32 + j * 4) =
-                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float* d = dst_row + half * 32 + j * 4;
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(v[4 * j])),
-                               "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
-                               "f"(__uint_as_float(v[4 * j + 3]))
-                               : "memory");
-                }
-              }
-            }
-          }
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++tap;
-          }
-        }
+        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, row_ok);
       }
     }
   }
@@ -197,6 +204,153 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster own two adjacent 128-row k-slabs of dW over the same pixel
+// range and the same group of (tap, 64-channel) items.  ONE tcgen05.mma of M = 256 serves both: each CTA stages its own
+// dY tile (A) and only HALF of the group's activation items (B) — the kernel is bound by the bytes an SM can pull into
+// shared memory (~40 B/clk: ncu, profiles/r2_ncu_per_kernel.md), and a pair needs (2 + g/2) atoms per CTA and stage for
+// the FLOPs the single-CTA kernel pays (2 + g) for.  Item t of the group lands in TMEM columns [64 t, 64 t + 64) of BOTH
+// CTAs: instruction i covers items 4i .. 4i+3, the first half from the even CTA's shared memory, the second half from
+// the odd CTA's.  Only the even CTA issues MMAs; TMA transaction bytes of both CTAs land on its full barriers, and its
+// commits arrive on the empty / done barriers of both.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                  const WgradKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kPixBlock = p.pix_block;
+  const int kAtomBytes = kPixBlock * 128;
+  const int b_atoms = p.group / 2;  // activation items this CTA stages per pipeline stage
+  const int stage_bytes = (2 + b_atoms) * kAtomBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0: leader (even CTA of the pair)
+
+  const int item0 = blockIdx.y * p.group;
+  const int g_count = min(p.group, p.num_items - item0);  // even (host)
+  const int k0 = blockIdx.z * 128;
+  const int blk_begin = blockIdx.x * p.mblocks_per_split;
+  const int blk_end = min(p.mblocks_total, blk_begin + p.mblocks_per_split);
+  const int nblk = blk_end - blk_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_pair<kTmemCols>(tmem_slot);
+  pdl_sync();  // everything above is CTA-local; global memory is first touched below
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nblk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = static_cast<uint32_t>(2 * (2 + g_count / 2) * kAtomBytes);  // both CTAs' loads
+        for (int blk = blk_begin; blk < blk_end; ++blk) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) {
+            atomicExch(p.error_flag, 14);
+            break;
+          }
+          const int m0 = blk * kPixBlock;
+          const int n_img = m0 / p.PQ;
+          const int rem = m0 - n_img * p.PQ;
+          const int pp = rem / p.Q;
+          const int qq = rem - pp * p.Q;
+          const int cw = p.base_w + qq * p.stride;
+          const int ch = p.base_h + pp * p.stride;
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + 2 * kAtomBytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+          for (int a = 0; a < 2; ++a) tma_load_2d_pair(&tmDy, &full_bar[stage], sa + a * kAtomBytes, k0 + a * 64, m0);
+          for (int i = 0; 4 * i < g_count; ++i) {
+            const int half = min(4, g_count - 4 * i) / 2;
+            for (int j = 0; j < half; ++j) {
+              const int item = item0 + 4 * i + static_cast<int>(rank) * half + j;
+              const int tap = item / p.cblocks;
+              const int cb = item - tap * p.cblocks;
+              tma_load_im2col_4d_pair(&tmX, &full_bar[stage], sb + (2 * i + j) * kAtomBytes, cb * 64, cw, ch, n_img,
+                                      p.tap_w[tap], p.tap_h[tap]);
+            }
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        pdl_done();  // all loads of this CTA are issued
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && rank == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int blk = 0; blk < nblk; ++blk) {
+          if (!mbar_wait(&full_bar[stage], phase)) {
+            atomicExch(p.error_flag, 15);
+            ok = false;
+            break;
+          }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 2 * kAtomBytes;
+          for (int ks = 0; ks < kPixBlock / 16; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + ks * 2048, kAtomBytes, 1024);
+            for (int i = 0; 4 * i < g_count; ++i) {
+              const int n = min(4, g_count - 4 * i) * 64;  // N of the pair: half of it from each CTA's shared memory
+              const uint32_t idesc = make_idesc(/*bf16*/ 1, 256, n, /*a MN-major*/ 1, /*b MN-major*/ 1);
+              const uint64_t db = make_smem_desc_sw128(b_addr + 2 * i * kAtomBytes + ks * 2048, kAtomBytes, 1024);
+              umma_bf16_pair(tmem_base + i * 256, da, db, idesc, (blk | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (ok) umma_commit_pair(done_bar, 3);
+      }
+    } else if (warp >= 4) {
+      const int ew = warp - 4;
+      const int row = ew * 32 + lane;  // dW row inside this CTA's 128-row slab
+      if (!mbar_wait(done_bar, 0)) {
+        if (lane == 0) atomicExch(p.error_flag, 16);
+      } else {
+        tc_fence_after();
+        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, k0 + row < p.Cout);
+      }
+    }
+  }
+
+  // neither CTA may retire (its shared memory is an MMA operand of the pair) before both are done
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 
@@ -271,15 +425,40 @@ int wgrad_smem_bytes(int group, int num_stages, int pix_block) {
 
 cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const WgradKernelParams& p, int splits,
                          int groups, int ktiles, cudaStream_t stream) {
-  static int configured_bytes = 0;
-  const int bytes = wgrad_smem_bytes(p.group, p.num_stages, p.pix_block);
-  if (bytes > configured_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
+  static int configured_bytes = 0, configured_pair_bytes = 0;
+  const int bytes = wgrad_smem_bytes(p.pair ? p.group / 2 : p.group, p.num_stages, p.pix_block);
+  if (p.pair && bytes > configured_pair_bytes) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (ce != cudaSuccess) return ce;
+    configured_pair_bytes = bytes;
+  }
+  if (!p.pair && bytes > configured_bytes) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (ce != cudaSuccess) return ce;
     configured_bytes = bytes;
   }
-  launch_kernel(wgrad_kernel, dim3(splits, groups, ktiles), 256, bytes, stream, tmDy, tmX, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(splits, groups, ktiles);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 1;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 2;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = (pdl_enabled() && g_pdl_suppress == 0) ? 2 : 1;
+    e = cudaLaunchKernelEx(&cfg, wgrad_pair_kernel, tmDy, tmX, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  } else {
+    launch_kernel(wgrad_kernel, dim3(splits, groups, ktiles), 256, bytes, stream, tmDy, tmX, p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess || p.scratch == nullptr) return e;
   const size_t n4 = p.dw_elems / 4;
   const float4* src = reinterpret_cast<const float4*>(p.scratch);

@@ -86,6 +86,37 @@ def test_conv_wgrad(lib, geom):
     assert rel(dw, ref) < 2e-5
 
 
+PAIR_GEOMS = [  # filter gradients that run on CTA pairs (cta_group::2): Cout % 256 == 0, an even number of (tap, 64-ch) items
+    (20, 14, 256, 256, 3, 1, 1),   # 36 items -> groups of 8 (last one 4), 31 pixel blocks: several pipeline rounds
+    (16, 28, 128, 512, 1, 1, 0),   # 2 items: one per CTA, N = 128 instructions
+    (9, 28, 512, 1024, 1, 2, 0),   # stride-2 downsample, 8 items
+    (7, 28, 256, 256, 3, 2, 1),    # stride-2 3x3
+    (11, 7, 512, 2048, 1, 1, 0),   # 16 k-tiles, ragged pixel tail (539 pixels)
+    (6, 14, 1024, 256, 1, 1, 0),   # 16 items -> two groups of 8
+    (5, 7, 512, 512, 3, 1, 1),     # 72 items -> nine groups
+]
+
+
+@pytest.mark.parametrize("geom", PAIR_GEOMS)
+def test_conv_wgrad_cta_pairs(lib, geom):
+    """wgrad_pair_kernel: ONE tcgen05.mma.cta_group::2 of M = 256 per CTA pair, each CTA staging its own dY tile and half of
+    the activation items (TMA loads of both CTAs signal the leader's mbarrier; commits multicast to both).  Same checker
+    and tolerance as the single-CTA kernel; run twice into the same buffer to check accumulation and determinism."""
+    N, H, Cin, Cout, R, stride, pad = geom
+    x, w, dy, P = _mk(geom, 3)
+    xn, dyn = x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous()
+    ref = torch.nn.grad.conv2d_weight(x.float(), w.shape, dy.float(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    outs = []
+    for _ in range(2):
+        dw = torch.zeros(Cout, R, R, Cin, device="cuda")
+        lib.check(lib.lib.r3m_b200_conv_wgrad(lib.ptr(dyn), lib.ptr(xn), lib.ptr(dw), N, H, H, Cin, Cout, R, R, stride,
+                                              pad, lib.current_stream()))
+        lib.check(lib.lib.r3m_b200_check_device_flag())
+        outs.append(dw)
+    assert rel(outs[0], ref) < 2e-5, rel(outs[0], ref)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("geom,res,relu", [((2, 56, 64, 256, 1, 1, 0), True, True), ((3, 14, 256, 256, 3, 1, 1), False, True),
                                             ((2, 28, 256, 512, 1, 2, 0), False, False), ((1, 7, 512, 2048, 1, 1, 0), True, True)])
 def test_conv_forward_folded_bn_epilogue(lib, geom, res, relu):
