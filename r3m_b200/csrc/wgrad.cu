@@ -28,13 +28,13 @@ constexpr int kTmemCols = 512;
 // Epilogue of one epilogue warp: its 32 rows of the CTA's 128 x (64 * g_count) slab, TMEM -> global.  Item t of the
 // group sits in TMEM columns [64 t, 64 t + 64).
 __device__ __forceinline__ void wgrad_store_slab(const WgradKernelParams& p, uint32_t tmem_base, int item0, int g_count,
-                                                 int k0, int ew, int row, bool row_ok) {
+                                                 int k0, int ew, int row, bool row_ok, int split) {
   int tap = item0 / p.cblocks;
   int cb = item0 - tap * p.cblocks;
   for (int g = 0; g < g_count; ++g) {
     // split-K partials go to this split's private copy of dW (summed in split order by wgrad_reduce_kernel: no
     // floating-point atomics, bit-identical from run to run); a single split adds straight into dW
-    float* base = p.scratch ? p.scratch + static_cast<size_t>(blockIdx.x) * p.dw_elems : p.dW;
+    float* base = p.scratch ? p.scratch + static_cast<size_t>(split) * p.dw_elems : p.dW;
     float* dst_row = base + static_cast<size_t>(k0 + row) * p.ldw + static_cast<size_t>(tap) * p.Cin + cb * 64;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
@@ -194,7 +194,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
         if (lane == 0) atomicExch(p.error_flag, 13);
       } else {
         tc_fence_after();
-        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, row_ok);
+        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, row_ok, blockIdx.x);
       }
     }
   }
@@ -237,8 +237,8 @@ wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
   const int item0 = blockIdx.y * p.group;
   const int g_count = min(p.group, p.num_items - item0);  // even (host)
-  const int k0 = blockIdx.z * 128;
-  const int blk_begin = blockIdx.x * p.mblocks_per_split;
+  const int k0 = blockIdx.x * 128;  // grid: (k-tiles [the pair axis], item groups, splits)
+  const int blk_begin = blockIdx.z * p.mblocks_per_split;
   const int blk_end = min(p.mblocks_total, blk_begin + p.mblocks_per_split);
   const int nblk = blk_end - blk_begin;
 
@@ -339,7 +339,7 @@ wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (lane == 0) atomicExch(p.error_flag, 16);
       } else {
         tc_fence_after();
-        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, k0 + row < p.Cout);
+        wgrad_store_slab(p, tmem_base, item0, g_count, k0, ew, row, k0 + row < p.Cout, blockIdx.z);
       }
     }
   }
@@ -440,15 +440,15 @@ cudaError_t wgrad_launch(const CUtensorMap& tmDy, const CUtensorMap& tmX, const 
   cudaError_t e;
   if (p.pair) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(splits, groups, ktiles);
+    cfg.gridDim = dim3(ktiles, groups, splits);  // the pair axis must be x (cluster 2 x 1 x 1)
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = 1;
+    attrs[0].val.clusterDim.x = 2;
     attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 2;
+    attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
