@@ -160,6 +160,12 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   const int M = d.N * d.P * d.Q;
   int pix = 128;
   if (const char* e = getenv("R3M_WGRAD_PIX")) pix = atoi(e);  // tuning aid
+  // CTA pairs (cta_group::2) wherever two adjacent 128-row k-slabs exist and the items split evenly: each CTA then
+  // stages half of the group's activation items (R3M_WGRAD_PAIR=0: single-CTA kernel everywhere)
+  static const bool pair_env = !(getenv("R3M_WGRAD_PAIR") && getenv("R3M_WGRAD_PAIR")[0] == '0');
+  const bool pair = pair_env && d.Cout % 256 == 0 && (d.ntaps * (d.C / 64)) % 2 == 0;
+  if (pair)
+    if (const char* e = getenv("R3M_WGRAD_PAIR_PIX")) pix = atoi(e);  // tuning aid
   if (pix != 64 && pix != 128) return "wgrad: pix_block must be 64 or 128";
   std::string err =
       encode_tiled_2d_map(&plan->tmDy, d.dy, (uint64_t)d.Cout, (uint64_t)M, (uint64_t)d.Cout * 2, 64, pix);
@@ -188,12 +194,11 @@ std::string plan_wgrad(const WgradDesc& d, WgradPlan* plan) {
   } else {
     p.group = std::min(group_pref, p.num_items);
   }
-  // CTA pairs (cta_group::2) wherever two adjacent 128-row k-slabs exist and the items split evenly: each CTA then
-  // stages half of the group's activation items (R3M_WGRAD_PAIR=0: single-CTA kernel everywhere)
-  static const bool pair_env = !(getenv("R3M_WGRAD_PAIR") && getenv("R3M_WGRAD_PAIR")[0] == '0');
-  p.pair = (pair_env && d.Cout % 256 == 0 && p.num_items % 2 == 0 && pix == 128) ? 1 : 0;
+  p.pair = pair ? 1 : 0;
   if (p.pair) {
-    const int groups = (p.num_items + 7) / 8;
+    int max_items = 8;  // per pair and group: 4 atoms per CTA, one N = 256 instruction per 4 items
+    if (const char* e = getenv("R3M_WGRAD_PAIR_ITEMS")) max_items = std::max(2, std::min(8, atoi(e) & ~1));  // tuning aid
+    const int groups = (p.num_items + max_items - 1) / max_items;
     p.group = (p.num_items + groups - 1) / groups;
     p.group += p.group & 1;  // even: the pair splits every group in two
   }
