@@ -36,8 +36,8 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kUnitCols = 64;  // one epilogue unit: 32 rows x 64 columns bf16 = 128-byte rows (TMA stores are paced per row)
 constexpr int kUnitBytes = 32 * kUnitCols * 2;
 template <int BN>
-struct StatC {  // per-CTA statistics / affine table capacity (channels): narrow tiles only serve Cout <= 512
-  static constexpr int value = (BN == 256) ? 2048 : 512;
+struct StatC {  // per-CTA statistics / affine table capacity (channels): narrow tiles serve Cout <= 1024
+  static constexpr int value = (BN == 256) ? 2048 : 1024;
 };
 
 // STAGES: depth of the TMA->MMA operand ring.  BUFS: staging buffers per epilogue warp (bulk stores in flight).

@@ -78,7 +78,12 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   std::string err = encode_im2col_map(&plan->tmA, g.src, g.C, g.W, g.H, g.N, g.base_w, g.base_h, upper_w, upper_h,
                                       kelems, 128, g.stride, eb);
   if (!err.empty()) return err;
-  const int bn = pick_bn(g.Cout);
+  int bn = pick_bn(g.Cout);
+  if (g.bn != 0) {
+    if ((g.bn != 64 && g.bn != 128 && g.bn != 256) || g.Cout % g.bn != 0) return "gather conv: bad N tile override";
+    bn = g.bn;
+  }
+  if (bn < 256 && g.Cout > 1024) return "gather conv: N tiles of 64 / 128 serve at most 1024 output channels per launch";
   const uint64_t kdim = (uint64_t)g.ntaps * g.C;
   err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, bn, 128, eb);
   if (!err.empty()) return err;

@@ -24,6 +24,7 @@ struct GatherConv {
   int oH = 0, oW = 0, o_stride = 1, o_h0 = 0, o_w0 = 0;
   int accumulate = 0;  // out += result (read-modify-write)
   int rev_m = 0;       // walk the M tiles last-to-first (see ConvKernelParams)
+  int bn = 0;          // N tile override (64 / 128 / 256; 0: widest that divides Cout): few-row GEMMs want more, narrower tiles
   float* stat_sum = nullptr;  // optional per-channel sum / sum of squares of the stored (bf16) output (written)
   float* stat_sq = nullptr;
   // deterministic two-level reduction of the statistics: [kStatScratchFloats] floats + [kStatTickets] zeroed ints; null:

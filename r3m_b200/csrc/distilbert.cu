@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "elementwise.cuh"
@@ -348,6 +349,9 @@ std::string DistilBert::bind(float* params, void* ws, size_t ws_bytes, int max_t
   P_ = params;
   max_tokens_ = max_tokens;
   plans_.clear();
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
   uint8_t* p = static_cast<uint8_t*>(ws);
   const size_t M = static_cast<size_t>(max_tokens);
   auto take = [&](size_t bytes) {
@@ -397,7 +401,11 @@ std::string DistilBert::plan_for(int M, Plans** out) {
   // affine table of the epilogue holds at most 2048 channels per launch, wider outputs go out as column slices
   auto gemm = [&](const float* src, int K3, size_t wt_off, size_t b_off, int Cout, float* dst, int ldo, const float* res,
                   int act) {
-    const int slices = (Cout + 2047) / 2048;
+    // few token rows (a c3 step encodes 64 sentences of ~12 tokens: six 128-row tiles): 64-wide N tiles put 4x more
+    // CTAs on the long split-tf32 reduction axis than 256-wide ones (2.35 -> measured below, tools/bench_bert.py)
+    const int bn = (M <= 1536) ? 64 : 0;
+    const int max_cols = bn ? 1024 : 2048;
+    const int slices = (Cout + max_cols - 1) / max_cols;
     const int per = Cout / slices;
     if (per * slices != Cout || per % 64 != 0) {
       err = "distilbert: cannot slice a Linear of width " + std::to_string(Cout);
@@ -421,6 +429,7 @@ std::string DistilBert::plan_for(int M, Plans** out) {
       g.ep_relu = act;
       g.ep_exact = 1;  // every consumer re-splits (or is fp32 SIMT): keep the fp32 result
       g.tf32 = 1;
+      g.bn = bn;
       ConvPlan cp;
       const std::string e2 = plan_conv(g, &cp);
       if (!e2.empty()) {
@@ -451,8 +460,55 @@ std::string DistilBert::forward(const int* ids, const float* mask, int B, int T,
   if (!ids || !mask || !out) return "distilbert: null argument";
   if (B < 1 || T < 1) return "distilbert: empty batch";
   if (T > d_.max_pos) return "distilbert: sequence longer than the position table";
+  if (B * T > max_tokens_) return "distilbert: more tokens than the workspace was sized for";
+  // ~75 launches of a few microseconds each: the call is launch bound.  Like the engine's training step, the sequence is
+  // replayed as ONE CUDA graph from the second call with the same buffers and shape on (R3M_STEP_GRAPH=0: plain launches).
+  static const bool graphs = !(std::getenv("R3M_STEP_GRAPH") && std::getenv("R3M_STEP_GRAPH")[0] == '0');
+  if (!graphs) return enqueue(ids, mask, B, T, out, hidden, stream);
+  const std::vector<uint64_t> key = {(uint64_t)reinterpret_cast<uintptr_t>(ids), (uint64_t)reinterpret_cast<uintptr_t>(mask),
+                                     (uint64_t)reinterpret_cast<uintptr_t>(out), (uint64_t)reinterpret_cast<uintptr_t>(hidden),
+                                     (uint64_t)B, (uint64_t)T};
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    if (graphs_.size() >= 8) return enqueue(ids, mask, B, T, out, hidden, stream);
+    it = graphs_.emplace(key, Graph()).first;
+  }
+  Graph& g = it->second;
+  if (g.exec == nullptr && !g.failed && g.seen >= 1) {
+    if (!cap_ && cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking) != cudaSuccess) cap_ = nullptr;
+    cudaGraph_t graph = nullptr;
+    if (cap_ && cudaStreamBeginCapture(cap_, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      const std::string cerr = enqueue(ids, mask, B, T, out, hidden, cap_);
+      const cudaError_t ee = cudaStreamEndCapture(cap_, &graph);
+      if (!cerr.empty() || ee != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+        g.exec = nullptr;
+        g.failed = true;
+      }
+      g.launches = launches_;
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+    } else {
+      g.failed = true;
+      (void)cudaGetLastError();
+    }
+  }
+  ++g.seen;
+  if (g.exec == nullptr) return enqueue(ids, mask, B, T, out, hidden, stream);
+  const cudaError_t e = cudaGraphLaunch(g.exec, stream);
+  if (e != cudaSuccess) return std::string("distilbert graph launch: ") + cudaGetErrorString(e);
+  launches_ = g.launches;
+  return std::string();
+}
+
+DistilBert::~DistilBert() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (cap_) cudaStreamDestroy(cap_);
+}
+
+std::string DistilBert::enqueue(const int* ids, const float* mask, int B, int T, float* out, float* hidden,
+                                cudaStream_t stream) {
   const int M = B * T;
-  if (M > max_tokens_) return "distilbert: more tokens than the workspace was sized for";
   Plans* pl = nullptr;
   std::string err = plan_for(M, &pl);
   if (!err.empty()) return err;

@@ -24,6 +24,7 @@ struct BertDims {
 class DistilBert {
  public:
   static std::string create(const BertDims& d, DistilBert** out);
+  ~DistilBert();
   // HF state_dict names ("embeddings.word_embeddings.weight", "transformer.layer.0.attention.q_lin.weight", ...) ->
   // element offsets inside the flat fp32 parameter buffer; Linear weights keep their [out][in] layout
   const std::vector<TensorInfo>& tensors() const { return tensors_; }
@@ -50,6 +51,14 @@ class DistilBert {
     int per_layer = 0;
   };
   std::string plan_for(int M, Plans** out);
+  std::string enqueue(const int* ids, const float* mask, int B, int T, float* out, float* hidden, cudaStream_t stream);
+  struct Graph {
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0, launches = 0;
+    bool failed = false;
+  };
+  std::map<std::vector<uint64_t>, Graph> graphs_;  // (buffers, shape) -> captured forward
+  cudaStream_t cap_ = nullptr;
 
   BertDims d_;
   std::vector<TensorInfo> tensors_;

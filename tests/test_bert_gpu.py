@@ -66,7 +66,7 @@ def test_full_size_encoder_matches_transformers(B, T):
     assert rel(got_h, want_h) < TOL, rel(got_h, want_h)
     assert rel(got, want) < TOL, rel(got, want)
     assert float((got_h - want_h).abs().max()) < 2e-3  # no single token is off (LayerNorm output is O(1))
-    assert enc.launches_last_call == 1 + 6 * 11 + 1
+    assert enc.launches_last_call == 1 + 6 * 12 + 1  # per layer: q, k, v, attention, out, LN, lin1 x 3 column slices, split, lin2, LN
 
 
 def test_long_sentences_take_the_tiled_attention_path():
