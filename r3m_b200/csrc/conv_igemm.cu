@@ -48,9 +48,11 @@ struct StatC {  // per-CTA statistics / affine table capacity (channels): narrow
 // bookkeeping (mbarrier try_wait ~90 cycles, expect_tx, descriptor math, op issue) costs ~450-600 cycles (measured:
 // per-stage time is flat in the number of MMAs and TMA ops), so a stage must carry at least that much tensor work:
 // 4 MMAs of N=256 (512 cycles) do, 4 MMAs of N=64 (128 cycles) do not -> narrow tiles put several K blocks in a stage.
-template <int BN, int STAGES, int BUFS, int EPI, int KPS>
+// PAIR: the CTA is one half of a cta_group::2 pair (two M tiles against one filter tile): it stages only HALF of the
+// filter tile's rows (the N columns of the pair's B operand are split between the two shared memories).
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, bool PAIR = false>
 struct Cfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBlockK * 2;
   static constexpr int kKbBytes = kABytes + kBBytes;   // one K block: A sub-tile then B sub-tile
   static constexpr int kStageBytes = KPS * kKbBytes;
   static constexpr int kStages = STAGES;
@@ -72,11 +74,20 @@ enum { kModeDense = 0, kModeStats = 1, kModeScatter = 2 };
 // core arithmetic and fp32 (tf32-rounded) output — the parity tier of the inference path (dense mode only).  The
 // 128-byte swizzle row then holds 32 channels instead of 64 and an MMA consumes K = 8 of them; tile BYTES, the operand
 // ring and the descriptor stepping are unchanged.
-template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE, int PREC = 0>
+// PAIR (bf16, BN = 256, dense / statistics modes): clusters of two CTAs; the pair computes two adjacent M tiles against
+// one filter tile with ONE tcgen05.mma.cta_group::2 of M = 256 per K step.  Each CTA loads its own activation tile and
+// half of the filter tile (32 KB of operands per K block instead of 48 KB: the kernel is bound by the bytes an SM can
+// pull into shared memory, profiles/r2_ncu_per_kernel.md), TMA bytes of both CTAs complete on the even CTA's full
+// barriers, only the even CTA issues MMAs, its commits arrive on the barriers of both, and the odd CTA's epilogue warps
+// release the accumulator stage on the even CTA's barrier.  An odd number of M tiles: the last pair's second CTA repeats
+// the first one's tile and discards the result.
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE, int PREC = 0, bool PAIR = false>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
-  using C = Cfg<BN, STAGES, BUFS, EPI, KPS>;
+  using C = Cfg<BN, STAGES, BUFS, EPI, KPS, PAIR>;
+  static_assert(!PAIR || (PREC == 0 && MODE != kModeScatter && BN == 256), "pairs: bf16, dense outputs, 256-wide tiles");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
@@ -107,11 +118,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * EPI : EPI);  // pairs: the epilogue warps of BOTH CTAs release the leader's stage
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR)
+      tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else
+      tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   pdl_sync();  // everything above is CTA-local; global memory is first touched below
   const bool do_affine = !STATS && (p.ep_scale != nullptr);
   if (do_affine) {
@@ -123,11 +139,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tiles of this CTA: tile0, tile0 + tile_step, ...; a pair walks pair-tiles (two M tiles x one N tile)
+  const int total_tiles = (PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+  const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = p.num_taps * p.cblocks;
+  // M tile of this CTA inside tile `t` (+ whether it is the discarded duplicate that completes an odd last pair)
+  auto m_tile_of = [&](int t_m_idx, bool* dup) {
+    int m_idx = t_m_idx;
+    *dup = false;
+    if constexpr (PAIR) {
+      m_idx = 2 * t_m_idx + static_cast<int>(rank);
+      if (m_idx >= p.num_m_tiles) {
+        m_idx = p.num_m_tiles - 1;
+        *dup = true;
+      }
+    }
+    return p.rev_m ? p.num_m_tiles - 1 - m_idx : m_idx;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -135,10 +168,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
         const int m_idx = tile / p.num_n_tiles;
         const int n_tile = tile - m_idx * p.num_n_tiles;
-        const int m_tile = p.rev_m ? p.num_m_tiles - 1 - m_idx : m_idx;
+        bool dup;
+        const int m_tile = m_tile_of(m_idx, &dup);
         const int m0 = m_tile * kBlockM;
         const int n_img = m0 / p.PQ;
         const int rem = m0 - n_img * p.PQ;
@@ -155,13 +189,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const int nk = min(KPS, num_kb - kb0);
           uint8_t* st = smem + stage * C::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk * C::kKbBytes));
+          if constexpr (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * nk * C::kKbBytes));  // both CTAs' loads
+          } else {
+            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk * C::kKbBytes));
+          }
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
               uint8_t* sa = st + j * C::kKbBytes;
+              if constexpr (PAIR) {
+                tma_load_im2col_4d_pair(&tmA, &full_bar[stage], sa, cb * kElemsK, cw, ch, n_img, p.tap_w[tap],
+                                        p.tap_h[tap]);
+                tma_load_2d_pair(&tmB, &full_bar[stage], sa + kABytes, (kb0 + j) * kElemsK,
+                                 n_tile * BN + static_cast<int>(rank) * (BN / 2));
+              } else {
               tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kElemsK, cw, ch, n_img, p.tap_w[tap], p.tap_h[tap]);
               tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, (kb0 + j) * kElemsK, n_tile * BN);
+              }
               if (++cb == p.cblocks) {
                 cb = 0;
                 ++tap;
@@ -178,14 +223,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(PREC ? /*tf32*/ 2 : /*bf16*/ 1, kBlockM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(PREC ? /*tf32*/ 2 : /*bf16*/ 1, PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) {
           atomicExch(p.error_flag, 2);
           break;
@@ -210,7 +255,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
                 // +32 bytes per MMA (K = 16 bf16 or 8 tf32) inside the 128-byte swizzle row (start-address field is >>4)
-                if constexpr (PREC == 0)
+                if constexpr (PAIR)
+                  umma_bf16_pair(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                 (kb0 | j | k) != 0 ? 1u : 0u);
+                else if constexpr (PREC == 0)
                   umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
                             (kb0 | j | k) != 0 ? 1u : 0u);
                 else
@@ -219,14 +267,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (PAIR)
+            umma_commit_pair(&empty_bar[stage], 3);
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);
+        if constexpr (PAIR)
+          umma_commit_pair(&tfull_bar[acc], 3);
+        else
+          umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -236,6 +290,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // warp (q, h): TMEM lane quadrant q = warp % 4 (rows 32q..32q+31 of the tile), 32-column units u = h, h+2, ...
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
+    auto release_acc = [&](uint64_t* bar) {  // the accumulator stage is free again: tell the (pair's) MMA issuer
+      if constexpr (PAIR)
+        mbar_arrive_leader(bar);
+      else
+        mbar_arrive(bar);
+    };
     const uint32_t stg_base = smem_u32(staging + (warp - 4) * (BUFS * kUnitBytes));
     int buf = 0;
     constexpr bool dense = (MODE != kModeScatter);
@@ -257,11 +317,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // end.  Then: per-quadrant partials -> shared memory, summed over the four quadrants in fixed order -> added to the
     // column block's fixed-point accumulators (fx_add: exact, order independent) -> the LAST CTA of the column block
     // (ticket) converts the totals to fp32.  No floating-point atomics: the sums are bit-identical from run to run.
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int m_idx = tile / p.num_n_tiles;
       const int n_tile = tile - m_idx * p.num_n_tiles;
-      const int m_tile = p.rev_m ? p.num_m_tiles - 1 - m_idx : m_idx;
-      const int m0 = m_tile * kBlockM + q * 32;
+      bool dup;
+      const int m_tile = m_tile_of(m_idx, &dup);
+      // a duplicate tile (odd last pair) is drained like any other but leaves no trace: its rows are placed beyond M
+      const int m0 = (dup ? p.num_m_tiles : m_tile) * kBlockM + q * 32;
       const int n0 = n_tile * BN;
       if constexpr (STATS) acc_ntile = n_tile;
       long long row_off[dense ? 1 : 8];
@@ -306,7 +368,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc(&tempty_bar[acc]);
           }
           if (do_affine) {
             const float* sc = s_sum + n0 + u * 32;
@@ -366,13 +428,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (h >= kUnits32) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) release_acc(&tempty_bar[acc]);
         }
       } else if (h >= kUnits) {
         // BN == 64: a single unit per quadrant; the second warp of the pair has nothing to drain
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) release_acc(&tempty_bar[acc]);
       } else {
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(t_row + h * kUnitCols, v0);
@@ -429,7 +491,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // the accumulator stage is fully in registers: hand it back to the MMA warp early
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc(&tempty_bar[acc]);
           }
           // the staging buffer about to be overwritten must no longer be read by the bulk store issued BUFS units ago
           const uint32_t stg_u32 = stg_base + buf * kUnitBytes;
@@ -545,7 +607,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
       const int et = threadIdx.x - 128;  // epilogue thread index
-      const int my_ntile = blockIdx.x % p.num_n_tiles;
+      const int my_ntile = tile0 % p.num_n_tiles;
       // this CTA's column sums -> fixed-point accumulators (exact integer adds: independent of the CTAs' arrival order)
       // raw mode (engine): the layer's own accumulators, converted by the consuming BatchNorm kernel — no tail at all
       unsigned long long* acc = (p.stat_raw ? reinterpret_cast<unsigned long long*>(p.stat_sum)
@@ -568,7 +630,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
       int* s_flag = reinterpret_cast<int*>(tmem_slot) + 2;
       if (et == 0) {
-        const int contributors = (gridDim.x - my_ntile + p.num_n_tiles - 1) / p.num_n_tiles;
+        const int contributors = (PAIR ? 2 : 1) * ((tile_step - my_ntile + p.num_n_tiles - 1) / p.num_n_tiles);
         const int t = atomicAdd(&p.stat_ticket[my_ntile], 1);
         *s_flag = (t == contributors - 1) ? 1 : 0;
       }
@@ -590,10 +652,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's shared memory is an operand of the pair's MMAs until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    if constexpr (PAIR)
+      tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else
+      tmem_dealloc<C::kTmemCols>(tmem_base);
   }
+}
+
+template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE>
+cudaError_t launch_pair_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                            const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  using C = Cfg<BN, STAGES, BUFS, EPI, KPS, true>;
+  auto kernel = conv_igemm_kernel<BN, STAGES, BUFS, EPI, KPS, MODE, 0, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (grid < 2 || (grid & 1)) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = (pdl_enabled() && g_pdl_suppress == 0) ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, p);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int BN, int STAGES, int BUFS, int EPI, int KPS, int MODE, int PREC = 0>
@@ -637,6 +733,21 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return launch_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense>(tmA, tmB, tmC, p, grid, stream);
 }
 
+// CTA pairs: the filter half-tile shrinks a stage from 48 to 32 KB, which buys the ring one (epilogue-bound
+// configuration) or two (MMA-bound configuration) more stages
+template <int BN, int STAGES, int BUFS, int EPI, int KPS>
+cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                        const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  if (p.tf32 || p.out_mode != 0) return cudaErrorInvalidValue;
+  if (p.stat_sum != nullptr) {
+    if (p.ep_scale != nullptr || (grid / 2) % p.num_n_tiles != 0 ||
+        (!p.stat_raw && (p.stat_sq == nullptr || p.stat_scratch == nullptr || p.stat_ticket == nullptr)))
+      return cudaErrorInvalidValue;
+    return launch_pair_cfg<BN, STAGES, BUFS, EPI, KPS, kModeStats>(tmA, tmB, tmC, p, grid, stream);
+  }
+  return launch_pair_cfg<BN, STAGES, BUFS, EPI, KPS, kModeDense>(tmA, tmB, tmC, p, grid, stream);
+}
+
 }  // namespace
 
 cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -653,6 +764,10 @@ cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap&
       if (num_kb >= 18 || scatter) return launch_bn<128, 3, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3
       return launch_bn<128, 4, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);
     case 256:
+      if (p.pair) {
+        if (num_kb >= 12) return launch_pair<256, 6, 1, 4, 1>(tmA, tmB, tmC, p, grid, stream);
+        return launch_pair<256, 4, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);
+      }
       if (num_kb >= 12 || scatter) return launch_bn<256, 4, 1, 4, 1>(tmA, tmB, tmC, p, grid, stream);  // MMA bound: deep ring
       return launch_bn<256, 3, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);                    // epilogue bound
     default:

@@ -22,6 +22,7 @@ struct ConvKernelParams {
   // GEMM N
   int Cout;
   int num_m_tiles, num_n_tiles;
+  int pair;   // 1: cta_group::2 CTA pairs (clusters of two along grid x, two M tiles per filter tile; tmB's box is BN / 2 rows)
   int rev_m;  // 1: M tiles are walked last-to-first (L2 reuse of the rows the producing kernel wrote last)
   // output
   void* out;     // bf16

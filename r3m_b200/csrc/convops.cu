@@ -85,10 +85,14 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   }
   if (bn < 256 && g.Cout > 1024) return "gather conv: N tiles of 64 / 128 serve at most 1024 output channels per launch";
   const uint64_t kdim = (uint64_t)g.ntaps * g.C;
-  err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, bn, 128, eb);
-  if (!err.empty()) return err;
   ConvKernelParams& p = plan->p;
   p.M_total = g.N * g.P * g.Q;
+  // CTA pairs (cta_group::2): bf16, dense outputs, 256-wide tiles, at least one pair of M tiles per filter tile
+  // (R3M_CONV_PAIR=0: single-CTA kernel everywhere)
+  static const bool pair_env = !(std::getenv("R3M_CONV_PAIR") && std::getenv("R3M_CONV_PAIR")[0] == '0');
+  p.pair = (pair_env && bn == 256 && !g.tf32 && g.out_mode == 0 && p.M_total > 128) ? 1 : 0;
+  err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, p.pair ? bn / 2 : bn, 128, eb);
+  if (!err.empty()) return err;
   if (g.out_mode == 0) {
     err = encode_tiled_2d_map(&plan->tmC, g.out, (uint64_t)g.Cout, (uint64_t)p.M_total, (uint64_t)g.ldo * eb, kelems, 32,
                               /*swizzle_bytes=*/128, eb);
@@ -145,12 +149,17 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   if (!p.error_flag) return "could not allocate the device error flag";
   plan->bn = bn;
   plan->grid = std::min(p.num_m_tiles * p.num_n_tiles, device_sm_count());
-  if (g.stat_sum) {
+  if (p.pair) {
+    int pairs = std::min(((p.num_m_tiles + 1) / 2) * p.num_n_tiles, device_sm_count() / 2);
+    if (g.stat_sum) pairs -= pairs % p.num_n_tiles;  // every pair keeps one column block
+    if (pairs < 1) return "gather conv: no room for a CTA pair per column block";
+    plan->grid = 2 * pairs;
+  } else if (g.stat_sum) {
     // deterministic statistics: every CTA keeps one column block (see conv_igemm.cu)
     plan->grid -= plan->grid % p.num_n_tiles;
-    if ((size_t)g.Cout * 16 > kStatScratchFloats || p.num_n_tiles > (int)kStatTickets)
-      return "gather conv: statistics scratch too small for this grid";
   }
+  if (g.stat_sum && ((size_t)g.Cout * 16 > kStatScratchFloats || p.num_n_tiles > (int)kStatTickets))
+    return "gather conv: statistics scratch too small for this grid";
   return std::string();
 }
 
