@@ -526,7 +526,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (do_stats) {
+          if (do_stats && !dup) {
             // lane owns columns (2*lane, 2*lane+1) of the unit; rows beyond M_total are exact zeros (TMA zero fill)
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8

@@ -90,7 +90,12 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   // CTA pairs (cta_group::2): bf16, dense outputs, 256-wide tiles, at least one pair of M tiles per filter tile
   // (R3M_CONV_PAIR=0: single-CTA kernel everywhere)
   static const bool pair_env = !(std::getenv("R3M_CONV_PAIR") && std::getenv("R3M_CONV_PAIR")[0] == '0');
-  p.pair = (pair_env && bn == 256 && !g.tf32 && g.out_mode == 0 && p.M_total > 128) ? 1 : 0;
+  // ... and a reduction axis of at least 8 K blocks: measured per launch in the ResNet-50 step, pairs win 6-12 % on the
+  // fill-bound shapes (3x3 convs and 4C -> C 1x1 convs of layers 3-4, K >= 512) and LOSE 10-35 % on the short-K,
+  // wide-output 1x1 convs (C -> 4C), which are bound by their epilogue and only pay for the lock-step of two CTAs
+  static const int pair_min_kb = std::getenv("R3M_CONV_PAIR_MIN_KB") ? atoi(std::getenv("R3M_CONV_PAIR_MIN_KB")) : 8;
+  p.pair = (pair_env && bn == 256 && !g.tf32 && g.out_mode == 0 && p.M_total > 128 &&
+            g.ntaps * (g.C / kelems) >= pair_min_kb) ? 1 : 0;
   err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, p.pair ? bn / 2 : bn, 128, eb);
   if (!err.empty()) return err;
   if (g.out_mode == 0) {
