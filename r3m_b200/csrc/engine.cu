@@ -282,6 +282,7 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
   for (int i = 0; i < 7; ++i) e->off_g_[i] = arena(N * kMaxActPerFrame * 2);
   // a model with a language head still embeds any number of frames (R3M.forward); only update() needs 5 * clips
   if (lang_head && e->B_ > 0) e->off_lang_ws_ = arena(lang_workspace_floats(e->lang_dims_) * 4);
+  if (lang_head && e->B_ > 0) e->off_lang_tc_ = arena(lang_tc_floats(e->lang_dims_) * 4);
   e->off_fold_ = arena(2 * e->convs_.size() * sizeof(BnFoldEntry));  // bf16 tier (stem excluded) | tf32 tier (all)
   e->off_pack_ = arena(kMaxPackEntries * sizeof(PackDgradEntry));
   if (frames <= kGraphMaxFrames) e->off_obs_stage_ = arena(N * 3 * 224 * 224 * 4);
@@ -370,6 +371,24 @@ std::string Engine::plan_all() {
     l2_order_ = !(env && env[0] == '0');
     // off by default: measured +0.1 ms per ResNet-50 step on B200 (the isolated kernels gain 0.2 ms, but the cooperative
     // launch cannot overlap its neighbours' prologues and the filter gradients lose their slot between the two passes)
+    env = std::getenv("R3M_LANG_TC");
+    lang_tc_ = LangTc();
+    if (lang_ && B_ > 0 && !(env && env[0] == '0')) {
+      // tensor-core path of the language head's hidden layers (R3M_LANG_TC=0: fp32 SIMT everywhere)
+      float* Pp = reinterpret_cast<float*>(pws_ + off_P_);
+      float* Gp = reinterpret_cast<float*>(pws_ + off_G_);
+      LangParams lp;
+      for (int l = 0; l < 5; ++l) {
+        lp.w[l] = Pp + lang_w_off_[l];
+        lp.b[l] = Pp + lang_b_off_[l];
+        lp.dw[l] = Gp + lang_w_off_[l];
+        lp.db[l] = Gp + lang_b_off_[l];
+      }
+      LangWorkspace lw;
+      lang_carve_workspace(reinterpret_cast<float*>(ws_ + off_lang_ws_), lang_dims_, &lw);
+      const std::string terr = lang_tc_plan(lang_dims_, lp, lw, reinterpret_cast<float*>(ws_ + off_lang_tc_), &lang_tc_);
+      if (!terr.empty()) return terr;
+    }
     env = std::getenv("R3M_FUSE_BN_BWD");
     fuse_bn_bwd_ = (env && env[0] == '1') && std::getenv("R3M_GRID_WAVES") == nullptr;
   }
@@ -1396,6 +1415,7 @@ std::string Engine::update_grads(const void* obs, const int* perms, const float*
       LangWorkspace lw;
       lang_carve_workspace(reinterpret_cast<float*>(ws_ + off_lang_ws_), lang_dims_, &lw);
       const LangDims ld = lang_dims_;
+      const LangTc* tc = &lang_tc_;
       const float langw = h.langweight;
       int n_lang = 0;
       int* n_ptr = &n_lang;
@@ -1407,7 +1427,7 @@ std::string Engine::update_grads(const void* obs, const int* perms, const float*
       const double fwd_mac = l1_mac + rows * (3 * H * H + H);
       const double bwd_mac = 2.0 * rows * 3 * H * H + (l1_mac + 6.0 * Bc * Dd * H);
       e = launch(Op([=](cudaStream_t s) {
-                   return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s);
+                   return lang_head_run(ld, lp, lw, E, dE, perms, lang_emb, lang_mask, langw, metrics, n_ptr, s, tc);
                  },
                  kFamLang, 2.0 * (fwd_mac + (eval ? 0.0 : bwd_mac)), 0.0),
                  st);

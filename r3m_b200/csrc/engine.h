@@ -190,7 +190,8 @@ class Engine {
   size_t off_det_ = 0, off_det_bn_ = 0, off_det_loss_ = 0, det_small_bytes_ = 0, off_wgrad_scratch_[2] = {0, 0};
   // language head (optional)
   size_t lang_w_off_[5] = {0, 0, 0, 0, 0}, lang_b_off_[5] = {0, 0, 0, 0, 0};
-  size_t off_lang_ws_ = 0;
+  size_t off_lang_ws_ = 0, off_lang_tc_ = 0;
+  LangTc lang_tc_;  // tensor-core path of the language head's hidden layers (plans + split operand buffers)
   size_t off_fold_ = 0;  // BnFoldEntry table (device) for the inference path
   size_t off_pack_ = 0;  // PackDgradEntry table (device): all dgrad filter re-packs in one launch
   // small-batch inference: the eval forward is replayed as a CUDA graph from a fixed staging copy of the frames

@@ -459,7 +459,132 @@ __global__ void vec_sum_kernel(const float* __restrict__ v, float* __restrict__ 
   }
 }
 
+__device__ __forceinline__ float tc_round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// Operand preparation of the tensor-core path, one 32 x 32 tile of src [R][C] per block: optional ReLU gate
+// (gate[r][c] > 0), optional dense copy of the gated values (may alias src), the row-major split copy [R][3C] and the
+// TRANSPOSED split copy [C][3Rp] (rows >= R zero filled: the padded tail of a reduction axis).  Split order: 0 =
+// activation (hi | lo | hi), 1 = weight (hi | hi | lo).
+__global__ void __launch_bounds__(256) lang_prep_kernel(const float* src, const float* __restrict__ gate,
+                                                        float* dense, float* __restrict__ split,
+                                                        float* __restrict__ tsplit, int R, int C, int Rp, int s_weights,
+                                                        int t_weights) {
+  __shared__ float tile[32][33];
+  pdl_sync();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rl = ty + 8 * j, r = blockIdx.y * 32 + rl;
+    float v = 0.f;
+    if (r < R) {
+      v = src[(size_t)r * C + c];
+      if (gate != nullptr && !(gate[(size_t)r * C + c] > 0.f)) v = 0.f;
+      if (dense != nullptr) dense[(size_t)r * C + c] = v;
+      if (split != nullptr) {
+        const float hi = tc_round_tf32(v), lo = tc_round_tf32(v - hi);
+        float* o = split + (size_t)r * 3 * C;
+        o[c] = hi;
+        o[C + c] = s_weights ? hi : lo;
+        o[2 * C + c] = s_weights ? lo : hi;
+      }
+    }
+    tile[rl][tx] = v;
+  }
+  if (tsplit == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cl = ty + 8 * j;
+    const float v = tile[tx][cl];  // element (row by*32 + tx, column bx*32 + cl)
+    const float hi = tc_round_tf32(v), lo = tc_round_tf32(v - hi);
+    float* o = tsplit + (size_t)(blockIdx.x * 32 + cl) * 3 * Rp + blockIdx.y * 32 + tx;
+    o[0] = hi;
+    o[Rp] = t_weights ? hi : lo;
+    o[2 * Rp] = t_weights ? lo : hi;
+  }
+}
+
+__global__ void lang_fill_kernel(float* p, int n, float v) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+cudaError_t launch_prep(const float* src, const float* gate, float* dense, float* split, float* tsplit, int R, int C,
+                        int Rp, int s_weights, int t_weights, cudaStream_t s) {
+  launch_kernel(lang_prep_kernel, dim3(C / 32, Rp / 32), dim3(256), 0, s, src, gate, dense, split, tsplit, R, C, Rp,
+                s_weights, t_weights);
+  return cudaGetLastError();
+}
+
+size_t up64(size_t v) { return (v + 63) / 64 * 64; }
+
 }  // namespace
+
+size_t lang_tc_floats(const LangDims& d) {
+  const size_t r = (size_t)d.rows(), H = (size_t)d.H, Rp = (r + 31) / 32 * 32;
+  return 3 * up64(r * 3 * H) + 3 * up64(H * 3 * Rp) + up64(r * 3 * H) + up64(H * 3 * Rp) + 6 * up64(H * 3 * H) + up64(H);
+}
+
+std::string lang_tc_plan(const LangDims& d, const LangParams& p, const LangWorkspace& ws, float* base, LangTc* tc) {
+  *tc = LangTc();
+  const int rows = d.rows(), H = d.H;
+  if (H % 64 != 0 || H > 1024) return std::string();  // plain fp32 SIMT path (tc->enabled stays false)
+  const int Rp = (rows + 31) / 32 * 32;
+  tc->Rp = Rp;
+  float* q = base;
+  auto take = [&](size_t n) {
+    float* r = q;
+    q += up64(n);
+    return r;
+  };
+  for (int i = 0; i < 3; ++i) tc->Hs[i] = take((size_t)rows * 3 * H);
+  for (int i = 0; i < 3; ++i) tc->HTs[i] = take((size_t)H * 3 * Rp);
+  tc->dHs = take((size_t)rows * 3 * H);
+  tc->dHTs = take((size_t)H * 3 * Rp);
+  for (int i = 0; i < 3; ++i) tc->Ws[i] = take((size_t)H * 3 * H);
+  for (int i = 0; i < 3; ++i) tc->WTs[i] = take((size_t)H * 3 * H);
+  tc->ones = take((size_t)H);
+  // out[M][H] = act(src[M][K3] . w[H][K3]^T (+ bias)): the conv kernel's tf32 tier as a plain GEMM, 64-wide N tiles
+  auto gemm = [&](const float* src, int M, int K3, const float* w, const float* bias, int relu, float* out,
+                  ConvPlan* plan) {
+    GatherConv g;
+    g.src = src;
+    g.N = M;
+    g.H = g.W = g.P = g.Q = 1;
+    g.C = K3;
+    g.stride = 1;
+    g.ntaps = 1;
+    g.wpk = w;
+    g.Cout = H;
+    g.out = out;
+    g.ldo = H;
+    if (bias != nullptr) {
+      g.ep_scale = tc->ones;
+      g.ep_shift = bias;
+    }
+    g.ep_relu = relu;
+    g.ep_exact = 1;
+    g.tf32 = 1;
+    g.bn = 64;
+    return plan_conv(g, plan);
+  };
+  int cur = 0;
+  for (int l = 3; l >= 1; --l) {  // the backward loop's ping-pong: dH_l lives in dH[cur], dH_{l-1} goes to dH[cur ^ 1]
+    std::string e = gemm(tc->dHs, rows, 3 * H, tc->WTs[l - 1], nullptr, 0, ws.dH[cur ^ 1], &tc->dx[l - 1]);
+    if (e.empty()) e = gemm(tc->dHTs, H, 3 * Rp, tc->HTs[l - 1], nullptr, 0, p.dw[l], &tc->dw[l - 1]);
+    if (e.empty()) e = gemm(tc->Hs[l - 1], rows, 3 * H, tc->Ws[l - 1], p.b[l], 1, ws.Hact[l], &tc->fwd[l - 1]);
+    if (!e.empty()) return "language head (tensor-core path): " + e;
+    cur ^= 1;
+  }
+  tc->enabled = true;
+  return std::string();
+}
 
 size_t lang_workspace_floats(const LangDims& d) {
   const size_t r = (size_t)d.rows();
@@ -501,7 +626,8 @@ void lang_carve_workspace(float* base, const LangDims& d, LangWorkspace* ws) {
 
 cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWorkspace& ws, const float* E, float* dE,
                           const int* perms, const float* lang_emb, const float* lang_mask, float langw,
-                          float* metrics, int* launches, cudaStream_t s) {
+                          float* metrics, int* launches, cudaStream_t s, const LangTc* tc) {
+  const bool use_tc = tc != nullptr && tc->enabled;
   const int rows = d.rows(), H = d.H, K1 = d.k1();
   int n = 0;
   cudaError_t e;
@@ -529,9 +655,22 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     R3M_TRY(cudaGetLastError());
   }
   // ---- layers 2-4: Linear + ReLU, then Linear(H -> 1)
+  if (use_tc) {
+    launch_kernel(lang_fill_kernel, dim3((H + 255) / 256), dim3(256), 0, s, tc->ones, H, 1.0f);
+    R3M_TRY(cudaGetLastError());
+    for (int l = 1; l < 4; ++l) {
+      // this step's weights: split W_l (forward operand) and, for the backward pass, split W_l^T (dX operand)
+      R3M_TRY(launch_prep(p.w[l], nullptr, nullptr, tc->Ws[l - 1], dE ? tc->WTs[l - 1] : nullptr, H, H, H, 1, 1, s));
+      // H_{l-1}: split (forward operand) and, for the backward pass, split H_{l-1}^T (dW operand)
+      R3M_TRY(launch_prep(ws.Hact[l - 1], nullptr, nullptr, tc->Hs[l - 1], dE ? tc->HTs[l - 1] : nullptr, rows, H, tc->Rp,
+                          0, 1, s));
+      R3M_TRY(run_conv(tc->fwd[l - 1], s));
+    }
+  } else {
   for (int l = 1; l < 4; ++l) {
     GemmArgs g{ws.Hact[l - 1], p.w[l], ws.Hact[l], rows, H, H, H, H, H, p.b[l], 1, nullptr, 0, 0};
     R3M_TRY((run_gemm<true, true>(g, s)));
+  }
   }
   launch_kernel(lang_score_kernel, rows, 256, 0, s, ws.Hact[3], p.w[4], p.b[4], ws.S, H);
   R3M_TRY(cudaGetLastError());
@@ -546,6 +685,23 @@ cudaError_t lang_head_run(const LangDims& d, const LangParams& p, const LangWork
     launch_kernel(lang_dscore_kernel, 148 * 4, 256, 0, s, ws.dS, p.w[4], ws.Hact[3], ws.dH[0], rows, H);
     R3M_TRY(cudaGetLastError());
     int cur = 0;
+    if (use_tc) {
+      for (int l = 3; l >= 1; --l) {
+        float* dHl = ws.dH[cur];
+        // dH_l: apply the ReLU gate of layer l to the raw dX product (l = 3 arrives gated from lang_dscore_kernel), keep
+        // the gated values (bias gradient, layer-1 backward), split it (dX operand) and split its transpose (dW operand)
+        R3M_TRY(launch_prep(dHl, l < 3 ? ws.Hact[l] : nullptr, l < 3 ? dHl : nullptr, tc->dHs, tc->dHTs, rows, H, tc->Rp, 0,
+                            0, s));
+        launch_kernel(col_sum_kernel, dim3((H + 15) / 16, 1), 1024, 0, s, (const float*)dHl, (const float*)nullptr,
+                      p.db[l], rows, H);
+        R3M_TRY(cudaGetLastError());
+        R3M_TRY(run_conv(tc->dw[l - 1], s));
+        R3M_TRY(run_conv(tc->dx[l - 1], s));
+        cur ^= 1;
+      }
+      // the raw dX of layer 1's output still needs its ReLU gate
+      R3M_TRY(launch_prep(ws.dH[cur], ws.Hact[0], ws.dH[cur], nullptr, nullptr, rows, H, tc->Rp, 0, 0, s));
+    } else
     for (int l = 3; l >= 1; --l) {
       const float* dHl = ws.dH[cur];
       // db_l = column sums of dH_l;  dW_l[n][k] = sum_m dH_l[m][n] * H_{l-1}[m][k]
