@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using C = Cfg<BN, STAGES, BUFS, EPI, KPS, PAIR>;
-  static_assert(!PAIR || (PREC == 0 && MODE != kModeScatter && BN == 256), "pairs: bf16, dense outputs, 256-wide tiles");
+  static_assert(!PAIR || (PREC == 0 && MODE != kModeScatter && BN >= 128), "pairs: bf16, dense outputs, 128/256-wide tiles");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -761,6 +761,7 @@ cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap&
       return launch_bn<64, 6, 4, 4, 1>(tmA, tmB, tmC, p, grid, stream);
     case 128:
       if (p.Cout > StatC<128>::value) return cudaErrorInvalidValue;
+      if (p.pair) return launch_pair<128, 4, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3 (host: >= 18 K blocks)
       if (num_kb >= 18 || scatter) return launch_bn<128, 3, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3
       return launch_bn<128, 4, 2, 8, 1>(tmA, tmB, tmC, p, grid, stream);
     case 256:

@@ -94,8 +94,11 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   // fill-bound shapes (3x3 convs and 4C -> C 1x1 convs of layers 3-4, K >= 512) and LOSE 10-35 % on the short-K,
   // wide-output 1x1 convs (C -> 4C), which are bound by their epilogue and only pay for the lock-step of two CTAs
   static const int pair_min_kb = std::getenv("R3M_CONV_PAIR_MIN_KB") ? atoi(std::getenv("R3M_CONV_PAIR_MIN_KB")) : 8;
-  p.pair = (pair_env && bn == 256 && !g.tf32 && g.out_mode == 0 && p.M_total > 128 &&
-            g.ntaps * (g.C / kelems) >= pair_min_kb) ? 1 : 0;
+  // 128-wide tiles (the 128-channel layers): only the 3x3 configuration (>= 18 K blocks) has a pair variant
+  static const bool pair128 = !(std::getenv("R3M_CONV_PAIR128") && std::getenv("R3M_CONV_PAIR128")[0] == '0');
+  const int nkb = g.ntaps * (g.C / kelems);
+  p.pair = (pair_env && !g.tf32 && g.out_mode == 0 && p.M_total > 128 &&
+            ((bn == 256 && nkb >= pair_min_kb) || (bn == 128 && pair128 && nkb >= 18))) ? 1 : 0;
   err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, p.pair ? bn / 2 : bn, 128, eb);
   if (!err.empty()) return err;
   if (g.out_mode == 0) {
