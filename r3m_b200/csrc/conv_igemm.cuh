@@ -54,6 +54,21 @@ struct ConvKernelParams {
 cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                               const ConvKernelParams& p, int grid, cudaStream_t stream);
 
+// 3x3 / stride-1 / 64 -> 64 channel convolutions with TAP REUSE (halo3x3.cu): an M tile is a 16 x 8 patch of output pixels,
+// ONE tiled TMA load brings its 18 x 10 x 64 input halo, and the nine taps are nine shifted views of that shared memory.
+struct HaloKernelParams {
+  int N, H, W;            // images; output (= input) height and width: H % 4 == 0, W % 8 == 0
+  int tiles_h, tiles_w;   // ceil(H / 16), W / 8
+  int num_taps;           // <= 9
+  uint16_t tap_w[9], tap_h[9];  // tap t reads input pixel (p - 1 + tap_h[t], q - 1 + tap_w[t]) with filter K block t
+  int rev;                // walk the tiles last-to-first
+  unsigned long long* stat_acc;  // optional raw fixed-point accumulators (64 channels x {sum, sum of squares}), added into
+  int base_offset_mode;   // experiment switch: 1 = descriptors carry the swizzle base offset of their start row
+  int* error_flag;
+};
+cudaError_t halo3x3_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY,
+                           const HaloKernelParams& p, int grid, cudaStream_t stream);
+
 struct WgradKernelParams {
   int M_total;
   int PQ, Q;

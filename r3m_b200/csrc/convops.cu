@@ -73,6 +73,43 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   if (g.stride < 1 || g.stride > 8) return "gather conv: stride out of range";
   if (g.ldo % 8 != 0) return "gather conv: output row pitch must be a multiple of 8 elements";
   *plan = {};
+  {
+    // Tap reuse (halo3x3.cu): 3x3-footprint, stride-1, pad-1 gather convs of 64 -> 64 channels with a dense bf16 output,
+    // no accumulation / affine epilogue, statistics (if any) straight into raw accumulators.  R3M_HALO=0 disables.
+    static const bool halo_env = !(std::getenv("R3M_HALO") && std::getenv("R3M_HALO")[0] == '0');
+    static const int halo_bo = std::getenv("R3M_HALO_BO") ? atoi(std::getenv("R3M_HALO_BO")) : 1;
+    bool ok = halo_env && !g.tf32 && g.C == 64 && g.Cout == 64 && g.stride == 1 && g.base_h == -1 && g.base_w == -1 &&
+              g.P == g.H && g.Q == g.W && g.W % 8 == 0 && g.H % 4 == 0 && g.ntaps >= 1 && g.ntaps <= 9 &&
+              g.out_mode == 0 && g.ldo == 64 && !g.accumulate && g.ep_scale == nullptr &&
+              (g.stat_sum == nullptr || g.stat_raw) && g.bn == 0;
+    for (int t = 0; ok && t < g.ntaps; ++t) ok = g.tap_h[t] >= 0 && g.tap_h[t] <= 2 && g.tap_w[t] >= 0 && g.tap_w[t] <= 2;
+    if (ok) {
+      std::string e = encode_tiled_4d_map(&plan->tmA, g.src, 64, g.W, g.H, g.N, 64, 10, 18);
+      if (e.empty())
+        e = encode_tiled_2d_map(&plan->tmB, g.wpk, (uint64_t)g.ntaps * 64, 64, (uint64_t)g.ntaps * 64 * 2, 64, 64, 128, 2);
+      if (e.empty()) e = encode_tiled_4d_map(&plan->tmC, g.out, 64, g.W, g.H, g.N, 64, 8, 4);
+      if (!e.empty()) return e;
+      HaloKernelParams& hp = plan->hp;
+      hp.N = g.N;
+      hp.H = g.H;
+      hp.W = g.W;
+      hp.tiles_h = (g.H + 15) / 16;
+      hp.tiles_w = g.W / 8;
+      hp.num_taps = g.ntaps;
+      for (int t = 0; t < g.ntaps; ++t) {
+        hp.tap_w[t] = (uint16_t)g.tap_w[t];
+        hp.tap_h[t] = (uint16_t)g.tap_h[t];
+      }
+      hp.rev = g.rev_m;
+      hp.stat_acc = reinterpret_cast<unsigned long long*>(g.stat_sum);
+      hp.base_offset_mode = halo_bo;
+      hp.error_flag = device_error_flag();
+      if (!hp.error_flag) return "could not allocate the device error flag";
+      plan->halo = 1;
+      plan->grid = std::min(hp.N * hp.tiles_h * hp.tiles_w, device_sm_count());
+      return std::string();
+    }
+  }
   const int upper_w = (g.Q - 1) * g.stride + 1 + g.base_w - g.W;
   const int upper_h = (g.P - 1) * g.stride + 1 + g.base_h - g.H;
   std::string err = encode_im2col_map(&plan->tmA, g.src, g.C, g.W, g.H, g.N, g.base_w, g.base_h, upper_w, upper_h,
@@ -172,6 +209,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
 }
 
 cudaError_t run_conv(const ConvPlan& plan, cudaStream_t stream) {
+  if (plan.halo) return halo3x3_launch(plan.tmA, plan.tmB, plan.tmC, plan.hp, plan.grid, stream);
   return conv_igemm_launch(plan.bn, plan.tmA, plan.tmB, plan.tmC, plan.p, plan.grid, stream);
 }
 

@@ -48,6 +48,10 @@ struct ConvPlan {
   ConvKernelParams p;
   int bn = 0;
   int grid = 0;
+  // 3x3 / stride 1 / 64 -> 64 channels: the tap-reuse kernel (halo3x3.cu); tmA = rank-4 tiled halo load, tmB = filter K
+  // blocks, tmC = rank-4 tiled store
+  int halo = 0;
+  HaloKernelParams hp;
 };
 
 struct WgradDesc {

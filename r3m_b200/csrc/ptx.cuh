@@ -110,6 +110,20 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// tiled mode, rank-4 tensor (C, W, H, N): a box starting at signed coordinates (elements outside the tensor read as zero)
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+// bulk tensor store of a rank-4 box (elements outside the tensor are dropped); completes in the caller's bulk group
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c, int w, int h, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src_smem), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
 // im2col mode, rank-4 tensor (C, W, H, N): coordinates name the *base pixel* inside the bounding box,
 // (off_w, off_h) the filter-tap offset added to it.
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w,
@@ -267,6 +281,12 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_
   d |= 1ull << 46;
   d |= 2ull << 61;
   return d;
+}
+// The same with a matrix base offset (bits [49,52)): for operands that do NOT start on a 1024-byte boundary of the 128-byte
+// swizzle pattern, base_offset = (start address >> 7) & 7 (the row of the 8-row pattern the matrix starts in).
+__host__ __device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                     uint32_t sbo_bytes, uint32_t base_offset) {
+  return make_smem_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
 }
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32; a_mn / b_mn: 1 = MN-major operand, 0 = K-major.

@@ -72,6 +72,23 @@ std::string encode_im2col_map(CUtensorMap* out, const void* base, int C, int W, 
   return std::string();
 }
 
+std::string encode_tiled_4d_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int box_c, int box_w,
+                                int box_h) {
+  std::call_once(g_once, resolve);
+  if (!g_tiled) return g_resolve_error;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return "cuTensorMapEncodeTiled (rank 4) failed (CUresult " + std::to_string((int)r) + ") for C=" + std::to_string(C) +
+           " W=" + std::to_string(W) + " H=" + std::to_string(H) + " N=" + std::to_string(N);
+  return std::string();
+}
+
 std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                                 uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes,
                                 int elem_bytes) {

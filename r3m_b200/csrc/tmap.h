@@ -25,4 +25,9 @@ std::string encode_tiled_2d_map(CUtensorMap* out, const void* base, uint64_t inn
                                 uint64_t row_stride_bytes, int box_inner, int box_outer, int swizzle_bytes = 128,
                                 int elem_bytes = 2);
 
+// NHWC bf16 tensor viewed as rank-4 (C, W, H, N) for TILED loads / stores of a (box_c, box_w, box_h, 1) box, 128-byte
+// swizzle (box_c * 2 == 128); coordinates may lie outside the tensor (zero fill on load, dropped on store).
+std::string encode_tiled_4d_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int box_c, int box_w,
+                                int box_h);
+
 }  // namespace r3m

@@ -86,6 +86,34 @@ def test_conv_wgrad(lib, geom):
     assert rel(dw, ref) < 2e-5
 
 
+@pytest.mark.parametrize("N,H,W", [(3, 56, 56), (2, 8, 8), (5, 12, 16), (2, 20, 8), (4, 16, 24)])
+def test_conv3x3_tap_reuse_kernel(lib, N, H, W):
+    """halo3x3_kernel (3x3, stride 1, 64 -> 64 channels): 16 x 8 output patches, ONE tiled TMA load of the 18 x 10 halo, the
+    nine taps as shifted descriptor views of that shared memory, resident filter.  Forward (no statistics: the C-ABI
+    statistics outputs are fp32 arrays, the kernel's are the engine's raw accumulators — covered by the block / full-size
+    engine tests) and data gradient, including images whose height is not a multiple of the 16-row patch."""
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(N, 64, H, W, generator=g).cuda().bfloat16()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).cuda().bfloat16()
+    dy = torch.randn(N, 64, H, W, generator=g).cuda().bfloat16()
+    xn, wk = x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).contiguous()
+    y = torch.full((N, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    s = lib.current_stream()
+    lib.check(lib.lib.r3m_b200_conv_fwd(lib.ptr(xn), lib.ptr(wk), lib.ptr(y), N, H, W, 64, 64, 3, 3, 1, 1, None, None, s))
+    lib.check(lib.lib.r3m_b200_check_device_flag())
+    ref = F.conv2d(x.float(), w.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel(y.float(), ref) < 2.5e-3, rel(y.float(), ref)
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    wm = w.float().permute(0, 2, 3, 1).contiguous()
+    wd = torch.empty(64 * 9 * 64, device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.lib.r3m_b200_pack_dgrad_filter(lib.ptr(wm), lib.ptr(wd), 64, 3, 3, 64, 1, 1, s))
+    dx = torch.full((N, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.lib.r3m_b200_conv_dgrad(lib.ptr(dyn), lib.ptr(wd), lib.ptr(dx), N, H, W, 64, 64, 3, 3, 1, 1, 0, s))
+    lib.check(lib.lib.r3m_b200_check_device_flag())
+    refd = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel(dx.float(), refd) < 2.5e-3, rel(dx.float(), refd)
+
+
 PAIR_GEOMS = [  # filter gradients that run on CTA pairs (cta_group::2): Cout % 256 == 0, an even number of (tap, 64-ch) items
     (20, 14, 256, 256, 3, 1, 1),   # 36 items -> groups of 8 (last one 4), 31 pixel blocks: several pipeline rounds
     (16, 28, 128, 512, 1, 1, 0),   # 2 items: one per CTA, N = 128 instructions
