@@ -77,7 +77,9 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
     // Tap reuse (halo3x3.cu): 3x3-footprint, stride-1, pad-1 gather convs of 64 -> 64 channels with a dense bf16 output,
     // no accumulation / affine epilogue, statistics (if any) straight into raw accumulators.  R3M_HALO=0 disables.
     static const bool halo_env = !(std::getenv("R3M_HALO") && std::getenv("R3M_HALO")[0] == '0');
-    static const int halo_bo = std::getenv("R3M_HALO_BO") ? atoi(std::getenv("R3M_HALO_BO")) : 1;
+    // measured on B200: the shifted views are correct with base offset 0 (TMA and UMMA both derive the swizzle phase from
+    // the absolute shared-memory address); setting the descriptor's base-offset field to the start row's phase is WRONG
+    static const int halo_bo = std::getenv("R3M_HALO_BO") ? atoi(std::getenv("R3M_HALO_BO")) : 0;
     bool ok = halo_env && !g.tf32 && g.C == 64 && g.Cout == 64 && g.stride == 1 && g.base_h == -1 && g.base_w == -1 &&
               g.P == g.H && g.Q == g.W && g.W % 8 == 0 && g.H % 4 == 0 && g.ntaps >= 1 && g.ntaps <= 9 &&
               g.out_mode == 0 && g.ldo == 64 && !g.accumulate && g.ep_scale == nullptr &&
