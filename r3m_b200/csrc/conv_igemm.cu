@@ -58,7 +58,6 @@ struct Cfg {
   static constexpr int kStages = STAGES;
   static constexpr int kStagingBytes = EPI * BUFS * kUnitBytes;
   static constexpr int kThreads = 128 + EPI * 32;
-  static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStagingBytes + 2 * StatC<BN>::value * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -105,6 +104,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool do_stats = STATS;
   static_assert(PREC == 0 || MODE == kModeDense, "the tf32 tier serves dense (inference) outputs only");
   constexpr int kElemsK = PREC ? 32 : 64;  // operand elements per 128-byte K block
+  // Chunked accumulation (tf32 tier, 64-wide tiles: the split-tf32 GEMMs of the sentence encoder and the language head,
+  // which must stay in the fp32 parity band): the tensor core adds each MMA's partial sum into the fp32 accumulator with
+  // truncation, a bias that grows with the number of MMAs of a reduction (2e-5 relative after 384 of them: ten times the
+  // round-off of an fp32 FMA chain, i.e. ten times as many ReLU pre-activations on the wrong side of zero).  So a
+  // reduction is cut into CH chunks that accumulate from zero in separate TMEM column blocks and are added in the
+  // epilogue with rounded fp32 adds.
+  constexpr int CH = (PREC == 1 && BN == 64) ? 4 : 1;
+  constexpr int kTmemCols = 2 * BN * CH;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -124,9 +131,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 2) {
     if constexpr (PAIR)
-      tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+      tmem_alloc_pair<kTmemCols>(tmem_slot);
     else
-      tmem_alloc<C::kTmemCols>(tmem_slot);
+      tmem_alloc<kTmemCols>(tmem_slot);
   }
   pdl_sync();  // everything above is CTA-local; global memory is first touched below
   const bool do_affine = !STATS && (p.ep_scale != nullptr);
@@ -148,6 +155,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = p.num_taps * p.cblocks;
+  const int num_steps = (num_kb + KPS - 1) / KPS;       // pipeline stages per tile
+  const int nch = CH < num_steps ? CH : num_steps;      // accumulation chunks per tile (every chunk gets >= 1 stage)
   // M tile of this CTA inside tile `t` (+ whether it is the discarded duplicate that completes an odd last pair)
   auto m_tile_of = [&](int t_m_idx, bool* dup) {
     int m_idx = t_m_idx;
@@ -236,8 +245,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           break;
         }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tile = tmem_base + static_cast<uint32_t>(acc * BN * CH);
+        int cur_chunk = -1;
         for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
+          const int chunk = CH > 1 ? ((kb0 / KPS) * nch) / num_steps : 0;
+          const bool fresh = chunk != cur_chunk;  // first stage of an accumulation chunk: its first MMA overwrites
+          cur_chunk = chunk;
+          const uint32_t d_tmem = d_tile + static_cast<uint32_t>(chunk * BN);
           if (!mbar_wait(&full_bar[stage], phase)) {
             atomicExch(p.error_flag, 3);
             ok = false;
@@ -257,13 +271,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // +32 bytes per MMA (K = 16 bf16 or 8 tf32) inside the 128-byte swizzle row (start-address field is >>4)
                 if constexpr (PAIR)
                   umma_bf16_pair(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                                 (kb0 | j | k) != 0 ? 1u : 0u);
+                                 (!fresh || (j | k) != 0) ? 1u : 0u);
                 else if constexpr (PREC == 0)
                   umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                            (kb0 | j | k) != 0 ? 1u : 0u);
+                            (!fresh || (j | k) != 0) ? 1u : 0u);
                 else
                   umma_tf32(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                            (kb0 | j | k) != 0 ? 1u : 0u);
+                            (!fresh || (j | k) != 0) ? 1u : 0u);
               }
             }
           }
@@ -349,7 +363,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         break;
       }
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN * CH);
       if constexpr (PREC == 1) {
         // fp32 output: units of 32 rows x 32 columns (128-byte rows); folded BatchNorm (+ fp32 residual) (+ ReLU) on the
         // accumulators, results rounded to tf32 (round-to-nearest: the next conv's tensor cores would truncate)
@@ -363,6 +377,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if constexpr (CH > 1) {
+#pragma unroll 1
+            for (int c = 1; c < nch; ++c) {  // the other accumulation chunks: rounded fp32 adds
+              tmem_ld_32x32(t_row + c * BN + u * 32, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+            }
+          }
           if (u + EPI / 4 < kUnits32) {
             tmem_ld_32x32(t_row + (u + EPI / 4) * 32, v);
           } else {
@@ -656,9 +679,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     if constexpr (PAIR)
-      tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+      tmem_dealloc_pair<kTmemCols>(tmem_base);
     else
-      tmem_dealloc<C::kTmemCols>(tmem_base);
+      tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

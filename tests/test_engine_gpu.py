@@ -20,6 +20,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+LARGE_BATCH_GRAD_TOL = 1e-2
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 HYPER = dict(l2weight=1e-5, l1weight=1e-5, tcnweight=1.0, lr=1e-4)
 
@@ -105,11 +107,15 @@ def _check_loss_heads(eng, named, params, emb, perms, hyper, lang_emb, mask, met
             if not (k.startswith("rewacc") or k == "aligned"):
                 assert abs(metrics[k] - v) <= 1e-4 * max(abs(v), 1e-6), (k, metrics[k], v)
         bad, err = mostly_close(eng.embedding_grads(), e_grad, rtol=2e-2)
-        assert bad <= 0.02 and err < 1e-2, ("dE", bad, err)
+        worst = [("dE", bad, err)]
         for k, g in grads.items():
             if not k.endswith("pred.8.bias"):
-                bad, err = mostly_close(named[k].grad, g, rtol=2e-2)
-                assert bad <= 0.02 and err < 1e-2, (k, bad, err)
+                bad_k, err_k = mostly_close(named[k].grad, g, rtol=2e-2)
+                worst.append((k, bad_k, err_k))
+        if os.environ.get("R3M_TEST_REPORT"):
+            print("LOSS_HEAD_LARGE_BATCH", max(worst, key=lambda t: t[2]), flush=True)
+        for k, bad_k, err_k in worst:
+            assert bad_k <= 0.02 and err_k < LARGE_BATCH_GRAD_TOL, (k, bad_k, err_k)
         return
     # pre-activations inside the round-off band (identical (e0, e_t) rows occur in several evaluations: dedupe)
     band = 4e-6
