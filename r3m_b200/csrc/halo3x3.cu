@@ -12,7 +12,7 @@
 // L2 -> shared-memory traffic per tile: 23 KB instead of 9 x 16 + 72 KB.  16 x 8 tiles: W must be a multiple of 8 and
 // H of 4 (rows past the image are computed and dropped: 56 = 3.5 x 16 wastes 12.5 % of the MMA rows).
 // Epilogue as in conv_igemm: TMEM -> bf16 -> swizzled staging -> BatchNorm statistics (registers) + one rank-4 bulk
-// tensor store of 4 rows x 8 columns x 64 channels per warp and tile.
+// tensor store of 4 rows x 8 columns x 64 channels per warp and tile; two warp sets drain alternate tiles.
 #include "conv_igemm.cuh"
 #include "launch.h"
 #include "ptx.cuh"
@@ -25,12 +25,16 @@ constexpr int kTileRows = 16, kTileCols = 8;          // output pixels of an M t
 constexpr int kHaloRows = 18, kHaloCols = 10;
 constexpr int kPatchBytes = kHaloRows * kHaloCols * 128;   // 23040
 constexpr int kPatchStride = 24 * 1024;                    // 1024-byte aligned slot
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kFilterBytes = 9 * 64 * 128;                 // nine K blocks of 64 filters x 64 channels
 constexpr int kBufs = 2;                                   // staging units per epilogue warp
 constexpr int kUnit = 32 * 128;                            // 32 rows x 64 channels bf16
-constexpr int kThreads = 256;
-constexpr int kSmem = kFilterBytes + kStages * kPatchStride + 4 * kBufs * kUnit + 4 * 64 * 2 * 4 + 256 + 1024;
+// Two epilogue warp sets (4 warps each, one per TMEM lane quadrant): set e drains the tiles whose accumulator lives in
+// TMEM stage e, i.e. every other tile of the CTA.  With one set the kernel was bound by the epilogue's latency chain
+// (TMEM load -> pack -> staging -> store -> statistics, ~2 us per tile against 0.6 us of MMAs).
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kSmem = kFilterBytes + kStages * kPatchStride + kEpiWarps * kBufs * kUnit + kEpiWarps * 64 * 2 * 4 + 256 + 1024;
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -41,8 +45,8 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint8_t* s_filter = smem;
   uint8_t* s_patch = s_filter + kFilterBytes;
   uint8_t* staging = s_patch + kStages * kPatchStride;
-  float* s_part = reinterpret_cast<float*>(staging + 4 * kBufs * kUnit);  // [4 quadrants][64 channels][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + 4 * 64 * 2);
+  float* s_part = reinterpret_cast<float*>(staging + kEpiWarps * kBufs * kUnit);  // [8 warps][64 channels][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + kEpiWarps * 64 * 2);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -151,15 +155,19 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: warp q owns output rows 4q .. 4q+3 of the tile
-    const int q = warp - 4;
-    const uint32_t stg_base = smem_u32(staging + q * (kBufs * kUnit));
+    // ------------------------------------------------------------------ epilogue: warp (set e, quadrant q) owns output rows
+    // 4q .. 4q+3 of every tile whose accumulator is TMEM stage e (the CTA's tiles alternate between the two stages)
+    const int q = warp & 3;
+    const int e = (warp - 4) >> 2;
+    const uint32_t stg_base = smem_u32(staging + (warp - 4) * (kBufs * kUnit));
     int buf = 0;
-    int acc = 0;
+    const int acc = e;
     uint32_t acc_phase = 0;
+    int local = 0;  // index of the tile among this CTA's tiles
     float r_s0 = 0.f, r_s1 = 0.f, r_q0 = 0.f, r_q1 = 0.f;  // BatchNorm statistics of columns (2 lane, 2 lane + 1)
     const bool do_stats = p.stat_acc != nullptr;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      if ((local & 1) != e) continue;
       int n, p0, q0;
       tile_coords(tile, &n, &p0, &q0);
       if (!mbar_wait(&tfull_bar[acc], acc_phase)) {
@@ -215,22 +223,21 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      acc_phase ^= 1u;  // this set's stage is used once per two tiles
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
-      float* dst = s_part + (q * 64 + 2 * lane) * 2;
+      float* dst = s_part + ((warp - 4) * 64 + 2 * lane) * 2;
       dst[0] = r_s0;
       dst[1] = r_q0;
       dst[2] = r_s1;
       dst[3] = r_q1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       const int et = threadIdx.x - 128;
       if (et < 64) {
         float sm = 0.f, sq = 0.f;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < kEpiWarps; ++qq) {
           sm += s_part[(qq * 64 + et) * 2];
           sq += s_part[(qq * 64 + et) * 2 + 1];
         }
