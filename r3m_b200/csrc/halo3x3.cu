@@ -32,6 +32,11 @@ constexpr int kUnit = 32 * 128;                            // 32 rows x 64 chann
 // Two epilogue warp sets (4 warps each, one per TMEM lane quadrant): set e drains the tiles whose accumulator lives in
 // TMEM stage e, i.e. every other tile of the CTA.  With one set the kernel was bound by the epilogue's latency chain
 // (TMEM load -> pack -> staging -> store -> statistics, ~2 us per tile against 0.6 us of MMAs).
+// MMAs that accumulate into the SAME tensor-memory accumulator are a dependent chain, and at N = 64 an instruction is 32
+// cycles of tensor work behind ~90 cycles of accumulate latency: one chain of 36 MMAs per tile kept the tensor pipe 34 %
+// busy (ncu).  So a tile's taps are dealt to kChains independent accumulators, issued round-robin, and added in the
+// epilogue (fp32).
+constexpr int kChains = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kSmem = kFilterBytes + kStages * kPatchStride + kEpiWarps * kBufs * kUnit + kEpiWarps * 64 * 2 * 4 + 256 + 1024;
@@ -73,7 +78,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     mbar_init(filter_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<128>(tmem_slot);  // two 64-column accumulators
+  if (warp == 2) tmem_alloc<512>(tmem_slot);  // 2 stages x kChains accumulators of 64 columns (384 used)
   pdl_sync();
   tc_fence_before();
   __syncthreads();
@@ -131,18 +136,27 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           break;
         }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 64);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kChains * 64);
         const uint32_t patch_addr = smem_u32(s_patch + stage * kPatchStride);
-        for (int t = 0; t < p.num_taps; ++t) {
-          // tap (r, s): rows 10 r + s ... of the halo; output row g of the tile = core group g, 10 halo rows further on
-          const uint32_t row0 = static_cast<uint32_t>(p.tap_h[t]) * kHaloCols + p.tap_w[t];
-          const uint32_t a_addr = patch_addr + row0 * 128;
-          const uint64_t da = make_smem_desc_sw128_bo(a_addr, 16, kHaloCols * 128, p.base_offset_mode ? (row0 & 7u) : 0u);
-          const uint64_t db = make_smem_desc_sw128(filter_addr + t * 8192, 16, 1024);
+        // chain c accumulates taps c, c + kChains, ...; consecutive instructions belong to different chains
+        for (int t0 = 0; t0 < p.num_taps; t0 += kChains) {
+          uint64_t da[kChains], db[kChains];
+#pragma unroll
+          for (int c = 0; c < kChains; ++c) {
+            const int t = min(t0 + c, p.num_taps - 1);
+            // tap (r, s): rows 10 r + s ... of the halo; output row g of the tile = core group g, 10 halo rows further on
+            const uint32_t row0 = static_cast<uint32_t>(p.tap_h[t]) * kHaloCols + p.tap_w[t];
+            da[c] = make_smem_desc_sw128_bo(patch_addr + row0 * 128, 16, kHaloCols * 128,
+                                            p.base_offset_mode ? (row0 & 7u) : 0u);
+            db[c] = make_smem_desc_sw128(filter_addr + t * 8192, 16, 1024);
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                      (t | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int c = 0; c < kChains; ++c)
+              if (t0 + c < p.num_taps)
+                umma_bf16(d_tmem + c * 64, da[c] + static_cast<uint64_t>(k * 2), db[c] + static_cast<uint64_t>(k * 2), idesc,
+                          (t0 | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
         umma_commit(&tfull_bar[acc]);
@@ -175,11 +189,24 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         break;
       }
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 64);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kChains * 64);
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(t_row, v0);
       tmem_ld_32x32(t_row + 32, v1);
       tc_wait_ld();
+      const int used_chains = p.num_taps < kChains ? p.num_taps : kChains;
+#pragma unroll 1
+      for (int c = 1; c < used_chains; ++c) {  // the other chains' partial sums
+        uint32_t u0[32], u1[32];
+        tmem_ld_32x32(t_row + c * 64, u0);
+        tmem_ld_32x32(t_row + c * 64 + 32, u1);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __uint_as_float(u0[j]));
+          v1[j] = __float_as_uint(__uint_as_float(v1[j]) + __uint_as_float(u1[j]));
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // the accumulator is in registers: hand the stage back
@@ -251,7 +278,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
