@@ -36,7 +36,11 @@ constexpr int kUnit = 32 * 128;                            // 32 rows x 64 chann
 // cycles of tensor work behind ~90 cycles of accumulate latency: one chain of 36 MMAs per tile kept the tensor pipe 34 %
 // busy (ncu).  So a tile's taps are dealt to kChains independent accumulators, issued round-robin, and added in the
 // epilogue (fp32).
-constexpr int kChains = 3;
+constexpr int kChains = 1;
+// Accumulator stages in tensor memory (64 columns x kChains each): tile l of a CTA uses stage l % kAccStages.  The round
+// trip MMA -> commit -> epilogue wake-up -> TMEM read -> release takes several microseconds whatever the tile does, so the
+// number of tiles in flight, not any unit's throughput, bounded the kernel with two stages.
+constexpr int kAccStages = 8;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kSmem = kFilterBytes + kStages * kPatchStride + kEpiWarps * kBufs * kUnit + kEpiWarps * 64 * 2 * 4 + 256 + 1024;
@@ -54,8 +58,8 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + kEpiWarps * 64 * 2);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* filter_bar = tempty_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + kAccStages;
+  uint64_t* filter_bar = tempty_bar + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(filter_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -71,7 +75,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
@@ -110,8 +114,12 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         int n, p0, q0;
         tile_coords(tile, &n, &p0, &q0);
-        mbar_expect_tx(&full_bar[stage], kPatchBytes);
-        tma_load_4d(&tmX, &full_bar[stage], s_patch + stage * kPatchStride, 0, q0 - 1, p0 - 1, n);
+        if (p.debug & 4) {
+          mbar_arrive(&full_bar[stage]);
+        } else {
+          mbar_expect_tx(&full_bar[stage], kPatchBytes);
+          tma_load_4d(&tmX, &full_bar[stage], s_patch + stage * kPatchStride, 0, q0 - 1, p0 - 1, n);
+        }
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
@@ -125,12 +133,13 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 128, 64, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int local = 0;
       bool ok = mbar_wait(filter_bar, 0);
       if (!ok) atomicExch(p.error_flag, 42);
       const uint32_t filter_addr = smem_u32(s_filter);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++local) {
+        const int acc = local % kAccStages;
+        const uint32_t acc_phase = static_cast<uint32_t>(local / kAccStages) & 1u;
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u) || !mbar_wait(&full_bar[stage], phase)) {
           atomicExch(p.error_flag, 43);
           break;
@@ -154,7 +163,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int c = 0; c < kChains; ++c)
-              if (t0 + c < p.num_taps)
+              if (t0 + c < p.num_taps && (!(p.debug & 2) || (t0 | k | c) == 0))
                 umma_bf16(d_tmem + c * 64, da[c] + static_cast<uint64_t>(k * 2), db[c] + static_cast<uint64_t>(k * 2), idesc,
                           (t0 | k) != 0 ? 1u : 0u);
         }
@@ -164,24 +173,22 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           stage = 0;
           phase ^= 1u;
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: warp (set e, quadrant q) owns output rows
-    // 4q .. 4q+3 of every tile whose accumulator is TMEM stage e (the CTA's tiles alternate between the two stages)
+    // 4q .. 4q+3 of every other tile of the CTA
     const int q = warp & 3;
     const int e = (warp - 4) >> 2;
     const uint32_t stg_base = smem_u32(staging + (warp - 4) * (kBufs * kUnit));
     int buf = 0;
-    const int acc = e;
-    uint32_t acc_phase = 0;
     int local = 0;  // index of the tile among this CTA's tiles
     float r_s0 = 0.f, r_s1 = 0.f, r_q0 = 0.f, r_q1 = 0.f;  // BatchNorm statistics of columns (2 lane, 2 lane + 1)
     const bool do_stats = p.stat_acc != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       if ((local & 1) != e) continue;
+      const int acc = local % kAccStages;
+      const uint32_t acc_phase = static_cast<uint32_t>(local / kAccStages) & 1u;
       int n, p0, q0;
       tile_coords(tile, &n, &p0, &q0);
       if (!mbar_wait(&tfull_bar[acc], acc_phase)) {
@@ -210,7 +217,7 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // the accumulator is in registers: hand the stage back
-      const bool valid = p0 + 4 * q < p.H;            // rows past the image (H % 4 == 0: the same for the whole warp)
+      const bool valid = p0 + 4 * q < p.H && !(p.debug & 1);  // rows past the image (H % 4 == 0: the same for the whole warp)
       if (valid) {
         uint32_t pk[32];
 #pragma unroll
@@ -250,7 +257,6 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
       }
-      acc_phase ^= 1u;  // this set's stage is used once per two tiles
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (do_stats) {
