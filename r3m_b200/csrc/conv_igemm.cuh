@@ -63,6 +63,7 @@ struct HaloKernelParams {
   uint16_t tap_w[9], tap_h[9];  // tap t reads input pixel (p - 1 + tap_h[t], q - 1 + tap_w[t]) with filter K block t
   int rev;                // walk the tiles last-to-first
   unsigned long long* stat_acc;  // optional raw fixed-point accumulators (64 channels x {sum, sum of squares}), added into
+  int acc_stages;         // accumulator stages in tensor memory (tiles in flight between the MMA issuer and the epilogue)
   int debug;              // experiment switches (R3M_HALO_DEBUG): 1 no epilogue work, 2 one MMA per tile, 4 no patch loads
   int base_offset_mode;   // experiment switch: 1 = descriptors carry the swizzle base offset of their start row
   int* error_flag;

@@ -105,6 +105,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
       hp.rev = g.rev_m;
       hp.stat_acc = reinterpret_cast<unsigned long long*>(g.stat_sum);
       hp.base_offset_mode = halo_bo;
+      hp.acc_stages = std::getenv("R3M_HALO_ACC") ? std::max(2, std::min(8, atoi(std::getenv("R3M_HALO_ACC")))) : 8;
       hp.debug = std::getenv("R3M_HALO_DEBUG") ? atoi(std::getenv("R3M_HALO_DEBUG")) : 0;
       hp.error_flag = device_error_flag();
       if (!hp.error_flag) return "could not allocate the device error flag";

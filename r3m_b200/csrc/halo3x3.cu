@@ -40,7 +40,7 @@ constexpr int kChains = 1;
 // Accumulator stages in tensor memory (64 columns x kChains each): tile l of a CTA uses stage l % kAccStages.  The round
 // trip MMA -> commit -> epilogue wake-up -> TMEM read -> release takes several microseconds whatever the tile does, so the
 // number of tiles in flight, not any unit's throughput, bounded the kernel with two stages.
-constexpr int kAccStages = 8;
+constexpr int kAccStages = 8;  // upper bound (512 TMEM columns / (64 kChains)); the launch uses acc_stages of them
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kSmem = kFilterBytes + kStages * kPatchStride + kEpiWarps * kBufs * kUnit + kEpiWarps * 64 * 2 * 4 + 256 + 1024;
@@ -138,8 +138,8 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (!ok) atomicExch(p.error_flag, 42);
       const uint32_t filter_addr = smem_u32(s_filter);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++local) {
-        const int acc = local % kAccStages;
-        const uint32_t acc_phase = static_cast<uint32_t>(local / kAccStages) & 1u;
+        const int acc = local % p.acc_stages;
+        const uint32_t acc_phase = static_cast<uint32_t>(local / p.acc_stages) & 1u;
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u) || !mbar_wait(&full_bar[stage], phase)) {
           atomicExch(p.error_flag, 43);
           break;
@@ -187,8 +187,8 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const bool do_stats = p.stat_acc != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       if ((local & 1) != e) continue;
-      const int acc = local % kAccStages;
-      const uint32_t acc_phase = static_cast<uint32_t>(local / kAccStages) & 1u;
+      const int acc = local % p.acc_stages;
+      const uint32_t acc_phase = static_cast<uint32_t>(local / p.acc_stages) & 1u;
       int n, p0, q0;
       tile_coords(tile, &n, &p0, &q0);
       if (!mbar_wait(&tfull_bar[acc], acc_phase)) {
