@@ -1124,10 +1124,19 @@ std::string Engine::run_cached(const std::vector<uint64_t>& key, cudaStream_t st
   if (!use_graph_ || profiling_ || capturing_) return body(stream);
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
-    if (graphs_.size() >= kMaxGraphs) return body(stream);
+    if (graphs_.size() >= kMaxGraphs) {
+      // evict the least recently used entry (input buffers that went away); a key is only captured on its second
+      // sighting, so a stream of never-repeating pointers costs map entries, not captures
+      auto victim = graphs_.begin();
+      for (auto jt = graphs_.begin(); jt != graphs_.end(); ++jt)
+        if (jt->second.last_use < victim->second.last_use) victim = jt;
+      if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+      graphs_.erase(victim);
+    }
     it = graphs_.emplace(key, GraphEntry()).first;
   }
   GraphEntry& ge = it->second;
+  ge.last_use = ++graph_clock_;
   if (ge.exec == nullptr && !ge.failed && ge.seen >= 1) {
     // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured)
     if (!cap_ && cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking) != cudaSuccess) cap_ = nullptr;

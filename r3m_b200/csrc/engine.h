@@ -170,7 +170,9 @@ class Engine {
     int seen = 0;
     int launches = 0;
     bool failed = false;
+    uint64_t last_use = 0;
   };
+  uint64_t graph_clock_ = 0;
   std::string run_cached(const std::vector<uint64_t>& key, cudaStream_t stream,
                          const std::function<std::string(cudaStream_t)>& body, bool* graphed);
   std::map<std::vector<uint64_t>, GraphEntry> graphs_;

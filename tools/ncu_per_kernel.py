@@ -58,20 +58,23 @@ def main(src, md, js):
                     f"{a['tensor_t'] / a['us']:.1f} | {a['lts'] / a['us'] / 1e3:.0f} | {int(a['regs'])} |\n")
     # DRAM traffic per kernel family, in the shape bench.py's roofline.traffic reads (per engine op: a wgrad op is the
     # tcgen05 kernel plus its split-K reduce)
-    fam_of = [("conv_igemm_kernel", "conv_igemm"), ("wgrad_kernel", "wgrad"), ("wgrad_reduce_kernel", "wgrad"),
+    fam_of = [("conv_igemm_kernel", "conv_igemm"), ("halo3x3_kernel", "conv_igemm"), ("wgrad_kernel", "wgrad"),
+              ("wgrad_pair_kernel", "wgrad"), ("wgrad_reduce_kernel", "wgrad"),
               ("bn_", "norm"), ("stem_bwd", "norm"), ("preprocess_stem", "norm"), ("stem_pool", "pool"),
               ("avgpool", "pool"), ("adam", "optim"), ("pack_dgrad", "optim"), ("stem_pack", "optim"),
               ("stem_unpack", "optim"), ("cast_bf16", "optim"), ("sgemm", "lang"), ("lang_", "lang"),
               ("splitk_reduce", "lang"), ("col_sum", "lang"), ("vec_sum", "lang"), ("loss_", "loss"),
               ("lp_finalize", "loss"), ("tcn_finalize", "loss"), ("publish_flag", "loss")]
-    ops_kernel = {"wgrad": "wgrad_kernel"}  # families whose op count is the count of ONE of their kernels
+    ops_kernel = {"wgrad": ("wgrad_kernel", "wgrad_pair_kernel")}  # families whose ops are counted on their main kernels
     fams = collections.OrderedDict()
     for k, a in agg.items():
         fam = next((f for pre, f in fam_of if k.startswith(pre)), "other")
+        if k.startswith("conv_igemm_kernel") and re.search(r", 1, [01]>$", k):
+            fam = "lang"  # the tf32 tier inside a training step: the language head's split-tf32 GEMMs
         r = fams.setdefault(fam, {"launches": 0, "ops": 0, "dram_bytes_per_step": 0.0, "l2_bytes_per_step": 0.0,
                                   "us_under_ncu": 0.0})
         r["launches"] += int(a["n"])
-        if fam not in ops_kernel or k.startswith(ops_kernel[fam]):
+        if fam not in ops_kernel or k.split("<")[0] in ops_kernel[fam]:
             r["ops"] += int(a["n"])
         r["dram_bytes_per_step"] += a["rd"] + a["wr"]
         r["l2_bytes_per_step"] += a["lts"]
