@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128 + EPI * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using C = Cfg<BN, STAGES, BUFS, EPI, KPS, PAIR>;
-  static_assert(!PAIR || (PREC == 0 && MODE != kModeScatter && BN >= 128), "pairs: bf16, dense outputs, 128/256-wide tiles");
+  static_assert(!PAIR || (PREC == 0 && MODE != kModeScatter), "pairs: bf16, dense outputs");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -780,6 +780,10 @@ cudaError_t conv_igemm_launch(int bn, const CUtensorMap& tmA, const CUtensorMap&
   switch (bn) {
     case 64:  // one unit per quadrant
       if (p.Cout > StatC<64>::value) return cudaErrorInvalidValue;
+      if (p.pair) {  // experiment (R3M_CONV_PAIR64=1): does an M = 256 instruction cost what an M = 128 one does at N = 64?
+        if (num_kb >= 9) return launch_pair<64, 4, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);
+        return launch_pair<64, 6, 4, 4, 1>(tmA, tmB, tmC, p, grid, stream);
+      }
       if (num_kb >= 9) return launch_bn<64, 4, 1, 4, 2>(tmA, tmB, tmC, p, grid, stream);  // 3x3: two K blocks per stage
       return launch_bn<64, 6, 4, 4, 1>(tmA, tmB, tmC, p, grid, stream);
     case 128:

@@ -137,9 +137,10 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   static const int pair_min_kb = std::getenv("R3M_CONV_PAIR_MIN_KB") ? atoi(std::getenv("R3M_CONV_PAIR_MIN_KB")) : 8;
   // 128-wide tiles (the 128-channel layers): only the 3x3 configuration (>= 18 K blocks) has a pair variant
   static const bool pair128 = !(std::getenv("R3M_CONV_PAIR128") && std::getenv("R3M_CONV_PAIR128")[0] == '0');
+  static const bool pair64 = std::getenv("R3M_CONV_PAIR64") && std::getenv("R3M_CONV_PAIR64")[0] == '1';  // experiment
   const int nkb = g.ntaps * (g.C / kelems);
   p.pair = (pair_env && !g.tf32 && g.out_mode == 0 && p.M_total > 128 &&
-            ((bn == 256 && nkb >= pair_min_kb) || (bn == 128 && pair128 && nkb >= 18))) ? 1 : 0;
+            ((bn == 256 && nkb >= pair_min_kb) || (bn == 128 && pair128 && nkb >= 18) || (bn == 64 && pair64))) ? 1 : 0;
   err = encode_tiled_2d_map(&plan->tmB, g.wpk, kdim, (uint64_t)g.Cout, kdim * eb, kelems, p.pair ? bn / 2 : bn, 128, eb);
   if (!err.empty()) return err;
   if (g.out_mode == 0) {
