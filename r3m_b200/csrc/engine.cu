@@ -345,7 +345,9 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.save_rstd = saved + c.save_off + c.Cout;
   if (train && relu) a.mask_out = c.mask;
   // the conv that has just written y walked the rows first-to-last, and the conv that reads `dst` next does too
-  a.reverse = (train && l2_order_) ? 1 : 0;
+  // (R3M_L2_ORDER_MIN_MB restricts it to tensors above a size; the per-launch profile suggests the small wide layers lose,
+  // the step says otherwise: with every tensor reversed it is 0.1-0.3 ms shorter than with 96 / 200 / 400 MB thresholds)
+  a.reverse = (train && l2_order_ && (double)a.M * a.C * 2 >= l2_order_min_bytes_) ? 1 : 0;
   if (second) {
     // downsample branch folded in: a = relu(bn(y) + bn_ds(y_ds)), bn_ds(y_ds) is never materialised
     const Conv& d = *second;
@@ -369,6 +371,8 @@ std::string Engine::plan_all() {
   {
     const char* env = std::getenv("R3M_L2_ORDER");
     l2_order_ = !(env && env[0] == '0');
+    env = std::getenv("R3M_L2_ORDER_MIN_MB");
+    l2_order_min_bytes_ = (env ? atof(env) : 0.0) * 1e6;  // measured: 0 (every tensor) is best; 96 / 200 / 400 MB cost 0.1-0.3 ms
     // off by default: measured +0.1 ms per ResNet-50 step on B200 (the isolated kernels gain 0.2 ms, but the cooperative
     // launch cannot overlap its neighbours' prologues and the filter gradients lose their slot between the two passes)
     env = std::getenv("R3M_LANG_TC");
@@ -747,9 +751,12 @@ std::string Engine::plan_all() {
   auto push_bn_bwd = [&](const Conv& c, const bf16* dA, const uint8_t* mask, bf16* dy, bf16* dz_out,
                          const Conv* second, bf16* dy2) {
     BnBwdArgs a;
-    if (l2_order_) {
+    const bool big = (double)N * c.P * c.Q * c.Cout * 2 >= l2_order_min_bytes_;
+    if (l2_order_ && big) {
       a.rev_reduce = !cur;
       a.rev_apply = cur;  // writes dy in direction `cur`
+    } else {
+      cur = 0;  // both passes first-to-last: dy is written first-to-last
     }
     a.dA = dA;
     a.mask = mask;
@@ -837,7 +844,8 @@ std::string Engine::plan_all() {
   };
   auto push_dgrad = [&](const Conv& c, const bf16* dy, bf16* dx, int accumulate) {
     // reads dy (written in direction `cur` by the apply pass) the other way round and leaves dx in that direction
-    const int dgrad_rev = l2_order_ ? !cur : 0;
+    const bool big_dy = (double)N * c.P * c.Q * c.Cout * 2 >= l2_order_min_bytes_;
+    const int dgrad_rev = (l2_order_ && big_dy) ? !cur : 0;
     cur = dgrad_rev;
     std::vector<DgradClass> cls = dgrad_classes(c.H, c.W, c.R, c.R, c.stride, c.pad);
     size_t off = 0;

@@ -215,6 +215,7 @@ class Engine {
   std::vector<cudaEvent_t> evs_;
   bool use_side_ = true;
   bool fuse_bn_bwd_ = false;  // small layers: BatchNorm backward as one launch with a grid barrier (R3M_FUSE_BN_BWD=1)
+  double l2_order_min_bytes_ = 0.0;  // tensors below this size keep the first-to-last walk (R3M_L2_ORDER_MIN_MB; default: none)
   bool l2_order_ = true;  // alternate the traversal direction of consecutive passes over a tensor (R3M_L2_ORDER=0: off)
 };
 
