@@ -470,10 +470,17 @@ std::string DistilBert::forward(const int* ids, const float* mask, int B, int T,
                                      (uint64_t)B, (uint64_t)T};
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
-    if (graphs_.size() >= 8) return enqueue(ids, mask, B, T, out, hidden, stream);
+    if (graphs_.size() >= 8) {  // evict the least recently used entry (buffers that went away)
+      auto victim = graphs_.begin();
+      for (auto jt = graphs_.begin(); jt != graphs_.end(); ++jt)
+        if (jt->second.last_use < victim->second.last_use) victim = jt;
+      if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+      graphs_.erase(victim);
+    }
     it = graphs_.emplace(key, Graph()).first;
   }
   Graph& g = it->second;
+  g.last_use = ++graph_clock_;
   if (g.exec == nullptr && !g.failed && g.seen >= 1) {
     if (!cap_ && cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking) != cudaSuccess) cap_ = nullptr;
     cudaGraph_t graph = nullptr;

@@ -56,7 +56,9 @@ class DistilBert {
     cudaGraphExec_t exec = nullptr;
     int seen = 0, launches = 0;
     bool failed = false;
+    uint64_t last_use = 0;
   };
+  uint64_t graph_clock_ = 0;
   std::map<std::vector<uint64_t>, Graph> graphs_;  // (buffers, shape) -> captured forward
   cudaStream_t cap_ = nullptr;
 
