@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--lang", type=int, default=1, help="language head on (c3) / off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the side measurements of BASELINE configs 0/1/3")
     ap.add_argument("--e2e-debug", default="", help="diagnostic: 'nocopy' skips the H2D copy in the e2e loop")
     return ap.parse_args()
 
@@ -257,6 +258,58 @@ def gpu_reference(args, clips, lang, dev):
     return out
 
 
+def other_configs(dev):
+    """The other BASELINE.json configs, measured in the same run at N = 1 (device-timed, inputs resident; parity at these
+    sizes is tests/test_fullsize_gpu.py's job): configs[0] ResNet-18 forward batch 4 (the load_r3m / example.py path, on
+    the GPU), configs[1] ResNet-50 forward batch 256 (eval: BatchNorm folded; train: batch statistics), configs[3]
+    ResNet-34 update() with 128 clips."""
+    import torch
+    import r3m_b200
+    from r3m_b200 import R3M, Trainer
+
+    def timed(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    try:
+        for key, size, batch in (("c1_resnet18_forward_b4", 18, 4), ("c2_resnet50_forward_b256", 50, 256)):
+            m = R3M("cuda", HYPER["lr"], HYPER["hidden_dim"], size=size, langweight=0.0).to(dev)
+            x = torch.randint(0, 255, (batch, 3, 224, 224), device=dev).float()
+            rec = {}
+            with torch.no_grad():
+                for mode in ("eval", "train"):
+                    m.eval() if mode == "eval" else m.train()
+                    ms = timed(lambda: m(x), 20, 5)
+                    rec[mode] = {"value": batch / ms * 1e3, "unit": "frames/s", "ms": ms}
+            out[key] = rec
+            del m, x
+            torch.cuda.empty_cache()
+        clips = 128
+        r3m_b200.set_lang_encoder_factory(StubLangEncoder)
+        m = R3M("cuda", HYPER["lr"], HYPER["hidden_dim"], size=34, l2weight=HYPER["l2weight"], l1weight=HYPER["l1weight"],
+                langweight=1.0, tcnweight=HYPER["tcnweight"])
+        model = torch.nn.DataParallel(m.to(dev), device_ids=[dev.index])
+        tr = Trainer(eval_freq=10 ** 9)
+        frames = torch.randint(0, 255, (clips, 5, 3, 224, 224), device=dev).float()
+        sents = sentences_for(clips)
+        ms = timed(lambda: tr.update(model, (frames, sents), 0), 8, 4)
+        out["c4_resnet34_update_b128"] = {"value": clips * 5 / ms * 1e3, "unit": "frames/s", "ms_per_step": ms}
+        del m, model, tr, frames
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 - a reported side measurement must not sink the bench line
+        out["error"] = repr(e)[:200]
+    return out
+
+
 def workload_config(args, clips_override=None):
     clips = clips_override or args.clips
     return {"workload": f"c3/c5: full Trainer.update(): ResNet-{args.size}, 5 frames/clip, {clips} clips per GPU, "
@@ -415,6 +468,8 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "launches_per_step": launches,
             "roofline": roofline, "last_metrics": metrics_box.get("m")}
     if rank == 0:
+        if world == 1 and not args.no_other_configs and args.size == 50 and B == CLIPS_PER_GPU:
+            line["other_configs"] = other_configs(dev)
         if world == 1 and not args.no_gpu_reference:
             line["gpu_reference"] = gpu_reference(args, B, lang, dev)
         if world == 1 and not args.no_cpu_baseline:

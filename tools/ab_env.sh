@@ -5,7 +5,7 @@ reps=${REPS:-2}
 for r in $(seq $reps); do
   for v in "$@"; do
     name="${v%%=*}"; envs="${v#*=}"
-    out=$(env $envs python bench.py --no-cpu-baseline --no-gpu-reference --steps 20 --warmup 5 2>/dev/null)
+    out=$(env $envs python bench.py --no-cpu-baseline --no-gpu-reference --no-other-configs --steps 20 --warmup 5 2>/dev/null)
     echo "$out" > gpurun_out/ab_${name}.json
     python - "$name" <<PY
 import json,sys
