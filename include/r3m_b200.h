@@ -125,6 +125,11 @@ int r3m_b200_stem_backward(const void* dA, const uint8_t* argmax, const void* ym
  * BatchNorm statistics / BatchNorm-backward sums (aten's cudnn_batch_norm reductions are order dependent; these are
  * not).  The result is independent of `blocks`. */
 int r3m_b200_ordered_sum(const float* x, size_t n, float* out, int blocks, void* stream);
+/* Test hook of the BatchNorm batch statistics as the engine computes them (aten::cudnn_batch_norm's mean / biased
+ * variance, tv resnet.py:89-105): out[0] = mean, out[1] = variance of x[0..n) from the fixed-point sum and sum of
+ * squares, with the E[x^2] - mean^2 subtraction carried out in fp64 so that channels with |mean| >> std do not lose
+ * their variance to cancellation. */
+int r3m_b200_ordered_moments(const float* x, int n, float* out, int blocks, void* stream);
 
 /* Side-band upload of the step's small host inputs (replaces the `.cuda()` calls of r3m/trainer.py:108 and the index
  * tensors of :86-92,135-137): dst (device) <- host_pinned (page-locked host memory, device-accessible under unified

@@ -62,6 +62,7 @@ _sig("r3m_b200_maxpool_backward", [c_void_p, c_void_p, c_void_p, c_void_p, c_int
 _sig("r3m_b200_loss_tcn_sim", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p])
 _sig("r3m_b200_engine_set_int", [c_void_p, c_int, c_int])
 _sig("r3m_b200_ordered_sum", [c_void_p, c_size_t, c_void_p, c_int, c_void_p])
+_sig("r3m_b200_ordered_moments", [c_void_p, c_int, c_void_p, c_int, c_void_p])
 _sig("r3m_b200_pull_host", [c_void_p, c_void_p, ctypes.c_size_t, c_void_p])
 _sig("r3m_b200_stem_backward", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 8)
 _sig("r3m_b200_avgpool_forward", [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])

@@ -217,6 +217,12 @@ int r3m_b200_ordered_sum(const float* x, size_t n, float* out, int blocks, void*
   return R3M_B200_OK;
 }
 
+int r3m_b200_ordered_moments(const float* x, int n, float* out, int blocks, void* stream) {
+  if (!x || !out || n < 1) return fail(R3M_B200_ERR_INVALID, "ordered_moments: null pointer or empty input");
+  CUDA_OR_FAIL(launch_ordered_moments(x, n, out, blocks, (cudaStream_t)stream), "ordered_moments");
+  return R3M_B200_OK;
+}
+
 int r3m_b200_bn_apply(const void* y, void* a, const void* residual, int M, int C, int relu, int train, const float* sum,
                       const float* sq, const float* gamma, const float* beta, float* running_mean, float* running_var,
                       float* save_mean, float* save_rstd, uint8_t* mask_out, const void* y2, const float* sum2,

@@ -104,21 +104,46 @@ __device__ __forceinline__ void st8(bf16* p, const F8& f) {
 //   conv statistics  raw layout: channel c -> kFxWords words of the sum, then kFxWords of the sum of squares
 //                    (sum == sq == base)
 //   backward sums    raw layout: entry i   -> kFxWords words
-__device__ __forceinline__ float stat_at(const float* p, int raw, int c, int which) {
-  if (!raw) return p[c];
-  return fx_to_float(reinterpret_cast<const unsigned long long*>(p) + (2 * c + which) * kFxWords);
-}
 __device__ __forceinline__ float bsum_at(const float* p, int raw, int i) {
   if (!raw) return p[i];
   return fx_to_float(reinterpret_cast<const unsigned long long*>(p) + i * kFxWords);
 }
 
-__device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, int raw, float inv_m,
+// Batch mean and biased variance of channel c from the per-channel sum / sum of squares of M elements.  The textbook
+// E[x^2] - mean^2 loses eps * mean^2 / var of the variance to cancellation when |mean| >> std, so the subtraction is
+// carried out in fp64: on the engine's path ("raw") the sums are exact (fixed-point accumulators, ptx.cuh) and are
+// converted straight to fp64, so the variance is good to ~1e-16 * mean^2 / var; with fp32 sums (kernel-level C ABI) the
+// inputs are already rounded and fp64 only keeps the subtraction itself from adding to that.  bn_apply / stem_pool
+// (bn_coeffs) and bn_publish (the statistics the backward pass reads) share this function: identical bits.
+__device__ __forceinline__ void bn_batch_moments(const float* sum, const float* sq, int raw, int c, int M, float& mean,
+                                                 float& var) {
+  if (raw == 2) {  // A/B aid: fp32 conversion of the sums and fp32 subtraction, as in round 1
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(sum);
+    const float inv_mf = 1.0f / (float)M;
+    mean = fx_to_float(p + (2 * c + 0) * kFxWords) * inv_mf;
+    var = fmaxf(fx_to_float(p + (2 * c + 1) * kFxWords) * inv_mf - mean * mean, 0.f);
+    return;
+  }
+  const double inv_m = 1.0 / (double)M;
+  double s, q;
+  if (raw) {
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(sum);
+    s = fx_to_double(p + (2 * c + 0) * kFxWords);
+    q = fx_to_double(p + (2 * c + 1) * kFxWords);
+  } else {
+    s = (double)sum[c];
+    q = (double)sq[c];
+  }
+  const double m = s * inv_m;
+  mean = (float)m;
+  var = fmaxf((float)(q * inv_m - m * m), 0.f);
+}
+
+__device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, int raw, int M,
                                           const float* gamma, const float* beta, const float* rm, const float* rv, int c,
                                           float& scale, float& shift, float& mean, float& var) {
   if (train) {
-    mean = stat_at(sum, raw, c, 0) * inv_m;
-    var = fmaxf(stat_at(sq, raw, c, 1) * inv_m - mean * mean, 0.f);
+    bn_batch_moments(sum, sq, raw, c, M, mean, var);
   } else {
     mean = rm[c];
     var = rv[c];
@@ -131,10 +156,9 @@ __device__ __forceinline__ void bn_coeffs(int train, const float* sum, const flo
 // block 0 publishes the batch statistics for backward and folds them into the running estimates
 __device__ __forceinline__ void bn_publish(int C, int M, const float* sum, const float* sq, int raw, float* save_mean,
                                            float* save_rstd, float* rm, float* rv, int update_running) {
-  const float inv_m = 1.0f / (float)M;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = stat_at(sum, raw, c, 0) * inv_m;
-    const float var = fmaxf(stat_at(sq, raw, c, 1) * inv_m - mean * mean, 0.f);
+    float mean, var;
+    bn_batch_moments(sum, sq, raw, c, M, mean, var);
     if (save_mean) save_mean[c] = mean;
     if (save_rstd) save_rstd[c] = 1.0f / sqrtf(var + kBnEps);
     if (update_running && rm && rv) {
@@ -414,7 +438,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int chunk = threadIdx.x % C8;
   const int rows_per_iter = blockDim.x / C8;
   const int r0 = threadIdx.x / C8;
-  const float inv_m = 1.0f / (float)a.M;
   constexpr bool dual = kDual;
   // The per-channel coefficients are computed ONCE per block into shared memory (statistics -> scale / shift: a sqrt, a
   // division and, on the engine's path, the conversion of the producers' fixed-point accumulators) instead of once per
@@ -423,11 +446,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   for (int cl = threadIdx.x; cl < Cs; cl += blockDim.x) {
     const int c = c_base + cl;
     float mean, var, scale, shift, scale2 = 0.f;
-    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, c, scale, shift,
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, a.M, a.gamma, a.beta, a.running_mean, a.running_var, c, scale, shift,
               mean, var);
     if (dual) {
       float shift2;
-      bn_coeffs(a.train, a.sum2, a.sq2, a.stat_raw, inv_m, a.gamma2, a.beta2, a.running_mean2, a.running_var2, c, scale2,
+      bn_coeffs(a.train, a.sum2, a.sq2, a.stat_raw, a.M, a.gamma2, a.beta2, a.running_mean2, a.running_var2, c, scale2,
                 shift2, mean, var);
       shift += shift2;
     }
@@ -518,7 +541,6 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
   pdl_sync();
   const int C8 = a.C >> 3;
   const int P = a.H / 2, Q = a.W / 2;
-  const float inv_m = 1.0f / ((float)a.N * a.H * a.W);
   const bf16* __restrict__ y = reinterpret_cast<const bf16*>(a.y);
   bf16* __restrict__ out = reinterpret_cast<bf16*>(a.a);
   // One block iteration = one pooled row (n, p); threads stride over (q, chunk) with 32-bit arithmetic only.  blockDim
@@ -527,8 +549,8 @@ __global__ void __launch_bounds__(224) stem_pool_kernel(const StemPoolArgs a) {
   __shared__ float s_sc[256], s_sh[256];  // C <= 256: coefficients once per block (see bn_apply_kernel)
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     float mean, var;
-    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, inv_m, a.gamma, a.beta, a.running_mean, a.running_var, c, s_sc[c], s_sh[c],
-              mean, var);
+    bn_coeffs(a.train, a.sum, a.sq, a.stat_raw, a.N * a.H * a.W, a.gamma, a.beta, a.running_mean, a.running_var, c, s_sc[c],
+              s_sh[c], mean, var);
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -1459,6 +1481,11 @@ cudaError_t launch_maxpool_bwd(const void* dA, const uint8_t* argmax, void* dz, 
   return cudaGetLastError();
 }
 
+int bn_stat_mode() {
+  static const int mode = (std::getenv("R3M_BN_FP32") && atoi(std::getenv("R3M_BN_FP32"))) ? 2 : 1;
+  return mode;
+}
+
 DetScratch device_det_scratch() {
   static DetScratch d;
   if (!d.scratch) {
@@ -1712,7 +1739,37 @@ __global__ void __launch_bounds__(256) ordered_sum_kernel(const float* __restric
     *ticket = 0;
   }
 }
+// the BatchNorm statistics law on a flat array: fixed-point sum and sum of squares, then bn_batch_moments
+__global__ void __launch_bounds__(256) ordered_moments_kernel(const float* __restrict__ x, int n, unsigned long long* acc,
+                                                              int* ticket, float* __restrict__ out) {
+  pdl_sync();
+  __shared__ int s_last;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = x[i];
+    fx_add(acc, v);
+    fx_add(acc + kFxWords, v * v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    bn_batch_moments(reinterpret_cast<const float*>(acc), nullptr, 1, 0, n, out[0], out[1]);
+    fx_clear(acc);
+    fx_clear(acc + kFxWords);
+    *ticket = 0;
+  }
+}
 }  // namespace
+
+cudaError_t launch_ordered_moments(const float* x, int n, float* out, int blocks, cudaStream_t s) {
+  DetScratch d = device_det_scratch();
+  if (!d.scratch) return cudaErrorMemoryAllocation;
+  launch_kernel(ordered_moments_kernel, std::max(1, std::min(blocks, 1024)), 256, 0, s, x, n,
+                reinterpret_cast<unsigned long long*>(d.scratch), d.tickets, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_ordered_sum(const float* x, size_t n, float* out, int blocks, cudaStream_t s) {
   DetScratch d = device_det_scratch();

@@ -38,7 +38,8 @@ struct BnApplyArgs {
   float* save_rstd = nullptr;
   int update_running = 1;
   // 1: sum (== sq) and sum2 (== sq2) point at the producing conv's raw fixed-point accumulators (8 64-bit words per
-  // channel: 4 limbs of the sum, 4 of the sum of squares; see fx_add) instead of fp32 arrays — the engine's path
+  // channel: 4 limbs of the sum, 4 of the sum of squares; see fx_add) instead of fp32 arrays — the engine's path.
+  // 2: the same, with the round-1 fp32 moments arithmetic (A/B aid, R3M_BN_FP32=1; see bn_batch_moments)
   int stat_raw = 0;
   // 1: walk the rows last-to-first.  The engine alternates the traversal direction of consecutive passes over a tensor:
   // the rows a producer wrote LAST are still in the 126 MB L2 when its consumer starts from that end
@@ -204,6 +205,9 @@ cudaError_t launch_stem_pack_f32(const float* w_oihw, float* wp, cudaStream_t s)
 
 // out[0] = the EXACT sum of x[0..n) rounded once to fp32, through the fixed-point accumulators every deterministic
 // reduction of the step uses (test hook: the result must not depend on `blocks`, i.e. on grouping and arrival order)
+// BnApplyArgs / StemPoolArgs::stat_raw of the engine's path: 1, or 2 under R3M_BN_FP32=1
+int bn_stat_mode();
 cudaError_t launch_ordered_sum(const float* x, size_t n, float* out, int blocks, cudaStream_t s);
+cudaError_t launch_ordered_moments(const float* x, int n, float* out, int blocks, cudaStream_t s);
 
 }  // namespace r3m

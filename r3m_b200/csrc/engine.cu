@@ -336,7 +336,7 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.train = train;
   a.sum = zero + c.zero_off;
   a.sq = a.sum;
-  a.stat_raw = 1;
+  a.stat_raw = bn_stat_mode();
   a.gamma = P + c.gamma_off;
   a.beta = P + c.beta_off;
   a.running_mean = buf + c.rm_off;
@@ -483,7 +483,7 @@ std::string Engine::plan_all() {
       a.train = train;
       a.sum = zero + st.zero_off;
       a.sq = a.sum;
-      a.stat_raw = 1;
+      a.stat_raw = bn_stat_mode();
       a.gamma = P + st.gamma_off;
       a.beta = P + st.beta_off;
       a.running_mean = buf + st.rm_off;

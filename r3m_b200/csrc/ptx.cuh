@@ -38,17 +38,6 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -369,6 +358,26 @@ __device__ __forceinline__ float fx_to_float(const unsigned long long* acc) {
   if (round_bit && (sticky || (mant & 1u))) ++mant;  // may reach 2^24: still exact in fp32
   // bit 127 of the shifted magnitude weighs 2^(63 - lz); it is bit 23 of mant
   const float v = (float)mant * __int_as_float((40 - lz + 127) << 23);
+  return neg ? -v : v;
+}
+// the accumulator as fp64: the top 64 significant bits of the magnitude rounded to 53 (relative error < 2^-52; a
+// function of the accumulator's bits only, so as reproducible as fx_to_float).  For the few places where an fp32
+// rounding of the sum would be amplified by a cancellation downstream (BatchNorm variance, elementwise.cu).
+__device__ __forceinline__ double fx_to_double(const unsigned long long* acc) {
+  __int128 t = 0;
+#pragma unroll
+  for (int k = kFxWords - 1; k >= 0; --k) t = (t << 32) + (__int128)(long long)__ldcg(acc + k);
+  const bool neg = t < 0;
+  const unsigned __int128 mag = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;
+  const unsigned long long hi = (unsigned long long)(mag >> 64), lo = (unsigned long long)mag;
+  if ((hi | lo) == 0ull) return 0.0;
+  const int lz = hi ? __clzll((long long)hi) : 64 + __clzll((long long)lo);
+  unsigned long long top;  // bits 127..64 of magnitude << lz
+  if (lz == 0) top = hi;
+  else if (lz < 64) top = (hi << lz) | (lo >> (64 - lz));
+  else top = lz == 64 ? lo : lo << (lz - 64);
+  // magnitude = top * 2^(64 - lz) accumulator units of 2^-64  ->  value = top * 2^-lz, lz in [0, 127]
+  const double v = __ull2double_rn(top) * __longlong_as_double((long long)(1023 - lz) << 52);
   return neg ? -v : v;
 }
 __device__ __forceinline__ void fx_clear(unsigned long long* acc) {

@@ -109,6 +109,29 @@ def test_fixed_point_accumulator_is_exact_and_order_independent(lib, scale):
     assert torch.equal(out.cpu(), outs[0])
 
 
+@pytest.mark.parametrize("ratio", [1.0, 30.0, 300.0, 1000.0])
+def test_batchnorm_variance_survives_large_means(lib, ratio):
+    """one-pass E[x^2] - mean^2 in fp32 loses eps * (mean / std)^2 of the variance (6 % at
+    |mean| = 1000 std).  The engine's statistics law (csrc/elementwise.cu: bn_batch_moments — exact fixed-point sums,
+    fp64 subtraction) keeps it.  Inputs sit on a 12-bit grid like a low-precision conv output, so that their squares
+    are exact in fp32 and the check against fp64 can be tight."""
+    import math
+
+    g = torch.Generator().manual_seed(int(ratio))
+    grid = 2.0 ** math.floor(math.log2(4095.0 / (ratio + 6.0)))
+    x = torch.round((torch.randn(400_000, generator=g).clamp(-5, 5) + ratio) * grid) / grid
+    want_mean, want_var = x.double().mean(), x.double().var(unbiased=False)
+    xd = x.cuda()
+    outs = []
+    for blocks in (1, 148, 1024):
+        out = torch.zeros(2, device="cuda")
+        lib.check(lib.lib.r3m_b200_ordered_moments(lib.ptr(xd), xd.numel(), lib.ptr(out), blocks, lib.current_stream()))
+        outs.append(out.cpu())
+    assert all(torch.equal(o, outs[0]) for o in outs)
+    assert abs(float(outs[0][0]) - float(want_mean)) <= 2e-7 * abs(float(want_mean))
+    assert abs(float(outs[0][1]) - float(want_var)) <= 1e-6 * float(want_var), (float(outs[0][1]), float(want_var))
+
+
 @pytest.mark.parametrize("size,clips,lang", [(18, 6, 1), (50, 10, 1)])
 def test_step_graph_replay_equals_plain_launches(monkeypatch, size, clips, lang):
     """Whole-step CUDA graphs (engine.cu: run_cached): from the second step with the same input buffers on, the train-mode
