@@ -662,8 +662,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // last CTA of the column block: totals -> fp32, accumulators and ticket back to zero for the next launch
         __threadfence();
         for (int c = et; c < BN; c += EPI * 32) {
-          p.stat_sum[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c);
-          p.stat_sq[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c + kFxWords);
+          if (p.stat_rows > 0) {
+            fx_moments(acc + 2 * kFxWords * c, acc + 2 * kFxWords * c + kFxWords, p.stat_rows,
+                       p.stat_sum[my_ntile * BN + c], p.stat_sq[my_ntile * BN + c]);
+          } else {
+            p.stat_sum[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c);
+            p.stat_sq[my_ntile * BN + c] = fx_to_float(acc + 2 * kFxWords * c + kFxWords);
+          }
           fx_clear(acc + 2 * kFxWords * c);
           fx_clear(acc + 2 * kFxWords * c + kFxWords);
         }

@@ -40,6 +40,9 @@ struct ConvKernelParams {
   int* stat_ticket;
   int stat_raw;  // 1: stat_sum points at the layer's own accumulators (Cout * 8 64-bit words, zero on entry); the kernel
                  // only adds into them and the consumer converts (no scratch, no ticket, no finalize tail)
+  int stat_rows;  // ticket mode (stat_raw == 0) only; > 0: the last CTA of a column block publishes the batch MOMENTS of
+                  // stat_rows values per channel — stat_sum[c] = mean, stat_sq[c] = biased variance (fx_moments) —
+                  // instead of the fp32-rounded sums
   // optional fused epilogue (inference: BatchNorm folded into a per-channel affine): out = [relu](acc * ep_scale[c] +
   // ep_shift[c] [+ ep_res[m][c]]).  Dense outputs only; mutually exclusive with the statistics.
   const float* ep_scale;

@@ -181,6 +181,7 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
   p.stat_scratch = g.stat_scratch;
   p.stat_ticket = g.stat_ticket;
   p.stat_raw = g.stat_raw;
+  p.stat_rows = g.stat_raw ? 0 : g.stat_rows;
   if (g.stat_sum && !g.stat_scratch && !g.stat_raw) {
     float* shared = device_stat_scratch();
     if (!shared) return "could not allocate the statistics scratch";

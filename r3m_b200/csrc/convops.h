@@ -32,6 +32,7 @@ struct GatherConv {
   float* stat_scratch = nullptr;
   int* stat_ticket = nullptr;
   int stat_raw = 0;  // 1: stat_sum is the layer's raw fixed-point accumulator block (see ConvKernelParams)
+  int stat_rows = 0;  // > 0 (ticket mode): publish (mean, variance) over stat_rows values instead of (sum, sum of squares)
   // fused inference epilogue (see ConvKernelParams): per-channel affine (+ residual) (+ ReLU) on the accumulators
   const float* ep_scale = nullptr;
   const float* ep_shift = nullptr;

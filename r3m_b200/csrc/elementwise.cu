@@ -124,19 +124,20 @@ __device__ __forceinline__ void bn_batch_moments(const float* sum, const float* 
     var = fmaxf(fx_to_float(p + (2 * c + 1) * kFxWords) * inv_mf - mean * mean, 0.f);
     return;
   }
-  const double inv_m = 1.0 / (double)M;
-  double s, q;
+  if (raw == 3) {  // the producing conv's last CTAs have already published (mean, variance) by the same law (fx_moments)
+    mean = sum[c];
+    var = sq[c];
+    return;
+  }
   if (raw) {
     const unsigned long long* p = reinterpret_cast<const unsigned long long*>(sum);
-    s = fx_to_double(p + (2 * c + 0) * kFxWords);
-    q = fx_to_double(p + (2 * c + 1) * kFxWords);
-  } else {
-    s = (double)sum[c];
-    q = (double)sq[c];
+    fx_moments(p + (2 * c + 0) * kFxWords, p + (2 * c + 1) * kFxWords, M, mean, var);
+    return;
   }
-  const double m = s * inv_m;
+  const double inv_m = 1.0 / (double)M;
+  const double m = (double)sum[c] * inv_m;
   mean = (float)m;
-  var = fmaxf((float)(q * inv_m - m * m), 0.f);
+  var = fmaxf((float)((double)sq[c] * inv_m - m * m), 0.f);
 }
 
 __device__ __forceinline__ void bn_coeffs(int train, const float* sum, const float* sq, int raw, int M,

@@ -19,6 +19,13 @@ constexpr double kFuseBnBwdBytes = 72e6;
 
 typedef __nv_bfloat16 bf16;
 
+// Layers with at most this many output rows (N * P * Q) have their BatchNorm reductions finalised by the producers (see
+// Conv::fin).  R3M_BN_FIN_ROWS overrides it (0: every layer converts on read).
+static long long bn_finalize_max_rows() {
+  static const long long rows = std::getenv("R3M_BN_FIN_ROWS") ? atoll(std::getenv("R3M_BN_FIN_ROWS")) : 260000;
+  return rows;
+}
+
 struct Engine::Conv {
   std::string name, bn;
   int Cin = 0, Cout = 0, R = 1, stride = 1, pad = 0, H = 0, W = 0, P = 0, Q = 0;
@@ -28,7 +35,11 @@ struct Engine::Conv {
   // per-step zeroed region (floats): fixed-point accumulators (fx_add, ptx.cuh) of the layer's BatchNorm reductions —
   // [0, 16C) forward statistics (sum, sum of squares: 4 64-bit words each per channel), [16C, 32C) backward sums (2C
   // entries of 4 words), [32C, 40C) the downsample branch's extra backward sum (C entries)
+  // Producer-finalised layers (`fin`, see Engine::create) use [40C + 8, 42C + 8) as fp32 batch moments (mean[C], var[C]) and
+  // the 64 ints behind them as the per-column-block tickets of the conv kernel's last-CTA conversion.
   size_t zero_off = 0;
+  bool fin = false;
+  size_t fin_off(int) const { return zero_off + 40 * (size_t)Cout + 8; }
   size_t save_off = 0;                            // saved batch statistics (floats): mean[C] rstd[C]
   size_t wd_off = 0;                              // dgrad-packed filters (bf16 elements)
   size_t y_off = 0, a_off = 0;                    // arena byte offsets of the raw / activated outputs
@@ -166,7 +177,13 @@ std::string Engine::create(int size, int frames, int lang_head, int hidden_dim, 
     c->beta_off = take(np, c->Cout, 128);
     c->rm_off = take(nb, c->Cout, 32);
     c->rv_off = take(nb, c->Cout, 32);
-    c->zero_off = take(nz, 40 * (size_t)c->Cout + 8, 32);  // + the grid-barrier counter of the fused BatchNorm backward
+    c->zero_off = take(nz, 42 * (size_t)c->Cout + 8 + 64, 32);  // + the grid-barrier counter of the fused BatchNorm
+                                                                // backward, + fp32 statistics and tickets (Conv::fin)
+    // Small-M layers: the producers finalise the reductions (last-CTA conversion of the fixed-point accumulators to
+    // fp32: conv statistics per column block, bn_bwd_reduce per channel slice) instead of every block of the consuming
+    // BatchNorm kernel converting all C channels in its prologue — with few rows per block that prologue moves more
+    // bytes through L2 than the payload (ncu: layer4.bn3 apply 541 MB of L2 traffic for 197 MB of tensors).
+    c->fin = !c->stem && (long long)frames * c->P * c->Q <= bn_finalize_max_rows();
     c->save_off = take(ns, 2 * (size_t)c->Cout, 32);
     if (!c->stem) c->wd_off = take(nwd, wn, 128);
     TensorInfo t;
@@ -334,9 +351,10 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
   a.C = c.Cout;
   a.relu = relu;
   a.train = train;
-  a.sum = zero + c.zero_off;
-  a.sq = a.sum;
-  a.stat_raw = bn_stat_mode();
+  const bool fin = c.fin && (!second || second->fin);
+  a.sum = fin ? zero + c.fin_off(0) : zero + c.zero_off;
+  a.sq = fin ? a.sum + c.Cout : a.sum;
+  a.stat_raw = fin ? 3 : bn_stat_mode();
   a.gamma = P + c.gamma_off;
   a.beta = P + c.beta_off;
   a.running_mean = buf + c.rm_off;
@@ -352,8 +370,8 @@ void Engine::add_bn_apply(std::vector<Op>& ops, const Conv& c, const void* resid
     // downsample branch folded in: a = relu(bn(y) + bn_ds(y_ds)), bn_ds(y_ds) is never materialised
     const Conv& d = *second;
     a.y2 = d.y;
-    a.sum2 = zero + d.zero_off;
-    a.sq2 = a.sum2;
+    a.sum2 = fin ? zero + d.fin_off(0) : zero + d.zero_off;
+    a.sq2 = fin ? a.sum2 + d.Cout : a.sum2;
     a.gamma2 = P + d.gamma_off;
     a.beta2 = P + d.beta_off;
     a.running_mean2 = buf + d.rm_off;
@@ -459,7 +477,14 @@ std::string Engine::plan_all() {
       fill_fwd_geometry(&gc, c.R, c.R, c.stride, c.pad);
       gc.wpk = Pb + c.w_off;
     }
-    if (train) {
+    if (train && c.fin) {
+      gc.stat_sum = zero + c.fin_off(0);  // (mean, variance) published by the last CTA of every column block
+      gc.stat_sq = gc.stat_sum + c.Cout;
+      gc.stat_rows = N * c.P * c.Q;
+      gc.stat_scratch = zero + c.zero_off;
+      gc.stat_ticket = reinterpret_cast<int*>(zero + c.fin_off(0) + 2 * (size_t)c.Cout);
+      gc.stat_raw = 0;
+    } else if (train) {
       gc.stat_sum = zero + c.zero_off;  // the layer's raw accumulators: the BatchNorm kernels convert on read
       gc.stat_sq = gc.stat_sum;
       gc.stat_raw = 1;
@@ -767,7 +792,7 @@ std::string Engine::plan_all() {
     a.rstd = saved + c.save_off + c.Cout;
     a.gamma = P + c.gamma_off;
     a.sums = zero + c.zero_off + 16 * c.Cout;
-    a.sums_raw = 1;
+    a.sums_raw = c.fin ? 0 : 1;  // 0: fp32 totals (sums[2C], sums2[C]) written by the reduce pass's last block per slice
     a.dy = dy;
     a.dz_out = dz_out;
     a.dgamma = G + c.gamma_off;

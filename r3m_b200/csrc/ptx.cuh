@@ -380,6 +380,16 @@ __device__ __forceinline__ double fx_to_double(const unsigned long long* acc) {
   const double v = __ull2double_rn(top) * __longlong_as_double((long long)(1023 - lz) << 52);
   return neg ? -v : v;
 }
+// mean and biased variance of M values from the exact accumulators of their sum and sum of squares: the division by M
+// and the E[x^2] - mean^2 subtraction in fp64, so that |mean| >> std costs ~1e-16 * (mean / std)^2 of the variance
+// instead of fp32's 6e-8 * (mean / std)^2 (BatchNorm statistics: elementwise.cu bn_batch_moments, conv_igemm.cu tail)
+__device__ __forceinline__ void fx_moments(const unsigned long long* acc_sum, const unsigned long long* acc_sq, int M,
+                                           float& mean, float& var) {
+  const double inv_m = 1.0 / (double)M;
+  const double m = fx_to_double(acc_sum) * inv_m;
+  mean = (float)m;
+  var = fmaxf((float)(fx_to_double(acc_sq) * inv_m - m * m), 0.f);
+}
 __device__ __forceinline__ void fx_clear(unsigned long long* acc) {
 #pragma unroll
   for (int k = 0; k < kFxWords; ++k) acc[k] = 0ull;
