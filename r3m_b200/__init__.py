@@ -18,7 +18,15 @@ from .bert import DistilBertEncoder  # noqa: F401
 from .checkpoint import load_snapshot, save_snapshot  # noqa: F401
 
 __all__ = ["R3M", "Trainer", "load_r3m", "load_r3m_reproduce", "set_lang_encoder_factory", "FrameFeeder", "GpuAugment",
-           "R3MBufferU8", "nvjpeg_batch_decoder", "DistilBertEncoder", "save_snapshot", "load_snapshot"]
+           "R3MBufferU8", "nvjpeg_batch_decoder", "DistilBertEncoder", "save_snapshot", "load_snapshot", "check_device"]
+
+
+def check_device():
+    """Synchronise the device and raise ``R3MB200Error`` if a tcgen05 / TMA pipeline watchdog fired in any kernel since
+    the last check.  ``Trainer.update`` performs this check every step (the flag travels with the metrics read-back);
+    forward-only use (``model.eval(); model(frames)``) enqueues its kernels without synchronising, so a serving loop
+    calls this where a synchronisation is acceptable — e.g. once per batch after copying the embeddings out."""
+    _lib.check(_lib.lib.r3m_b200_check_device_flag())
 
 VALID_ARGS = ["_target_", "device", "lr", "hidden_dim", "size", "l2weight", "l1weight", "langweight", "tcnweight",
               "l2dist", "bs"]  # r3m/__init__.py:15
