@@ -63,7 +63,10 @@ struct HaloKernelParams {
   int N, H, W;            // images; output (= input) height and width: H % 4 == 0, W % 8 == 0
   int tiles_h, tiles_w;   // ceil(H / 16), W / 8
   int num_taps;           // <= 9
-  uint16_t tap_w[9], tap_h[9];  // tap t reads input pixel (p - 1 + tap_h[t], q - 1 + tap_w[t]) with filter K block t
+  uint16_t tap_w[9], tap_h[9];  // tap t reads input pixel (p + org_h + tap_h[t], q + org_w + tap_w[t]) with filter K block t
+  int org_h, org_w;       // halo origin relative to the tile's first output pixel: (-1, -1) for the 3x3 convs, (-2, 0) for
+                          // the stem's four vertical taps
+  int patch_bytes;        // bytes of one halo load: (16 + max tap_h) rows x 10 columns x 128
   int rev;                // walk the tiles last-to-first
   unsigned long long* stat_acc;  // optional raw fixed-point accumulators (64 channels x {sum, sum of squares}), added into
   int acc_stages;         // accumulator stages in tensor memory (tiles in flight between the MMA issuer and the epilogue)

@@ -80,13 +80,21 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
     // measured on B200: the shifted views are correct with base offset 0 (TMA and UMMA both derive the swizzle phase from
     // the absolute shared-memory address); setting the descriptor's base-offset field to the start row's phase is WRONG
     static const int halo_bo = std::getenv("R3M_HALO_BO") ? atoi(std::getenv("R3M_HALO_BO")) : 0;
-    bool ok = halo_env && !g.tf32 && g.C == 64 && g.Cout == 64 && g.stride == 1 && g.base_h == -1 && g.base_w == -1 &&
+    // two footprints: the 3x3 / pad 1 convs (halo origin (-1, -1), taps (0..2, 0..2)) and the stem's four vertical taps
+    // (origin (-2, 0), taps (0..3, 0): one more halo row, no halo columns; R3M_HALO_STEM=0 keeps it on conv_igemm)
+    static const bool halo_stem_env = !(std::getenv("R3M_HALO_STEM") && std::getenv("R3M_HALO_STEM")[0] == '0');
+    const bool k3 = g.base_h == -1 && g.base_w == -1;
+    const bool stem4 = halo_stem_env && g.base_h == -2 && g.base_w == 0;
+    const int max_th = k3 ? 2 : 3, max_tw = k3 ? 2 : 0;
+    bool ok = halo_env && !g.tf32 && g.C == 64 && g.Cout == 64 && g.stride == 1 && (k3 || stem4) &&
               g.P == g.H && g.Q == g.W && g.W % 8 == 0 && g.H % 4 == 0 && g.ntaps >= 1 && g.ntaps <= 9 &&
               g.out_mode == 0 && g.ldo == 64 && !g.accumulate && g.ep_scale == nullptr &&
               (g.stat_sum == nullptr || g.stat_raw) && g.bn == 0;
-    for (int t = 0; ok && t < g.ntaps; ++t) ok = g.tap_h[t] >= 0 && g.tap_h[t] <= 2 && g.tap_w[t] >= 0 && g.tap_w[t] <= 2;
+    for (int t = 0; ok && t < g.ntaps; ++t)
+      ok = g.tap_h[t] >= 0 && g.tap_h[t] <= max_th && g.tap_w[t] >= 0 && g.tap_w[t] <= max_tw;
     if (ok) {
-      std::string e = encode_tiled_4d_map(&plan->tmA, g.src, 64, g.W, g.H, g.N, 64, 10, 18);
+      const int halo_rows = 16 + max_th;
+      std::string e = encode_tiled_4d_map(&plan->tmA, g.src, 64, g.W, g.H, g.N, 64, 10, halo_rows);
       if (e.empty())
         e = encode_tiled_2d_map(&plan->tmB, g.wpk, (uint64_t)g.ntaps * 64, 64, (uint64_t)g.ntaps * 64 * 2, 64, 64, 128, 2);
       if (e.empty()) e = encode_tiled_4d_map(&plan->tmC, g.out, 64, g.W, g.H, g.N, 64, 8, 4);
@@ -102,6 +110,9 @@ std::string plan_conv(const GatherConv& g, ConvPlan* plan) {
         hp.tap_w[t] = (uint16_t)g.tap_w[t];
         hp.tap_h[t] = (uint16_t)g.tap_h[t];
       }
+      hp.org_h = g.base_h;
+      hp.org_w = g.base_w;
+      hp.patch_bytes = halo_rows * 10 * 128;
       hp.rev = g.rev_m;
       hp.stat_acc = reinterpret_cast<unsigned long long*>(g.stat_sum);
       hp.base_offset_mode = halo_bo;

@@ -1,4 +1,6 @@
-// 3x3 stride-1 convolution of 64 -> 64 channels (ResNet-50 layer1 conv2: forward and data gradient) with TAP REUSE.
+// 3x3 stride-1 convolution of 64 -> 64 channels (ResNet-50 layer1 conv2: forward and data gradient) with TAP REUSE — and
+// the stem (7x7 / stride 2 re-expressed as FOUR VERTICAL taps over the 64-"channel" space-to-depth operand):
+// the same kernel with a 19 x 10 halo whose origin is two rows above the tile and taps (0..3, 0).
 //
 // conv_igemm fetches one 128-pixel x 64-channel im2col tile PER TAP, so every input pixel crosses L2 -> shared memory nine
 // times, and at N = 64 a tile carries only ~128 tensor cycles per 16 KB: those launches are bound by the operand fill rate
@@ -22,9 +24,10 @@ namespace r3m {
 namespace {
 
 constexpr int kTileRows = 16, kTileCols = 8;          // output pixels of an M tile (16 x 8 = 128 GEMM rows)
-constexpr int kHaloRows = 18, kHaloCols = 10;
-constexpr int kPatchBytes = kHaloRows * kHaloCols * 128;   // 23040
+constexpr int kHaloCols = 10;                              // halo row pitch in 128-byte rows (the descriptors' group stride)
+constexpr int kMaxHaloRows = 19;                           // 18 for the 3x3 convs, 19 for the stem's four vertical taps
 constexpr int kPatchStride = 24 * 1024;                    // 1024-byte aligned slot
+static_assert(kMaxHaloRows * kHaloCols * 128 <= kPatchStride, "halo slot");
 constexpr int kStages = 3;
 constexpr int kFilterBytes = 9 * 64 * 128;                 // nine K blocks of 64 filters x 64 channels
 constexpr int kBufs = 2;                                   // staging units per epilogue warp
@@ -117,8 +120,8 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (p.debug & 4) {
           mbar_arrive(&full_bar[stage]);
         } else {
-          mbar_expect_tx(&full_bar[stage], kPatchBytes);
-          tma_load_4d(&tmX, &full_bar[stage], s_patch + stage * kPatchStride, 0, q0 - 1, p0 - 1, n);
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.patch_bytes));
+          tma_load_4d(&tmX, &full_bar[stage], s_patch + stage * kPatchStride, 0, q0 + p.org_w, p0 + p.org_h, n);
         }
         if (++stage == kStages) {
           stage = 0;
