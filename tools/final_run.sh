@@ -5,10 +5,10 @@ p=${1:-final}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${p}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${p}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${p}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/${p}_smoke.log
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${p}_bench_ref.json 2> gpurun_out/${p}_bench_ref.err
+[ -n "${SKIP_REF:-}" ] || python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${p}_bench_ref.json 2> gpurun_out/${p}_bench_ref.err
 python bench.py > gpurun_out/${p}_bench_n1.json 2> gpurun_out/${p}_bench_n1.err; echo "bench rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${p}_launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-other-configs > gpurun_out/${p}_launches_bench.log 2>&1
+timeout ${NCU_TIMEOUT:-600} ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-2000} --csv --log-file gpurun_out/${p}_launches.csv \
+  python bench.py --steps ${NCU_STEPS:-2} --warmup ${NCU_WARMUP:-3} --no-cpu-baseline --no-gpu-reference --no-other-configs > gpurun_out/${p}_launches_bench.log 2>&1
 echo "ncu rc=$?"
 tail -3 gpurun_out/${p}_pytest.log; tail -1 gpurun_out/${p}_smoke.log
 python - <<PY
